@@ -1,0 +1,216 @@
+/*
+ * cno.h -- C ABI of the B200-native batched unconstrained-minimisation engine.
+ *
+ * This is the drop-in boundary for ONE path of PatWie/CppNumericalSolvers
+ * (cppoptlib 2.0.0): solver::{Lbfgs,Bfgs,NewtonDescent}::Minimize with the
+ * MoreThuente / Armijo line searches and the Progress stopping rules, with a
+ * batch axis added (B independent instances, one warp per instance on sm_100a).
+ *
+ * Plain C: pointers and sizes only, no C++/torch types.  All citations are
+ * relative to the reference tree (include/cppoptlib/...).
+ *
+ *   reference interface                         replaced / mirrored here
+ *   ------------------------------------------  -----------------------------
+ *   solver/progress.h:37-47   enum Status       cno_status_t
+ *   solver/progress.h:82-140  Progress fields   cno_stop_t (stop thresholds)
+ *                                               cno_batch_out_t (per-instance
+ *                                               progress values)
+ *   solver/progress.h:353-431 Default preset    cno_default_stop()
+ *   solver/progress.h:456-464 Conservative      cno_conservative_stop()
+ *   solver/solver.h:181-224   Solver::Minimize  cno_minimize() /
+ *                                               cno_minimize_host()
+ *   solver/lbfgs.h:40-324     Lbfgs<F,m=10>     solver = CNO_LBFGS
+ *   solver/bfgs.h:39-145      Bfgs<F>           solver = CNO_BFGS
+ *   solver/newton_descent.h:38-85 NewtonDescent solver = CNO_NEWTON
+ *   function_base.h:96-126    FunctionCRTP      cno_problem_t names a functor
+ *                                               that was compiled for the
+ *                                               device
+ *   function_base.h:298-332   FunctionState     x / value / gradient arrays
+ *
+ * Error behaviour (solver/progress.h: numerical outcomes are reported through
+ * Progress::status, never thrown): every entry point returns 0 on success or a
+ * negative cno_error_t; numerical outcomes are per-instance status codes.
+ * There is NO CPU fallback: without a CUDA device every compute entry point
+ * returns CNO_ERR_NO_DEVICE.
+ */
+#ifndef CNO_H_
+#define CNO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNO_VERSION_MAJOR 0
+#define CNO_VERSION_MINOR 1
+
+/* solver/progress.h:37-47 (same numeric values as the reference enum). */
+typedef enum cno_status {
+  CNO_STATUS_NOT_STARTED = -1,
+  CNO_STATUS_CONTINUE = 0,
+  CNO_STATUS_ITERATION_LIMIT = 1,
+  CNO_STATUS_X_DELTA_VIOLATION = 2,
+  CNO_STATUS_F_DELTA_VIOLATION = 3,
+  CNO_STATUS_GRADIENT_NORM_VIOLATION = 4,
+  CNO_STATUS_HESSIAN_CONDITION_VIOLATION = 5,
+  CNO_STATUS_FINISHED = 6
+} cno_status_t;
+
+typedef enum cno_error {
+  CNO_OK = 0,
+  CNO_ERR_INVALID_ARGUMENT = -1,
+  CNO_ERR_UNSUPPORTED = -2,   /* no kernel instantiated for <solver,functor,T,d> */
+  CNO_ERR_NO_DEVICE = -3,     /* no CUDA device: there is no CPU fallback */
+  CNO_ERR_CUDA = -4,          /* see cno_last_cuda_error() */
+  CNO_ERR_WORKSPACE = -5      /* workspace too small / misaligned */
+} cno_error_t;
+
+typedef enum cno_solver {
+  CNO_LBFGS = 0,  /* solver/lbfgs.h, m = 10, MoreThuente */
+  CNO_BFGS = 1,   /* solver/bfgs.h, MoreThuente */
+  CNO_NEWTON = 2  /* solver/newton_descent.h, Armijo<F,2> */
+} cno_solver_t;
+
+typedef enum cno_dtype { CNO_F64 = 0, CNO_F32 = 1 } cno_dtype_t;
+
+/* Objective families with a device functor compiled into libcno.so.  Users add
+ * their own with CNO_INSTANTIATE_* (include/cppoptlib_b200/device.cuh). */
+typedef enum cno_family {
+  /* chained Rosenbrock; reduces to src/test/verify.cc:58-69 at d = 2 */
+  CNO_FN_ROSENBROCK = 0,
+  /* sum_i c_i x_i^2 + c0 with c = (5, 100), c0 = 5: Dockerfile.test:21-29 */
+  CNO_FN_DIAG_QUADRATIC = 1,
+  /* 0.5 * ||x||^2: src/test/augmented_lagrangian_test.cc:123-130 */
+  CNO_FN_HALF_SQUARED_NORM = 2,
+  /* sum_j log1p(exp(-y_j x_j.w)) + lambda/2 ||w||^2, per-instance data */
+  CNO_FN_LOGISTIC = 3,
+  /* 0.5 x'Ax - b'x (Second mode), per-instance A,b: src/examples/debug.cc:43-65 */
+  CNO_FN_DENSE_QUADRATIC = 4
+} cno_family_t;
+
+/* Reduction-order policy = the arithmetic specification every dot/norm on the
+ * path follows (DESIGN.md "Arithmetic specification").  Oracle and kernel are
+ * bit-identical under the same policy. */
+typedef enum cno_policy {
+  CNO_POLICY_WARP_TREE = 0,  /* lane-blocked partials + xor butterfly */
+  CNO_POLICY_EIGEN_SSE2 = 1  /* model of Eigen 3.4 SSE2 redux (oracle + slow kernel) */
+} cno_policy_t;
+
+/* Stopping thresholds: the fields of solver::Progress that
+ * DefaultStoppingSolverProgress() sets (solver/progress.h:87-136). */
+typedef struct cno_stop {
+  uint64_t num_iterations;        /* :87  0 = unlimited */
+  double x_delta;                 /* :88 */
+  int32_t x_delta_violations;     /* :89 */
+  double f_delta;                 /* :90 */
+  int32_t f_delta_violations;     /* :91 */
+  int32_t f_delta_relative;       /* :98 */
+  double gradient_norm;           /* :99 */
+  int32_t gradient_norm_relative; /* :109 */
+  double condition_hessian;       /* :110 */
+  int32_t past;                   /* :135 (<= CNO_MAX_PAST) */
+  double past_delta;              /* :136 */
+} cno_stop_t;
+
+#define CNO_MAX_PAST 8
+#define CNO_LBFGS_M 10
+
+/* Which objective, which scalar type, which dimension. */
+typedef struct cno_problem {
+  int32_t family;      /* cno_family_t */
+  int32_t dtype;       /* cno_dtype_t */
+  int32_t d;           /* dimension of x */
+  int32_t n;           /* CNO_FN_LOGISTIC: samples per instance */
+  double param;        /* CNO_FN_LOGISTIC: lambda */
+  const void* data;    /* per-instance data, [B, data_stride] scalars (device ptr
+                          for cno_minimize, host ptr for cno_minimize_host/oracle) */
+  int64_t data_stride; /* scalars per instance */
+  int32_t policy;      /* cno_policy_t */
+  int32_t reserved;
+} cno_problem_t;
+
+/* Per-instance outputs.  Any pointer may be NULL (not written).  x, value,
+ * gradient = the returned FunctionState (function_base.h:298-332); the rest =
+ * the returned Progress (solver/progress.h:87-127). Scalars are of problem.dtype. */
+typedef struct cno_batch_out {
+  void* x;                 /* [B, d] */
+  void* value;             /* [B] */
+  void* gradient;          /* [B, d] */
+  uint32_t* num_iterations;/* [B] */
+  int8_t* status;          /* [B] cno_status_t */
+  uint32_t* nfev;          /* [B] objective evaluations (not exposed by the reference) */
+  void* x_delta;           /* [B] */
+  void* f_delta;           /* [B] */
+  void* gradient_norm;     /* [B] */
+} cno_batch_out_t;
+
+/* Launch record of the last cno_minimize* call on this thread. */
+typedef struct cno_launch_info {
+  int32_t kernel_launches; /* kernels of this library launched by the call */
+  int32_t grid;            /* CTAs */
+  int32_t block;           /* threads per CTA */
+  int32_t warps_per_cta;
+  int64_t dynamic_smem;    /* bytes per CTA */
+  float kernel_ms;         /* device time of the solve kernel(s), CUDA events */
+  float total_ms;          /* cno_minimize_host: including H2D/D2H */
+  int64_t h2d_bytes;
+  int64_t d2h_bytes;
+} cno_launch_info_t;
+
+void cno_version(int* major, int* minor);
+const char* cno_error_string(int err);
+/* cudaError_t of the last CNO_ERR_CUDA on this thread and its string. */
+int cno_last_cuda_error(const char** msg);
+
+/* solver/progress.h:353-431 and :456-464. */
+void cno_default_stop(cno_stop_t* stop);
+void cno_conservative_stop(cno_stop_t* stop);
+
+/* 0 if a kernel is instantiated for (solver, problem), else CNO_ERR_UNSUPPORTED. */
+int cno_supported(int solver, const cno_problem_t* problem);
+
+/* Scratch the caller must provide for cno_minimize (may be 0). */
+int cno_workspace_bytes(int solver, const cno_problem_t* problem, int64_t batch,
+                        size_t* bytes);
+
+/* Batched Solver::Minimize (solver/solver.h:181-224).  All pointers are DEVICE
+ * pointers on the current device; stream is a cudaStream_t (NULL = default).
+ * Asynchronous with respect to the host unless info != NULL (timing needs a
+ * synchronisation). */
+int cno_minimize(int solver, const cno_problem_t* problem, int64_t batch,
+                 const void* x0, const cno_stop_t* stop,
+                 const cno_batch_out_t* out, void* workspace,
+                 size_t workspace_bytes, void* stream, cno_launch_info_t* info);
+
+/* Same call with HOST pointers (x0, problem->data and every non-NULL member of
+ * out): stages through pinned memory, copies H2D, solves, copies D2H.  This is
+ * the call a host-side user of the reference makes; bench.py times it for e2e. */
+int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch,
+                      const void* x0, const cno_stop_t* stop,
+                      const cno_batch_out_t* out, cno_launch_info_t* info);
+
+/* Counter-based start generator: element with global counter
+ * n = first + k gets lo + (hi - lo) * u, u = (mix64(seed + (n+1)*GOLDEN) >> 11)
+ * * 2^-53 (f64) or (>> 40) * 2^-24 (f32).  dst is a device pointer. */
+int cno_fill_uniform(int dtype, void* dst, int64_t first, int64_t count,
+                     uint64_t seed, double lo, double hi, void* stream);
+
+/* Packs status != CONTINUE into a bitmap, one bit per instance ([ceil(B/32)]
+ * uint32 words, device pointers): the per-GPU convergence bitmap that ranks
+ * all-gather for the global stop test. */
+int cno_done_bitmap(const int8_t* status, int64_t batch, uint32_t* words,
+                    void* stream);
+
+/* Device-side known-answer hook for MoreThuente::cstep
+ * (linesearch/more_thuente.h:261-407): runs the device cstep on one thread.
+ * io = {stx, fx, dx, sty, fy, dy, stp, fp, dp, stpmin, stpmax} (host, f64),
+ * brackt/info in-out, ret = cstep's return value. */
+int cno_device_cstep(double io[11], int* brackt, int* info, int* ret);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+
+#endif /* CNO_H_ */
