@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- batched L-BFGS instances/second, Rosenbrock d=128 fp64, m=10
+(BASELINE.json configs[1]), on N B200s of one node.
+
+One "step" = one batched Solver::Minimize over B = 2^20 instances per GPU
+(x0 generated on the device by the counter-based generator of SURVEY.md 8(d),
+resident in HBM when the timed region starts; 1 GiB of x0 per GPU > 126 MB L2,
+so nothing is cache-warm between steps).  Timing: CUDA events on the launching
+stream bracketed by barrier + synchronize, max over ranks.
+
+  value     whole-job instances/s, device-resident inputs
+  e2e       the same metric through the host-buffer C-ABI call
+            cno_minimize_host (pinned host x0 -> H2D -> solve -> D2H of the whole
+            returned state/progress), copies inside the timed region
+  roofline  ALGORITHMIC bytes of the state-streaming model (SURVEY.md 8(d):
+            w*d*(2 k_t + 6) per iteration, from the run's own iteration counts)
+            / kernel time, against MEASURED_PEAKS.json's HBM copy bandwidth.
+            The fused persistent kernel keeps the (s,y) history in shared
+            memory, so frac can exceed 1: `traffic` (ncu DRAM bytes per launch,
+            profiles/) shows what HBM really moved.
+  cpu_baseline  the CPU oracle (plain-C port of the reference path, OpenMP over
+            instances, all host cores) on a bounded prefix of the same batch.
+
+--impl reference times the reference's own CPU implementation of the path on the
+host cores: oracle/_ref (the reference's headers compiled against the Eigen-API
+shim) or the plain-C oracle port -- whichever is present; it says which.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+D = 128
+M = 10
+SEED = 12345
+LOG2_B = 20
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def algorithmic_bytes(iters, w=8, d=D, m=M):
+    """sum_t w*d*(2*min(t, m) + 6), t = 0..K-1, summed over instances."""
+    import numpy as np
+    K = iters.astype(np.int64)
+    full = np.maximum(K - m, 0)
+    ramp = np.minimum(K, m)
+    pairs = full * m + ramp * (ramp - 1) // 2
+    return int((w * d * (6 * K + 2 * pairs)).sum())
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                     "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_leg(kind_pref: str, target_seconds: float, log2_b: int):
+    """Times the CPU implementation on a bounded prefix of the batch (same x0)."""
+    import numpy as np
+    from oracle import oracle_binding as ob
+    kind = "port"
+    impl = "oracle"
+    if kind_pref == "reference" and ob.ref_available():
+        kind, impl = "reference", "ref"
+    cores = ob.num_threads()
+    chunk = 64 * cores
+    done, t_total, first = 0, 0.0, 0
+    iters = []
+    while t_total < target_seconds and done < (1 << log2_b):
+        x0 = ob.fill_uniform((chunk, D), first, SEED, -2.0, 2.0)
+        r = ob.minimize(ob.LBFGS, ob.FN_ROSENBROCK, x0, impl=impl)
+        t_total += r["seconds"]
+        done += chunk
+        first += chunk * D
+        iters.append(r["num_iterations"])
+    return {"value": done / t_total, "unit": "instances/s", "cores": cores, "kind": kind,
+            "sample": f"first {done} instances of the batch (same x0 stream), {t_total:.1f} s, "
+                      f"OpenMP schedule(dynamic), mean {float(np.concatenate(iters).mean()):.1f} iterations"
+            }, done, t_total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals = []
+    for _ in range(args.warmup):
+        cpu_leg("reference", 0.5, LOG2_B)
+    base = None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        base, done, secs = cpu_leg("reference", args.ref_seconds, LOG2_B)
+        vals.append((done, secs))
+    total_inst = sum(v[0] for v in vals)
+    total_s = sum(v[1] for v in vals)
+    value = total_inst / total_s
+    base["value"] = value
+    line = {
+        "impl": "reference", "metric": "batched L-BFGS instances/sec (Rosenbrock d=128)",
+        "value": value, "unit": "instances/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_s / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"Rosenbrock d=128 fp64, L-BFGS m=10, default stopping preset, "
+                               f"bounded prefix of the B=2^{LOG2_B} batch per step"},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "instances/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-batch", type=int, default=LOG2_B, help="per-GPU batch = 2^this")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-seconds", type=float, default=20.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import cppnumericalsolvers_b200 as cn
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = 1 << args.log2_batch
+    fn = cn.Rosenbrock(D)
+    solver = cn.Lbfgs()
+    x0 = torch.empty(B, D, dtype=torch.float64, device=dev)
+    # shard = contiguous instance range [rank*B, (rank+1)*B) of the global batch
+    cn.fill_uniform(x0, rank * B * D, SEED, -2.0, 2.0)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        state, prog = solver.Minimize(fn, cn.BatchedFunctionState(x0))
+        # global stop test: per-GPU convergence bitmaps, ONE all-gather (NCCL)
+        bitmap = prog.done_bitmap()
+        if world > 1:
+            gathered = torch.empty(world * bitmap.numel(), dtype=bitmap.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, bitmap)
+            bitmap = gathered
+        return state, prog, bitmap
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            state, prog, bitmap = step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    all_done = bool((bitmap == -1).all().item())  # every bit set
+
+    # kernel-only timing for the roofline (CUDA events inside cno_minimize, same stream)
+    kms = []
+    for _ in range(min(args.steps, 3)):
+        _, p2 = solver.Minimize(fn, cn.BatchedFunctionState(x0), timed=True)
+        kms.append(p2.launch.kernel_ms)
+    kernel_ms = sum(kms) / len(kms)
+    iters = prog.num_iterations.cpu().numpy()
+    nfev = prog.nfev.cpu().numpy()
+    status = prog.status.cpu().numpy()
+    alg_bytes = algorithmic_bytes(iters)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e through the host-buffer C ABI call ----
+    e2e = None
+    if not args.no_e2e:
+        hx0 = torch.empty(B, D, dtype=torch.float64).pin_memory()
+        hx0.copy_(x0)
+        solver.MinimizeHost(fn, hx0)  # warm-up (allocations, first touch)
+        barrier()
+        tt = time.perf_counter()
+        ems, h2d, d2h = 0.0, 0, 0
+        for _ in range(args.steps):
+            hstate, hprog = solver.MinimizeHost(fn, hx0)
+            ems += hprog.launch.total_ms
+            h2d, d2h = hprog.launch.h2d_bytes, hprog.launch.d2h_bytes
+        wall = time.perf_counter() - tt
+        t = torch.tensor([ems, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t[0].item())
+        assert torch.equal(hstate.x[:1024], state.x[:1024].cpu())
+        e2e = {"value": world * B * args.steps / (ems * 1e-3), "unit": "instances/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": ems / args.steps, "wall_ms_per_step": float(t[1].item()) / args.steps,
+               "api": "cno_minimize_host (pinned host buffers; device-event timed incl. copies)"}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu and world == 1:
+            cpu, _, _ = cpu_leg("port", args.cpu_seconds, args.log2_batch)
+        line = {
+            "metric": "batched L-BFGS instances/sec (Rosenbrock d=128)",
+            "value": value, "unit": "instances/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"Rosenbrock d=128 fp64, L-BFGS m=10, default stopping preset "
+                            f"(BASELINE.json configs[1])",
+                "batch_per_gpu": B, "global_batch": world * B, "parallelism": f"shard{world}",
+                "l2": "x0 is 1 GiB per GPU (> 126 MB L2); no flush needed",
+                "start_generator": f"splitmix64 counter stream, seed {SEED}, U(-2,2)",
+                "mean_iterations": float(iters.mean()), "mean_nfev": float(nfev.mean()),
+                "status_histogram": {str(k): int(v) for k, v in enumerate(np.bincount(status.astype(np.int64) + 1))},
+                "all_done_bitmap": all_done,
+            },
+            "e2e": e2e,
+            "gpu_launches": args.steps * 2,  # lbfgs_minimize_kernel + done_bitmap_kernel per step
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "kernel": "lbfgs_minimize_kernel<RosenbrockFn<double,128>,10>",
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "algorithmic bytes = state-streaming model w*d*(2k+6)/iteration; the fused "
+                        "kernel keeps the (s,y) history in shared memory, so frac > 1 means the "
+                        "traffic was removed (see profiles/ for ncu DRAM bytes and pipe utilisation)",
+            },
+            "cpu_baseline": cpu,
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,111 @@
+"""ctypes binding of libcno.so's C ABI (include/cno.h).
+
+There is no CPU fallback: if the CUDA library has not been built, loading fails
+loudly (ImportError) instead of degrading.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcno.so")
+
+# enums of include/cno.h
+LBFGS, BFGS, NEWTON = 0, 1, 2
+F64, F32 = 0, 1
+FN_ROSENBROCK, FN_DIAG_QUADRATIC, FN_HALF_SQUARED_NORM, FN_LOGISTIC, FN_DENSE_QUADRATIC = range(5)
+POLICY_WARP_TREE, POLICY_EIGEN_SSE2 = 0, 1
+OK, ERR_INVALID_ARGUMENT, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
+
+
+class Stop(C.Structure):  # cno_stop_t
+    _fields_ = [
+        ("num_iterations", C.c_uint64), ("x_delta", C.c_double),
+        ("x_delta_violations", C.c_int32), ("f_delta", C.c_double),
+        ("f_delta_violations", C.c_int32), ("f_delta_relative", C.c_int32),
+        ("gradient_norm", C.c_double), ("gradient_norm_relative", C.c_int32),
+        ("condition_hessian", C.c_double), ("past", C.c_int32),
+        ("past_delta", C.c_double),
+    ]
+
+
+class Problem(C.Structure):  # cno_problem_t
+    _fields_ = [
+        ("family", C.c_int32), ("dtype", C.c_int32), ("d", C.c_int32), ("n", C.c_int32),
+        ("param", C.c_double), ("data", C.c_void_p), ("data_stride", C.c_int64),
+        ("policy", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class BatchOut(C.Structure):  # cno_batch_out_t
+    _fields_ = [(n, C.c_void_p) for n in (
+        "x", "value", "gradient", "num_iterations", "status", "nfev",
+        "x_delta", "f_delta", "gradient_norm")]
+
+
+class LaunchInfo(C.Structure):  # cno_launch_info_t
+    _fields_ = [
+        ("kernel_launches", C.c_int32), ("grid", C.c_int32), ("block", C.c_int32),
+        ("warps_per_cta", C.c_int32), ("dynamic_smem", C.c_int64),
+        ("kernel_ms", C.c_float), ("total_ms", C.c_float),
+        ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+    ]
+
+
+# every symbol include/cno.h declares
+EXPORTS = (
+    "cno_version", "cno_error_string", "cno_last_cuda_error", "cno_default_stop",
+    "cno_conservative_stop", "cno_supported", "cno_workspace_bytes", "cno_minimize",
+    "cno_minimize_host", "cno_fill_uniform", "cno_done_bitmap", "cno_device_cstep",
+)
+
+_lib = None
+
+
+class CnoError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        self.code = code
+        msg = lib().cno_error_string(code).decode()
+        if code == ERR_CUDA:
+            s = C.c_char_p()
+            lib().cno_last_cuda_error(C.byref(s))
+            msg += f": {s.value.decode() if s.value else '?'}"
+        super().__init__(f"{where}: {msg} ({code})")
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m cppnumericalsolvers_b200.build` "
+                "(or __graft_entry__.build()). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.cno_error_string.restype = C.c_char_p
+        L.cno_error_string.argtypes = [C.c_int]
+        L.cno_last_cuda_error.argtypes = [C.POINTER(C.c_char_p)]
+        L.cno_default_stop.argtypes = [C.POINTER(Stop)]
+        L.cno_default_stop.restype = None
+        L.cno_conservative_stop.argtypes = [C.POINTER(Stop)]
+        L.cno_conservative_stop.restype = None
+        L.cno_supported.argtypes = [C.c_int, C.POINTER(Problem)]
+        L.cno_workspace_bytes.argtypes = [C.c_int, C.POINTER(Problem), C.c_int64, C.POINTER(C.c_size_t)]
+        L.cno_minimize.argtypes = [
+            C.c_int, C.POINTER(Problem), C.c_int64, C.c_void_p, C.POINTER(Stop),
+            C.POINTER(BatchOut), C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(LaunchInfo)]
+        L.cno_minimize_host.argtypes = [
+            C.c_int, C.POINTER(Problem), C.c_int64, C.c_void_p, C.POINTER(Stop),
+            C.POINTER(BatchOut), C.POINTER(LaunchInfo)]
+        L.cno_fill_uniform.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64,
+                                       C.c_double, C.c_double, C.c_void_p]
+        L.cno_done_bitmap.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.cno_device_cstep.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                       C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+def check(code: int, where: str) -> None:
+    if code != OK:
+        raise CnoError(code, where)

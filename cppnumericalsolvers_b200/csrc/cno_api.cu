@@ -1,0 +1,441 @@
+// cno_api.cu -- the extern "C" layer of libcno.so (include/cno.h) and the
+// table of kernels instantiated for the built-in objective families.
+//
+// Build (see cppnumericalsolvers_b200/build.py):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false ...
+// -fmad=false is part of the arithmetic specification: the reference's
+// canonical build forms no FMAs (generator.bzl:13, Dockerfile.test:111).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/cno.h"
+#include "cno_functors.cuh"
+#include "cno_kernel_params.h"
+#include "cno_lbfgs.cuh"
+
+namespace {
+
+thread_local cudaError_t g_last_cuda = cudaSuccess;
+thread_local cno_launch_info_t g_last_info;
+
+#define CNO_CUDA(expr)                       \
+  do {                                       \
+    cudaError_t e__ = (expr);                \
+    if (e__ != cudaSuccess) {                \
+      g_last_cuda = e__;                     \
+      return CNO_ERR_CUDA;                   \
+    }                                        \
+  } while (0)
+
+int device_sm_count(int* sms) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { g_last_cuda = e; return CNO_ERR_NO_DEVICE; }
+  e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) { g_last_cuda = e; return CNO_ERR_NO_DEVICE; }
+  return CNO_OK;
+}
+
+struct LaunchArgs {
+  const cno_problem_t* problem;
+  long long batch;
+  const void* x0;
+  const cno_stop_t* stop;
+  const cno_batch_out_t* out;
+  void* workspace;
+  cudaStream_t stream;
+  cno_launch_info_t* info;
+};
+
+// One persistent launch of lbfgs_minimize_kernel<Fn, M>.
+template <class Fn, int M>
+int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
+  using T = typename Fn::Scalar;
+  using SM = cno::LbfgsSmem<T, Fn::Dim, M>;
+  auto kernel = cno::lbfgs_minimize_kernel<Fn, M>;
+  const size_t smem = SM::kWarpBytes * SM::kWarps;
+  CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  // never launch more warps than instances
+  long long ctas = (a.batch + SM::kWarps - 1) / SM::kWarps;
+  const int grid = (int)(ctas < sms ? (ctas < 1 ? 1 : ctas) : sms);
+  unsigned long long* queue = static_cast<unsigned long long*>(a.workspace);
+  CNO_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), a.stream));
+  const cno::StopParams<T> stop = cno::make_stop<T>(*a.stop);
+  const cno::BatchOut<T> out = cno::make_out<T>(*a.out);
+  kernel<<<grid, SM::kWarps * 32, smem, a.stream>>>(fn, static_cast<const T*>(a.x0), a.batch,
+                                                    stop, out, queue);
+  CNO_CUDA(cudaGetLastError());
+  if (a.info) {
+    a.info->kernel_launches += 1;
+    a.info->grid = grid;
+    a.info->block = SM::kWarps * 32;
+    a.info->warps_per_cta = SM::kWarps;
+    a.info->dynamic_smem = (int64_t)smem;
+  }
+  return CNO_OK;
+}
+
+template <class T, int D>
+int lbfgs_rosenbrock(const LaunchArgs& a) {
+  return launch_lbfgs<cno::RosenbrockFn<T, D>, CNO_LBFGS_M>(cno::RosenbrockFn<T, D>{}, a);
+}
+template <class T, int D>
+int lbfgs_half_sq_norm(const LaunchArgs& a) {
+  return launch_lbfgs<cno::HalfSquaredNormFn<T, D>, CNO_LBFGS_M>(cno::HalfSquaredNormFn<T, D>{}, a);
+}
+template <class T>
+int lbfgs_diag_quadratic(const LaunchArgs& a) {
+  return launch_lbfgs<cno::DiagQuadraticFn<T>, CNO_LBFGS_M>(cno::DiagQuadraticFn<T>{}, a);
+}
+
+typedef int (*launcher_t)(const LaunchArgs&);
+
+struct Entry {
+  int solver, family, dtype, d;
+  launcher_t fn;
+};
+
+// Every (solver, functor, T, D) compiled into this library.
+const Entry kTable[] = {
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 2, lbfgs_rosenbrock<double, 2>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 3, lbfgs_rosenbrock<double, 3>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 8, lbfgs_rosenbrock<double, 8>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 32, lbfgs_rosenbrock<double, 32>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock<double, 37>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 64, lbfgs_rosenbrock<double, 64>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock<double, 128>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 2, lbfgs_rosenbrock<float, 2>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 37, lbfgs_rosenbrock<float, 37>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 128, lbfgs_rosenbrock<float, 128>},
+    {CNO_LBFGS, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, lbfgs_diag_quadratic<double>},
+    {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, lbfgs_half_sq_norm<double, 2>},
+    {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 50, lbfgs_half_sq_norm<double, 50>},
+};
+
+const Entry* find_entry(int solver, const cno_problem_t* p) {
+  for (const Entry& e : kTable)
+    if (e.solver == solver && e.family == p->family && e.dtype == p->dtype && e.d == p->d)
+      return &e;
+  return nullptr;
+}
+
+int check_args(int solver, const cno_problem_t* p) {
+  if (!p) return CNO_ERR_INVALID_ARGUMENT;
+  if (solver < CNO_LBFGS || solver > CNO_NEWTON) return CNO_ERR_INVALID_ARGUMENT;
+  if (p->dtype != CNO_F64 && p->dtype != CNO_F32) return CNO_ERR_INVALID_ARGUMENT;
+  if (p->d <= 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (p->policy != CNO_POLICY_WARP_TREE) return CNO_ERR_UNSUPPORTED;
+  if (!find_entry(solver, p)) return CNO_ERR_UNSUPPORTED;
+  return CNO_OK;
+}
+
+constexpr size_t kWorkspaceBytes = 256;
+
+// ---- small utility kernels ---------------------------------------------------
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ULL;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return z;
+}
+
+template <class T>
+__global__ void fill_uniform_kernel(T* dst, long long first, long long count,
+                                    unsigned long long seed, T lo, T hi) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+    const unsigned long long n = (unsigned long long)(first + k) + 1ULL;
+    const unsigned long long z = mix64(seed + n * 0x9E3779B97F4A7C15ULL);
+    T u;
+    if (sizeof(T) == 8)
+      u = (T)((double)(z >> 11) * 0x1.0p-53);
+    else
+      u = (T)((float)(z >> 40) * 0x1.0p-24f);
+    dst[k] = lo + (hi - lo) * u;
+  }
+}
+
+__global__ void done_bitmap_kernel(const int8_t* status, long long batch, uint32_t* words) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool done = (i < batch) && (status[i] != CNO_STATUS_CONTINUE) &&
+                    (status[i] != CNO_STATUS_NOT_STARTED);
+  const unsigned m = __ballot_sync(0xffffffffu, done);
+  if ((threadIdx.x & 31) == 0 && i < batch) words[i >> 5] = m;
+}
+
+__global__ void cstep_kernel(double* io, int* flags) {
+  bool brackt = flags[0] != 0;
+  int info = flags[1];
+  const int ret = cno::cstep<double>(io[0], io[1], io[2], io[3], io[4], io[5], io[6], io[7],
+                                     io[8], brackt, io[9], io[10], info);
+  flags[0] = brackt ? 1 : 0;
+  flags[1] = info;
+  flags[2] = ret;
+}
+
+bool have_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { g_last_cuda = e; (void)cudaGetLastError(); return false; }
+  return n > 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void cno_version(int* major, int* minor) {
+  if (major) *major = CNO_VERSION_MAJOR;
+  if (minor) *minor = CNO_VERSION_MINOR;
+}
+
+const char* cno_error_string(int err) {
+  switch (err) {
+    case CNO_OK: return "ok";
+    case CNO_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case CNO_ERR_UNSUPPORTED: return "no kernel instantiated for this (solver, functor, dtype, d, policy)";
+    case CNO_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+    case CNO_ERR_CUDA: return "CUDA error (see cno_last_cuda_error)";
+    case CNO_ERR_WORKSPACE: return "workspace too small or misaligned";
+  }
+  return "unknown error";
+}
+
+int cno_last_cuda_error(const char** msg) {
+  if (msg) *msg = cudaGetErrorString(g_last_cuda);
+  return (int)g_last_cuda;
+}
+
+void cno_default_stop(cno_stop_t* s) {  // solver/progress.h:353-431
+  if (!s) return;
+  memset(s, 0, sizeof(*s));
+  s->num_iterations = 10000;
+  s->x_delta = 1e-9;
+  s->x_delta_violations = 1;
+  s->f_delta = 0;
+  s->f_delta_violations = 1;
+  s->f_delta_relative = 0;
+  s->gradient_norm = 1e-5;
+  s->gradient_norm_relative = 1;
+  s->condition_hessian = 0;
+  s->past = 3;
+  s->past_delta = 1e-6;
+}
+
+void cno_conservative_stop(cno_stop_t* s) {  // solver/progress.h:456-464
+  if (!s) return;
+  cno_default_stop(s);
+  s->gradient_norm = 5e-6;
+  s->past = 5;
+  s->past_delta = 1e-10;
+}
+
+int cno_supported(int solver, const cno_problem_t* problem) { return check_args(solver, problem); }
+
+int cno_workspace_bytes(int solver, const cno_problem_t* problem, int64_t batch, size_t* bytes) {
+  (void)batch;
+  int rc = check_args(solver, problem);
+  if (rc) return rc;
+  if (!bytes) return CNO_ERR_INVALID_ARGUMENT;
+  *bytes = kWorkspaceBytes;
+  return CNO_OK;
+}
+
+int cno_minimize(int solver, const cno_problem_t* problem, int64_t batch, const void* x0,
+                 const cno_stop_t* stop, const cno_batch_out_t* out, void* workspace,
+                 size_t workspace_bytes, void* stream, cno_launch_info_t* info) {
+  int rc = check_args(solver, problem);
+  if (rc) return rc;
+  if (batch < 0 || !x0 || !out) return CNO_ERR_INVALID_ARGUMENT;
+  if (!workspace || workspace_bytes < kWorkspaceBytes || ((uintptr_t)workspace & 7))
+    return CNO_ERR_WORKSPACE;
+  if (((uintptr_t)x0 & 15) || ((uintptr_t)out->x & 15) || ((uintptr_t)out->gradient & 15))
+    return CNO_ERR_INVALID_ARGUMENT;
+  cno_stop_t dflt;
+  if (!stop) {
+    cno_default_stop(&dflt);
+    stop = &dflt;
+  }
+  if (stop->past > CNO_MAX_PAST || stop->past < 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (!have_device()) return CNO_ERR_NO_DEVICE;
+  if (info) memset(info, 0, sizeof(*info));
+  if (batch == 0) return CNO_OK;
+
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (info) {
+    CNO_CUDA(cudaEventCreate(&e0));
+    CNO_CUDA(cudaEventCreate(&e1));
+    CNO_CUDA(cudaEventRecord(e0, s));
+  }
+  const LaunchArgs a{problem, (long long)batch, x0, stop, out, workspace, s, info};
+  rc = find_entry(solver, problem)->fn(a);
+  if (rc) return rc;
+  if (info) {
+    CNO_CUDA(cudaEventRecord(e1, s));
+    CNO_CUDA(cudaEventSynchronize(e1));
+    CNO_CUDA(cudaEventElapsedTime(&info->kernel_ms, e0, e1));
+    info->total_ms = info->kernel_ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    g_last_info = *info;
+  }
+  return CNO_OK;
+}
+
+int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, const void* x0,
+                      const cno_stop_t* stop, const cno_batch_out_t* out,
+                      cno_launch_info_t* info) {
+  int rc = check_args(solver, problem);
+  if (rc) return rc;
+  if (batch < 0 || !x0 || !out) return CNO_ERR_INVALID_ARGUMENT;
+  if (!have_device()) return CNO_ERR_NO_DEVICE;
+  cno_launch_info_t local;
+  memset(&local, 0, sizeof(local));
+  if (batch == 0) { if (info) *info = local; return CNO_OK; }
+
+  const size_t ts = problem->dtype == CNO_F64 ? 8 : 4;
+  const size_t d = (size_t)problem->d;
+  const size_t vec_bytes = (size_t)batch * d * ts, sc_bytes = (size_t)batch * ts;
+  cudaStream_t s = nullptr;
+  CNO_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  cudaEvent_t e0, e1;
+  CNO_CUDA(cudaEventCreate(&e0));
+  CNO_CUDA(cudaEventCreate(&e1));
+
+  // One device arena: x0 | x | g | value | x_delta | f_delta | gnorm | iters | nfev | status | ws | data
+  const size_t data_bytes = problem->data ? (size_t)batch * (size_t)problem->data_stride * ts : 0;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t off = 0;
+  const size_t o_x0 = off; off += up(vec_bytes);
+  const size_t o_x = off; off += out->x ? up(vec_bytes) : 0;
+  const size_t o_g = off; off += out->gradient ? up(vec_bytes) : 0;
+  const size_t o_f = off; off += out->value ? up(sc_bytes) : 0;
+  const size_t o_xd = off; off += out->x_delta ? up(sc_bytes) : 0;
+  const size_t o_fd = off; off += out->f_delta ? up(sc_bytes) : 0;
+  const size_t o_gn = off; off += out->gradient_norm ? up(sc_bytes) : 0;
+  const size_t o_it = off; off += out->num_iterations ? up((size_t)batch * 4) : 0;
+  const size_t o_nf = off; off += out->nfev ? up((size_t)batch * 4) : 0;
+  const size_t o_st = off; off += out->status ? up((size_t)batch) : 0;
+  const size_t o_ws = off; off += kWorkspaceBytes;
+  const size_t o_data = off; off += up(data_bytes);
+  unsigned char* arena = nullptr;
+  CNO_CUDA(cudaMalloc(&arena, off));
+
+  CNO_CUDA(cudaEventRecord(e0, s));
+  CNO_CUDA(cudaMemcpyAsync(arena + o_x0, x0, vec_bytes, cudaMemcpyHostToDevice, s));
+  local.h2d_bytes += (int64_t)vec_bytes;
+  cno_problem_t dprob = *problem;
+  if (data_bytes) {
+    CNO_CUDA(cudaMemcpyAsync(arena + o_data, problem->data, data_bytes, cudaMemcpyHostToDevice, s));
+    dprob.data = arena + o_data;
+    local.h2d_bytes += (int64_t)data_bytes;
+  }
+  cno_batch_out_t dout;
+  dout.x = out->x ? arena + o_x : nullptr;
+  dout.gradient = out->gradient ? arena + o_g : nullptr;
+  dout.value = out->value ? arena + o_f : nullptr;
+  dout.x_delta = out->x_delta ? arena + o_xd : nullptr;
+  dout.f_delta = out->f_delta ? arena + o_fd : nullptr;
+  dout.gradient_norm = out->gradient_norm ? arena + o_gn : nullptr;
+  dout.num_iterations = out->num_iterations ? (uint32_t*)(arena + o_it) : nullptr;
+  dout.nfev = out->nfev ? (uint32_t*)(arena + o_nf) : nullptr;
+  dout.status = out->status ? (int8_t*)(arena + o_st) : nullptr;
+
+  cno_launch_info_t kinfo;
+  rc = cno_minimize(solver, &dprob, batch, arena + o_x0, stop, &dout, arena + o_ws,
+                    kWorkspaceBytes, s, &kinfo);
+  if (rc) { cudaFree(arena); return rc; }
+
+  auto down = [&](void* host, size_t o, size_t bytes) -> cudaError_t {
+    if (!host) return cudaSuccess;
+    local.d2h_bytes += (int64_t)bytes;
+    return cudaMemcpyAsync(host, arena + o, bytes, cudaMemcpyDeviceToHost, s);
+  };
+  CNO_CUDA(down(out->x, o_x, vec_bytes));
+  CNO_CUDA(down(out->gradient, o_g, vec_bytes));
+  CNO_CUDA(down(out->value, o_f, sc_bytes));
+  CNO_CUDA(down(out->x_delta, o_xd, sc_bytes));
+  CNO_CUDA(down(out->f_delta, o_fd, sc_bytes));
+  CNO_CUDA(down(out->gradient_norm, o_gn, sc_bytes));
+  CNO_CUDA(down(out->num_iterations, o_it, (size_t)batch * 4));
+  CNO_CUDA(down(out->nfev, o_nf, (size_t)batch * 4));
+  CNO_CUDA(down(out->status, o_st, (size_t)batch));
+  CNO_CUDA(cudaEventRecord(e1, s));
+  CNO_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  CNO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  const int64_t h2d = local.h2d_bytes, d2h = local.d2h_bytes;
+  local = kinfo;
+  local.h2d_bytes = h2d;
+  local.d2h_bytes = d2h;
+  local.total_ms = ms;
+  cudaFree(arena);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(s);
+  if (info) *info = local;
+  g_last_info = local;
+  return CNO_OK;
+}
+
+int cno_fill_uniform(int dtype, void* dst, int64_t first, int64_t count, uint64_t seed,
+                     double lo, double hi, void* stream) {
+  if (!dst || count < 0 || (dtype != CNO_F64 && dtype != CNO_F32)) return CNO_ERR_INVALID_ARGUMENT;
+  if (!have_device()) return CNO_ERR_NO_DEVICE;
+  if (count == 0) return CNO_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int block = 256;
+  long long blocks = (count + block - 1) / block;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == CNO_F64)
+    fill_uniform_kernel<double><<<(int)blocks, block, 0, s>>>((double*)dst, first, count, seed, lo, hi);
+  else
+    fill_uniform_kernel<float><<<(int)blocks, block, 0, s>>>((float*)dst, first, count, seed, (float)lo, (float)hi);
+  CNO_CUDA(cudaGetLastError());
+  return CNO_OK;
+}
+
+int cno_done_bitmap(const int8_t* status, int64_t batch, uint32_t* words, void* stream) {
+  if (!status || !words || batch < 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (!have_device()) return CNO_ERR_NO_DEVICE;
+  if (batch == 0) return CNO_OK;
+  const int block = 256;
+  const long long blocks = (batch + block - 1) / block;
+  done_bitmap_kernel<<<(unsigned)blocks, block, 0, static_cast<cudaStream_t>(stream)>>>(status, batch, words);
+  CNO_CUDA(cudaGetLastError());
+  return CNO_OK;
+}
+
+int cno_device_cstep(double io[11], int* brackt, int* info, int* ret) {
+  if (!io || !brackt || !info || !ret) return CNO_ERR_INVALID_ARGUMENT;
+  if (!have_device()) return CNO_ERR_NO_DEVICE;
+  double* dio = nullptr;
+  int* dfl = nullptr;
+  CNO_CUDA(cudaMalloc(&dio, 11 * sizeof(double)));
+  CNO_CUDA(cudaMalloc(&dfl, 3 * sizeof(int)));
+  int fl[3] = {*brackt, *info, 0};
+  CNO_CUDA(cudaMemcpy(dio, io, 11 * sizeof(double), cudaMemcpyHostToDevice));
+  CNO_CUDA(cudaMemcpy(dfl, fl, sizeof(fl), cudaMemcpyHostToDevice));
+  cstep_kernel<<<1, 1>>>(dio, dfl);
+  CNO_CUDA(cudaGetLastError());
+  CNO_CUDA(cudaMemcpy(io, dio, 11 * sizeof(double), cudaMemcpyDeviceToHost));
+  CNO_CUDA(cudaMemcpy(fl, dfl, sizeof(fl), cudaMemcpyDeviceToHost));
+  cudaFree(dio);
+  cudaFree(dfl);
+  *brackt = fl[0];
+  *info = fl[1];
+  *ret = fl[2];
+  return CNO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// cno_functors.cuh -- device objective functors compiled into libcno.so.
+//
+// Device functor concept (the warp-cooperative form of the reference's
+// FunctionCRTP::operator()(x, grad, hess), function_base.h:96-126):
+//
+//   struct F {
+//     using Scalar = double|float;
+//     static constexpr int Dim = D;           // compile-time dimension
+//     static constexpr int Mode = 1|2;        // DifferentiabilityMode First/Second
+//     // every lane passes its E = ceil(D/32) elements of x; returns f(x)
+//     // (identical in all lanes) and, if grad != nullptr, this lane's slice
+//     // of the gradient.
+//     __device__ Scalar operator()(const cno::EvalCtx&, const Scalar (&x)[E],
+//                                  Scalar (*grad)[E]) const;
+//   };
+//
+// The operation order of each functor below is restated one-for-one by the
+// CPU oracle (oracle/cno_oracle_impl.inc: eval_*), so values and gradients
+// agree bit for bit.
+#ifndef CNO_FUNCTORS_CUH_
+#define CNO_FUNCTORS_CUH_
+
+#include "cno_device.cuh"
+
+namespace cno {
+
+// Chained Rosenbrock: f = sum_{i<d-1} (1-x_i)^2 + 100 (x_{i+1}-x_i^2)^2.
+// At D = 2 the expressions are exactly src/test/verify.cc:58-69.
+template <class T, int D>
+struct RosenbrockFn {
+  using Scalar = T;
+  static constexpr int Dim = D;
+  static constexpr int Mode = 1;
+  static constexpr int E = Shape<D>::E;
+
+  __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&x)[E],
+                                          T (*grad)[E]) const {
+    const int lane = c.lane;
+    // x_{i+1} of this lane's last element lives in lane+1, slot 0.
+    const T x_next_lane = __shfl_down_sync(kFullMask, x[0], 1);
+    T term[E], A[E], Bv[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int i = lane * E + j;
+      const T xi = x[j];
+      const T xn = (j + 1 < E) ? x[(j + 1 < E) ? j + 1 : 0] : x_next_lane;
+      const T t1 = (1 - xi);
+      const T t2 = (xn - xi * xi);
+      const bool live = (i + 1 < D);
+      term[j] = live ? (t1 * t1 + 100 * t2 * t2) : T(0);
+      A[j] = -2 * (1 - xi) + 200 * (xn - xi * xi) * (-2 * xi);
+      Bv[j] = 200 * (xn - xi * xi);
+    }
+    if (grad) {
+      // g_i = B_{i-1} + A_i ; g_0 = A_0 ; g_{D-1} = B_{D-2}
+      const T b_prev_lane = __shfl_up_sync(kFullMask, Bv[E - 1], 1);
+#pragma unroll
+      for (int j = 0; j < E; ++j) {
+        const int i = lane * E + j;
+        const T bprev = (j > 0) ? Bv[(j > 0) ? j - 1 : 0] : b_prev_lane;
+        T gi;
+        if (D == 1) gi = T(0);
+        else if (i == 0) gi = A[j];
+        else if (i == D - 1) gi = bprev;
+        else gi = bprev + A[j];
+        (*grad)[j] = (i < D) ? gi : T(0);
+      }
+    }
+    return butterfly_sum(lane_tree<T, E>(term));
+  }
+};
+
+// Dockerfile.test:21-29: 5 x0^2 + 100 x1^2 + 5 (D = 2).
+template <class T>
+struct DiagQuadraticFn {
+  using Scalar = T;
+  static constexpr int Dim = 2;
+  static constexpr int Mode = 1;
+  static constexpr int E = 1;
+  __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&x)[1],
+                                          T (*grad)[1]) const {
+    const T x0 = __shfl_sync(kFullMask, x[0], 0);
+    const T x1 = __shfl_sync(kFullMask, x[0], 1);
+    if (grad) (*grad)[0] = (c.lane == 0) ? (10 * x0) : ((c.lane == 1) ? (200 * x1) : T(0));
+    return 5 * x0 * x0 + 100 * x1 * x1 + 5;
+  }
+};
+
+// src/test/augmented_lagrangian_test.cc:123-130: 0.5 * x.squaredNorm().
+template <class T, int D>
+struct HalfSquaredNormFn {
+  using Scalar = T;
+  static constexpr int Dim = D;
+  static constexpr int Mode = 1;
+  static constexpr int E = Shape<D>::E;
+  __device__ __forceinline__ T operator()(const EvalCtx&, const T (&x)[E],
+                                          T (*grad)[E]) const {
+    if (grad) {
+#pragma unroll
+      for (int j = 0; j < E; ++j) (*grad)[j] = x[j];
+    }
+    return T(0.5) * warp_dot<T, E>(x, x);
+  }
+};
+
+}  // namespace cno
+
+#endif  // CNO_FUNCTORS_CUH_

@@ -1,0 +1,328 @@
+// cno_lbfgs.cuh -- batched Lbfgs<F, m>::Minimize, one warp per instance, the
+// whole Solver::Minimize loop fused into ONE persistent kernel (sm_100a).
+//
+// Reference path (include/cppoptlib/...):
+//   solver/solver.h:181-224   Solver::Minimize driver loop
+//   solver/lbfgs.h:72-87      InitializeSolver
+//   solver/lbfgs.h:89-303     OptimizationStep (two-loop recursion, descent
+//                             test / fallback, pair + gamma update)
+//   linesearch/more_thuente.h MoreThuente::Search / cvsrch / cstep
+//   solver/progress.h:153-327 Progress::Update
+//
+// B200 design: grid = #SMs persistent CTAs; each warp pulls instance ids from
+// a global atomic queue (instances run 20..10000 iterations, so retire +
+// refill is what keeps all warps busy through the tail).  The m-deep (s, y)
+// history of the instance a warp is working on lives in that warp's private
+// slice of shared memory for the instance's whole lifetime; x, g, the search
+// direction and the trial point live in registers.  HBM is touched twice per
+// instance: one coalesced vectorised read of x0 and one write of the result.
+// Inner products are warp-shuffle butterflies (the arithmetic specification in
+// cno_device.cuh); s_i.y_i is cached per slot when the pair is stored (the
+// reference recomputes the same dot twice per pair per iteration,
+// lbfgs.h:163-164,187-188 -- same operands, same order, same bits).
+#ifndef CNO_LBFGS_CUH_
+#define CNO_LBFGS_CUH_
+
+#include "cno_device.cuh"
+#include "cno_linesearch.cuh"
+#include "cno_kernel_params.h"
+
+namespace cno {
+
+template <class T, int D, int M>
+struct LbfgsSmem {
+  static constexpr int E = Shape<D>::E;
+  static constexpr int kVec = 32 * E;                        // elements per stored vector
+  static constexpr int kWarpElems = 2 * M * kVec + 2 * M;    // S, Y, denom[M], alpha[M]
+  static constexpr size_t kWarpBytes = (size_t)kWarpElems * sizeof(T);
+  // warps per CTA: as many as fit in 227 KB, at most 16 (register budget).
+  static constexpr int kMaxSmem = 227 * 1024;
+  static constexpr int kWarpsFit = (int)(kMaxSmem / kWarpBytes);
+  static constexpr int kWarps = kWarpsFit > 16 ? 16 : (kWarpsFit < 1 ? 1 : kWarpsFit);
+};
+
+// progress.h:153-327 on warp-uniform scalars (FunctionState branch).
+template <class T>
+struct ProgressState {
+  uint32_t num_iterations;
+  int x_delta_violations;
+  int f_delta_violations;
+  T x_delta, f_delta, gradient_norm;
+  T ring[CNO_MAX_PAST];
+  int ring_size, ring_pos;
+  int status;
+};
+
+template <class T>
+__device__ __forceinline__ void progress_update(ProgressState<T>& p, const StopParams<T>& stop,
+                                                T prev_value, T cur_value, T x_delta,
+                                                T gradient_norm, T x_inf) {
+  p.num_iterations++;
+  p.f_delta = cabs(cur_value - prev_value);
+  p.x_delta = x_delta;
+  p.gradient_norm = gradient_norm;
+  if ((stop.num_iterations > 0) && ((unsigned long long)p.num_iterations > stop.num_iterations)) {
+    p.status = CNO_STATUS_ITERATION_LIMIT;
+    return;
+  }
+  if ((stop.x_delta > 0) && (p.x_delta < stop.x_delta)) {
+    p.x_delta_violations++;
+    if (p.x_delta_violations >= stop.x_delta_violations) {
+      p.status = CNO_STATUS_X_DELTA_VIOLATION;
+      return;
+    }
+  } else {
+    p.x_delta_violations = 0;
+  }
+  if ((stop.f_delta > 0) &&
+      (p.f_delta < stop.f_delta * (stop.f_delta_relative
+                                       ? smax(smax(cabs(cur_value), cabs(prev_value)), T(1))
+                                       : T(1)))) {
+    p.f_delta_violations++;
+    if (p.f_delta_violations >= stop.f_delta_violations) {
+      p.status = CNO_STATUS_F_DELTA_VIOLATION;
+      return;
+    }
+  } else {
+    p.f_delta_violations = 0;
+  }
+  if (stop.past > 0) {
+    const int pp = stop.past;
+    if (p.ring_size != pp) {
+#pragma unroll
+      for (int i = 0; i < CNO_MAX_PAST; ++i) p.ring[i] = cur_value;
+      p.ring_size = pp;
+      p.ring_pos = 0;
+    }
+    if ((int)p.num_iterations > pp) {
+      T past_f = p.ring[0];
+#pragma unroll
+      for (int i = 1; i < CNO_MAX_PAST; ++i) past_f = (p.ring_pos == i) ? p.ring[i] : past_f;
+      const T rate = cabs(past_f - cur_value) / smax(T(1), cabs(cur_value));
+      if (rate < stop.past_delta) {
+        p.status = CNO_STATUS_F_DELTA_VIOLATION;
+        return;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CNO_MAX_PAST; ++i)
+      if (p.ring_pos == i) p.ring[i] = cur_value;
+    p.ring_pos = (p.ring_pos + 1) % pp;
+  }
+  if (stop.gradient_norm > 0) {
+    const T scale = stop.gradient_norm_relative ? smax(T(1), x_inf) : T(1);
+    if (p.gradient_norm < stop.gradient_norm * scale) {
+      p.status = CNO_STATUS_GRADIENT_NORM_VIOLATION;
+      return;
+    }
+  }
+  p.status = CNO_STATUS_CONTINUE;
+}
+
+template <class Fn, int M>
+__global__ void __launch_bounds__(LbfgsSmem<typename Fn::Scalar, Fn::Dim, M>::kWarps * 32, 1)
+lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
+                      const long long batch, const StopParams<typename Fn::Scalar> stop,
+                      const BatchOut<typename Fn::Scalar> out,
+                      unsigned long long* __restrict__ queue) {
+  using T = typename Fn::Scalar;
+  constexpr int D = Fn::Dim;
+  constexpr int E = Shape<D>::E;
+  using SM = LbfgsSmem<T, D, M>;
+  using SV = SmemVec<T, E>;
+  constexpr T eps = Num<T>::eps;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  T* const S = reinterpret_cast<T*>(smem_raw) + (size_t)warp * SM::kWarpElems;
+  T* const Y = S + M * SM::kVec;
+  T* const denom = Y + M * SM::kVec;
+  T* const alpha = denom + M;
+
+  for (;;) {
+    // ---- retire + refill: next instance from the global queue ----
+    unsigned long long b = 0;
+    if (lane == 0) b = atomicAdd(queue, 1ULL);
+    b = __shfl_sync(kFullMask, b, 0);
+    if (b >= (unsigned long long)batch) break;
+    const EvalCtx ctx{lane, (long long)b};
+
+    // ---- solver.h:189-192: evaluate once at the start point ----
+    T x[E], g[E];
+    load_row<T, D>(x0 + b * D, lane, x);
+    T f = fn(ctx, x, &g);
+    uint32_t nfev = 1;
+
+    // ---- lbfgs.h:72-87 InitializeSolver ----
+    int mem_count = 0, mem_pos = 0;
+    T gamma = T(1);
+
+    ProgressState<T> prog;
+    prog.num_iterations = 0;
+    prog.x_delta_violations = 0;
+    prog.f_delta_violations = 0;
+    prog.x_delta = prog.f_delta = prog.gradient_norm = T(0);
+    prog.ring_size = 0;
+    prog.ring_pos = 0;
+    prog.status = CNO_STATUS_NOT_STARTED;
+
+    // squared norms carried across iterations (same dots the reference
+    // recomputes at lbfgs.h:95 and :221).
+    T xx, gg;
+    {
+      T a = lane_dot<T, E>(x, x), c = lane_dot<T, E>(g, g);
+      butterfly_sum2(a, c);
+      xx = a;
+      gg = c;
+    }
+
+    do {  // solver.h:196-220
+      // ================= Lbfgs::OptimizationStep (lbfgs.h:89-303) =========
+      const T relative_eps = eps * smax(T(1.0), csqrt(xx));  // :93-95
+
+      T q[E];  // search_direction
+#pragma unroll
+      for (int j = 0; j < E; ++j) q[j] = g[j];  // :145
+      const int k = mem_count;
+
+      // ---- first loop (:157-171) ----
+      for (int i = k - 1; i >= 0; --i) {
+        const int idx = (mem_count < M) ? i : ((mem_pos + i) % M);
+        const T den = denom[idx];
+        if (cabs(den) < eps) continue;
+        const T rho = T(1) / den;
+        T sv[E], yv[E];
+        SV::load(S + idx * SM::kVec, lane, sv);
+        SV::load(Y + idx * SM::kVec, lane, yv);
+        const T a = rho * warp_dot<T, E>(sv, q);
+        if (lane == 0) alpha[i] = a;
+#pragma unroll
+        for (int j = 0; j < E; ++j) q[j] = q[j] - a * yv[j];
+      }
+      __syncwarp();
+      // ---- H0 scaling (:181) ----
+#pragma unroll
+      for (int j = 0; j < E; ++j) q[j] = q[j] * gamma;
+      // ---- second loop (:185-196) ----
+      for (int i = 0; i < k; ++i) {
+        const int idx = (mem_count < M) ? i : ((mem_pos + i) % M);
+        const T den = denom[idx];
+        if (cabs(den) < eps) continue;
+        const T rho = T(1) / den;
+        T sv[E], yv[E];
+        SV::load(S + idx * SM::kVec, lane, sv);
+        SV::load(Y + idx * SM::kVec, lane, yv);
+        const T beta = rho * warp_dot<T, E>(yv, q);
+        const T coef = alpha[i] - beta;
+#pragma unroll
+        for (int j = 0; j < E; ++j) q[j] = q[j] + sv[j] * coef;
+      }
+
+      // ---- descent test, alpha_init, fallback (:199-224) ----
+      T gq = lane_dot<T, E>(g, q);
+      T qq = lane_dot<T, E>(q, q);
+      butterfly_sum2(gq, qq);
+      const T descent_direction = -gq;
+      T alpha_init = T(1);
+      if (mem_count == 0) {
+        const T qn = csqrt(qq);
+        alpha_init = (qn > eps) ? T(1) / qn : T(1);
+      }
+      T dginit = descent_direction;  // = g.(-q), bit for bit
+      T sdir[E];
+      if (!cfinite(descent_direction) || descent_direction > -eps * relative_eps) {
+        // fallback: search_direction = -g, and the reference then searches
+        // along -search_direction = +g: dginit = g.g >= 0.
+#pragma unroll
+        for (int j = 0; j < E; ++j) sdir[j] = g[j];
+        mem_count = 0;
+        mem_pos = 0;
+        const T gn = csqrt(gg);
+        alpha_init = (gn > eps) ? T(1) / gn : T(1);
+        dginit = gg;
+      } else {
+#pragma unroll
+        for (int j = 0; j < E; ++j) sdir[j] = -q[j];
+      }
+
+      // ---- MoreThuente::Search (:231-232) ----
+      T xn[E], gn[E];
+#pragma unroll
+      for (int j = 0; j < E; ++j) { xn[j] = x[j]; gn[j] = g[j]; }
+      T fn_val = f;
+      T stp = alpha_init;
+      nfev += cvsrch<Fn, T, E>(fn, ctx, xn, fn_val, gn, stp, sdir, dginit);
+
+      const T prev_value = f;
+      T x_delta, gnorm_inf, x_inf;
+      if (!cfinite(fn_val)) {
+        // :239-241 return current: x, g, f unchanged -> x_delta = 0.
+        T m1 = lane_maxabs<T, E>(g), m2 = lane_maxabs<T, E>(x);
+        gnorm_inf = butterfly_max(m1);
+        x_inf = butterfly_max(m2);
+        x_delta = T(0);
+      } else {
+        // ---- pair + gamma update (:248-298) ----
+        T sd[E], yd[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) { sd[j] = xn[j] - x[j]; yd[j] = gn[j] - g[j]; }
+        T sy = lane_dot<T, E>(sd, yd), ss = lane_dot<T, E>(sd, sd), yy = lane_dot<T, E>(yd, yd);
+        butterfly_sum3(sy, ss, yy);
+        const T sy_threshold = eps * csqrt(ss) * csqrt(yy);
+        if (sy > sy_threshold) {
+          int slot;
+          if (mem_count < M) {
+            slot = mem_count;
+            mem_count++;
+          } else {
+            slot = mem_pos;
+            mem_pos = (mem_pos + 1) % M;
+          }
+          SV::store(S + slot * SM::kVec, lane, sd);
+          SV::store(Y + slot * SM::kVec, lane, yd);
+          if (lane == 0) denom[slot] = sy;
+        }
+        if (yy > eps) {
+          const T temp_scaling = sy / yy;
+          if (cfinite(temp_scaling) && cabs(temp_scaling) <= T(1e7)) gamma = smax(temp_scaling, eps);
+        }
+        // next state + the norms Progress::Update and the next step need
+        T m0 = lane_maxabs<T, E>(sd);
+#pragma unroll
+        for (int j = 0; j < E; ++j) { x[j] = xn[j]; g[j] = gn[j]; }
+        f = fn_val;
+        T m1 = lane_maxabs<T, E>(g), m2 = lane_maxabs<T, E>(x);
+        x_delta = butterfly_max(m0);
+        gnorm_inf = butterfly_max(m1);
+        x_inf = butterfly_max(m2);
+        T a = lane_dot<T, E>(x, x), c = lane_dot<T, E>(g, g);
+        butterfly_sum2(a, c);
+        xx = a;
+        gg = c;
+        __syncwarp();
+      }
+
+      // ================= Progress::Update (progress.h:153-327) ============
+      progress_update<T>(prog, stop, prev_value, f, x_delta, gnorm_inf, x_inf);
+    } while (prog.status == CNO_STATUS_CONTINUE);
+
+    // ---- write the returned FunctionState + Progress ----
+    if (out.x) store_row<T, D>(out.x + b * D, lane, x);
+    if (out.gradient) store_row<T, D>(out.gradient + b * D, lane, g);
+    if (lane == 0) {
+      if (out.value) out.value[b] = f;
+      if (out.num_iterations) out.num_iterations[b] = prog.num_iterations;
+      if (out.status) out.status[b] = (int8_t)prog.status;
+      if (out.nfev) out.nfev[b] = nfev;
+      if (out.x_delta) out.x_delta[b] = prog.x_delta;
+      if (out.f_delta) out.f_delta[b] = prog.f_delta;
+      if (out.gradient_norm) out.gradient_norm[b] = prog.gradient_norm;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace cno
+
+#endif  // CNO_LBFGS_CUH_

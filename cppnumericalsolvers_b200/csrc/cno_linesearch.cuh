@@ -1,0 +1,250 @@
+// cno_linesearch.cuh -- MoreThuente strong-Wolfe line search, one warp per
+// instance, fused with the user's device functor (trial points never leave
+// registers: 0 HBM bytes per trial).
+//
+// Mirrors linesearch/more_thuente.h of the reference:
+//   cstep   :261-407  (scalar, warp-uniform: every lane computes the same bits)
+//   cvsrch  :137-256
+//   Search(State...) :120-135
+// including the quirks that shape trajectories (SURVEY.md 7.2 c-f): evaluation
+// at the returned step even on failure, info codes 6,5,4,3,2,1 assigned in that
+// order, cstep's early "return -1" leaving infoc = 0, cstep receiving the
+// loop-local stmin/stmax.
+#ifndef CNO_LINESEARCH_CUH_
+#define CNO_LINESEARCH_CUH_
+
+#include "cno_device.cuh"
+
+namespace cno {
+
+template <class T>
+__device__ __forceinline__ T max_abs3(T x, T y, T z) {  // more_thuente.h:409-411
+  return smax(cabs(x), smax(cabs(y), cabs(z)));
+}
+
+// more_thuente.h:261-407
+template <class T>
+__device__ __noinline__ int cstep(T& stx, T& fx, T& dx, T& sty, T& fy, T& dy,
+                                  T& stp, T fp, T dp, bool& brackt, T stpmin,
+                                  T stpmax, int& info) {
+  info = 0;
+  bool bound = false;
+
+  if ((brackt && ((stp <= smin(stx, sty)) || (stp >= smax(stx, sty)))) ||
+      (dx * (stp - stx) >= T(0)) || (stpmax < stpmin)) {
+    return -1;
+  }
+
+  const T sgnd = dp * (dx / cabs(dx));
+
+  T stpf = 0, stpc = 0, stpq = 0;
+
+  if (fp > fx) {
+    info = 1;
+    bound = true;
+    const T theta = T(3) * (fx - fp) / (stp - stx) + dx + dp;
+    const T s = max_abs3(theta, dx, dp);
+    T gamma = s * csqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+    if (stp < stx) gamma = -gamma;
+    const T p = (gamma - dx) + theta;
+    const T q = ((gamma - dx) + gamma) + dp;
+    const T r = p / q;
+    stpc = stx + r * (stp - stx);
+    stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / T(2)) * (stp - stx);
+    if (cabs(stpc - stx) < cabs(stpq - stx))
+      stpf = stpc;
+    else
+      stpf = stpc + (stpq - stpc) / 2;
+    brackt = true;
+  } else if (sgnd < T(0)) {
+    info = 2;
+    bound = false;
+    const T theta = 3 * (fx - fp) / (stp - stx) + dx + dp;
+    const T s = max_abs3(theta, dx, dp);
+    T gamma = s * csqrt((theta / s) * (theta / s) - (dx / s) * (dp / s));
+    if (stp > stx) gamma = -gamma;
+    const T p = (gamma - dp) + theta;
+    const T q = ((gamma - dp) + gamma) + dx;
+    const T r = p / q;
+    stpc = stp + r * (stx - stp);
+    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    if (cabs(stpc - stp) > cabs(stpq - stp))
+      stpf = stpc;
+    else
+      stpf = stpq;
+    brackt = true;
+  } else if (cabs(dp) < cabs(dx)) {
+    info = 3;
+    bound = true;
+    const T theta = 3 * (fx - fp) / (stp - stx) + dx + dp;
+    const T s = max_abs3(theta, dx, dp);
+    T gamma = s * csqrt(smax(T(0.), (theta / s) * (theta / s) - (dx / s) * (dp / s)));
+    if (stp > stx) gamma = -gamma;
+    const T p = (gamma - dp) + theta;
+    const T q = (gamma + (dx - dp)) + gamma;
+    const T r = p / q;
+    if ((r < T(0)) & (gamma != T(0))) {
+      stpc = stp + r * (stx - stp);
+    } else if (stp > stx) {
+      stpc = stpmax;
+    } else {
+      stpc = stpmin;
+    }
+    stpq = stp + (dp / (dp - dx)) * (stx - stp);
+    if (brackt) {
+      if (cabs(stp - stpc) < cabs(stp - stpq))
+        stpf = stpc;
+      else
+        stpf = stpq;
+    } else {
+      if (cabs(stp - stpc) > cabs(stp - stpq))
+        stpf = stpc;
+      else
+        stpf = stpq;
+    }
+  } else {
+    info = 4;
+    bound = false;
+    if (brackt) {
+      const T theta = 3 * (fp - fy) / (sty - stp) + dy + dp;
+      const T s = max_abs3(theta, dy, dp);
+      T gamma = s * csqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
+      if (stp > sty) gamma = -gamma;
+      const T p = (gamma - dp) + theta;
+      const T q = ((gamma - dp) + gamma) + dy;
+      const T r = p / q;
+      stpc = stp + r * (sty - stp);
+      stpf = stpc;
+    } else if (stp > stx) {
+      stpf = stpmax;
+    } else {
+      stpf = stpmin;
+    }
+  }
+
+  if (fp > fx) {
+    sty = stp;
+    fy = fp;
+    dy = dp;
+  } else {
+    if (sgnd < T(0)) {
+      sty = stx;
+      fy = fx;
+      dy = dx;
+    }
+    stx = stp;
+    fx = fp;
+    dx = dp;
+  }
+
+  stpf = sclamp(stpf, stpmin, stpmax);
+  stp = stpf;
+
+  if (brackt & bound) {
+    if (sty > stx) {
+      stp = smin(stx + T(0.66) * (sty - stx), stp);
+    } else {
+      stp = smax(stx + T(0.66) * (sty - stx), stp);
+    }
+  }
+  return 0;
+}
+
+// more_thuente.h:137-256.  On entry x/g/f are the start state (wa = x), s the
+// direction, dginit = g.s (the caller already has it: for L-BFGS it equals the
+// descent test value bit for bit because negation commutes with rounding).
+// On exit x/g/f hold the last evaluated point, exactly as in the reference.
+// Returns the number of objective evaluations.
+template <class Fn, class T, int E>
+__device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx,
+                                      T (&x)[E], T& f, T (&g)[E], T& stp,
+                                      const T (&s)[E], const T dginit) {
+  int info = 0;
+  int infoc = 1;
+  const T xtol = T(1e-15);
+  const T ftol = T(1e-4);
+  const T gtol = T(0.9);
+  const T stpmin = T(1e-15);
+  const T stpmax = T(1e15);
+  const T xtrapf = T(4);
+  const int maxfev = 20;
+  int nfev = 0;
+
+  if (dginit >= T(0)) return 0;  // :152-156 (state untouched)
+
+  bool brackt = false;
+  bool stage1 = true;
+
+  const T finit = f;
+  const T dgtest = ftol * dginit;
+  T width = stpmax - stpmin;
+  T width1 = T(2) * width;
+  T wa[E];
+#pragma unroll
+  for (int j = 0; j < E; ++j) wa[j] = x[j];
+
+  T stx = T(0), fx = finit, dgx = dginit;
+  T sty = T(0), fy = finit, dgy = dginit;
+  T stmin, stmax;
+
+  for (;;) {
+    if (brackt) {
+      stmin = smin(stx, sty);
+      stmax = smax(stx, sty);
+    } else {
+      stmin = stx;
+      stmax = stp + xtrapf * (stp - stx);
+    }
+    stp = sclamp(stp, stpmin, stpmax);
+    if ((brackt && ((stp <= stmin) || (stp >= stmax))) || (nfev >= maxfev - 1) ||
+        (infoc == 0) || (brackt && ((stmax - stmin) <= (xtol * stmax)))) {
+      stp = stx;
+    }
+
+#pragma unroll
+    for (int j = 0; j < E; ++j) x[j] = wa[j] + stp * s[j];
+    T fl = fn(ctx, x, &g);  // returns the already-reduced value
+    nfev++;
+    T dg = lane_dot<T, E>(g, s);
+    dg = butterfly_sum(dg);
+    f = fl;
+    const T ftest1 = finit + stp * dgtest;
+
+    if ((brackt & ((stp <= stmin) | (stp >= stmax))) | (infoc == 0)) info = 6;
+    if ((stp == stpmax) & (f <= ftest1) & (dg <= dgtest)) info = 5;
+    if ((stp == stpmin) & ((f > ftest1) | (dg >= dgtest))) info = 4;
+    if (nfev >= maxfev) info = 3;
+    if (brackt & (stmax - stmin <= xtol * stmax)) info = 2;
+    if ((f <= ftest1) & (cabs(dg) <= gtol * (-dginit))) info = 1;
+
+    if (info != 0) return nfev;
+
+    if (stage1 & (f <= ftest1) & (dg >= smin(ftol, gtol) * dginit)) stage1 = false;
+
+    if (stage1 & (f <= fx) & (f > ftest1)) {
+      T fm = f - stp * dgtest;
+      T fxm = fx - stx * dgtest;
+      T fym = fy - sty * dgtest;
+      T dgm = dg - dgtest;
+      T dgxm = dgx - dgtest;
+      T dgym = dgy - dgtest;
+      cstep<T>(stx, fxm, dgxm, sty, fym, dgym, stp, fm, dgm, brackt, stmin, stmax, infoc);
+      fx = fxm + stx * dgtest;
+      fy = fym + sty * dgtest;
+      dgx = dgxm + dgtest;
+      dgy = dgym + dgtest;
+    } else {
+      cstep<T>(stx, fx, dgx, sty, fy, dgy, stp, f, dg, brackt, stmin, stmax, infoc);
+    }
+
+    if (brackt) {
+      if (cabs(sty - stx) >= T(0.66) * width1) stp = stx + T(0.5) * (sty - stx);
+      width1 = width;
+      width = cabs(sty - stx);
+    }
+  }
+}
+
+}  // namespace cno
+
+#endif  // CNO_LINESEARCH_CUH_

@@ -1,0 +1,86 @@
+"""Objective descriptors: the host-side mirror of the reference's function model
+(include/cppoptlib/function_base.h) with a batch axis.
+
+A Python object here only *names* a device functor that was compiled into
+libcno.so (csrc/cno_functors.cuh); evaluation never leaves the GPU.
+`BatchedFunctionState` is `FunctionState` (function_base.h:298-332) with a
+leading batch dimension: x [B, d], value [B], gradient [B, d].
+"""
+from __future__ import annotations
+
+import enum
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+class DifferentiabilityMode(enum.IntEnum):  # function_base.h:42-46
+    NONE = 0
+    First = 1
+    Second = 2
+
+
+_DTYPES = {torch.float64: _lib.F64, torch.float32: _lib.F32}
+
+
+@dataclass
+class Function:
+    """Base descriptor (FunctionCRTP's static members, function_base.h:96-102)."""
+    Dimension: int
+    ScalarType: torch.dtype = torch.float64
+    Differentiability: DifferentiabilityMode = DifferentiabilityMode.First
+    family: int = -1
+    n: int = 0
+    param: float = 0.0
+    data: Optional[torch.Tensor] = None  # per-instance data [B, stride]
+    policy: int = _lib.POLICY_WARP_TREE
+
+    def problem(self) -> _lib.Problem:
+        data_ptr, stride = None, 0
+        if self.data is not None:
+            assert self.data.dtype == self.ScalarType and self.data.is_contiguous()
+            data_ptr, stride = self.data.data_ptr(), self.data.shape[1]
+        return _lib.Problem(self.family, _DTYPES[self.ScalarType], self.Dimension, self.n,
+                            float(self.param), data_ptr, stride, self.policy, 0)
+
+
+def Rosenbrock(d: int, dtype: torch.dtype = torch.float64) -> Function:
+    """Chained Rosenbrock; d = 2 is src/test/verify.cc:58-69."""
+    return Function(d, dtype, DifferentiabilityMode.First, _lib.FN_ROSENBROCK)
+
+
+def DiagQuadratic(dtype: torch.dtype = torch.float64) -> Function:
+    """5 x0^2 + 100 x1^2 + 5 (Dockerfile.test:21-29)."""
+    return Function(2, dtype, DifferentiabilityMode.First, _lib.FN_DIAG_QUADRATIC)
+
+
+def HalfSquaredNorm(d: int, dtype: torch.dtype = torch.float64) -> Function:
+    """0.5 ||x||^2 (src/test/augmented_lagrangian_test.cc:123-130)."""
+    return Function(d, dtype, DifferentiabilityMode.First, _lib.FN_HALF_SQUARED_NORM)
+
+
+def Logistic(data: torch.Tensor, n: int, d: int, lam: float) -> Function:
+    """Batched logistic regression; data[b] = [X (n x d row-major) | y (n)]."""
+    return Function(d, data.dtype, DifferentiabilityMode.First, _lib.FN_LOGISTIC, n=n,
+                    param=lam, data=data)
+
+
+def DenseQuadratic(data: torch.Tensor, d: int) -> Function:
+    """0.5 x'Ax - b'x; data[b] = [A (d x d col-major) | b (d)]; Second mode."""
+    return Function(d, data.dtype, DifferentiabilityMode.Second, _lib.FN_DENSE_QUADRATIC,
+                    data=data)
+
+
+@dataclass
+class BatchedFunctionState:
+    """FunctionState with a batch axis (function_base.h:298-332)."""
+    x: torch.Tensor
+    value: Optional[torch.Tensor] = None
+    gradient: Optional[torch.Tensor] = None
+
+    @property
+    def batch(self) -> int:
+        return self.x.shape[0]

@@ -1,0 +1,208 @@
+"""Host-side mirror of the reference's solver interface with a batch axis.
+
+  reference                                     here
+  --------------------------------------------  ----------------------------------
+  solver/progress.h:37-47   Status              Status
+  solver/progress.h:82-140  Progress            Progress (thresholds) /
+                                                BatchedProgress (per-instance)
+  solver/progress.h:353-431 DefaultStopping...  DefaultStoppingSolverProgress()
+  solver/progress.h:456-464 Conservative...     ConservativeStoppingSolverProgress()
+  solver/solver.h:156-231   Solver<F,State>     Solver (stopping_progress, Minimize)
+  solver/lbfgs.h            Lbfgs<F, m=10>      Lbfgs
+  solver/bfgs.h             Bfgs<F>             Bfgs
+  solver/newton_descent.h   NewtonDescent<F>    NewtonDescent
+
+`Minimize(function, state)` returns `(BatchedFunctionState, BatchedProgress)`
+like the reference returns `tuple<State, Progress>`.  All compute happens in
+libcno.so's CUDA kernels; PyTorch only owns device memory and streams.
+Per-iteration `SetCallback` callbacks cannot exist when the whole loop is fused
+on the device; per-instance Progress arrays are returned instead.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from .function import BatchedFunctionState, Function
+
+
+class Status(enum.IntEnum):  # solver/progress.h:37-47
+    NotStarted = -1
+    Continue = 0
+    IterationLimit = 1
+    XDeltaViolation = 2
+    FDeltaViolation = 3
+    GradientNormViolation = 4
+    HessianConditionViolation = 5
+    Finished = 6
+
+
+@dataclass
+class Progress:
+    """Stopping thresholds (the fields of solver::Progress a preset sets)."""
+    num_iterations: int = 0
+    x_delta: float = 0.0
+    x_delta_violations: int = 0
+    f_delta: float = 0.0
+    f_delta_violations: int = 0
+    f_delta_relative: bool = False
+    gradient_norm: float = 0.0
+    gradient_norm_relative: bool = True
+    condition_hessian: float = 0.0
+    past: int = 0
+    past_delta: float = 1e-6
+
+    def to_c(self) -> _lib.Stop:
+        return _lib.Stop(self.num_iterations, self.x_delta, self.x_delta_violations,
+                         self.f_delta, self.f_delta_violations, int(self.f_delta_relative),
+                         self.gradient_norm, int(self.gradient_norm_relative),
+                         self.condition_hessian, self.past, self.past_delta)
+
+    @staticmethod
+    def from_c(s: _lib.Stop) -> "Progress":
+        return Progress(s.num_iterations, s.x_delta, s.x_delta_violations, s.f_delta,
+                        s.f_delta_violations, bool(s.f_delta_relative), s.gradient_norm,
+                        bool(s.gradient_norm_relative), s.condition_hessian, s.past,
+                        s.past_delta)
+
+
+def DefaultStoppingSolverProgress() -> Progress:  # solver/progress.h:353-431
+    s = _lib.Stop()
+    _lib.lib().cno_default_stop(C.byref(s))
+    return Progress.from_c(s)
+
+
+def ConservativeStoppingSolverProgress() -> Progress:  # solver/progress.h:456-464
+    s = _lib.Stop()
+    _lib.lib().cno_conservative_stop(C.byref(s))
+    return Progress.from_c(s)
+
+
+@dataclass
+class BatchedProgress:
+    """Per-instance Progress values returned by Minimize."""
+    num_iterations: torch.Tensor  # uint32 stored as int32 tensor view
+    status: torch.Tensor          # int8, Status values
+    nfev: torch.Tensor
+    x_delta: torch.Tensor
+    f_delta: torch.Tensor
+    gradient_norm: torch.Tensor
+    launch: Optional[_lib.LaunchInfo] = None
+
+    def done_bitmap(self) -> torch.Tensor:
+        """Per-GPU convergence bitmap (1 bit / instance) for the global stop test."""
+        b = self.status.shape[0]
+        words = torch.zeros((b + 31) // 32, dtype=torch.int32, device=self.status.device)
+        _lib.check(_lib.lib().cno_done_bitmap(
+            self.status.data_ptr(), b, words.data_ptr(),
+            torch.cuda.current_stream(self.status.device).cuda_stream), "cno_done_bitmap")
+        return words
+
+
+class Solver:
+    """solver/solver.h:156-231 with a batch axis."""
+    _solver_id = -1
+
+    def __init__(self, progress: Optional[Progress] = None):
+        self.stopping_progress = progress if progress is not None else DefaultStoppingSolverProgress()
+        self._workspace: Optional[torch.Tensor] = None
+
+    def supported(self, function: Function) -> bool:
+        p = function.problem()
+        return _lib.lib().cno_supported(self._solver_id, C.byref(p)) == _lib.OK
+
+    def Minimize(self, function: Function, state: BatchedFunctionState,
+                 timed: bool = False) -> Tuple[BatchedFunctionState, BatchedProgress]:
+        x0 = state.x
+        if not x0.is_cuda:
+            raise RuntimeError("Minimize needs CUDA tensors (there is no CPU fallback); "
+                               "use MinimizeHost for host buffers")
+        if x0.dtype != function.ScalarType or x0.dim() != 2 or x0.shape[1] != function.Dimension:
+            raise ValueError("x0 must be [B, d] of the function's scalar type")
+        x0 = x0.contiguous()
+        dev, dt, B, d = x0.device, x0.dtype, x0.shape[0], x0.shape[1]
+        L = _lib.lib()
+        prob = function.problem()
+        with torch.cuda.device(dev):
+            x = torch.empty_like(x0)
+            g = torch.empty_like(x0)
+            f = torch.empty(B, dtype=dt, device=dev)
+            xd = torch.empty(B, dtype=dt, device=dev)
+            fd = torch.empty(B, dtype=dt, device=dev)
+            gn = torch.empty(B, dtype=dt, device=dev)
+            it = torch.empty(B, dtype=torch.int32, device=dev)
+            nf = torch.empty(B, dtype=torch.int32, device=dev)
+            st = torch.empty(B, dtype=torch.int8, device=dev)
+            nbytes = C.c_size_t(0)
+            _lib.check(L.cno_workspace_bytes(self._solver_id, C.byref(prob), B, C.byref(nbytes)),
+                       "cno_workspace_bytes")
+            if self._workspace is None or self._workspace.numel() < nbytes.value or \
+                    self._workspace.device != dev:
+                self._workspace = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
+            out = _lib.BatchOut(x.data_ptr(), f.data_ptr(), g.data_ptr(), it.data_ptr(),
+                                st.data_ptr(), nf.data_ptr(), xd.data_ptr(), fd.data_ptr(),
+                                gn.data_ptr())
+            stop = self.stopping_progress.to_c()
+            info = _lib.LaunchInfo() if timed else None
+            _lib.check(L.cno_minimize(
+                self._solver_id, C.byref(prob), B, x0.data_ptr(), C.byref(stop), C.byref(out),
+                self._workspace.data_ptr(), self._workspace.numel(),
+                torch.cuda.current_stream(dev).cuda_stream,
+                C.byref(info) if info is not None else None), "cno_minimize")
+        return (BatchedFunctionState(x, f, g),
+                BatchedProgress(it, st, nf, xd, fd, gn, info))
+
+    def MinimizeHost(self, function: Function, x0: torch.Tensor
+                     ) -> Tuple[BatchedFunctionState, BatchedProgress]:
+        """Same call with host tensors (pinned for full-speed copies): H2D, solve,
+        D2H inside libcno.so (cno_minimize_host)."""
+        if x0.is_cuda:
+            raise ValueError("MinimizeHost takes host tensors")
+        x0 = x0.contiguous()
+        B, dt = x0.shape[0], x0.dtype
+        pin = x0.is_pinned()
+        mk = lambda *s, dtype=dt: torch.empty(*s, dtype=dtype, pin_memory=pin)
+        x, g = mk(*x0.shape), mk(*x0.shape)
+        f, xd, fd, gn = mk(B), mk(B), mk(B), mk(B)
+        it, nf = mk(B, dtype=torch.int32), mk(B, dtype=torch.int32)
+        st = mk(B, dtype=torch.int8)
+        out = _lib.BatchOut(x.data_ptr(), f.data_ptr(), g.data_ptr(), it.data_ptr(),
+                            st.data_ptr(), nf.data_ptr(), xd.data_ptr(), fd.data_ptr(),
+                            gn.data_ptr())
+        prob = function.problem()
+        stop = self.stopping_progress.to_c()
+        info = _lib.LaunchInfo()
+        _lib.check(_lib.lib().cno_minimize_host(
+            self._solver_id, C.byref(prob), B, x0.data_ptr(), C.byref(stop), C.byref(out),
+            C.byref(info)), "cno_minimize_host")
+        return (BatchedFunctionState(x, f, g), BatchedProgress(it, st, nf, xd, fd, gn, info))
+
+
+class Lbfgs(Solver):
+    """solver/lbfgs.h:40-324 (m = 10, MoreThuente)."""
+    _solver_id = _lib.LBFGS
+
+
+class Bfgs(Solver):
+    """solver/bfgs.h:39-145 (MoreThuente)."""
+    _solver_id = _lib.BFGS
+
+
+class NewtonDescent(Solver):
+    """solver/newton_descent.h:38-85 (Armijo<F,2>)."""
+    _solver_id = _lib.NEWTON
+
+
+def fill_uniform(t: torch.Tensor, first: int, seed: int, lo: float, hi: float) -> torch.Tensor:
+    """Counter-based start generator on the device."""
+    assert t.is_cuda and t.is_contiguous()
+    dt = _lib.F64 if t.dtype == torch.float64 else _lib.F32
+    _lib.check(_lib.lib().cno_fill_uniform(dt, t.data_ptr(), first, t.numel(), seed, lo, hi,
+                                           torch.cuda.current_stream(t.device).cuda_stream),
+               "cno_fill_uniform")
+    return t

@@ -1,0 +1,62 @@
+"""Generates tests/golden/*.npz from oracle/_ref = the REFERENCE'S OWN headers
+(/root/reference/include, compiled against oracle/ref_shim) run in this
+container.  /root/reference does not exist on the GPU box, so the vectors are
+committed; rerun this script here to regenerate them:
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle_binding as ob  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SEED = 12345
+
+CASES = [
+    # name, solver, family, d, dtype, B
+    ("lbfgs_rosenbrock_d128_f64", ob.LBFGS, ob.FN_ROSENBROCK, 128, np.float64, 48),
+    ("lbfgs_rosenbrock_d37_f64", ob.LBFGS, ob.FN_ROSENBROCK, 37, np.float64, 32),
+    ("lbfgs_rosenbrock_d2_f64", ob.LBFGS, ob.FN_ROSENBROCK, 2, np.float64, 64),
+    ("lbfgs_rosenbrock_d128_f32", ob.LBFGS, ob.FN_ROSENBROCK, 128, np.float32, 32),
+    ("bfgs_rosenbrock_d32_f64", ob.BFGS, ob.FN_ROSENBROCK, 32, np.float64, 48),
+    ("bfgs_rosenbrock_d2_f64", ob.BFGS, ob.FN_ROSENBROCK, 2, np.float64, 32),
+]
+
+
+def main():
+    assert ob.ref_available(), "oracle/_ref is not built (needs /root/reference)"
+    for name, solver, family, d, dtype, B in CASES:
+        x0 = ob.fill_uniform((B, d), 0, SEED, -2.0, 2.0, dtype)
+        r = ob.minimize(solver, family, x0, impl="ref")
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), x0=x0, x=r["x"], value=r["value"],
+                            gradient=r["gradient"], num_iterations=r["num_iterations"],
+                            status=r["status"], nfev=r["nfev"], solver=solver, family=family)
+        print(name, "mean iters", r["num_iterations"].mean())
+    # the two verify.cc starts + Dockerfile.test + AL-test half norm (reference code, d = 2)
+    pins = {}
+    for tag, solver, family, x0 in [
+        ("lbfgs_far", ob.LBFGS, ob.FN_ROSENBROCK, [15.0, 8.0]),
+        ("lbfgs_near", ob.LBFGS, ob.FN_ROSENBROCK, [-1.0, 2.0]),
+        ("bfgs_far", ob.BFGS, ob.FN_ROSENBROCK, [15.0, 8.0]),
+        ("bfgs_near", ob.BFGS, ob.FN_ROSENBROCK, [-1.0, 2.0]),
+        ("newton_far", ob.NEWTON, ob.FN_ROSENBROCK, [15.0, 8.0]),
+        ("newton_near", ob.NEWTON, ob.FN_ROSENBROCK, [-1.0, 2.0]),
+        ("lbfgs_quadratic", ob.LBFGS, ob.FN_DIAG_QUADRATIC, [-10.0, 2.0]),
+        ("lbfgs_halfnorm", ob.LBFGS, ob.FN_HALF_SQUARED_NORM, [5.0, 5.0]),
+    ]:
+        r = ob.minimize(solver, family, np.array([x0]), impl="ref")
+        pins[tag + "_x"] = r["x"][0]
+        pins[tag + "_f"] = r["value"][0]
+        pins[tag + "_it"] = r["num_iterations"][0]
+        pins[tag + "_status"] = r["status"][0]
+        print(tag, r["x"][0], r["value"][0], r["num_iterations"][0], r["status"][0])
+    np.savez_compressed(os.path.join(HERE, "reference_pins_d2.npz"), **pins)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""C-ABI checks that need no GPU: libcno.so loads, exports every symbol that
+include/cno.h declares, presets match the reference, and compute entry points
+fail loudly (CNO_ERR_NO_DEVICE) instead of falling back to the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from cppnumericalsolvers_b200 import _lib
+import cppnumericalsolvers_b200 as cn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_all_exported():
+    hdr = open(os.path.join(ROOT, "include", "cno.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)  # declarations only, not comments
+    declared = set(re.findall(r"\b(cno_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS)
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_version_and_error_strings():
+    L = _lib.lib()
+    a, b = C.c_int(), C.c_int()
+    L.cno_version(C.byref(a), C.byref(b))
+    assert (a.value, b.value) == (0, 1)
+    assert b"no CPU fallback" in L.cno_error_string(_lib.ERR_NO_DEVICE)
+
+
+def test_default_preset_matches_reference():  # solver/progress.h:353-431
+    p = cn.DefaultStoppingSolverProgress()
+    assert (p.num_iterations, p.x_delta, p.x_delta_violations) == (10000, 1e-9, 1)
+    assert (p.f_delta, p.f_delta_violations, p.f_delta_relative) == (0.0, 1, False)
+    assert (p.gradient_norm, p.gradient_norm_relative) == (1e-5, True)
+    assert (p.condition_hessian, p.past, p.past_delta) == (0.0, 3, 1e-6)
+    q = cn.ConservativeStoppingSolverProgress()  # :456-464
+    assert (q.gradient_norm, q.past, q.past_delta) == (5e-6, 5, 1e-10)
+
+
+def test_status_enum_values():  # solver/progress.h:37-47
+    assert [int(s) for s in cn.Status] == [-1, 0, 1, 2, 3, 4, 5, 6]
+
+
+def test_supported_table():
+    assert cn.Lbfgs().supported(cn.Rosenbrock(128))
+    assert cn.Lbfgs().supported(cn.Rosenbrock(2))
+    assert cn.Lbfgs().supported(cn.Rosenbrock(128, torch.float32))
+    assert not cn.Lbfgs().supported(cn.Rosenbrock(129))
+
+
+def test_struct_layouts_match_oracle_binding():
+    from oracle import oracle_binding as ob
+    for a, b in ((ob.Stop, _lib.Stop), (ob.Problem, _lib.Problem), (ob.BatchOut, _lib.BatchOut)):
+        assert C.sizeof(a) == C.sizeof(b)
+        assert [f[0] for f in a._fields_] == [f[0] for f in b._fields_]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_device_fails_loudly_no_cpu_fallback():
+    L = _lib.lib()
+    x0 = np.zeros((4, 128))
+    out = _lib.BatchOut(x0.ctypes.data, None, None, None, None, None, None, None, None)
+    prob = cn.Rosenbrock(128).problem()
+    rc = L.cno_minimize_host(_lib.LBFGS, C.byref(prob), 4, x0.ctypes.data, None, C.byref(out), None)
+    assert rc == _lib.ERR_NO_DEVICE
+    ws = np.zeros(64, np.uint64)
+    rc = L.cno_minimize(_lib.LBFGS, C.byref(prob), 4, x0.ctypes.data, None, C.byref(out),
+                        ws.ctypes.data, 512, None, None)
+    assert rc == _lib.ERR_NO_DEVICE
+    with pytest.raises(RuntimeError):
+        cn.Lbfgs().Minimize(cn.Rosenbrock(128), cn.BatchedFunctionState(torch.zeros(4, 128, dtype=torch.float64)))
+
+
+def test_invalid_arguments():
+    L = _lib.lib()
+    prob = cn.Rosenbrock(128).problem()
+    assert L.cno_minimize_host(7, C.byref(prob), 4, None, None, None, None) == _lib.ERR_INVALID_ARGUMENT
+    bad = cn.Rosenbrock(129).problem()
+    assert L.cno_supported(_lib.LBFGS, C.byref(bad)) == _lib.ERR_UNSUPPORTED
+    n = C.c_size_t()
+    assert L.cno_workspace_bytes(_lib.LBFGS, C.byref(prob), 10, C.byref(n)) == 0 and n.value >= 8
