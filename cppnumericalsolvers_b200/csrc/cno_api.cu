@@ -255,7 +255,12 @@ int cno_minimize(int solver, const cno_problem_t* problem, int64_t batch, const 
                  size_t workspace_bytes, void* stream, cno_launch_info_t* info) {
   int rc = check_args(solver, problem);
   if (rc) return rc;
-  if (batch < 0 || !x0 || !out) return CNO_ERR_INVALID_ARGUMENT;
+  if (batch < 0 || !out) return CNO_ERR_INVALID_ARGUMENT;
+  if (batch == 0) {
+    if (info) memset(info, 0, sizeof(*info));
+    return have_device() ? CNO_OK : CNO_ERR_NO_DEVICE;
+  }
+  if (!x0) return CNO_ERR_INVALID_ARGUMENT;
   if (!workspace || workspace_bytes < kWorkspaceBytes || ((uintptr_t)workspace & 7))
     return CNO_ERR_WORKSPACE;
   if (((uintptr_t)x0 & 15) || ((uintptr_t)out->x & 15) || ((uintptr_t)out->gradient & 15))

@@ -33,7 +33,8 @@ template <class T, int D, int M>
 struct LbfgsSmem {
   static constexpr int E = Shape<D>::E;
   static constexpr int kVec = 32 * E;                        // elements per stored vector
-  static constexpr int kWarpElems = 2 * M * kVec + 2 * M;    // S, Y, denom[M], alpha[M]
+  static constexpr int kScalars = 2 * M + CNO_MAX_PAST;      // rho[M], alpha[M], f ring
+  static constexpr int kWarpElems = 2 * M * kVec + ((kScalars + 1) / 2) * 2;  // + S, Y
   static constexpr size_t kWarpBytes = (size_t)kWarpElems * sizeof(T);
   // warps per CTA: as many as fit in 227 KB, at most 16 (register budget).
   static constexpr int kMaxSmem = 227 * 1024;
@@ -41,82 +42,79 @@ struct LbfgsSmem {
   static constexpr int kWarps = kWarpsFit > 16 ? 16 : (kWarpsFit < 1 ? 1 : kWarpsFit);
 };
 
-// progress.h:153-327 on warp-uniform scalars (FunctionState branch).
+// progress.h:153-327 on warp-uniform scalars (FunctionState branch).  The
+// past-f ring (progress.h:138-140) lives in the warp's shared-memory slice.
 template <class T>
 struct ProgressState {
   uint32_t num_iterations;
   int x_delta_violations;
   int f_delta_violations;
   T x_delta, f_delta, gradient_norm;
-  T ring[CNO_MAX_PAST];
   int ring_size, ring_pos;
   int status;
 };
 
 template <class T>
 __device__ __forceinline__ void progress_update(ProgressState<T>& p, const StopParams<T>& stop,
+                                                T* __restrict__ ring, const int lane,
                                                 T prev_value, T cur_value, T x_delta,
                                                 T gradient_norm, T x_inf) {
   p.num_iterations++;
   p.f_delta = cabs(cur_value - prev_value);
   p.x_delta = x_delta;
   p.gradient_norm = gradient_norm;
-  if ((stop.num_iterations > 0) && ((unsigned long long)p.num_iterations > stop.num_iterations)) {
-    p.status = CNO_STATUS_ITERATION_LIMIT;
-    return;
-  }
-  if ((stop.x_delta > 0) && (p.x_delta < stop.x_delta)) {
-    p.x_delta_violations++;
-    if (p.x_delta_violations >= stop.x_delta_violations) {
-      p.status = CNO_STATUS_X_DELTA_VIOLATION;
-      return;
+  int status = CNO_STATUS_CONTINUE;
+  // Tests in the reference's order; the first that fires wins (each `return`
+  // of progress.h becomes "status already set").
+  if ((stop.num_iterations > 0) && ((unsigned long long)p.num_iterations > stop.num_iterations))
+    status = CNO_STATUS_ITERATION_LIMIT;  // :212-216
+  if (status == CNO_STATUS_CONTINUE) {    // :254-262
+    if ((stop.x_delta > 0) && (p.x_delta < stop.x_delta)) {
+      p.x_delta_violations++;
+      if (p.x_delta_violations >= stop.x_delta_violations) status = CNO_STATUS_X_DELTA_VIOLATION;
+    } else {
+      p.x_delta_violations = 0;
     }
-  } else {
-    p.x_delta_violations = 0;
   }
-  if ((stop.f_delta > 0) &&
-      (p.f_delta < stop.f_delta * (stop.f_delta_relative
-                                       ? smax(smax(cabs(cur_value), cabs(prev_value)), T(1))
-                                       : T(1)))) {
-    p.f_delta_violations++;
-    if (p.f_delta_violations >= stop.f_delta_violations) {
-      p.status = CNO_STATUS_F_DELTA_VIOLATION;
-      return;
+  if (status == CNO_STATUS_CONTINUE) {  // :263-277
+    if ((stop.f_delta > 0) &&
+        (p.f_delta < stop.f_delta * (stop.f_delta_relative
+                                         ? smax(smax(cabs(cur_value), cabs(prev_value)), T(1))
+                                         : T(1)))) {
+      p.f_delta_violations++;
+      if (p.f_delta_violations >= stop.f_delta_violations) status = CNO_STATUS_F_DELTA_VIOLATION;
+    } else {
+      p.f_delta_violations = 0;
     }
-  } else {
-    p.f_delta_violations = 0;
   }
-  if (stop.past > 0) {
+  if (uni(status == CNO_STATUS_CONTINUE && stop.past > 0)) {  // :280-298
     const int pp = stop.past;
-    if (p.ring_size != pp) {
-#pragma unroll
-      for (int i = 0; i < CNO_MAX_PAST; ++i) p.ring[i] = cur_value;
+    if (uni(p.ring_size != pp)) {
+      if (lane < pp) ring[lane] = cur_value;
       p.ring_size = pp;
       p.ring_pos = 0;
+      __syncwarp();
     }
-    if ((int)p.num_iterations > pp) {
-      T past_f = p.ring[0];
-#pragma unroll
-      for (int i = 1; i < CNO_MAX_PAST; ++i) past_f = (p.ring_pos == i) ? p.ring[i] : past_f;
+    bool fired = false;
+    if (uni((int)p.num_iterations > pp)) {
+      const T past_f = ring[p.ring_pos];
       const T rate = cabs(past_f - cur_value) / smax(T(1), cabs(cur_value));
-      if (rate < stop.past_delta) {
-        p.status = CNO_STATUS_F_DELTA_VIOLATION;
-        return;
-      }
+      fired = rate < stop.past_delta;
     }
-#pragma unroll
-    for (int i = 0; i < CNO_MAX_PAST; ++i)
-      if (p.ring_pos == i) p.ring[i] = cur_value;
-    p.ring_pos = (p.ring_pos + 1) % pp;
+    if (uni(fired)) {
+      status = CNO_STATUS_F_DELTA_VIOLATION;
+    } else {
+      __syncwarp();
+      if (lane == 0) ring[p.ring_pos] = cur_value;
+      p.ring_pos = (p.ring_pos + 1 == pp) ? 0 : p.ring_pos + 1;
+      __syncwarp();
+    }
   }
-  if (stop.gradient_norm > 0) {
+  if (status == CNO_STATUS_CONTINUE && stop.gradient_norm > 0) {  // :299-317
     const T scale = stop.gradient_norm_relative ? smax(T(1), x_inf) : T(1);
-    if (p.gradient_norm < stop.gradient_norm * scale) {
-      p.status = CNO_STATUS_GRADIENT_NORM_VIOLATION;
-      return;
-    }
+    if (p.gradient_norm < stop.gradient_norm * scale) status = CNO_STATUS_GRADIENT_NORM_VIOLATION;
   }
-  p.status = CNO_STATUS_CONTINUE;
+  p.status = status;
 }
 
 template <class Fn, int M>
@@ -137,15 +135,16 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   const int warp = threadIdx.x >> 5;
   T* const S = reinterpret_cast<T*>(smem_raw) + (size_t)warp * SM::kWarpElems;
   T* const Y = S + M * SM::kVec;
-  T* const denom = Y + M * SM::kVec;
-  T* const alpha = denom + M;
+  T* const rho_s = Y + M * SM::kVec;  // 1 / (s_i . y_i) per slot
+  T* const alpha = rho_s + M;
+  T* const ring = alpha + M;
 
   for (;;) {
     // ---- retire + refill: next instance from the global queue ----
     unsigned long long b = 0;
     if (lane == 0) b = atomicAdd(queue, 1ULL);
     b = __shfl_sync(kFullMask, b, 0);
-    if (b >= (unsigned long long)batch) break;
+    if (uni(b >= (unsigned long long)batch)) break;
     const EvalCtx ctx{lane, (long long)b};
 
     // ---- solver.h:189-192: evaluate once at the start point ----
@@ -156,6 +155,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
     // ---- lbfgs.h:72-87 InitializeSolver ----
     int mem_count = 0, mem_pos = 0;
+    unsigned valid = 0;  // bit idx set <=> !(|s_idx . y_idx| < eps)  (lbfgs.h:165,189)
     T gamma = T(1);
 
     ProgressState<T> prog;
@@ -167,15 +167,10 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     prog.ring_pos = 0;
     prog.status = CNO_STATUS_NOT_STARTED;
 
-    // squared norms carried across iterations (same dots the reference
+    // squared norms carried across iterations (the same dots the reference
     // recomputes at lbfgs.h:95 and :221).
-    T xx, gg;
-    {
-      T a = lane_dot<T, E>(x, x), c = lane_dot<T, E>(g, g);
-      butterfly_sum2(a, c);
-      xx = a;
-      gg = c;
-    }
+    T xx = lane_dot<T, E>(x, x), gg = lane_dot<T, E>(g, g);
+    butterfly_sum2(xx, gg);
 
     do {  // solver.h:196-220
       // ================= Lbfgs::OptimizationStep (lbfgs.h:89-303) =========
@@ -186,37 +181,46 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       for (int j = 0; j < E; ++j) q[j] = g[j];  // :145
       const int k = mem_count;
 
-      // ---- first loop (:157-171) ----
-      for (int i = k - 1; i >= 0; --i) {
-        const int idx = (mem_count < M) ? i : ((mem_pos + i) % M);
-        const T den = denom[idx];
-        if (cabs(den) < eps) continue;
-        const T rho = T(1) / den;
-        T sv[E], yv[E];
-        SV::load(S + idx * SM::kVec, lane, sv);
-        SV::load(Y + idx * SM::kVec, lane, yv);
-        const T a = rho * warp_dot<T, E>(sv, q);
-        if (lane == 0) alpha[i] = a;
+      // ---- first loop (:157-171): newest pair first ----
+      // chronological i -> slot (mem_pos + i) mod M; mem_pos stays 0 until the
+      // buffer is full, so this is the reference's index map (:162).
+      {
+        int idx = mem_pos + k - 1;
+        idx = (idx >= M) ? idx - M : idx;
+#pragma unroll 1
+        for (int i = k - 1; uni(i >= 0); --i) {
+          if (uni((valid >> idx) & 1u)) {
+            T sv[E], yv[E];
+            SV::load(S + idx * SM::kVec, lane, sv);
+            SV::load(Y + idx * SM::kVec, lane, yv);
+            const T a = rho_s[idx] * butterfly_sum(lane_dot<T, E>(sv, q));
+            if (lane == 0) alpha[i] = a;
 #pragma unroll
-        for (int j = 0; j < E; ++j) q[j] = q[j] - a * yv[j];
+            for (int j = 0; j < E; ++j) q[j] = q[j] - a * yv[j];
+          }
+          idx = (idx == 0) ? M - 1 : idx - 1;
+        }
       }
       __syncwarp();
       // ---- H0 scaling (:181) ----
 #pragma unroll
       for (int j = 0; j < E; ++j) q[j] = q[j] * gamma;
-      // ---- second loop (:185-196) ----
-      for (int i = 0; i < k; ++i) {
-        const int idx = (mem_count < M) ? i : ((mem_pos + i) % M);
-        const T den = denom[idx];
-        if (cabs(den) < eps) continue;
-        const T rho = T(1) / den;
-        T sv[E], yv[E];
-        SV::load(S + idx * SM::kVec, lane, sv);
-        SV::load(Y + idx * SM::kVec, lane, yv);
-        const T beta = rho * warp_dot<T, E>(yv, q);
-        const T coef = alpha[i] - beta;
+      // ---- second loop (:185-196): oldest pair first ----
+      {
+        int idx = mem_pos;
+#pragma unroll 1
+        for (int i = 0; uni(i < k); ++i) {
+          if (uni((valid >> idx) & 1u)) {
+            T sv[E], yv[E];
+            SV::load(S + idx * SM::kVec, lane, sv);
+            SV::load(Y + idx * SM::kVec, lane, yv);
+            const T beta = rho_s[idx] * butterfly_sum(lane_dot<T, E>(yv, q));
+            const T coef = alpha[i] - beta;
 #pragma unroll
-        for (int j = 0; j < E; ++j) q[j] = q[j] + sv[j] * coef;
+            for (int j = 0; j < E; ++j) q[j] = q[j] + sv[j] * coef;
+          }
+          idx = (idx + 1 == M) ? 0 : idx + 1;
+        }
       }
 
       // ---- descent test, alpha_init, fallback (:199-224) ----
@@ -225,19 +229,20 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       butterfly_sum2(gq, qq);
       const T descent_direction = -gq;
       T alpha_init = T(1);
-      if (mem_count == 0) {
+      if (uni(mem_count == 0)) {
         const T qn = csqrt(qq);
         alpha_init = (qn > eps) ? T(1) / qn : T(1);
       }
       T dginit = descent_direction;  // = g.(-q), bit for bit
       T sdir[E];
-      if (!cfinite(descent_direction) || descent_direction > -eps * relative_eps) {
+      if (uni(!cfinite(descent_direction) || descent_direction > -eps * relative_eps)) {
         // fallback: search_direction = -g, and the reference then searches
         // along -search_direction = +g: dginit = g.g >= 0.
 #pragma unroll
         for (int j = 0; j < E; ++j) sdir[j] = g[j];
         mem_count = 0;
         mem_pos = 0;
+        valid = 0;
         const T gn = csqrt(gg);
         alpha_init = (gn > eps) ? T(1) / gn : T(1);
         dginit = gg;
@@ -248,19 +253,15 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
       // ---- MoreThuente::Search (:231-232) ----
       T xn[E], gn[E];
-#pragma unroll
-      for (int j = 0; j < E; ++j) { xn[j] = x[j]; gn[j] = g[j]; }
-      T fn_val = f;
-      T stp = alpha_init;
-      nfev += cvsrch<Fn, T, E>(fn, ctx, xn, fn_val, gn, stp, sdir, dginit);
+      T fn_val;
+      nfev += cvsrch<Fn, T, E>(fn, ctx, x, f, g, xn, fn_val, gn, alpha_init, sdir, dginit);
 
       const T prev_value = f;
       T x_delta, gnorm_inf, x_inf;
-      if (!cfinite(fn_val)) {
+      if (uni(!cfinite(fn_val))) {
         // :239-241 return current: x, g, f unchanged -> x_delta = 0.
-        T m1 = lane_maxabs<T, E>(g), m2 = lane_maxabs<T, E>(x);
-        gnorm_inf = butterfly_max(m1);
-        x_inf = butterfly_max(m2);
+        gnorm_inf = butterfly_max(lane_maxabs<T, E>(g));
+        x_inf = butterfly_max(lane_maxabs<T, E>(x));
         x_delta = T(0);
       } else {
         // ---- pair + gamma update (:248-298) ----
@@ -270,18 +271,20 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         T sy = lane_dot<T, E>(sd, yd), ss = lane_dot<T, E>(sd, sd), yy = lane_dot<T, E>(yd, yd);
         butterfly_sum3(sy, ss, yy);
         const T sy_threshold = eps * csqrt(ss) * csqrt(yy);
-        if (sy > sy_threshold) {
+        if (uni(sy > sy_threshold)) {
           int slot;
           if (mem_count < M) {
             slot = mem_count;
             mem_count++;
           } else {
             slot = mem_pos;
-            mem_pos = (mem_pos + 1) % M;
+            mem_pos = (mem_pos + 1 == M) ? 0 : mem_pos + 1;
           }
           SV::store(S + slot * SM::kVec, lane, sd);
           SV::store(Y + slot * SM::kVec, lane, yd);
-          if (lane == 0) denom[slot] = sy;
+          // s.y is exactly the dot the reference recomputes per use; cache 1/(s.y)
+          if (lane == 0) rho_s[slot] = T(1) / sy;
+          valid = (cabs(sy) < eps) ? (valid & ~(1u << slot)) : (valid | (1u << slot));
         }
         if (yy > eps) {
           const T temp_scaling = sy / yy;
@@ -293,19 +296,19 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         for (int j = 0; j < E; ++j) { x[j] = xn[j]; g[j] = gn[j]; }
         f = fn_val;
         T m1 = lane_maxabs<T, E>(g), m2 = lane_maxabs<T, E>(x);
-        x_delta = butterfly_max(m0);
-        gnorm_inf = butterfly_max(m1);
-        x_inf = butterfly_max(m2);
-        T a = lane_dot<T, E>(x, x), c = lane_dot<T, E>(g, g);
-        butterfly_sum2(a, c);
-        xx = a;
-        gg = c;
+        butterfly_max3(m0, m1, m2);
+        x_delta = m0;
+        gnorm_inf = m1;
+        x_inf = m2;
+        xx = lane_dot<T, E>(x, x);
+        gg = lane_dot<T, E>(g, g);
+        butterfly_sum2(xx, gg);
         __syncwarp();
       }
 
       // ================= Progress::Update (progress.h:153-327) ============
-      progress_update<T>(prog, stop, prev_value, f, x_delta, gnorm_inf, x_inf);
-    } while (prog.status == CNO_STATUS_CONTINUE);
+      progress_update<T>(prog, stop, ring, lane, prev_value, f, x_delta, gnorm_inf, x_inf);
+    } while (uni(prog.status == CNO_STATUS_CONTINUE));
 
     // ---- write the returned FunctionState + Progress ----
     if (out.x) store_row<T, D>(out.x + b * D, lane, x);

@@ -24,14 +24,14 @@ __device__ __forceinline__ T max_abs3(T x, T y, T z) {  // more_thuente.h:409-41
 
 // more_thuente.h:261-407
 template <class T>
-__device__ __noinline__ int cstep(T& stx, T& fx, T& dx, T& sty, T& fy, T& dy,
+__device__ __forceinline__ int cstep(T& stx, T& fx, T& dx, T& sty, T& fy, T& dy,
                                   T& stp, T fp, T dp, bool& brackt, T stpmin,
                                   T stpmax, int& info) {
   info = 0;
   bool bound = false;
 
-  if ((brackt && ((stp <= smin(stx, sty)) || (stp >= smax(stx, sty)))) ||
-      (dx * (stp - stx) >= T(0)) || (stpmax < stpmin)) {
+  if (uni((brackt && ((stp <= smin(stx, sty)) || (stp >= smax(stx, sty)))) ||
+          (dx * (stp - stx) >= T(0)) || (stpmax < stpmin))) {
     return -1;
   }
 
@@ -39,7 +39,7 @@ __device__ __noinline__ int cstep(T& stx, T& fx, T& dx, T& sty, T& fy, T& dy,
 
   T stpf = 0, stpc = 0, stpq = 0;
 
-  if (fp > fx) {
+  if (uni(fp > fx)) {
     info = 1;
     bound = true;
     const T theta = T(3) * (fx - fp) / (stp - stx) + dx + dp;
@@ -51,12 +51,9 @@ __device__ __noinline__ int cstep(T& stx, T& fx, T& dx, T& sty, T& fy, T& dy,
     const T r = p / q;
     stpc = stx + r * (stp - stx);
     stpq = stx + ((dx / ((fx - fp) / (stp - stx) + dx)) / T(2)) * (stp - stx);
-    if (cabs(stpc - stx) < cabs(stpq - stx))
-      stpf = stpc;
-    else
-      stpf = stpc + (stpq - stpc) / 2;
+    stpf = (cabs(stpc - stx) < cabs(stpq - stx)) ? stpc : (stpc + (stpq - stpc) / 2);
     brackt = true;
-  } else if (sgnd < T(0)) {
+  } else if (uni(sgnd < T(0))) {
     info = 2;
     bound = false;
     const T theta = 3 * (fx - fp) / (stp - stx) + dx + dp;
@@ -68,12 +65,9 @@ __device__ __noinline__ int cstep(T& stx, T& fx, T& dx, T& sty, T& fy, T& dy,
     const T r = p / q;
     stpc = stp + r * (stx - stp);
     stpq = stp + (dp / (dp - dx)) * (stx - stp);
-    if (cabs(stpc - stp) > cabs(stpq - stp))
-      stpf = stpc;
-    else
-      stpf = stpq;
+    stpf = (cabs(stpc - stp) > cabs(stpq - stp)) ? stpc : stpq;
     brackt = true;
-  } else if (cabs(dp) < cabs(dx)) {
+  } else if (uni(cabs(dp) < cabs(dx))) {
     info = 3;
     bound = true;
     const T theta = 3 * (fx - fp) / (stp - stx) + dx + dp;
@@ -83,29 +77,18 @@ __device__ __noinline__ int cstep(T& stx, T& fx, T& dx, T& sty, T& fy, T& dy,
     const T p = (gamma - dp) + theta;
     const T q = (gamma + (dx - dp)) + gamma;
     const T r = p / q;
-    if ((r < T(0)) & (gamma != T(0))) {
-      stpc = stp + r * (stx - stp);
-    } else if (stp > stx) {
-      stpc = stpmax;
-    } else {
-      stpc = stpmin;
-    }
+    stpc = ((r < T(0)) & (gamma != T(0))) ? (stp + r * (stx - stp))
+                                          : ((stp > stx) ? stpmax : stpmin);
     stpq = stp + (dp / (dp - dx)) * (stx - stp);
     if (brackt) {
-      if (cabs(stp - stpc) < cabs(stp - stpq))
-        stpf = stpc;
-      else
-        stpf = stpq;
+      stpf = (cabs(stp - stpc) < cabs(stp - stpq)) ? stpc : stpq;
     } else {
-      if (cabs(stp - stpc) > cabs(stp - stpq))
-        stpf = stpc;
-      else
-        stpf = stpq;
+      stpf = (cabs(stp - stpc) > cabs(stp - stpq)) ? stpc : stpq;
     }
   } else {
     info = 4;
     bound = false;
-    if (brackt) {
+    if (uni(brackt)) {
       const T theta = 3 * (fp - fy) / (sty - stp) + dy + dp;
       const T s = max_abs3(theta, dy, dp);
       T gamma = s * csqrt((theta / s) * (theta / s) - (dy / s) * (dp / s));
@@ -115,50 +98,46 @@ __device__ __noinline__ int cstep(T& stx, T& fx, T& dx, T& sty, T& fy, T& dy,
       const T r = p / q;
       stpc = stp + r * (sty - stp);
       stpf = stpc;
-    } else if (stp > stx) {
-      stpf = stpmax;
     } else {
-      stpf = stpmin;
+      stpf = (stp > stx) ? stpmax : stpmin;
     }
   }
 
-  if (fp > fx) {
-    sty = stp;
-    fy = fp;
-    dy = dp;
-  } else {
-    if (sgnd < T(0)) {
-      sty = stx;
-      fy = fx;
-      dy = dx;
-    }
-    stx = stp;
-    fx = fp;
-    dx = dp;
+  {  // :377-391 as selects (no control flow)
+    const bool up = fp > fx;
+    const bool flip = !up && (sgnd < T(0));
+    const T nsty = up ? stp : (flip ? stx : sty);
+    const T nfy = up ? fp : (flip ? fx : fy);
+    const T ndy = up ? dp : (flip ? dx : dy);
+    stx = up ? stx : stp;
+    fx = up ? fx : fp;
+    dx = up ? dx : dp;
+    sty = nsty;
+    fy = nfy;
+    dy = ndy;
   }
 
   stpf = sclamp(stpf, stpmin, stpmax);
   stp = stpf;
 
   if (brackt & bound) {
-    if (sty > stx) {
-      stp = smin(stx + T(0.66) * (sty - stx), stp);
-    } else {
-      stp = smax(stx + T(0.66) * (sty - stx), stp);
-    }
+    const T lim = stx + T(0.66) * (sty - stx);
+    stp = (sty > stx) ? smin(lim, stp) : smax(lim, stp);
   }
   return 0;
 }
 
-// more_thuente.h:137-256.  On entry x/g/f are the start state (wa = x), s the
-// direction, dginit = g.s (the caller already has it: for L-BFGS it equals the
-// descent test value bit for bit because negation commutes with rounding).
-// On exit x/g/f hold the last evaluated point, exactly as in the reference.
-// Returns the number of objective evaluations.
+// more_thuente.h:137-256 fused with Search(State...) :120-135.
+// x0/g0/f0 = the start state (the reference's `wa` and the copies made at
+// :125-129), s = the direction, dginit = g0.s (the caller already has it: for
+// L-BFGS it equals the descent-test value bit for bit because negation commutes
+// with rounding).  On exit x/g/f hold the last evaluated point exactly as in the
+// reference; when dginit >= 0 the search returns at once (:152-156) and
+// x/g/f = x0/g0/f0.  Returns the number of objective evaluations.
 template <class Fn, class T, int E>
-__device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx,
-                                      T (&x)[E], T& f, T (&g)[E], T& stp,
-                                      const T (&s)[E], const T dginit) {
+__device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx, const T (&x0)[E],
+                                      const T f0, const T (&g0)[E], T (&x)[E], T& f,
+                                      T (&g)[E], T stp, const T (&s)[E], const T dginit) {
   int info = 0;
   int infoc = 1;
   const T xtol = T(1e-15);
@@ -170,24 +149,26 @@ __device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx,
   const int maxfev = 20;
   int nfev = 0;
 
-  if (dginit >= T(0)) return 0;  // :152-156 (state untouched)
+  if (uni(dginit >= T(0))) {  // :152-156 (state untouched)
+#pragma unroll
+    for (int j = 0; j < E; ++j) { x[j] = x0[j]; g[j] = g0[j]; }
+    f = f0;
+    return 0;
+  }
 
   bool brackt = false;
   bool stage1 = true;
 
-  const T finit = f;
+  const T finit = f0;
   const T dgtest = ftol * dginit;
   T width = stpmax - stpmin;
   T width1 = T(2) * width;
-  T wa[E];
-#pragma unroll
-  for (int j = 0; j < E; ++j) wa[j] = x[j];
 
   T stx = T(0), fx = finit, dgx = dginit;
   T sty = T(0), fy = finit, dgy = dginit;
-  T stmin, stmax;
 
   for (;;) {
+    T stmin, stmax;
     if (brackt) {
       stmin = smin(stx, sty);
       stmax = smax(stx, sty);
@@ -202,12 +183,10 @@ __device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx,
     }
 
 #pragma unroll
-    for (int j = 0; j < E; ++j) x[j] = wa[j] + stp * s[j];
-    T fl = fn(ctx, x, &g);  // returns the already-reduced value
+    for (int j = 0; j < E; ++j) x[j] = x0[j] + stp * s[j];  // :198
+    f = fn(ctx, x, &g);                                      // :199 (already reduced)
     nfev++;
-    T dg = lane_dot<T, E>(g, s);
-    dg = butterfly_sum(dg);
-    f = fl;
+    const T dg = butterfly_sum(lane_dot<T, E>(g, s));        // :201
     const T ftest1 = finit + stp * dgtest;
 
     if ((brackt & ((stp <= stmin) | (stp >= stmax))) | (infoc == 0)) info = 6;
@@ -217,25 +196,25 @@ __device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx,
     if (brackt & (stmax - stmin <= xtol * stmax)) info = 2;
     if ((f <= ftest1) & (cabs(dg) <= gtol * (-dginit))) info = 1;
 
-    if (info != 0) return nfev;
+    if (uni(info != 0)) return nfev;  // :219
 
     if (stage1 & (f <= ftest1) & (dg >= smin(ftol, gtol) * dginit)) stage1 = false;
 
-    if (stage1 & (f <= fx) & (f > ftest1)) {
-      T fm = f - stp * dgtest;
-      T fxm = fx - stx * dgtest;
-      T fym = fy - sty * dgtest;
-      T dgm = dg - dgtest;
-      T dgxm = dgx - dgtest;
-      T dgym = dgy - dgtest;
-      cstep<T>(stx, fxm, dgxm, sty, fym, dgym, stp, fm, dgm, brackt, stmin, stmax, infoc);
-      fx = fxm + stx * dgtest;
-      fy = fym + sty * dgtest;
-      dgx = dgxm + dgtest;
-      dgy = dgym + dgtest;
-    } else {
-      cstep<T>(stx, fx, dgx, sty, fy, dgy, stp, f, dg, brackt, stmin, stmax, infoc);
-    }
+    // :225-244 with ONE cstep call site: the modified-function values are formed
+    // and undone by selects (x - 0 and x + 0 are exact, but selects keep even
+    // the sign of zero identical to the reference's two branches).
+    const bool mod = stage1 & (f <= fx) & (f > ftest1);
+    T a_fx = mod ? (fx - stx * dgtest) : fx;
+    T a_fy = mod ? (fy - sty * dgtest) : fy;
+    T a_dx = mod ? (dgx - dgtest) : dgx;
+    T a_dy = mod ? (dgy - dgtest) : dgy;
+    const T a_fp = mod ? (f - stp * dgtest) : f;
+    const T a_dp = mod ? (dg - dgtest) : dg;
+    cstep<T>(stx, a_fx, a_dx, sty, a_fy, a_dy, stp, a_fp, a_dp, brackt, stmin, stmax, infoc);
+    fx = mod ? (a_fx + stx * dgtest) : a_fx;
+    fy = mod ? (a_fy + sty * dgtest) : a_fy;
+    dgx = mod ? (a_dx + dgtest) : a_dx;
+    dgy = mod ? (a_dy + dgtest) : a_dy;
 
     if (brackt) {
       if (cabs(sty - stx) >= T(0.66) * width1) stp = stx + T(0.5) * (sty - stx);
