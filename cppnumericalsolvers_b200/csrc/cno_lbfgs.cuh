@@ -167,10 +167,9 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     prog.ring_pos = 0;
     prog.status = CNO_STATUS_NOT_STARTED;
 
-    // squared norms carried across iterations (the same dots the reference
-    // recomputes at lbfgs.h:95 and :221).
-    T xx = lane_dot<T, E>(x, x), gg = lane_dot<T, E>(g, g);
-    butterfly_sum2(xx, gg);
+    // ||x||^2 carried across iterations (the dot the reference recomputes at
+    // lbfgs.h:95).
+    T xx = butterfly_sum(lane_dot<T, E>(x, x));
 
     do {  // solver.h:196-220
       // ================= Lbfgs::OptimizationStep (lbfgs.h:89-303) =========
@@ -183,22 +182,28 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
       // ---- first loop (:157-171): newest pair first ----
       // chronological i -> slot (mem_pos + i) mod M; mem_pos stays 0 until the
-      // buffer is full, so this is the reference's index map (:162).
-      {
+      // buffer is full, so this is the reference's index map (:162).  The loads
+      // of the next pair are issued before the current reduction (software
+      // pipelining: the butterfly is the critical path, LDS latency hides under it).
+      if (uni(k > 0)) {
         int idx = mem_pos + k - 1;
         idx = (idx >= M) ? idx - M : idx;
+        T sv[E];
+        SV::load(S + idx * SM::kVec, lane, sv);
 #pragma unroll 1
         for (int i = k - 1; uni(i >= 0); --i) {
-          if (uni((valid >> idx) & 1u)) {
-            T sv[E], yv[E];
-            SV::load(S + idx * SM::kVec, lane, sv);
-            SV::load(Y + idx * SM::kVec, lane, yv);
-            const T a = rho_s[idx] * butterfly_sum(lane_dot<T, E>(sv, q));
+          const int idx_next = (idx == 0) ? M - 1 : idx - 1;
+          T part = lane_dot<T, E>(sv, q);
+          T yv[E];
+          SV::load(Y + idx * SM::kVec, lane, yv);
+          SV::load(S + idx_next * SM::kVec, lane, sv);  // prefetch (harmless at i == 0)
+          const T a = rho_s[idx] * butterfly_sum(part);
+          if (uni((valid >> idx) & 1u)) {  // lbfgs.h:165 skip
             if (lane == 0) alpha[i] = a;
 #pragma unroll
             for (int j = 0; j < E; ++j) q[j] = q[j] - a * yv[j];
           }
-          idx = (idx == 0) ? M - 1 : idx - 1;
+          idx = idx_next;
         }
       }
       __syncwarp();
@@ -206,33 +211,39 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 #pragma unroll
       for (int j = 0; j < E; ++j) q[j] = q[j] * gamma;
       // ---- second loop (:185-196): oldest pair first ----
-      {
+      if (uni(k > 0)) {
         int idx = mem_pos;
+        T yv[E];
+        SV::load(Y + idx * SM::kVec, lane, yv);
 #pragma unroll 1
         for (int i = 0; uni(i < k); ++i) {
-          if (uni((valid >> idx) & 1u)) {
-            T sv[E], yv[E];
-            SV::load(S + idx * SM::kVec, lane, sv);
-            SV::load(Y + idx * SM::kVec, lane, yv);
-            const T beta = rho_s[idx] * butterfly_sum(lane_dot<T, E>(yv, q));
+          const int idx_next = (idx + 1 == M) ? 0 : idx + 1;
+          T part = lane_dot<T, E>(yv, q);
+          T sv[E];
+          SV::load(S + idx * SM::kVec, lane, sv);
+          SV::load(Y + idx_next * SM::kVec, lane, yv);  // prefetch
+          const T beta = rho_s[idx] * butterfly_sum(part);
+          if (uni((valid >> idx) & 1u)) {  // lbfgs.h:189 skip
             const T coef = alpha[i] - beta;
 #pragma unroll
             for (int j = 0; j < E; ++j) q[j] = q[j] + sv[j] * coef;
           }
-          idx = (idx + 1 == M) ? 0 : idx + 1;
+          idx = idx_next;
         }
       }
 
       // ---- descent test, alpha_init, fallback (:199-224) ----
-      T gq = lane_dot<T, E>(g, q);
-      T qq = lane_dot<T, E>(q, q);
-      butterfly_sum2(gq, qq);
-      const T descent_direction = -gq;
       T alpha_init = T(1);
-      if (uni(mem_count == 0)) {
+      T gq = lane_dot<T, E>(g, q);
+      if (uni(mem_count == 0)) {  // :208-213 (||q|| only matters without history)
+        T qq = lane_dot<T, E>(q, q);
+        butterfly_sum2(gq, qq);
         const T qn = csqrt(qq);
         alpha_init = (qn > eps) ? T(1) / qn : T(1);
+      } else {
+        gq = butterfly_sum(gq);
       }
+      const T descent_direction = -gq;
       T dginit = descent_direction;  // = g.(-q), bit for bit
       T sdir[E];
       if (uni(!cfinite(descent_direction) || descent_direction > -eps * relative_eps)) {
@@ -243,6 +254,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         mem_count = 0;
         mem_pos = 0;
         valid = 0;
+        const T gg = butterfly_sum(lane_dot<T, E>(g, g));  // :221 (rare path)
         const T gn = csqrt(gg);
         alpha_init = (gn > eps) ? T(1) / gn : T(1);
         dginit = gg;
@@ -260,8 +272,8 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       T x_delta, gnorm_inf, x_inf;
       if (uni(!cfinite(fn_val))) {
         // :239-241 return current: x, g, f unchanged -> x_delta = 0.
-        gnorm_inf = butterfly_max(lane_maxabs<T, E>(g));
-        x_inf = butterfly_max(lane_maxabs<T, E>(x));
+        gnorm_inf = warp_max_nonneg(lane_maxabs<T, E>(g));
+        x_inf = warp_max_nonneg(lane_maxabs<T, E>(x));
         x_delta = T(0);
       } else {
         // ---- pair + gamma update (:248-298) ----
@@ -291,18 +303,13 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
           if (cfinite(temp_scaling) && cabs(temp_scaling) <= T(1e7)) gamma = smax(temp_scaling, eps);
         }
         // next state + the norms Progress::Update and the next step need
-        T m0 = lane_maxabs<T, E>(sd);
+        x_delta = warp_max_nonneg(lane_maxabs<T, E>(sd));
 #pragma unroll
         for (int j = 0; j < E; ++j) { x[j] = xn[j]; g[j] = gn[j]; }
         f = fn_val;
-        T m1 = lane_maxabs<T, E>(g), m2 = lane_maxabs<T, E>(x);
-        butterfly_max3(m0, m1, m2);
-        x_delta = m0;
-        gnorm_inf = m1;
-        x_inf = m2;
-        xx = lane_dot<T, E>(x, x);
-        gg = lane_dot<T, E>(g, g);
-        butterfly_sum2(xx, gg);
+        gnorm_inf = warp_max_nonneg(lane_maxabs<T, E>(g));
+        x_inf = warp_max_nonneg(lane_maxabs<T, E>(x));
+        xx = butterfly_sum(lane_dot<T, E>(x, x));
         __syncwarp();
       }
 
