@@ -255,6 +255,12 @@ def main():
     else:
         peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("batch") == B:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
 
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -305,7 +311,7 @@ def main():
             "gpu_launches": args.steps * 2,  # lbfgs_minimize_kernel + done_bitmap_kernel per step
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": "lbfgs_minimize_kernel<RosenbrockFn<double,128>,10>",
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "algorithmic bytes = state-streaming model w*d*(2k+6)/iteration; the fused "

@@ -15,6 +15,7 @@
 #include "cno_functors.cuh"
 #include "cno_kernel_params.h"
 #include "cno_lbfgs.cuh"
+#include "cno_bfgs.cuh"
 
 namespace {
 
@@ -81,6 +82,48 @@ int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
   return CNO_OK;
 }
 
+// One persistent launch of bfgs_minimize_kernel<Fn>.
+template <class Fn>
+int launch_bfgs(const Fn& fn, const LaunchArgs& a) {
+  using T = typename Fn::Scalar;
+  using SM = cno::BfgsSmem<T, Fn::Dim>;
+  auto kernel = cno::bfgs_minimize_kernel<Fn>;
+  const size_t smem = SM::kWarpBytes * SM::kWarps;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  long long ctas = (a.batch + SM::kWarps - 1) / SM::kWarps;
+  const int grid = (int)(ctas < sms ? (ctas < 1 ? 1 : ctas) : sms);
+  unsigned long long* queue = static_cast<unsigned long long*>(a.workspace);
+  CNO_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), a.stream));
+  const cno::StopParams<T> stop = cno::make_stop<T>(*a.stop);
+  const cno::BatchOut<T> out = cno::make_out<T>(*a.out);
+  kernel<<<grid, SM::kWarps * 32, smem, a.stream>>>(fn, static_cast<const T*>(a.x0), a.batch,
+                                                    stop, out, queue);
+  CNO_CUDA(cudaGetLastError());
+  if (a.info) {
+    a.info->kernel_launches += 1;
+    a.info->grid = grid;
+    a.info->block = SM::kWarps * 32;
+    a.info->warps_per_cta = SM::kWarps;
+    a.info->dynamic_smem = (int64_t)smem;
+  }
+  return CNO_OK;
+}
+
+template <class T, int D>
+int bfgs_rosenbrock(const LaunchArgs& a) {
+  return launch_bfgs<cno::RosenbrockFn<T, D>>(cno::RosenbrockFn<T, D>{}, a);
+}
+template <class T, int D>
+int bfgs_half_sq_norm(const LaunchArgs& a) {
+  return launch_bfgs<cno::HalfSquaredNormFn<T, D>>(cno::HalfSquaredNormFn<T, D>{}, a);
+}
+template <class T>
+int bfgs_diag_quadratic(const LaunchArgs& a) {
+  return launch_bfgs<cno::DiagQuadraticFn<T>>(cno::DiagQuadraticFn<T>{}, a);
+}
+
 template <class T, int D>
 int lbfgs_rosenbrock(const LaunchArgs& a) {
   return launch_lbfgs<cno::RosenbrockFn<T, D>, CNO_LBFGS_M>(cno::RosenbrockFn<T, D>{}, a);
@@ -116,6 +159,12 @@ const Entry kTable[] = {
     {CNO_LBFGS, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, lbfgs_diag_quadratic<double>},
     {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, lbfgs_half_sq_norm<double, 2>},
     {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 50, lbfgs_half_sq_norm<double, 50>},
+    {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 2, bfgs_rosenbrock<double, 2>},
+    {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 8, bfgs_rosenbrock<double, 8>},
+    {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 32, bfgs_rosenbrock<double, 32>},
+    {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F32, 32, bfgs_rosenbrock<float, 32>},
+    {CNO_BFGS, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, bfgs_diag_quadratic<double>},
+    {CNO_BFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, bfgs_half_sq_norm<double, 2>},
 };
 
 const Entry* find_entry(int solver, const cno_problem_t* p) {
