@@ -16,6 +16,7 @@
 #include "cno_kernel_params.h"
 #include "cno_lbfgs.cuh"
 #include "cno_bfgs.cuh"
+#include "cno_newton.cuh"
 
 namespace {
 
@@ -111,6 +112,51 @@ int launch_bfgs(const Fn& fn, const LaunchArgs& a) {
   return CNO_OK;
 }
 
+// One persistent launch of newton_minimize_kernel<Fn>.
+template <class Fn>
+int launch_newton(const Fn& fn, const LaunchArgs& a) {
+  using T = typename Fn::Scalar;
+  using SM = cno::NewtonSmem<T, Fn::Dim>;
+  if (a.stop->condition_hessian > 0) return CNO_ERR_UNSUPPORTED;  // see cno_newton.cuh
+  auto kernel = cno::newton_minimize_kernel<Fn>;
+  const size_t smem = SM::kWarpBytes * SM::kWarps;
+  CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  long long ctas = (a.batch + SM::kWarps - 1) / SM::kWarps;
+  const int grid = (int)(ctas < sms ? (ctas < 1 ? 1 : ctas) : sms);
+  unsigned long long* queue = static_cast<unsigned long long*>(a.workspace);
+  CNO_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), a.stream));
+  const cno::StopParams<T> stop = cno::make_stop<T>(*a.stop);
+  const cno::BatchOut<T> out = cno::make_out<T>(*a.out);
+  kernel<<<grid, SM::kWarps * 32, smem, a.stream>>>(fn, static_cast<const T*>(a.x0), a.batch,
+                                                    stop, out, queue);
+  CNO_CUDA(cudaGetLastError());
+  if (a.info) {
+    a.info->kernel_launches += 1;
+    a.info->grid = grid;
+    a.info->block = SM::kWarps * 32;
+    a.info->warps_per_cta = SM::kWarps;
+    a.info->dynamic_smem = (int64_t)smem;
+  }
+  return CNO_OK;
+}
+
+template <class T, int D>
+int newton_dense_quadratic(const LaunchArgs& a) {
+  const cno_problem_t* p = a.problem;
+  if (!p->data || p->data_stride < (int64_t)D * D + D) return CNO_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)p->data & 15) || ((size_t)p->data_stride * sizeof(T)) % 16)
+    return CNO_ERR_INVALID_ARGUMENT;  // TMA bulk copies need 16-byte aligned blocks
+  return launch_newton<cno::DenseQuadraticFn<T, D>>(
+      cno::DenseQuadraticFn<T, D>{static_cast<const T*>(p->data), (long long)p->data_stride}, a);
+}
+template <class T, int D>
+int newton_rosenbrock(const LaunchArgs& a) {
+  return launch_newton<cno::RosenbrockFullFn<T, D>>(cno::RosenbrockFullFn<T, D>{}, a);
+}
+
 template <class T, int D>
 int bfgs_rosenbrock(const LaunchArgs& a) {
   return launch_bfgs<cno::RosenbrockFn<T, D>>(cno::RosenbrockFn<T, D>{}, a);
@@ -165,6 +211,11 @@ const Entry kTable[] = {
     {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F32, 32, bfgs_rosenbrock<float, 32>},
     {CNO_BFGS, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, bfgs_diag_quadratic<double>},
     {CNO_BFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, bfgs_half_sq_norm<double, 2>},
+    {CNO_NEWTON, CNO_FN_DENSE_QUADRATIC, CNO_F64, 64, newton_dense_quadratic<double, 64>},
+    {CNO_NEWTON, CNO_FN_DENSE_QUADRATIC, CNO_F64, 12, newton_dense_quadratic<double, 12>},
+    {CNO_NEWTON, CNO_FN_DENSE_QUADRATIC, CNO_F32, 64, newton_dense_quadratic<float, 64>},
+    {CNO_NEWTON, CNO_FN_ROSENBROCK, CNO_F64, 2, newton_rosenbrock<double, 2>},
+    {CNO_NEWTON, CNO_FN_ROSENBROCK, CNO_F64, 8, newton_rosenbrock<double, 8>},
 };
 
 const Entry* find_entry(int solver, const cno_problem_t* p) {
