@@ -186,6 +186,7 @@ def main():
     import torch.distributed as dist
 
     import cppnumericalsolvers_b200 as cn
+    from cppnumericalsolvers_b200 import distributed as cd
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -214,11 +215,7 @@ def main():
     def step():
         state, prog = solver.Minimize(fn, cn.BatchedFunctionState(x0))
         # global stop test: per-GPU convergence bitmaps, ONE all-gather (NCCL)
-        bitmap = prog.done_bitmap()
-        if world > 1:
-            gathered = torch.empty(world * bitmap.numel(), dtype=bitmap.dtype, device=dev)
-            dist.all_gather_into_tensor(gathered, bitmap)
-            bitmap = gathered
+        bitmap = cd.gather_done_bitmaps(prog.done_bitmap(), max_words=B // 32)
         return state, prog, bitmap
 
     for _ in range(args.warmup):

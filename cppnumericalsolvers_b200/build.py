@@ -47,6 +47,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_cpp_tests(verbose: bool = False) -> list:
+    """Compiles the C++ host-API programs under tests/cpp (g++ and nvcc translation
+    units) into tests/cpp/build/ (git-ignored, travels to the GPU box)."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tests", "cpp")
+    out = os.path.join(src, "build")
+    os.makedirs(out, exist_ok=True)
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    inc = ["-I" + os.path.join(root, "include"), "-I" + CSRC, f"-I{cuda}/include"]
+    link = [f"-L{HERE}", "-lcno", f"-L{cuda}/lib64", "-lcudart", f"-Wl,-rpath,{HERE}", f"-Wl,-rpath,{cuda}/lib64"]
+    exes = []
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", os.path.join(src, "verify_host.cc"), *inc,
+           "-o", os.path.join(out, "verify_host"), *link]
+    subprocess.run(cmd, check=True)
+    exes.append(os.path.join(out, "verify_host"))
+    nvcc = os.environ.get("NVCC", f"{cuda}/bin/nvcc")
+    xlink = ["-Xlinker", f"-rpath={HERE}"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-fmad=false", os.path.join(src, "user_functor.cu"), *inc, "-o",
+           os.path.join(out, "user_functor"), f"-L{HERE}", "-lcno", *xlink]
+    subprocess.run(cmd, check=True)
+    exes.append(os.path.join(out, "user_functor"))
+    return exes
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(LIB)

@@ -1,0 +1,397 @@
+// cppoptlib_b200/cppoptlib.h -- C++17 host-side mirror of cppoptlib's solver
+// interface with a batch axis, over the extern "C" layer of libcno.so
+// (include/cno.h).  Header only; compiles with g++ -std=c++17 (no nvcc), links
+// against libcno.so and libcudart.
+//
+//   reference (include/cppoptlib/...)            here
+//   -------------------------------------------  --------------------------------
+//   function_base.h:42-46  DifferentiabilityMode  function::DifferentiabilityMode
+//   function_base.h:96-126 FunctionCRTP           function::FunctionCRTP (static
+//                                                 members; the device operator()
+//                                                 lives in the functor's .cuh)
+//   function_base.h:194-260 FunctionExpr          function::FunctionExpr (erases
+//                                                 the LAUNCHER, not a virtual call:
+//                                                 SURVEY.md 7 hard part 3)
+//   function_base.h:298-332 FunctionState         function::BatchedFunctionState
+//   solver/progress.h:37-47 Status                solver::Status
+//   solver/progress.h:82-140 Progress             solver::Progress /
+//                                                 solver::BatchedProgress
+//   solver/progress.h:353-464 presets             solver::DefaultStopping...,
+//                                                 solver::ConservativeStopping...
+//   solver/solver.h:156-231 Solver<F,State>       solver::Solver<F>
+//   solver/lbfgs.h / bfgs.h / newton_descent.h    solver::Lbfgs / Bfgs / NewtonDescent
+//
+// Error behaviour follows the reference: numerical outcomes are per-instance
+// Status codes; only API misuse / CUDA failures throw std::runtime_error.
+#ifndef CPPOPTLIB_B200_CPPOPTLIB_H_
+#define CPPOPTLIB_B200_CPPOPTLIB_H_
+
+#include <cuda_runtime_api.h>
+
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../cno.h"
+
+namespace cppoptlib {
+
+namespace detail {
+inline void check_cuda(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+inline void check_cno(int rc, const char* what) {
+  if (rc == CNO_OK) return;
+  std::string msg = std::string(what) + ": " + cno_error_string(rc);
+  if (rc == CNO_ERR_CUDA) {
+    const char* m = nullptr;
+    cno_last_cuda_error(&m);
+    if (m) msg += std::string(" (") + m + ")";
+  }
+  throw std::runtime_error(msg);
+}
+// RAII device array (values everywhere, like the reference's Eigen members).
+template <class T>
+class DeviceArray {
+ public:
+  DeviceArray() = default;
+  explicit DeviceArray(size_t n) : n_(n) {
+    if (n) check_cuda(cudaMalloc(&p_, n * sizeof(T)), "cudaMalloc");
+  }
+  DeviceArray(const DeviceArray& o) : DeviceArray(o.n_) {
+    if (n_) check_cuda(cudaMemcpy(p_, o.p_, n_ * sizeof(T), cudaMemcpyDeviceToDevice), "cudaMemcpy");
+  }
+  DeviceArray(DeviceArray&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+  DeviceArray& operator=(DeviceArray o) noexcept { std::swap(p_, o.p_); std::swap(n_, o.n_); return *this; }
+  ~DeviceArray() { if (p_) cudaFree(p_); }
+  static DeviceArray FromHost(const std::vector<T>& h) {
+    DeviceArray a(h.size());
+    if (!h.empty()) check_cuda(cudaMemcpy(a.p_, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice), "H2D");
+    return a;
+  }
+  std::vector<T> ToHost() const {
+    std::vector<T> h(n_);
+    if (n_) check_cuda(cudaMemcpy(h.data(), p_, n_ * sizeof(T), cudaMemcpyDeviceToHost), "D2H");
+    return h;
+  }
+  T* data() const { return static_cast<T*>(p_); }
+  size_t size() const { return n_; }
+
+ private:
+  void* p_ = nullptr;
+  size_t n_ = 0;
+};
+template <class T> struct DType;
+template <> struct DType<double> { static constexpr int value = CNO_F64; };
+template <> struct DType<float> { static constexpr int value = CNO_F32; };
+}  // namespace detail
+
+namespace function {
+
+enum class DifferentiabilityMode { None = 0, First = 1, Second = 2 };  // function_base.h:42-46
+
+// function_base.h:96-126.  A user objective derives from FunctionCRTP exactly as
+// with the reference; its operator() is the warp-cooperative __device__ form
+// documented in cppnumericalsolvers_b200/csrc/cno_functors.cuh and is compiled by
+// nvcc in the translation unit that says CNO_INSTANTIATE_FUNCTION (device.cuh).
+template <class Derived, class TScalar, DifferentiabilityMode TMode, int TDimension>
+struct FunctionCRTP {
+  static constexpr int Dimension = TDimension;
+  using ScalarType = TScalar;
+  static constexpr DifferentiabilityMode Differentiability = TMode;
+  // device functor concept names (cno_functors.cuh)
+  using Scalar = TScalar;
+  static constexpr int Dim = TDimension;
+  static constexpr int Mode = static_cast<int>(TMode);
+};
+
+// What a solver needs to know about an objective: which kernels to launch.
+// Built-in families go through cno_minimize's table; user functors through the
+// extern "C" symbols generated by CNO_INSTANTIATE_FUNCTION(tag, F).
+typedef int (*RawMinimizeFn)(int solver, const void* functor_bytes, int64_t batch, const void* x0,
+                             const cno_stop_t* stop, const cno_batch_out_t* out, void* workspace,
+                             size_t workspace_bytes, void* stream, cno_launch_info_t* info);
+
+template <class F, class = void>
+struct LauncherTraits;  // specialised by CNO_DECLARE_FUNCTION / the built-ins below
+
+// function_base.h:194-260: value-semantic, type-erased handle.  Erasure happens
+// at the launcher (a function pointer + the functor's POD bytes), so nothing
+// virtual ever has to cross to the device.
+template <class TScalar, DifferentiabilityMode TMode = DifferentiabilityMode::First, int TDimension = -1>
+struct FunctionExpr {
+  using ScalarType = TScalar;
+  static constexpr int Dimension = TDimension;
+  static constexpr DifferentiabilityMode Differentiability = TMode;
+
+  cno_problem_t problem{};          // built-in family (raw == nullptr)
+  RawMinimizeFn raw = nullptr;      // user functor launcher
+  std::vector<unsigned char> pod;   // the user functor's bytes
+
+  FunctionExpr() = default;
+  template <class F, class = std::enable_if_t<!std::is_same_v<std::decay_t<F>, FunctionExpr>>>
+  FunctionExpr(const F& f) {  // NOLINT (converting, like function_base.h:210)
+    static_assert(static_cast<int>(F::Differentiability) >= static_cast<int>(TMode),
+                  "Differentiability mode mismatch (downgrades are accepted, upgrades are not)");
+    static_assert(std::is_same_v<typename F::ScalarType, TScalar>, "scalar-type mismatch");
+    static_assert(TDimension == -1 || F::Dimension == TDimension, "Dimension mismatch");
+    LauncherTraits<F>::Bind(f, *this);
+  }
+};
+
+// FunctionState with a batch axis (function_base.h:298-332): x [B, d] row-major,
+// value [B], gradient [B, d], all on the device.
+template <class TScalar, int TDimension>
+struct BatchedFunctionState {
+  using ScalarType = TScalar;
+  static constexpr bool IsConstrained = false;
+  int64_t batch = 0;
+  detail::DeviceArray<TScalar> x, value, gradient;
+
+  BatchedFunctionState() = default;
+  // "legacy x-only constructor" (:315): Minimize evaluates the function itself.
+  static BatchedFunctionState FromHost(const std::vector<TScalar>& x_host, int64_t batch) {
+    if ((int64_t)x_host.size() != batch * TDimension) throw std::runtime_error("x0 must be [B, d]");
+    BatchedFunctionState s;
+    s.batch = batch;
+    s.x = detail::DeviceArray<TScalar>::FromHost(x_host);
+    return s;
+  }
+};
+
+// ---- objective families compiled into libcno.so --------------------------------
+template <class T, int D>
+struct Rosenbrock : FunctionCRTP<Rosenbrock<T, D>, T, DifferentiabilityMode::First, D> {};
+template <class T, int D>
+struct RosenbrockFull : FunctionCRTP<RosenbrockFull<T, D>, T, DifferentiabilityMode::Second, D> {};
+template <class T>
+struct DiagQuadratic : FunctionCRTP<DiagQuadratic<T>, T, DifferentiabilityMode::First, 2> {};
+template <class T, int D>
+struct HalfSquaredNorm : FunctionCRTP<HalfSquaredNorm<T, D>, T, DifferentiabilityMode::First, D> {};
+// 0.5 x'Ax - b'x; data[b] = [A (d x d col-major, symmetric) | b] on the device.
+template <class T, int D>
+struct DenseQuadratic : FunctionCRTP<DenseQuadratic<T, D>, T, DifferentiabilityMode::Second, D> {
+  const T* data = nullptr;
+  int64_t data_stride = 0;
+};
+
+namespace detail_builtin {
+template <class T, int D>
+inline cno_problem_t make(int family) {
+  cno_problem_t p{};
+  p.family = family;
+  p.dtype = detail::DType<T>::value;
+  p.d = D;
+  p.policy = CNO_POLICY_WARP_TREE;
+  return p;
+}
+}  // namespace detail_builtin
+
+template <class T, int D>
+struct LauncherTraits<Rosenbrock<T, D>> {
+  template <class E> static void Bind(const Rosenbrock<T, D>&, E& e) { e.problem = detail_builtin::make<T, D>(CNO_FN_ROSENBROCK); }
+};
+template <class T, int D>
+struct LauncherTraits<RosenbrockFull<T, D>> {
+  template <class E> static void Bind(const RosenbrockFull<T, D>&, E& e) { e.problem = detail_builtin::make<T, D>(CNO_FN_ROSENBROCK); }
+};
+template <class T>
+struct LauncherTraits<DiagQuadratic<T>> {
+  template <class E> static void Bind(const DiagQuadratic<T>&, E& e) { e.problem = detail_builtin::make<T, 2>(CNO_FN_DIAG_QUADRATIC); }
+};
+template <class T, int D>
+struct LauncherTraits<HalfSquaredNorm<T, D>> {
+  template <class E> static void Bind(const HalfSquaredNorm<T, D>&, E& e) { e.problem = detail_builtin::make<T, D>(CNO_FN_HALF_SQUARED_NORM); }
+};
+template <class T, int D>
+struct LauncherTraits<DenseQuadratic<T, D>> {
+  template <class E> static void Bind(const DenseQuadratic<T, D>& f, E& e) {
+    e.problem = detail_builtin::make<T, D>(CNO_FN_DENSE_QUADRATIC);
+    e.problem.data = f.data;
+    e.problem.data_stride = f.data_stride;
+  }
+};
+
+}  // namespace function
+
+namespace solver {
+
+enum class Status {  // solver/progress.h:37-47
+  NotStarted = -1, Continue = 0, IterationLimit, XDeltaViolation, FDeltaViolation,
+  GradientNormViolation, HessianConditionViolation, Finished
+};
+
+// Stopping thresholds (solver/progress.h:82-140; same field names).
+template <class FunctionType = void, class StateType = void>
+struct Progress {
+  size_t num_iterations = 0;
+  double x_delta = 0;
+  int x_delta_violations = 0;
+  double f_delta = 0;
+  int f_delta_violations = 0;
+  bool f_delta_relative = false;
+  double gradient_norm = 0;
+  bool gradient_norm_relative = true;
+  double condition_hessian = 0;
+  int past = 0;
+  double past_delta = 1e-6;
+  Status status = Status::NotStarted;
+
+  cno_stop_t to_c() const {
+    cno_stop_t s{};
+    s.num_iterations = num_iterations;
+    s.x_delta = x_delta;
+    s.x_delta_violations = x_delta_violations;
+    s.f_delta = f_delta;
+    s.f_delta_violations = f_delta_violations;
+    s.f_delta_relative = f_delta_relative;
+    s.gradient_norm = gradient_norm;
+    s.gradient_norm_relative = gradient_norm_relative;
+    s.condition_hessian = condition_hessian;
+    s.past = past;
+    s.past_delta = past_delta;
+    return s;
+  }
+  static Progress from_c(const cno_stop_t& s) {
+    Progress p;
+    p.num_iterations = s.num_iterations;
+    p.x_delta = s.x_delta;
+    p.x_delta_violations = s.x_delta_violations;
+    p.f_delta = s.f_delta;
+    p.f_delta_violations = s.f_delta_violations;
+    p.f_delta_relative = s.f_delta_relative != 0;
+    p.gradient_norm = s.gradient_norm;
+    p.gradient_norm_relative = s.gradient_norm_relative != 0;
+    p.condition_hessian = s.condition_hessian;
+    p.past = s.past;
+    p.past_delta = s.past_delta;
+    return p;
+  }
+};
+
+template <class FunctionType = void, class StateType = void>
+Progress<FunctionType, StateType> DefaultStoppingSolverProgress() {  // solver/progress.h:353-431
+  cno_stop_t s;
+  cno_default_stop(&s);
+  return Progress<FunctionType, StateType>::from_c(s);
+}
+template <class FunctionType = void, class StateType = void>
+Progress<FunctionType, StateType> ConservativeStoppingSolverProgress() {  // :456-464
+  cno_stop_t s;
+  cno_conservative_stop(&s);
+  return Progress<FunctionType, StateType>::from_c(s);
+}
+
+// Per-instance Progress values (device arrays).
+template <class T>
+struct BatchedProgress {
+  int64_t batch = 0;
+  detail::DeviceArray<uint32_t> num_iterations, nfev;
+  detail::DeviceArray<int8_t> status;
+  detail::DeviceArray<T> x_delta, f_delta, gradient_norm;
+  cno_launch_info_t launch{};
+};
+
+// solver/solver.h:156-231 with a batch axis.
+template <class FunctionTypeT, int SolverId>
+class Solver {
+ public:
+  using FunctionType = FunctionTypeT;
+  using ScalarType = typename FunctionType::ScalarType;
+  using StateType = function::BatchedFunctionState<ScalarType, FunctionType::Dimension>;
+  using ProgressType = Progress<FunctionType, StateType>;
+
+  ProgressType stopping_progress;
+
+  explicit Solver(const ProgressType& progress = DefaultStoppingSolverProgress<FunctionType, StateType>())
+      : stopping_progress(progress) {}
+  virtual ~Solver() = default;
+
+  // Batched Minimize: returns {state at the solution, per-instance progress}.
+  virtual std::tuple<StateType, BatchedProgress<ScalarType>> Minimize(const FunctionType& function,
+                                                                      const StateType& function_state,
+                                                                      cudaStream_t stream = nullptr) {
+    using T = ScalarType;
+    constexpr int D = FunctionType::Dimension;
+    const int64_t B = function_state.batch;
+    function::FunctionExpr<T, FunctionType::Differentiability, D> expr(function);
+
+    StateType result;
+    result.batch = B;
+    result.x = detail::DeviceArray<T>(B * D);
+    result.gradient = detail::DeviceArray<T>(B * D);
+    result.value = detail::DeviceArray<T>(B);
+    BatchedProgress<T> prog;
+    prog.batch = B;
+    prog.num_iterations = detail::DeviceArray<uint32_t>(B);
+    prog.nfev = detail::DeviceArray<uint32_t>(B);
+    prog.status = detail::DeviceArray<int8_t>(B);
+    prog.x_delta = detail::DeviceArray<T>(B);
+    prog.f_delta = detail::DeviceArray<T>(B);
+    prog.gradient_norm = detail::DeviceArray<T>(B);
+
+    cno_batch_out_t out{};
+    out.x = result.x.data();
+    out.value = result.value.data();
+    out.gradient = result.gradient.data();
+    out.num_iterations = prog.num_iterations.data();
+    out.status = prog.status.data();
+    out.nfev = prog.nfev.data();
+    out.x_delta = prog.x_delta.data();
+    out.f_delta = prog.f_delta.data();
+    out.gradient_norm = prog.gradient_norm.data();
+
+    detail::DeviceArray<unsigned char> workspace(256);
+    const cno_stop_t stop = stopping_progress.to_c();
+    int rc;
+    if (expr.raw) {
+      rc = expr.raw(SolverId, expr.pod.data(), B, function_state.x.data(), &stop, &out,
+                    workspace.data(), workspace.size(), stream, &prog.launch);
+    } else {
+      rc = cno_minimize(SolverId, &expr.problem, B, function_state.x.data(), &stop, &out,
+                        workspace.data(), workspace.size(), stream, &prog.launch);
+    }
+    detail::check_cno(rc, "Minimize");
+    return {std::move(result), std::move(prog)};
+  }
+};
+
+template <class F> class Lbfgs : public Solver<F, CNO_LBFGS> { using Solver<F, CNO_LBFGS>::Solver; };
+template <class F> class Bfgs : public Solver<F, CNO_BFGS> { using Solver<F, CNO_BFGS>::Solver; };
+template <class F> class NewtonDescent : public Solver<F, CNO_NEWTON> {
+  static_assert(F::Differentiability == function::DifferentiabilityMode::Second,
+                "NewtonDescent only supports second-order differentiable functions");
+  using Solver<F, CNO_NEWTON>::Solver;
+};
+
+}  // namespace solver
+}  // namespace cppoptlib
+
+// Declares (for a host translation unit) the extern "C" launcher that
+// CNO_INSTANTIATE_FUNCTION(tag, F) defines in an nvcc translation unit, and
+// binds F to it.
+#define CNO_DECLARE_FUNCTION(tag, F)                                                              \
+  extern "C" int cno_##tag##_minimize(int solver, const void* functor_bytes, int64_t batch,       \
+                                      const void* x0, const cno_stop_t* stop,                      \
+                                      const cno_batch_out_t* out, void* workspace,                 \
+                                      size_t workspace_bytes, void* stream,                        \
+                                      cno_launch_info_t* info);                                    \
+  namespace cppoptlib::function {                                                                  \
+  template <>                                                                                      \
+  struct LauncherTraits<F> {                                                                       \
+    template <class E>                                                                             \
+    static void Bind(const F& f, E& e) {                                                           \
+      static_assert(std::is_trivially_copyable_v<F>, "device functors are passed by value");      \
+      e.raw = &cno_##tag##_minimize;                                                               \
+      e.pod.assign(reinterpret_cast<const unsigned char*>(&f),                                    \
+                   reinterpret_cast<const unsigned char*>(&f) + sizeof(F));                       \
+    }                                                                                              \
+  };                                                                                               \
+  }
+
+#endif  // CPPOPTLIB_B200_CPPOPTLIB_H_

@@ -1,0 +1,77 @@
+// tests/cpp/verify_host.cc -- reads like the reference's src/test/verify.cc
+// (SOLVE_PROBLEM, :113-129) and Dockerfile.test's main.cpp, but through the
+// batched C++17 mirror (include/cppoptlib_b200/cppoptlib.h) on the GPU.
+// Plain g++ translation unit: no nvcc, links libcno.so + libcudart.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "cppoptlib_b200/cppoptlib.h"
+
+constexpr double PRECISION = 1e-4;  // verify.cc:23
+static int failures = 0;
+#define EXPECT_NEAR(a, b, tol)                                                        \
+  do {                                                                                \
+    if (!(std::fabs((a) - (b)) <= (tol))) {                                           \
+      std::printf("FAIL %s:%d: |%g - %g| > %g\n", __FILE__, __LINE__, (double)(a), (double)(b), (double)(tol)); \
+      ++failures;                                                                     \
+    }                                                                                 \
+  } while (0)
+
+static double rosen2(const double* x) {  // verify.cc:45-48
+  const double t1 = (1 - x[0]);
+  const double t2 = (x[1] - x[0] * x[0]);
+  return t1 * t1 + 100 * t2 * t2;
+}
+
+// SOLVE_PROBLEM(sol, func, a, b, fx) of verify.cc:113-129 with B = 2 (Far, Near).
+template <template <class> class Sol, class Function>
+void solve_far_near() {
+  using Solver = Sol<Function>;
+  Function f;
+  auto initial_state =
+      cppoptlib::function::BatchedFunctionState<double, 2>::FromHost({15.0, 8.0, -1.0, 2.0}, 2);
+  Solver solver;
+  auto [solution, solver_state] = solver.Minimize(f, initial_state);
+  const std::vector<double> x = solution.x.ToHost();
+  const std::vector<int8_t> st = solver_state.status.ToHost();
+  for (int b = 0; b < 2; ++b) {
+    if (st[b] == (int8_t)cppoptlib::solver::Status::IterationLimit) std::printf("Iteration limit reached.\n");
+    EXPECT_NEAR(0.0, rosen2(&x[2 * b]), PRECISION);
+  }
+}
+
+int main() {
+  using namespace cppoptlib;
+  // SOLVER_SETUP(Bfgs, RosenbrockGradient), (Lbfgs, ...), (NewtonDescent, RosenbrockFull): verify.cc:187-192
+  solve_far_near<solver::Lbfgs, function::Rosenbrock<double, 2>>();
+  solve_far_near<solver::Bfgs, function::Rosenbrock<double, 2>>();
+  solve_far_near<solver::NewtonDescent, function::RosenbrockFull<double, 2>>();
+
+  {  // Dockerfile.test:30-45
+    function::DiagQuadratic<double> f;
+    solver::Lbfgs<function::DiagQuadratic<double>> solver;
+    auto [solution, state] =
+        solver.Minimize(f, function::BatchedFunctionState<double, 2>::FromHost({-10.0, 2.0}, 1));
+    const auto x = solution.x.ToHost();
+    const auto v = solution.value.ToHost();
+    EXPECT_NEAR(0.0, x[0], 1e-4);
+    EXPECT_NEAR(0.0, x[1], 1e-4);
+    EXPECT_NEAR(5.0, v[0], 1e-4);
+    std::printf("iterations = %u\n", state.num_iterations.ToHost()[0]);
+  }
+  {  // user-tunable stopping preset on a copyable solver (augmented_lagrangian.h:347, 532-540)
+    using F = function::Rosenbrock<double, 128>;
+    solver::Lbfgs<F> tmpl;
+    solver::Lbfgs<F> inner = tmpl;  // solvers stay copyable
+    inner.stopping_progress.num_iterations = 25;
+    const int B = 64;
+    std::vector<double> x0(B * 128);
+    for (size_t i = 0; i < x0.size(); ++i) x0[i] = -1.2 + 0.001 * (double)(i % 97);
+    auto [solution, state] = inner.Minimize(F{}, function::BatchedFunctionState<double, 128>::FromHost(x0, B));
+    for (uint32_t it : state.num_iterations.ToHost()) EXPECT_NEAR(26.0, (double)it, 0.0);  // ">" limit, progress.h:212
+    for (int8_t s : state.status.ToHost()) EXPECT_NEAR((double)solver::Status::IterationLimit, (double)s, 0.0);
+  }
+  if (failures == 0) std::printf("PASS\n");
+  return failures != 0;
+}
