@@ -17,6 +17,7 @@
 #include "cno_lbfgs.cuh"
 #include "cno_bfgs.cuh"
 #include "cno_newton.cuh"
+#include "cno_logistic.cuh"
 
 namespace {
 
@@ -56,7 +57,7 @@ struct LaunchArgs {
 template <class Fn, int M>
 int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
   using T = typename Fn::Scalar;
-  using SM = cno::LbfgsSmem<T, Fn::Dim, M>;
+  using SM = cno::LbfgsSmem<T, Fn::Dim, M, cno::StageElems<Fn>::value>;
   auto kernel = cno::lbfgs_minimize_kernel<Fn, M>;
   const size_t smem = SM::kWarpBytes * SM::kWarps;
   CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -183,6 +184,16 @@ int lbfgs_diag_quadratic(const LaunchArgs& a) {
   return launch_lbfgs<cno::DiagQuadraticFn<T>, CNO_LBFGS_M>(cno::DiagQuadraticFn<T>{}, a);
 }
 
+template <class T, int D, int N>
+int lbfgs_logistic(const LaunchArgs& a) {
+  const cno_problem_t* p = a.problem;
+  using Fn = cno::LogisticFn<T, D, N>;
+  if (p->n != N || !p->data || p->data_stride < (int64_t)Fn::kBlockElems) return CNO_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)p->data & 15) || ((size_t)p->data_stride * sizeof(T)) % 16)
+    return CNO_ERR_INVALID_ARGUMENT;  // TMA bulk copies need 16-byte aligned blocks
+  return launch_lbfgs<Fn, CNO_LBFGS_M>(Fn{static_cast<const T*>(p->data), (long long)p->data_stride, (T)p->param}, a);
+}
+
 typedef int (*launcher_t)(const LaunchArgs&);
 
 struct Entry {
@@ -205,6 +216,7 @@ const Entry kTable[] = {
     {CNO_LBFGS, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, lbfgs_diag_quadratic<double>},
     {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, lbfgs_half_sq_norm<double, 2>},
     {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 50, lbfgs_half_sq_norm<double, 50>},
+    {CNO_LBFGS, CNO_FN_LOGISTIC, CNO_F32, 64, lbfgs_logistic<float, 64, 256>},
     {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 2, bfgs_rosenbrock<double, 2>},
     {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 8, bfgs_rosenbrock<double, 8>},
     {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 32, bfgs_rosenbrock<double, 32>},

@@ -70,7 +70,7 @@ bfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     if (lane == 0) b = atomicAdd(queue, 1ULL);
     b = __shfl_sync(kFullMask, b, 0);
     if (uni(b >= (unsigned long long)batch)) break;
-    const EvalCtx ctx{lane, (long long)b};
+    const EvalCtx ctx{lane, (long long)b, nullptr};
 
     // solver.h:189-192
     T x[1], g[1];

@@ -29,12 +29,13 @@
 
 namespace cno {
 
-template <class T, int D, int M>
+template <class T, int D, int M, int kStage = 0>
 struct LbfgsSmem {
   static constexpr int E = Shape<D>::E;
   static constexpr int kVec = 32 * E;                        // elements per stored vector
   static constexpr int kScalars = 2 * M + CNO_MAX_PAST;      // rho[M], alpha[M], f ring
-  static constexpr int kWarpElems = 2 * M * kVec + ((kScalars + 1) / 2) * 2;  // + S, Y
+  static constexpr int kHistElems = 2 * M * kVec + ((kScalars + 3) / 4) * 4;  // S, Y + scalars
+  static constexpr int kWarpElems = kHistElems + kStage;     // + the functor's staged block
   static constexpr size_t kWarpBytes = (size_t)kWarpElems * sizeof(T);
   // warps per CTA: as many as fit in 227 KB, at most 16 (register budget).
   static constexpr int kMaxSmem = 227 * 1024;
@@ -118,7 +119,7 @@ __device__ __forceinline__ void progress_update(ProgressState<T>& p, const StopP
 }
 
 template <class Fn, int M>
-__global__ void __launch_bounds__(LbfgsSmem<typename Fn::Scalar, Fn::Dim, M>::kWarps * 32, 1)
+__global__ void __launch_bounds__(LbfgsSmem<typename Fn::Scalar, Fn::Dim, M, StageElems<Fn>::value>::kWarps * 32, 1)
 lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
                       const long long batch, const StopParams<typename Fn::Scalar> stop,
                       const BatchOut<typename Fn::Scalar> out,
@@ -126,7 +127,8 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   using T = typename Fn::Scalar;
   constexpr int D = Fn::Dim;
   constexpr int E = Shape<D>::E;
-  using SM = LbfgsSmem<T, D, M>;
+  constexpr int kStage = StageElems<Fn>::value;
+  using SM = LbfgsSmem<T, D, M, kStage>;
   using SV = SmemVec<T, E>;
   constexpr T eps = Num<T>::eps;
 
@@ -138,6 +140,9 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   T* const rho_s = Y + M * SM::kVec;  // 1 / (s_i . y_i) per slot
   T* const alpha = rho_s + M;
   T* const ring = alpha + M;
+  void* const stage_ptr = (kStage > 0) ? static_cast<void*>(S + SM::kHistElems) : nullptr;
+  uint32_t stage_parity = 0;
+  if constexpr (kStage > 0) fn.init_stage(EvalCtx{lane, 0, stage_ptr});
 
   for (;;) {
     // ---- retire + refill: next instance from the global queue ----
@@ -145,7 +150,8 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     if (lane == 0) b = atomicAdd(queue, 1ULL);
     b = __shfl_sync(kFullMask, b, 0);
     if (uni(b >= (unsigned long long)batch)) break;
-    const EvalCtx ctx{lane, (long long)b};
+    const EvalCtx ctx{lane, (long long)b, stage_ptr};
+    if constexpr (kStage > 0) fn.stage(ctx, stage_parity);  // per-instance data -> shared memory (TMA)
 
     // ---- solver.h:189-192: evaluate once at the start point ----
     T x[E], g[E];

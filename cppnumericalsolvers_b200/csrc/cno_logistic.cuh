@@ -1,0 +1,207 @@
+// cno_logistic.cuh -- batched logistic regression objective (BASELINE config 3:
+// n = 256 samples, d = 64 features, fp32), a device functor with PER-INSTANCE
+// DATA staged into shared memory by one TMA bulk copy per instance.
+//
+// Not in the reference (SURVEY.md 8(d) defines it).  Data block per instance:
+//   [Xt (d x n, feature-major: Xt[i*n + j]) | y (n)]        66,560 B at fp32
+// The block is read twice per evaluation (margins, gradient) and an instance
+// needs ~30 evaluations, so it is staged ONCE per instance (cp.async.bulk +
+// mbarrier) and stays in the warp's shared-memory slice: HBM traffic = one read
+// of the block per instance instead of one per evaluation.
+//
+// Lane ownership inside the functor: lane l owns samples 128c + 4l .. 4l+3 of
+// each 128-sample chunk c, so every shared-memory access is a contiguous
+// conflict-free LDS.128.  Arithmetic definition = oracle eval_logistic
+// (oracle/cno_oracle_impl.inc), op for op, incl. the shared exp/log1p kernels
+// (glibc's and CUDA's differ in ulps, SURVEY.md 7 hard part 6).
+#ifndef CNO_LOGISTIC_CUH_
+#define CNO_LOGISTIC_CUH_
+
+#include "cno_device.cuh"
+#include "cno_newton.cuh"  // TMA + mbarrier helpers
+
+namespace cno {
+
+// exp(x), x <= 0 in practice: 2^k * exp(r), degree-9 Taylor (no FMA).
+__device__ __forceinline__ float cno_exp(float x) {
+  if (x > 88.f) x = 88.f;
+  if (x < -87.f) return 0.f;
+  const float kf = rintf(x * 1.44269504088896341f);
+  const float r = (x - kf * 0.693145751953125f) - kf * 1.42860682030941723212e-6f;
+  float p = (float)(1.0 / 362880.0);
+  p = p * r + (float)(1.0 / 40320.0);
+  p = p * r + (float)(1.0 / 5040.0);
+  p = p * r + (float)(1.0 / 720.0);
+  p = p * r + (float)(1.0 / 120.0);
+  p = p * r + (float)(1.0 / 24.0);
+  p = p * r + (float)(1.0 / 6.0);
+  p = p * r + 0.5f;
+  p = p * r + 1.f;
+  p = p * r + 1.f;
+  return ldexpf(p, (int)kf);
+}
+__device__ __forceinline__ double cno_exp(double x) {
+  if (x > 88.0) x = 88.0;
+  if (x < -87.0) return 0.0;
+  const double kf = rint(x * 1.44269504088896341);
+  const double r = (x - kf * 0.693145751953125) - kf * 1.42860682030941723212e-6;
+  double p = (1.0 / 362880.0);
+  p = p * r + (1.0 / 40320.0);
+  p = p * r + (1.0 / 5040.0);
+  p = p * r + (1.0 / 720.0);
+  p = p * r + (1.0 / 120.0);
+  p = p * r + (1.0 / 24.0);
+  p = p * r + (1.0 / 6.0);
+  p = p * r + 0.5;
+  p = p * r + 1.0;
+  p = p * r + 1.0;
+  return ldexp(p, (int)kf);
+}
+// log1p(u), u in [0, 1]: 2 atanh(u / (2 + u)).
+template <class T>
+__device__ __forceinline__ T cno_log1p01(T u) {
+  const T z = u / (T(2) + u);
+  const T z2 = z * z;
+  T p = (T)(1.0 / 19.0);
+  p = p * z2 + (T)(1.0 / 17.0);
+  p = p * z2 + (T)(1.0 / 15.0);
+  p = p * z2 + (T)(1.0 / 13.0);
+  p = p * z2 + (T)(1.0 / 11.0);
+  p = p * z2 + (T)(1.0 / 9.0);
+  p = p * z2 + (T)(1.0 / 7.0);
+  p = p * z2 + (T)(1.0 / 5.0);
+  p = p * z2 + (T)(1.0 / 3.0);
+  p = p * z2 + T(1);
+  return (T(2) * z) * p;
+}
+
+template <class T, int D, int N>
+struct LogisticFn {
+  using Scalar = T;
+  static constexpr int Dim = D;
+  static constexpr int Mode = 1;
+  static constexpr int E = Shape<D>::E;
+  static_assert(N % 128 == 0, "samples come in chunks of 128 (32 lanes x 4)");
+  static_assert(sizeof(T) == 4, "LDS.128 = 4 samples; instantiate for float");
+  static constexpr int C = N / 128;             // chunks
+  static constexpr int kBlockElems = D * N + N;  // [Xt | y]
+  static constexpr uint32_t kBlockBytes = (uint32_t)(kBlockElems * sizeof(T));
+  static constexpr int kWvec = ((D + 3) / 4) * 4;
+  // staged block + broadcast copy of w + the mbarrier (8 bytes)
+  static constexpr int kStageElems = ((kBlockElems + kWvec + 8 / (int)sizeof(T) + 3) / 4) * 4;
+
+  const T* data;
+  long long stride;
+  T lambda;
+
+  // once per instance: TMA bulk copy of the data block into ctx.stage
+  __device__ __forceinline__ void stage(const EvalCtx& c, uint32_t& parity) const {
+    T* blk = static_cast<T*>(c.stage);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(blk + kBlockElems + kWvec);
+    __syncwarp();
+    if (c.lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(bar, kBlockBytes);
+      tma_bulk_g2s(blk, data + c.instance * stride, kBlockBytes, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+  }
+  __device__ __forceinline__ void init_stage(const EvalCtx& c) const {
+    T* blk = static_cast<T*>(c.stage);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(blk + kBlockElems + kWvec);
+    if (c.lane == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+
+  __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&w)[E], T (*grad)[E]) const {
+    const T* Xt = static_cast<const T*>(c.stage);
+    const T* y = Xt + D * N;
+    T* wv = const_cast<T*>(y) + N;
+    const int lane = c.lane;
+    using P4 = Pack<T, 4>;
+    // broadcast copy of w
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (lane * E + e < D) wv[lane * E + e] = w[e];
+    __syncwarp();
+    // ---- margins z_j = sum_i Xt[i][j] w_i (i ascending), 4C samples per lane ----
+    T z[4 * C];
+#pragma unroll 4
+    for (int i = 0; i < D; ++i) {
+      const T wi = wv[i];
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) {
+        T xv[4];
+        P4::get(*reinterpret_cast<const typename P4::type*>(Xt + i * N + cc * 128 + 4 * lane), xv);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) z[cc * 4 + t] = (i == 0) ? (xv[t] * wi) : (z[cc * 4 + t] + xv[t] * wi);
+      }
+    }
+    // ---- per-sample loss and coefficient ----
+    T coef[4 * C];
+    T lsum = T(0);
+#pragma unroll
+    for (int cc = 0; cc < C; ++cc) {
+      T yv[4], ls[4];
+      P4::get(*reinterpret_cast<const typename P4::type*>(y + cc * 128 + 4 * lane), yv);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const T m = yv[t] * z[cc * 4 + t];
+        const T e = cno_exp(-cabs(m));
+        const T l1p = cno_log1p01<T>(e);
+        ls[t] = (m < T(0)) ? (l1p - m) : l1p;
+        const T sig = (m < T(0)) ? (T(1) / (T(1) + e)) : (e / (T(1) + e));
+        coef[cc * 4 + t] = -(yv[t] * sig);
+      }
+      const T part = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      lsum = (cc == 0) ? part : (lsum + part);
+    }
+    const T data_loss = butterfly_sum(lsum);
+    const T reg = (T(0.5) * lambda) * warp_dot<T, E>(w, w);
+    // ---- gradient g_i = reduce_samples(coef_j Xt[i][j]) + lambda w_i ----
+    if (grad) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) (*grad)[e] = T(0);
+#pragma unroll 2
+      for (int i0 = 0; i0 < D; i0 += 4) {  // 4 independent butterflies in flight
+        T p[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q;
+          T acc = T(0);
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc) {
+            T xv[4];
+            P4::get(*reinterpret_cast<const typename P4::type*>(Xt + i * N + cc * 128 + 4 * lane), xv);
+            const T part = (coef[cc * 4 + 0] * xv[0] + coef[cc * 4 + 1] * xv[1]) +
+                           (coef[cc * 4 + 2] * xv[2] + coef[cc * 4 + 3] * xv[3]);
+            acc = (cc == 0) ? part : (acc + part);
+          }
+          p[q] = acc;
+        }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) p[q] = p[q] + __shfl_xor_sync(kFullMask, p[q], off);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q;
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            if (lane * E + e == i) (*grad)[e] = p[q] + lambda * w[e];
+        }
+      }
+    }
+    return data_loss + reg;
+  }
+};
+
+}  // namespace cno
+
+#endif  // CNO_LOGISTIC_CUH_

@@ -361,7 +361,7 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     if (lane == 0) b = atomicAdd(queue, 1ULL);
     b = __shfl_sync(kFullMask, b, 0);
     if (uni(b >= (unsigned long long)batch)) break;
-    const EvalCtx ctx{lane, (long long)b};
+    const EvalCtx ctx{lane, (long long)b, nullptr};
 
     T x[E], g[E];
     load_row<T, D>(x0 + b * D, lane, x);

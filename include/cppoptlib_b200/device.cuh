@@ -92,7 +92,7 @@ struct BfgsDispatch<F, true> {
     F fn;                                                                                           \
     memcpy(&fn, functor_bytes, sizeof(F));                                                          \
     if (solver == CNO_LBFGS)                                                                        \
-      return cno::launch_user<F, cno::LbfgsSmem<typename F::Scalar, F::Dim, CNO_LBFGS_M>>(          \
+      return cno::launch_user<F, cno::LbfgsSmem<typename F::Scalar, F::Dim, CNO_LBFGS_M, cno::StageElems<F>::value>>(          \
           cno::lbfgs_minimize_kernel<F, CNO_LBFGS_M>, fn, batch, x0, stop, out, workspace,          \
           workspace_bytes, stream, info);                                                           \
     if (solver == CNO_BFGS)                                                                         \

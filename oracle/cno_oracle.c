@@ -77,7 +77,7 @@ static int check_problem(int solver, const cno_problem_t* p) {
       if (p->d != 2) return CNO_ERR_INVALID_ARGUMENT;
       break;
     case CNO_FN_LOGISTIC:
-      if (!p->data || p->n <= 0 || p->n > CNO_MAX_D) return CNO_ERR_INVALID_ARGUMENT;
+      if (!p->data || p->n <= 0 || p->n > CNO_MAX_D || p->n % 128) return CNO_ERR_INVALID_ARGUMENT;
       if (solver == CNO_NEWTON) return CNO_ERR_UNSUPPORTED; /* First mode only */
       break;
     case CNO_FN_DENSE_QUADRATIC:

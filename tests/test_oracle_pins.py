@@ -230,3 +230,20 @@ def test_fill_uniform_is_splitmix64():
         z = mix(12345 + (k + 1) * 0x9E3779B97F4A7C15)
         u = (z >> 11) * 2.0 ** -53
         assert a[k] == -2.0 + 4.0 * u
+
+
+def test_oracle_logistic_matches_closed_form():
+    """The logistic functor (not in the reference) against numpy."""
+    rng = np.random.default_rng(5)
+    B, n, d, lam = 3, 256, 64, 1e-2
+    X = rng.uniform(-1, 1, (B, n, d))
+    y = np.sign(rng.normal(size=(B, n)))
+    w = rng.normal(size=(B, d)) * 0.3
+    data = np.concatenate([X.transpose(0, 2, 1).reshape(B, -1), y], axis=1)
+    for dtype, tol in ((np.float64, 1e-9), (np.float32, 2e-4)):
+        f, g = ob.evaluate(ob.FN_LOGISTIC, w.astype(dtype), data=data.astype(dtype), n=n, param=lam)
+        m = y * np.einsum("bnd,bd->bn", X, w)
+        f_ref = np.log1p(np.exp(-m)).sum(1) + 0.5 * lam * (w * w).sum(1)
+        g_ref = -np.einsum("bn,bnd->bd", y / (1 + np.exp(m)), X) + lam * w
+        assert np.allclose(f, f_ref, rtol=tol * 10, atol=tol * 100)
+        assert np.allclose(g, g_ref, rtol=0, atol=tol * 500)
