@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""bench_configs.py -- device timing of the BASELINE.json configs that are NOT
+bench.py's headline (configs[2..4]) plus the headline for reference.  These are
+parity-test cases per the contract; this script only reports their throughput
+and the SURVEY.md 8(d) algorithmic-byte roofline next to it.  One JSON object
+per config on stdout.  Usage: python bench_configs.py [c2 c3 c4 c5] [--scale k]
+(--scale k divides the batch by 2^k)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import cppnumericalsolvers_b200 as cn  # noqa: E402
+
+DEV = "cuda"
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def run(name, solver, fn, x0, bytes_fn, reps=3):
+    ms = []
+    for _ in range(reps + 1):
+        st, pr = solver.Minimize(fn, cn.BatchedFunctionState(x0), timed=True)
+        ms.append(pr.launch.kernel_ms)
+    ms = float(np.mean(ms[1:]))
+    it = pr.num_iterations.cpu().numpy().astype(np.int64)
+    nf = pr.nfev.cpu().numpy().astype(np.int64)
+    B = x0.shape[0]
+    alg = float(bytes_fn(it, nf))
+    out = {"config": name, "batch": B, "kernel_ms": ms, "instances_per_s": B / ms * 1e3,
+           "mean_iterations": float(it.mean()), "mean_nfev": float(nf.mean()),
+           "status_histogram": np.bincount(pr.status.cpu().numpy().astype(np.int64) + 1).tolist(),
+           "algorithmic_GBps": alg / ms / 1e6, "hbm_peak_GBps": peak(),
+           "frac_of_hbm_roofline": alg / ms / 1e6 / peak(),
+           "grid": pr.launch.grid, "warps_per_cta": pr.launch.warps_per_cta,
+           "dynamic_smem": pr.launch.dynamic_smem}
+    print(json.dumps(out), flush=True)
+
+
+def lbfgs_bytes(w, d, m=10):
+    def f(it, nf):
+        full = np.maximum(it - m, 0)
+        ramp = np.minimum(it, m)
+        pairs = full * m + ramp * (ramp - 1) // 2
+        return (w * d * (6 * it + 2 * pairs)).sum()
+    return f
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    scale = int(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 0
+    which = args or ["c2", "c3", "c4", "c5"]
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(0)
+    if "c2" in which:  # Rosenbrock d=128 fp64 L-BFGS, B = 2^20
+        B = (1 << 20) >> scale
+        x0 = torch.empty(B, 128, dtype=torch.float64, device=DEV)
+        cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
+        run("c2 lbfgs rosenbrock d128 f64", cn.Lbfgs(), cn.Rosenbrock(128), x0, lbfgs_bytes(8, 128))
+        del x0
+    if "c3" in which:  # logistic n=256 d=64 fp32 L-BFGS, B = 2^18
+        B, n, d, lam = (1 << 18) >> scale, 256, 64, 1e-2
+        data = torch.empty(B, d * n + n, dtype=torch.float32, device=DEV)
+        chunk = 1 << 14
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            X = torch.rand(hi - lo, n, d, device=DEV, generator=gen) * 2 - 1
+            ws = torch.randn(hi - lo, d, device=DEV, generator=gen)
+            y = torch.sign(torch.einsum("bnd,bd->bn", X, ws) + 0.1 * torch.randn(hi - lo, n, device=DEV, generator=gen))
+            y[y == 0] = 1
+            data[lo:hi, : d * n] = X.transpose(1, 2).reshape(hi - lo, -1)
+            data[lo:hi, d * n:] = y
+        x0 = torch.zeros(B, d, dtype=torch.float32, device=DEV)
+        lb = lbfgs_bytes(4, d)
+        run("c3 lbfgs logistic n256 d64 f32", cn.Lbfgs(), cn.Logistic(data, n, d, lam), x0,
+            lambda it, nf: lb(it, nf) + (nf * 4 * (n * d + n)).sum())
+        del data, x0
+    if "c4" in which:  # BFGS Rosenbrock d=32 fp64, B = 2^19
+        B = (1 << 19) >> scale
+        x0 = torch.empty(B, 32, dtype=torch.float64, device=DEV)
+        cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
+        run("c4 bfgs rosenbrock d32 f64", cn.Bfgs(), cn.Rosenbrock(32), x0,
+            lambda it, nf: (8 * (2 * 32 * 32 + 4 * 32) * it).sum())
+        del x0
+    if "c5" in which:  # NewtonDescent dense quadratic d=64 fp64, B = 2^17
+        B, d = (1 << 17) >> scale, 64
+        data = torch.empty(B, d * d + d, dtype=torch.float64, device=DEV)
+        chunk = 1 << 13
+        eye = torch.eye(d, dtype=torch.float64, device=DEV)
+        for lo in range(0, B, chunk):
+            hi = min(B, lo + chunk)
+            M = torch.rand(hi - lo, d, d, dtype=torch.float64, device=DEV, generator=gen) * 2 - 1
+            A = torch.bmm(M.transpose(1, 2), M) / d + eye
+            A = (A + A.transpose(1, 2)) / 2
+            data[lo:hi, : d * d] = A.transpose(1, 2).reshape(hi - lo, -1)
+            data[lo:hi, d * d:] = torch.rand(hi - lo, d, dtype=torch.float64, device=DEV, generator=gen) * 2 - 1
+        x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
+        cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
+        run("c5 newton dense quadratic d64 f64", cn.NewtonDescent(), cn.DenseQuadratic(data, d), x0,
+            lambda it, nf: (8 * (d * d + 3 * d) * it).sum())
+
+
+if __name__ == "__main__":
+    main()
