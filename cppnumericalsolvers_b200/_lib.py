@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libcno.so")
 LBFGS, BFGS, NEWTON = 0, 1, 2
 F64, F32 = 0, 1
 FN_ROSENBROCK, FN_DIAG_QUADRATIC, FN_HALF_SQUARED_NORM, FN_LOGISTIC, FN_DENSE_QUADRATIC = range(5)
-POLICY_WARP_TREE, POLICY_EIGEN_SSE2 = 0, 1
+POLICY_WARP_TREE, POLICY_EIGEN_SSE2, POLICY_DMMA_TREE = 0, 1, 2
 OK, ERR_INVALID_ARGUMENT, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
 
 

@@ -242,7 +242,9 @@ int check_args(int solver, const cno_problem_t* p) {
   if (solver < CNO_LBFGS || solver > CNO_NEWTON) return CNO_ERR_INVALID_ARGUMENT;
   if (p->dtype != CNO_F64 && p->dtype != CNO_F32) return CNO_ERR_INVALID_ARGUMENT;
   if (p->d <= 0) return CNO_ERR_INVALID_ARGUMENT;
-  if (p->policy != CNO_POLICY_WARP_TREE) return CNO_ERR_UNSUPPORTED;
+  // the reduction policy is compiled into the kernels: fp64 = tensor-core tree, fp32 = butterfly
+  if (p->policy != (p->dtype == CNO_F64 ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE))
+    return CNO_ERR_UNSUPPORTED;
   if (!find_entry(solver, p)) return CNO_ERR_UNSUPPORTED;
   return CNO_OK;
 }

@@ -102,18 +102,18 @@ bfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       dir[0] = (lane < D) ? -gemv_row<T, D>(Hrow, va) : T(0);
 
       // ---- reset test (:87-92) ----
-      T phi = butterfly_sum(lane_dot<T, 1>(g, dir));
+      T phi = warp_sum(lane_dot<T, 1>(g, dir));
       if (uni((phi > 0) || (phi != phi))) {
 #pragma unroll
         for (int j = 0; j < D; ++j) Hrow[j] = (j == lane) ? T(1) : T(0);
         dir[0] = -g[0];
         fresh = true;
-        phi = -butterfly_sum(lane_dot<T, 1>(g, g));  // = g.(-g), bit for bit
+        phi = -warp_sum(lane_dot<T, 1>(g, g));  // = g.(-g), bit for bit
       }
       // ---- alpha_init (:100-106) ----
       T alpha_init = T(1);
       if (uni(fresh)) {
-        const T dn = csqrt(butterfly_sum(lane_dot<T, 1>(dir, dir)));
+        const T dn = csqrt(warp_sum(lane_dot<T, 1>(dir, dir)));
         alpha_init = (dn > eps) ? T(1) / dn : T(1);
       }
       // ---- MoreThuente::Search (:111-112); dginit = g.d = phi ----
@@ -126,7 +126,7 @@ bfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       s[0] = xn[0] - x[0];
       y[0] = gn[0] - g[0];
       T ys = lane_dot<T, 1>(y, s), ss = lane_dot<T, 1>(s, s), yy = lane_dot<T, 1>(y, y);
-      butterfly_sum3(ys, ss, yy);
+      warp_sum3(ys, ss, yy);
       if (uni(ys > eps * csqrt(ss) * csqrt(yy))) {
         const T rho = T(1) / ys;
         __syncwarp();
@@ -134,7 +134,7 @@ bfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         __syncwarp();
         T Hy[1];
         Hy[0] = (lane < D) ? gemv_row<T, D>(Hrow, va) : T(0);
-        const T yHy = butterfly_sum(lane_dot<T, 1>(y, Hy));
+        const T yHy = warp_sum(lane_dot<T, 1>(y, Hy));
         const T c2 = rho * (rho * yHy + T(1));
         __syncwarp();
         va[lane] = s[0];

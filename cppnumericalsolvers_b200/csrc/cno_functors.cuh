@@ -66,7 +66,7 @@ struct RosenbrockFn {
         (*grad)[j] = (i < D) ? gi : T(0);
       }
     }
-    return butterfly_sum(lane_tree<T, E>(term));
+    return warp_sum(lane_tree<T, E>(term));
   }
 };
 

@@ -175,7 +175,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
     // ||x||^2 carried across iterations (the dot the reference recomputes at
     // lbfgs.h:95).
-    T xx = butterfly_sum(lane_dot<T, E>(x, x));
+    T xx = warp_sum(lane_dot<T, E>(x, x));
 
     do {  // solver.h:196-220
       // ================= Lbfgs::OptimizationStep (lbfgs.h:89-303) =========
@@ -203,7 +203,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
           T yv[E];
           SV::load(Y + idx * SM::kVec, lane, yv);
           SV::load(S + idx_next * SM::kVec, lane, sv);  // prefetch (harmless at i == 0)
-          const T a = rho_s[idx] * butterfly_sum(part);
+          const T a = rho_s[idx] * warp_sum(part);
           if (uni((valid >> idx) & 1u)) {  // lbfgs.h:165 skip
             if (lane == 0) alpha[i] = a;
 #pragma unroll
@@ -228,7 +228,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
           T sv[E];
           SV::load(S + idx * SM::kVec, lane, sv);
           SV::load(Y + idx_next * SM::kVec, lane, yv);  // prefetch
-          const T beta = rho_s[idx] * butterfly_sum(part);
+          const T beta = rho_s[idx] * warp_sum(part);
           if (uni((valid >> idx) & 1u)) {  // lbfgs.h:189 skip
             const T coef = alpha[i] - beta;
 #pragma unroll
@@ -243,11 +243,11 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       T gq = lane_dot<T, E>(g, q);
       if (uni(mem_count == 0)) {  // :208-213 (||q|| only matters without history)
         T qq = lane_dot<T, E>(q, q);
-        butterfly_sum2(gq, qq);
+        warp_sum2(gq, qq);
         const T qn = csqrt(qq);
         alpha_init = (qn > eps) ? T(1) / qn : T(1);
       } else {
-        gq = butterfly_sum(gq);
+        gq = warp_sum(gq);
       }
       const T descent_direction = -gq;
       T dginit = descent_direction;  // = g.(-q), bit for bit
@@ -260,7 +260,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         mem_count = 0;
         mem_pos = 0;
         valid = 0;
-        const T gg = butterfly_sum(lane_dot<T, E>(g, g));  // :221 (rare path)
+        const T gg = warp_sum(lane_dot<T, E>(g, g));  // :221 (rare path)
         const T gn = csqrt(gg);
         alpha_init = (gn > eps) ? T(1) / gn : T(1);
         dginit = gg;
@@ -287,7 +287,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 #pragma unroll
         for (int j = 0; j < E; ++j) { sd[j] = xn[j] - x[j]; yd[j] = gn[j] - g[j]; }
         T sy = lane_dot<T, E>(sd, yd), ss = lane_dot<T, E>(sd, sd), yy = lane_dot<T, E>(yd, yd);
-        butterfly_sum3(sy, ss, yy);
+        warp_sum3(sy, ss, yy);
         const T sy_threshold = eps * csqrt(ss) * csqrt(yy);
         if (uni(sy > sy_threshold)) {
           int slot;
@@ -315,7 +315,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         f = fn_val;
         gnorm_inf = warp_max_nonneg(lane_maxabs<T, E>(g));
         x_inf = warp_max_nonneg(lane_maxabs<T, E>(x));
-        xx = butterfly_sum(lane_dot<T, E>(x, x));
+        xx = warp_sum(lane_dot<T, E>(x, x));
         __syncwarp();
       }
 

@@ -186,7 +186,7 @@ __device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx, const T 
     for (int j = 0; j < E; ++j) x[j] = x0[j] + stp * s[j];  // :198
     f = fn(ctx, x, &g);                                      // :199 (already reduced)
     nfev++;
-    const T dg = butterfly_sum(lane_dot<T, E>(g, s));        // :201
+    const T dg = warp_sum(lane_dot<T, E>(g, s));        // :201
     const T ftest1 = finit + stp * dgtest;
 
     if ((brackt & ((stp <= stmin) | (stp >= stmax))) | (infoc == 0)) info = 6;

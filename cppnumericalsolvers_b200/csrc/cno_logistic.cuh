@@ -161,7 +161,7 @@ struct LogisticFn {
       const T part = (ls[0] + ls[1]) + (ls[2] + ls[3]);
       lsum = (cc == 0) ? part : (lsum + part);
     }
-    const T data_loss = butterfly_sum(lsum);
+    const T data_loss = warp_sum(lsum);
     const T reg = (T(0.5) * lambda) * warp_dot<T, E>(w, w);
     // ---- gradient g_i = reduce_samples(coef_j Xt[i][j]) + lambda w_i ----
     if (grad) {

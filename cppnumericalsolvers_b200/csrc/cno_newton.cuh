@@ -178,7 +178,7 @@ struct DenseQuadraticFn {
       for (int e = 0; e < E; ++e) (*grad)[e] = (c.lane * E + e < D) ? (Ax[e] - bb[e]) : T(0);
     }
     T p1 = lane_dot<T, E>(x, Ax), p2 = lane_dot<T, E>(bb, x);
-    butterfly_sum2(p1, p2);
+    warp_sum2(p1, p2);
     return T(0.5) * p1 - p2;
   }
 };
@@ -408,7 +408,7 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       __syncwarp();
       SV::gemv(aug, vec, lane, r);  // ((0.5 c^2) d') H, H bitwise symmetric
       T p1 = lane_dot<T, E>(g, delta), p2 = lane_dot<T, E>(r, delta);
-      butterfly_sum2(p1, p2);
+      warp_sum2(p1, p2);
       const T cache = cc * p1 + p2;
       T alpha = T(1.0);
       T xt[E], gt[E];

@@ -26,6 +26,12 @@ class DifferentiabilityMode(enum.IntEnum):  # function_base.h:42-46
 _DTYPES = {torch.float64: _lib.F64, torch.float32: _lib.F32}
 
 
+def default_policy(dtype: torch.dtype) -> int:
+    """fp64 kernels reduce on the FP64 tensor core (DMMA tree), fp32 kernels with
+    the shuffle butterfly -- DESIGN.md "Arithmetic specification"."""
+    return _lib.POLICY_DMMA_TREE if dtype == torch.float64 else _lib.POLICY_WARP_TREE
+
+
 @dataclass
 class Function:
     """Base descriptor (FunctionCRTP's static members, function_base.h:96-102)."""
@@ -36,15 +42,18 @@ class Function:
     n: int = 0
     param: float = 0.0
     data: Optional[torch.Tensor] = None  # per-instance data [B, stride]
-    policy: int = _lib.POLICY_WARP_TREE
+    policy: Optional[int] = None  # None = the policy the kernels of this dtype implement
 
     def problem(self) -> _lib.Problem:
         data_ptr, stride = None, 0
         if self.data is not None:
             assert self.data.dtype == self.ScalarType and self.data.is_contiguous()
             data_ptr, stride = self.data.data_ptr(), self.data.shape[1]
+        policy = self.policy
+        if policy is None:
+            policy = default_policy(self.ScalarType)
         return _lib.Problem(self.family, _DTYPES[self.ScalarType], self.Dimension, self.n,
-                            float(self.param), data_ptr, stride, self.policy, 0)
+                            float(self.param), data_ptr, stride, policy, 0)
 
 
 def Rosenbrock(d: int, dtype: torch.dtype = torch.float64) -> Function:

@@ -94,8 +94,9 @@ typedef enum cno_family {
  * path follows (DESIGN.md "Arithmetic specification").  Oracle and kernel are
  * bit-identical under the same policy. */
 typedef enum cno_policy {
-  CNO_POLICY_WARP_TREE = 0,  /* lane-blocked partials + xor butterfly */
-  CNO_POLICY_EIGEN_SSE2 = 1  /* model of Eigen 3.4 SSE2 redux (oracle + slow kernel) */
+  CNO_POLICY_WARP_TREE = 0,  /* lane-blocked partials + xor butterfly (fp32 kernels) */
+  CNO_POLICY_EIGEN_SSE2 = 1, /* model of Eigen 3.4 SSE2 redux (oracle only) */
+  CNO_POLICY_DMMA_TREE = 2   /* lane-blocked partials + two FP64 tensor-core MMAs (fp64 kernels) */
 } cno_policy_t;
 
 /* Stopping thresholds: the fields of solver::Progress that

@@ -187,7 +187,7 @@ inline cno_problem_t make(int family) {
   p.family = family;
   p.dtype = detail::DType<T>::value;
   p.d = D;
-  p.policy = CNO_POLICY_WARP_TREE;
+  p.policy = std::is_same_v<T, double> ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE;
   return p;
 }
 }  // namespace detail_builtin

@@ -18,7 +18,12 @@ REF_LIB = os.path.join(HERE, "_ref", "libcno_ref.so")
 
 LBFGS, BFGS, NEWTON = 0, 1, 2
 FN_ROSENBROCK, FN_DIAG_QUADRATIC, FN_HALF_SQUARED_NORM, FN_LOGISTIC, FN_DENSE_QUADRATIC = range(5)
-POLICY_WARP_TREE, POLICY_EIGEN_SSE2 = 0, 1
+POLICY_WARP_TREE, POLICY_EIGEN_SSE2, POLICY_DMMA_TREE = 0, 1, 2
+
+
+def device_policy(dtype) -> int:
+    """The reduction policy the CUDA kernels of this dtype implement."""
+    return POLICY_DMMA_TREE if np.dtype(dtype) == np.float64 else POLICY_WARP_TREE
 
 
 class Stop(C.Structure):
@@ -82,7 +87,7 @@ def _np_dtype(a):
     return 0 if a.dtype == np.float64 else 1
 
 
-def minimize(solver: int, family: int, x0: np.ndarray, *, policy: int = 0, stop: Stop | None = None,
+def minimize(solver: int, family: int, x0: np.ndarray, *, policy: int | None = None, stop: Stop | None = None,
              data: np.ndarray | None = None, n: int = 0, param: float = 0.0, threads: int = 0,
              impl: str = "oracle") -> dict:
     """Runs the CPU oracle ("oracle") or the reference-headers build ("ref")."""
@@ -90,6 +95,8 @@ def minimize(solver: int, family: int, x0: np.ndarray, *, policy: int = 0, stop:
     assert x0.dtype in (np.float64, np.float32) and x0.ndim == 2
     B, d = x0.shape
     dt = x0.dtype
+    if policy is None:
+        policy = device_policy(dt)
     if data is not None:
         data = np.ascontiguousarray(data, dtype=dt)
     p = Problem(family, _np_dtype(x0), d, n, param,
@@ -112,11 +119,13 @@ def minimize(solver: int, family: int, x0: np.ndarray, *, policy: int = 0, stop:
     return r
 
 
-def evaluate(family: int, x: np.ndarray, *, policy: int = 0, data=None, n: int = 0,
+def evaluate(family: int, x: np.ndarray, *, policy: int | None = None, data=None, n: int = 0,
              param: float = 0.0, hessian: bool = False):
     x = np.ascontiguousarray(x)
     B, d = x.shape
     dt = x.dtype
+    if policy is None:
+        policy = device_policy(dt)
     if data is not None:
         data = np.ascontiguousarray(data, dtype=dt)
     p = Problem(family, _np_dtype(x), d, n, param,

@@ -27,7 +27,7 @@ struct Bowl : FunctionCRTP<Bowl<D>, double, DifferentiabilityMode::First, D> {
       t[e] = (i < D) ? a * r * r : 0.0;
       if (grad) (*grad)[e] = (i < D) ? 2.0 * a * r : 0.0;
     }
-    return cno::butterfly_sum(cno::lane_tree<double, E>(t));
+    return cno::warp_sum(cno::lane_tree<double, E>(t));
   }
 };
 using Bowl64 = Bowl<64>;

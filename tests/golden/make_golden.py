@@ -32,7 +32,7 @@ def main():
     assert ob.ref_available(), "oracle/_ref is not built (needs /root/reference)"
     for name, solver, family, d, dtype, B in CASES:
         x0 = ob.fill_uniform((B, d), 0, SEED, -2.0, 2.0, dtype)
-        r = ob.minimize(solver, family, x0, impl="ref")
+        r = ob.minimize(solver, family, x0, impl="ref")  # policy = the device policy of this dtype
         np.savez_compressed(os.path.join(HERE, name + ".npz"), x0=x0, x=r["x"], value=r["value"],
                             gradient=r["gradient"], num_iterations=r["num_iterations"],
                             status=r["status"], nfev=r["nfev"], solver=solver, family=family)

@@ -138,7 +138,7 @@ def _same(a, b, keys=KEYS):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("policy", [ob.POLICY_WARP_TREE, ob.POLICY_EIGEN_SSE2])
+@pytest.mark.parametrize("policy", [ob.POLICY_WARP_TREE, ob.POLICY_EIGEN_SSE2, ob.POLICY_DMMA_TREE])
 @pytest.mark.parametrize("solver,d", [(ob.LBFGS, 2), (ob.LBFGS, 3), (ob.LBFGS, 37), (ob.LBFGS, 128),
                                       (ob.BFGS, 2), (ob.BFGS, 32), (ob.BFGS, 37),
                                       (ob.NEWTON, 2), (ob.NEWTON, 8)])
@@ -213,6 +213,30 @@ def test_reduction_spec_warp_tree_matches_numpy_model():
         got = ob.oracle_lib().cno_oracle_reduce_sum_f64(
             t.ctypes.data_as(C.POINTER(C.c_double)), d, ob.POLICY_WARP_TREE)
         assert got == p[0]
+
+
+def test_reduction_spec_dmma_tree_matches_numpy_model():
+    """CNO_POLICY_DMMA_TREE = what two mma.sync.m8n8k4.f64 (A = ones) compute."""
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    for d in (1, 2, 32, 37, 128, 200):
+        t = rng.normal(size=d)
+        E = (d + 31) // 32
+        v = np.zeros(32 * E)
+        v[:d] = t
+        v = v.reshape(32, E).copy()
+        w = 1
+        while w < E:
+            for j in range(0, E - w, 2 * w):
+                v[:, j] = v[:, j] + v[:, j + w]
+            w *= 2
+        p = v[:, 0]
+        S = [(((0.0 + p[4 * n]) + p[4 * n + 1]) + p[4 * n + 2]) + p[4 * n + 3] for n in range(8)]
+        T = [S[2 * j] + S[2 * j + 1] for j in range(4)]
+        want = (((0.0 + T[0]) + T[1]) + T[2]) + T[3]
+        got = ob.oracle_lib().cno_oracle_reduce_sum_f64(
+            t.ctypes.data_as(C.POINTER(C.c_double)), d, ob.POLICY_DMMA_TREE)
+        assert got == want
 
 
 def test_fill_uniform_is_splitmix64():
