@@ -186,55 +186,101 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       for (int j = 0; j < E; ++j) q[j] = g[j];  // :145
       const int k = mem_count;
 
-      // ---- first loop (:157-171): newest pair first ----
+      // ================= two-loop recursion (:157-196) =====================
       // chronological i -> slot (mem_pos + i) mod M; mem_pos stays 0 until the
-      // buffer is full, so this is the reference's index map (:162).  The loads
-      // of the next pair are issued before the current reduction (software
-      // pipelining: the butterfly is the critical path, LDS latency hides under it).
-      if (uni(k > 0)) {
-        int idx = mem_pos + k - 1;
+      // buffer is full, so this is the reference's index map (:162).  In both
+      // loops the loads of the next pair are issued before the current reduction
+      // (the reduction is the critical path; LDS latency hides under it).
+      if (uni(k == M && valid == ((1u << M) - 1u))) {
+        // ---- steady state (full history, every pair usable): both loops fully
+        //      unrolled, alpha_i in registers, no per-pair control flow ----
+        T alpha_r[M];
+        int idx = mem_pos + M - 1;
         idx = (idx >= M) ? idx - M : idx;
-        T sv[E];
+        T sv[E], yv[E];
         SV::load(S + idx * SM::kVec, lane, sv);
-#pragma unroll 1
-        for (int i = k - 1; uni(i >= 0); --i) {
-          const int idx_next = (idx == 0) ? M - 1 : idx - 1;
-          T part = lane_dot<T, E>(sv, q);
-          T yv[E];
-          SV::load(Y + idx * SM::kVec, lane, yv);
-          SV::load(S + idx_next * SM::kVec, lane, sv);  // prefetch (harmless at i == 0)
-          const T a = rho_s[idx] * warp_sum(part);
-          if (uni((valid >> idx) & 1u)) {  // lbfgs.h:165 skip
-            if (lane == 0) alpha[i] = a;
 #pragma unroll
-            for (int j = 0; j < E; ++j) q[j] = q[j] - a * yv[j];
-          }
+        for (int i = M - 1; i >= 0; --i) {  // first loop (:157-171): newest pair first
+          const int idx_next = (idx == 0) ? M - 1 : idx - 1;
+          const T part = lane_dot<T, E>(sv, q);
+          const T r = rho_s[idx];
+          SV::load(Y + idx * SM::kVec, lane, yv);
+          if (i > 0) SV::load(S + idx_next * SM::kVec, lane, sv);
+          const T a = r * warp_sum(part);
+          alpha_r[i] = a;
+#pragma unroll
+          for (int j = 0; j < E; ++j) q[j] = q[j] - a * yv[j];
           idx = idx_next;
         }
-      }
-      __syncwarp();
-      // ---- H0 scaling (:181) ----
 #pragma unroll
-      for (int j = 0; j < E; ++j) q[j] = q[j] * gamma;
-      // ---- second loop (:185-196): oldest pair first ----
-      if (uni(k > 0)) {
-        int idx = mem_pos;
-        T yv[E];
-        SV::load(Y + idx * SM::kVec, lane, yv);
-#pragma unroll 1
-        for (int i = 0; uni(i < k); ++i) {
+        for (int j = 0; j < E; ++j) q[j] = q[j] * gamma;  // H0 scaling (:181)
+        idx = mem_pos;
+        // (yv still holds y of the oldest pair: the last pair of loop 1 is the first of loop 2)
+#pragma unroll
+        for (int i = 0; i < M; ++i) {  // second loop (:185-196): oldest pair first
           const int idx_next = (idx + 1 == M) ? 0 : idx + 1;
-          T part = lane_dot<T, E>(yv, q);
+          const T part = lane_dot<T, E>(yv, q);
+          const T r = rho_s[idx];
+          SV::load(S + idx * SM::kVec, lane, sv);
+          if (i + 1 < M) SV::load(Y + idx_next * SM::kVec, lane, yv);
+          const T beta = r * warp_sum(part);
+          const T coef = alpha_r[i] - beta;
+#pragma unroll
+          for (int j = 0; j < E; ++j) q[j] = q[j] + sv[j] * coef;
+          idx = idx_next;
+        }
+      } else {
+        // ---- warm-up (k < M) or a skipped pair: generic rolled loops ----
+        // ---- first loop (:157-171): newest pair first ----
+        // chronological i -> slot (mem_pos + i) mod M; mem_pos stays 0 until the
+        // buffer is full, so this is the reference's index map (:162).  The loads
+        // of the next pair are issued before the current reduction (software
+        // pipelining: the butterfly is the critical path, LDS latency hides under it).
+        if (uni(k > 0)) {
+          int idx = mem_pos + k - 1;
+          idx = (idx >= M) ? idx - M : idx;
           T sv[E];
           SV::load(S + idx * SM::kVec, lane, sv);
-          SV::load(Y + idx_next * SM::kVec, lane, yv);  // prefetch
-          const T beta = rho_s[idx] * warp_sum(part);
-          if (uni((valid >> idx) & 1u)) {  // lbfgs.h:189 skip
-            const T coef = alpha[i] - beta;
-#pragma unroll
-            for (int j = 0; j < E; ++j) q[j] = q[j] + sv[j] * coef;
+  #pragma unroll 1
+          for (int i = k - 1; uni(i >= 0); --i) {
+            const int idx_next = (idx == 0) ? M - 1 : idx - 1;
+            T part = lane_dot<T, E>(sv, q);
+            T yv[E];
+            SV::load(Y + idx * SM::kVec, lane, yv);
+            SV::load(S + idx_next * SM::kVec, lane, sv);  // prefetch (harmless at i == 0)
+            const T a = rho_s[idx] * warp_sum(part);
+            if (uni((valid >> idx) & 1u)) {  // lbfgs.h:165 skip
+              if (lane == 0) alpha[i] = a;
+  #pragma unroll
+              for (int j = 0; j < E; ++j) q[j] = q[j] - a * yv[j];
+            }
+            idx = idx_next;
           }
-          idx = idx_next;
+        }
+        __syncwarp();
+        // ---- H0 scaling (:181) ----
+  #pragma unroll
+        for (int j = 0; j < E; ++j) q[j] = q[j] * gamma;
+        // ---- second loop (:185-196): oldest pair first ----
+        if (uni(k > 0)) {
+          int idx = mem_pos;
+          T yv[E];
+          SV::load(Y + idx * SM::kVec, lane, yv);
+  #pragma unroll 1
+          for (int i = 0; uni(i < k); ++i) {
+            const int idx_next = (idx + 1 == M) ? 0 : idx + 1;
+            T part = lane_dot<T, E>(yv, q);
+            T sv[E];
+            SV::load(S + idx * SM::kVec, lane, sv);
+            SV::load(Y + idx_next * SM::kVec, lane, yv);  // prefetch
+            const T beta = rho_s[idx] * warp_sum(part);
+            if (uni((valid >> idx) & 1u)) {  // lbfgs.h:189 skip
+              const T coef = alpha[i] - beta;
+  #pragma unroll
+              for (int j = 0; j < E; ++j) q[j] = q[j] + sv[j] * coef;
+            }
+            idx = idx_next;
+          }
         }
       }
 
