@@ -445,50 +445,79 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, c
   const size_t o_it = off; off += out->num_iterations ? up((size_t)batch * 4) : 0;
   const size_t o_nf = off; off += out->nfev ? up((size_t)batch * 4) : 0;
   const size_t o_st = off; off += out->status ? up((size_t)batch) : 0;
-  const size_t o_ws = off; off += kWorkspaceBytes;
+  const size_t o_ws = off; off += kWorkspaceBytes;  // one 16-byte queue slot per chunk
   const size_t o_data = off; off += up(data_bytes);
   unsigned char* arena = nullptr;
   CNO_CUDA(cudaMalloc(&arena, off));
 
+  // Chunked pipeline on two streams: H2D of chunk c+1 and D2H of chunk c-1 overlap
+  // the solve of chunk c, so only ~1/kChunks of the copy time is exposed.
+  cudaStream_t s2 = nullptr;
+  CNO_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+  cudaStream_t streams[2] = {s, s2};
+  const int64_t min_chunk = 16384;
+  int chunks = (int)((batch + min_chunk - 1) / min_chunk);
+  if (chunks > 8) chunks = 8;
+  if (chunks < 1) chunks = 1;
+  const int64_t per = (batch + chunks - 1) / chunks;
+  cudaEvent_t e_start2;
+  CNO_CUDA(cudaEventCreate(&e_start2));
   CNO_CUDA(cudaEventRecord(e0, s));
-  CNO_CUDA(cudaMemcpyAsync(arena + o_x0, x0, vec_bytes, cudaMemcpyHostToDevice, s));
-  local.h2d_bytes += (int64_t)vec_bytes;
-  cno_problem_t dprob = *problem;
-  if (data_bytes) {
-    CNO_CUDA(cudaMemcpyAsync(arena + o_data, problem->data, data_bytes, cudaMemcpyHostToDevice, s));
-    dprob.data = arena + o_data;
-    local.h2d_bytes += (int64_t)data_bytes;
-  }
-  cno_batch_out_t dout;
-  dout.x = out->x ? arena + o_x : nullptr;
-  dout.gradient = out->gradient ? arena + o_g : nullptr;
-  dout.value = out->value ? arena + o_f : nullptr;
-  dout.x_delta = out->x_delta ? arena + o_xd : nullptr;
-  dout.f_delta = out->f_delta ? arena + o_fd : nullptr;
-  dout.gradient_norm = out->gradient_norm ? arena + o_gn : nullptr;
-  dout.num_iterations = out->num_iterations ? (uint32_t*)(arena + o_it) : nullptr;
-  dout.nfev = out->nfev ? (uint32_t*)(arena + o_nf) : nullptr;
-  dout.status = out->status ? (int8_t*)(arena + o_st) : nullptr;
-
+  CNO_CUDA(cudaStreamWaitEvent(s2, e0, 0));  // both streams start after e0
   cno_launch_info_t kinfo;
-  rc = cno_minimize(solver, &dprob, batch, arena + o_x0, stop, &dout, arena + o_ws,
-                    kWorkspaceBytes, s, &kinfo);
-  if (rc) { cudaFree(arena); return rc; }
-
-  auto down = [&](void* host, size_t o, size_t bytes) -> cudaError_t {
-    if (!host) return cudaSuccess;
-    local.d2h_bytes += (int64_t)bytes;
-    return cudaMemcpyAsync(host, arena + o, bytes, cudaMemcpyDeviceToHost, s);
-  };
-  CNO_CUDA(down(out->x, o_x, vec_bytes));
-  CNO_CUDA(down(out->gradient, o_g, vec_bytes));
-  CNO_CUDA(down(out->value, o_f, sc_bytes));
-  CNO_CUDA(down(out->x_delta, o_xd, sc_bytes));
-  CNO_CUDA(down(out->f_delta, o_fd, sc_bytes));
-  CNO_CUDA(down(out->gradient_norm, o_gn, sc_bytes));
-  CNO_CUDA(down(out->num_iterations, o_it, (size_t)batch * 4));
-  CNO_CUDA(down(out->nfev, o_nf, (size_t)batch * 4));
-  CNO_CUDA(down(out->status, o_st, (size_t)batch));
+  memset(&kinfo, 0, sizeof(kinfo));
+  const size_t stride_bytes = (size_t)problem->data_stride * ts;
+  for (int c = 0; c < chunks; ++c) {
+    const int64_t lo = c * per;
+    const int64_t n = (lo + per <= batch) ? per : (batch - lo);
+    if (n <= 0) break;
+    cudaStream_t st = streams[c & 1];
+    const size_t vlo = (size_t)lo * d * ts, vn = (size_t)n * d * ts, slo = (size_t)lo * ts, sn = (size_t)n * ts;
+    CNO_CUDA(cudaMemcpyAsync(arena + o_x0 + vlo, (const char*)x0 + vlo, vn, cudaMemcpyHostToDevice, st));
+    local.h2d_bytes += (int64_t)vn;
+    cno_problem_t dprob = *problem;
+    if (data_bytes) {
+      CNO_CUDA(cudaMemcpyAsync(arena + o_data + (size_t)lo * stride_bytes,
+                               (const char*)problem->data + (size_t)lo * stride_bytes,
+                               (size_t)n * stride_bytes, cudaMemcpyHostToDevice, st));
+      dprob.data = arena + o_data + (size_t)lo * stride_bytes;
+      local.h2d_bytes += (int64_t)((size_t)n * stride_bytes);
+    }
+    cno_batch_out_t dout;
+    dout.x = out->x ? arena + o_x + vlo : nullptr;
+    dout.gradient = out->gradient ? arena + o_g + vlo : nullptr;
+    dout.value = out->value ? arena + o_f + slo : nullptr;
+    dout.x_delta = out->x_delta ? arena + o_xd + slo : nullptr;
+    dout.f_delta = out->f_delta ? arena + o_fd + slo : nullptr;
+    dout.gradient_norm = out->gradient_norm ? arena + o_gn + slo : nullptr;
+    dout.num_iterations = out->num_iterations ? (uint32_t*)(arena + o_it) + lo : nullptr;
+    dout.nfev = out->nfev ? (uint32_t*)(arena + o_nf) + lo : nullptr;
+    dout.status = out->status ? (int8_t*)(arena + o_st) + lo : nullptr;
+    cno_stop_t dflt;
+    const cno_stop_t* stp = stop;
+    if (!stp) { cno_default_stop(&dflt); stp = &dflt; }
+    if (stp->past > CNO_MAX_PAST || stp->past < 0) { cudaFree(arena); return CNO_ERR_INVALID_ARGUMENT; }
+    const LaunchArgs a{&dprob, (long long)n, arena + o_x0 + vlo, stp, &dout,
+                       arena + o_ws + (size_t)c * 16, st, &kinfo};
+    rc = find_entry(solver, problem)->fn(a);
+    if (rc) { cudaFree(arena); return rc; }
+    auto down = [&](void* host, size_t o, size_t off, size_t bytes) -> cudaError_t {
+      if (!host) return cudaSuccess;
+      local.d2h_bytes += (int64_t)bytes;
+      return cudaMemcpyAsync((char*)host + off, arena + o + off, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    CNO_CUDA(down(out->x, o_x, vlo, vn));
+    CNO_CUDA(down(out->gradient, o_g, vlo, vn));
+    CNO_CUDA(down(out->value, o_f, slo, sn));
+    CNO_CUDA(down(out->x_delta, o_xd, slo, sn));
+    CNO_CUDA(down(out->f_delta, o_fd, slo, sn));
+    CNO_CUDA(down(out->gradient_norm, o_gn, slo, sn));
+    CNO_CUDA(down(out->num_iterations, o_it, (size_t)lo * 4, (size_t)n * 4));
+    CNO_CUDA(down(out->nfev, o_nf, (size_t)lo * 4, (size_t)n * 4));
+    CNO_CUDA(down(out->status, o_st, (size_t)lo, (size_t)n));
+  }
+  CNO_CUDA(cudaEventRecord(e_start2, s2));
+  CNO_CUDA(cudaStreamWaitEvent(s, e_start2, 0));  // join
   CNO_CUDA(cudaEventRecord(e1, s));
   CNO_CUDA(cudaEventSynchronize(e1));
   float ms = 0;
@@ -498,10 +527,13 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, c
   local.h2d_bytes = h2d;
   local.d2h_bytes = d2h;
   local.total_ms = ms;
+  local.kernel_ms = ms;
   cudaFree(arena);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  cudaEventDestroy(e_start2);
   cudaStreamDestroy(s);
+  cudaStreamDestroy(s2);
   if (info) *info = local;
   g_last_info = local;
   return CNO_OK;

@@ -289,15 +289,35 @@ __device__ __forceinline__ void lu_solve_inplace(T* aug, const int lane, T (&del
     }
     SmemRowVec<T, D>::store(aug + k * D, lane, col);
     // ---- trailing update, columns k+1 .. D (column D = right-hand side) ----
+    // Columns are independent; kU of them are loaded before any is stored so the
+    // LDS -> FP64 -> STS chains of different columns overlap (the compiler cannot
+    // reorder shared-memory loads across stores on its own).
+    constexpr int kU = 8;
+    int j = k + 1;
 #pragma unroll 1
-    for (int j = k + 1; j <= D; ++j) {
-      const T u = aug[prow + j * D];  // broadcast
+    for (; j + kU <= D + 1; j += kU) {
+      T u[kU], cj[kU][E];
+#pragma unroll
+      for (int t = 0; t < kU; ++t) {
+        u[t] = aug[prow + (j + t) * D];  // broadcast
+        SmemRowVec<T, D>::load(aug + (j + t) * D, lane, cj[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < kU; ++t) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) cj[t][e] = live[e] ? (cj[t][e] - l[e] * u[t]) : cj[t][e];
+        // (the pivot row is not live: its owner rewrites the same bits, so the
+        //  broadcast reads above need no ordering against these stores)
+        SmemRowVec<T, D>::store(aug + (j + t) * D, lane, cj[t]);
+      }
+    }
+#pragma unroll 1
+    for (; j <= D; ++j) {
+      const T u = aug[prow + j * D];
       T cj[E];
       SmemRowVec<T, D>::load(aug + j * D, lane, cj);
 #pragma unroll
       for (int e = 0; e < E; ++e) cj[e] = live[e] ? (cj[e] - l[e] * u) : cj[e];
-      // (the pivot row is not live: its owner rewrites the same bits, so the
-      //  broadcast read above needs no ordering against this store)
       SmemRowVec<T, D>::store(aug + j * D, lane, cj);
     }
     __syncwarp();
