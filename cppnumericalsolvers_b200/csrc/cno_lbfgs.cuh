@@ -34,13 +34,41 @@ struct LbfgsSmem {
   static constexpr int E = Shape<D>::E;
   static constexpr int kVec = 32 * E;                        // elements per stored vector
   static constexpr int kScalars = 2 * M + CNO_MAX_PAST;      // rho[M], alpha[M], f ring
-  static constexpr int kHistElems = 2 * M * kVec + ((kScalars + 3) / 4) * 4;  // S, Y + scalars
+  // y-history in Tensor Memory (8 columns per stored vector, M*8 <= 128 columns per
+  // warp at 16 warps/CTA) when a lane's slice is exactly 4 doubles: this lifts the
+  // shared-memory cap on resident warps (11 -> 16 per SM at d = 128 fp64).
+  static constexpr bool kTmemY = (sizeof(T) == 8 && E == 4 && M * 8 <= 128 && kStage == 0);
+  static constexpr int kHistElems = (kTmemY ? 1 : 2) * M * kVec + ((kScalars + 3) / 4) * 4;  // S (, Y) + scalars
   static constexpr int kWarpElems = kHistElems + kStage;     // + the functor's staged block
   static constexpr size_t kWarpBytes = (size_t)kWarpElems * sizeof(T);
   // warps per CTA: as many as fit in 227 KB, at most 16 (register budget).
   static constexpr int kMaxSmem = 227 * 1024;
   static constexpr int kWarpsFit = (int)(kMaxSmem / kWarpBytes);
   static constexpr int kWarps = kWarpsFit > 16 ? 16 : (kWarpsFit < 1 ? 1 : kWarpsFit);
+  static constexpr int kTmemColsPerWarp = 128;               // 512 columns / 4 warps per lane quadrant
+};
+
+// y-history accessors: shared memory (chunk-interleaved) or Tensor Memory.
+template <class T, int E, bool kTmem>
+struct YHist;
+template <class T, int E>
+struct YHist<T, E, false> {
+  T* base;
+  int lane;
+  struct Pending {};
+  __device__ __forceinline__ void store(int slot, const T (&v)[E]) const { SmemVec<T, E>::store(base + slot * 32 * E, lane, v); }
+  __device__ __forceinline__ void issue(int slot, T (&v)[E], Pending&) const { SmemVec<T, E>::load(base + slot * 32 * E, lane, v); }
+  __device__ __forceinline__ void wait(T (&)[E], Pending&) const {}
+  __device__ __forceinline__ void fence_store() const {}
+};
+template <>
+struct YHist<double, 4, true> {
+  uint32_t taddr;  // this warp's TMEM window
+  struct Pending { uint32_t r[8]; };
+  __device__ __forceinline__ void store(int slot, const double (&v)[4]) const { tmem_st4(taddr + slot * 8, v); }
+  __device__ __forceinline__ void issue(int slot, double (&)[4], Pending& p) const { tmem_ld4_issue(taddr + slot * 8, p.r); }
+  __device__ __forceinline__ void wait(double (&v)[4], Pending& p) const { tmem_ld4_wait(p.r, v); }
+  __device__ __forceinline__ void fence_store() const { tmem_wait_st(); }
 };
 
 // progress.h:153-327 on warp-uniform scalars (FunctionState branch).  The
@@ -136,8 +164,30 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   T* const S = reinterpret_cast<T*>(smem_raw) + (size_t)warp * SM::kWarpElems;
-  T* const Y = S + M * SM::kVec;
-  T* const rho_s = Y + M * SM::kVec;  // 1 / (s_i . y_i) per slot
+  T* const Ysm = S + M * SM::kVec;     // (unused when the y-history lives in TMEM)
+  T* const rho_s = S + (SM::kTmemY ? 1 : 2) * M * SM::kVec;  // 1 / (s_i . y_i) per slot
+  uint32_t tmem_base = 0;
+  if constexpr (SM::kTmemY) {
+    __shared__ uint32_t tmem_base_s;
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(&tmem_base_s)),
+                   "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    tmem_base = tmem_base_s;
+  }
+  YHist<T, E, SM::kTmemY> Y;
+  if constexpr (SM::kTmemY) {
+    Y.taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * SM::kTmemColsPerWarp);
+  } else {
+    Y.base = Ysm;
+    Y.lane = lane;
+  }
+  typename YHist<T, E, SM::kTmemY>::Pending ypend;
   T* const alpha = rho_s + M;
   T* const ring = alpha + M;
   void* const stage_ptr = (kStage > 0) ? static_cast<void*>(S + SM::kHistElems) : nullptr;
@@ -194,7 +244,6 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       if (uni(k == M && valid == ((1u << M) - 1u))) {
         // ---- steady state (full history, every pair usable): both loops fully
         //      unrolled, alpha_i in registers, no per-pair control flow ----
-        T alpha_r[M];
         int idx = mem_pos + M - 1;
         idx = (idx >= M) ? idx - M : idx;
         T sv[E], yv[E];
@@ -204,14 +253,16 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
           const int idx_next = (idx == 0) ? M - 1 : idx - 1;
           const T part = lane_dot<T, E>(sv, q);
           const T r = rho_s[idx];
-          SV::load(Y + idx * SM::kVec, lane, yv);
+          Y.issue(idx, yv, ypend);
           if (i > 0) SV::load(S + idx_next * SM::kVec, lane, sv);
           const T a = r * warp_sum(part);
-          alpha_r[i] = a;
+          if (lane == 0) alpha[i] = a;
+          Y.wait(yv, ypend);
 #pragma unroll
           for (int j = 0; j < E; ++j) q[j] = q[j] - a * yv[j];
           idx = idx_next;
         }
+        __syncwarp();
 #pragma unroll
         for (int j = 0; j < E; ++j) q[j] = q[j] * gamma;  // H0 scaling (:181)
         idx = mem_pos;
@@ -221,12 +272,14 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
           const int idx_next = (idx + 1 == M) ? 0 : idx + 1;
           const T part = lane_dot<T, E>(yv, q);
           const T r = rho_s[idx];
+          const T al = alpha[i];
           SV::load(S + idx * SM::kVec, lane, sv);
-          if (i + 1 < M) SV::load(Y + idx_next * SM::kVec, lane, yv);
+          if (i + 1 < M) Y.issue(idx_next, yv, ypend);
           const T beta = r * warp_sum(part);
-          const T coef = alpha_r[i] - beta;
+          const T coef = al - beta;
 #pragma unroll
           for (int j = 0; j < E; ++j) q[j] = q[j] + sv[j] * coef;
+          if (i + 1 < M) Y.wait(yv, ypend);
           idx = idx_next;
         }
       } else {
@@ -246,9 +299,10 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
             const int idx_next = (idx == 0) ? M - 1 : idx - 1;
             T part = lane_dot<T, E>(sv, q);
             T yv[E];
-            SV::load(Y + idx * SM::kVec, lane, yv);
+            Y.issue(idx, yv, ypend);
             SV::load(S + idx_next * SM::kVec, lane, sv);  // prefetch (harmless at i == 0)
             const T a = rho_s[idx] * warp_sum(part);
+            Y.wait(yv, ypend);
             if (uni((valid >> idx) & 1u)) {  // lbfgs.h:165 skip
               if (lane == 0) alpha[i] = a;
   #pragma unroll
@@ -265,15 +319,17 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         if (uni(k > 0)) {
           int idx = mem_pos;
           T yv[E];
-          SV::load(Y + idx * SM::kVec, lane, yv);
+          Y.issue(idx, yv, ypend);
+          Y.wait(yv, ypend);
   #pragma unroll 1
           for (int i = 0; uni(i < k); ++i) {
             const int idx_next = (idx + 1 == M) ? 0 : idx + 1;
             T part = lane_dot<T, E>(yv, q);
             T sv[E];
             SV::load(S + idx * SM::kVec, lane, sv);
-            SV::load(Y + idx_next * SM::kVec, lane, yv);  // prefetch
+            Y.issue(idx_next, yv, ypend);  // prefetch (harmless past the end: a valid slot)
             const T beta = rho_s[idx] * warp_sum(part);
+            Y.wait(yv, ypend);
             if (uni((valid >> idx) & 1u)) {  // lbfgs.h:189 skip
               const T coef = alpha[i] - beta;
   #pragma unroll
@@ -345,7 +401,8 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
             mem_pos = (mem_pos + 1 == M) ? 0 : mem_pos + 1;
           }
           SV::store(S + slot * SM::kVec, lane, sd);
-          SV::store(Y + slot * SM::kVec, lane, yd);
+          Y.store(slot, yd);
+          Y.fence_store();
           // s.y is exactly the dot the reference recomputes per use; cache 1/(s.y)
           if (lane == 0) rho_s[slot] = T(1) / sy;
           valid = (cabs(sy) < eps) ? (valid & ~(1u << slot)) : (valid | (1u << slot));
@@ -382,6 +439,11 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       if (out.gradient_norm) out.gradient_norm[b] = prog.gradient_norm;
     }
     __syncwarp();
+  }
+  if constexpr (SM::kTmemY) {
+    __syncthreads();  // every warp is done with its TMEM window
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
 
