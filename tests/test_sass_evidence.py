@@ -1,0 +1,61 @@
+"""Static evidence that libcno.so is Blackwell-native code for this path (no GPU
+needed: cuobjdump reads the cubin): FP64 tensor-core MMAs for the reductions,
+Tensor Memory loads/stores for the y-history, TMA bulk copies for the staged
+per-instance blocks, warp votes instead of divergence slow paths, and no FMA
+contraction in the arithmetic (the spec forbids it)."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from cppnumericalsolvers_b200 import _lib
+
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+@pytest.fixture(scope="module")
+def kernels():
+    if not os.path.exists(CUOBJDUMP):
+        pytest.skip("cuobjdump not available")
+    txt = subprocess.run([CUOBJDUMP, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    out = {}
+    for f in re.split(r"\n\s*Function : ", txt)[1:]:
+        out[f.split("\n")[0]] = f
+    return out
+
+
+def _find(kernels, *needles):
+    hits = [v for k, v in kernels.items() if all(n in k for n in needles)]
+    assert hits, needles
+    return hits[0]
+
+
+def test_compiled_for_sm_100a():
+    txt = subprocess.run([CUOBJDUMP, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in txt
+
+
+def test_lbfgs_d128_uses_tensor_core_reductions_and_tmem(kernels):
+    k = _find(kernels, "lbfgs_minimize_kernel", "RosenbrockFnIdLi128")
+    assert k.count("DMMA") >= 20          # fp64 reductions on the FP64 tensor core
+    assert "LDTM" in k and "STTM" in k    # y-history in Tensor Memory
+    assert "VOTE" in k and "BRA.DIV" not in k   # provably converged warps
+    assert "REDUX" in k                   # lpNorm<Infinity> via REDUX.MAX
+
+
+def test_newton_and_logistic_stage_with_tma(kernels):
+    for k in (_find(kernels, "newton_minimize_kernel", "DenseQuadraticFnIdLi64"),
+              _find(kernels, "lbfgs_minimize_kernel", "LogisticFn")):
+        assert "UBLKCP" in k and "SYNCS" in k   # cp.async.bulk + mbarrier
+
+
+def test_no_fma_contraction_in_fp32_kernels(kernels):
+    """fp32 arithmetic must be FMUL/FADD (spec: products rounded before they are added);
+    FFMA may only appear inside division / sqrt sequences, which are rare."""
+    k = _find(kernels, "lbfgs_minimize_kernel", "RosenbrockFnIfLi128")
+    ffma = len(re.findall(r"\bFFMA\b", k))
+    fmul = len(re.findall(r"\bFMUL\b", k))
+    fadd = len(re.findall(r"\bFADD\b", k))
+    assert fmul > 100 and fadd > 100 and ffma < (fmul + fadd) // 2
