@@ -404,6 +404,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
           Y.store(slot, yd);
           Y.fence_store();
           // s.y is exactly the dot the reference recomputes per use; cache 1/(s.y)
+          __syncwarp();  // all lanes are done reading rho_s in this iteration's loops
           if (lane == 0) rho_s[slot] = T(1) / sy;
           valid = (cabs(sy) < eps) ? (valid & ~(1u << slot)) : (valid | (1u << slot));
         }

@@ -302,12 +302,11 @@ __device__ __forceinline__ void lu_solve_inplace(T* aug, const int lane, T (&del
         u[t] = aug[prow + (j + t) * D];  // broadcast
         SmemRowVec<T, D>::load(aug + (j + t) * D, lane, cj[t]);
       }
+      __syncwarp();  // every lane has read the pivot row's entries before its owner rewrites them
 #pragma unroll
       for (int t = 0; t < kU; ++t) {
 #pragma unroll
         for (int e = 0; e < E; ++e) cj[t][e] = live[e] ? (cj[t][e] - l[e] * u[t]) : cj[t][e];
-        // (the pivot row is not live: its owner rewrites the same bits, so the
-        //  broadcast reads above need no ordering against these stores)
         SmemRowVec<T, D>::store(aug + (j + t) * D, lane, cj[t]);
       }
     }
@@ -318,6 +317,7 @@ __device__ __forceinline__ void lu_solve_inplace(T* aug, const int lane, T (&del
       SmemRowVec<T, D>::load(aug + j * D, lane, cj);
 #pragma unroll
       for (int e = 0; e < E; ++e) cj[e] = live[e] ? (cj[e] - l[e] * u) : cj[e];
+      __syncwarp();
       SmemRowVec<T, D>::store(aug + j * D, lane, cj);
     }
     __syncwarp();
