@@ -12,13 +12,16 @@
 // B200 design: grid = #SMs persistent CTAs; each warp pulls instance ids from
 // a global atomic queue (instances run 20..10000 iterations, so retire +
 // refill is what keeps all warps busy through the tail).  The m-deep (s, y)
-// history of the instance a warp is working on lives in that warp's private
-// slice of shared memory for the instance's whole lifetime; x, g, the search
-// direction and the trial point live in registers.  HBM is touched twice per
-// instance: one coalesced vectorised read of x0 and one write of the result.
-// Inner products are warp-shuffle butterflies (the arithmetic specification in
-// cno_device.cuh); s_i.y_i is cached per slot when the pair is stored (the
-// reference recomputes the same dot twice per pair per iteration,
+// history of the instance a warp is working on stays ON CHIP for the instance's
+// whole lifetime: s_i in the warp's private slice of shared memory and -- when a
+// lane's slice is 4 doubles (d = 128 fp64) -- y_i in Tensor Memory (YHist), which
+// lifts the shared-memory cap on resident warps (11 -> 16 per SM); x, g, the
+// search direction and the trial point live in registers.  HBM is touched twice
+// per instance: one coalesced vectorised read of x0 and one write of the result.
+// Inner products: in-lane tree, then the cross-lane sum on the FP64 tensor core
+// (fp64: 2 DMMA + 1 DADD) or a shuffle butterfly (fp32) -- the arithmetic
+// specification in cno_device.cuh; s_i.y_i is cached per slot when the pair is
+// stored (the reference recomputes the same dot twice per pair per iteration,
 // lbfgs.h:163-164,187-188 -- same operands, same order, same bits).
 #ifndef CNO_LBFGS_CUH_
 #define CNO_LBFGS_CUH_
