@@ -57,7 +57,8 @@ struct LaunchArgs {
 template <class Fn, int M>
 int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
   using T = typename Fn::Scalar;
-  using SM = cno::LbfgsSmem<T, Fn::Dim, M, cno::StageElems<Fn>::value>;
+  using SM = cno::LbfgsSmem<T, Fn::Dim, M, cno::StageElems<Fn>::value,
+                            cno::PolicyScratch<typename cno::PolicyOf<Fn>::type>::kElemsPerLane>;
   auto kernel = cno::lbfgs_minimize_kernel<Fn, M>;
   const size_t smem = SM::kWarpBytes * SM::kWarps;
   CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -175,6 +176,11 @@ template <class T, int D>
 int lbfgs_rosenbrock(const LaunchArgs& a) {
   return launch_lbfgs<cno::RosenbrockFn<T, D>, CNO_LBFGS_M>(cno::RosenbrockFn<T, D>{}, a);
 }
+// "parity mode": Eigen-SSE2-model reduction order (CNO_POLICY_EIGEN_SSE2), d = 128 fp64
+int lbfgs_rosenbrock_d128_eigen(const LaunchArgs& a) {
+  using Fn = cno::RosenbrockFn<double, 128, cno::PolicyEigenSSE2>;
+  return launch_lbfgs<Fn, CNO_LBFGS_M>(Fn{}, a);
+}
 template <class T, int D>
 int lbfgs_half_sq_norm(const LaunchArgs& a) {
   return launch_lbfgs<cno::HalfSquaredNormFn<T, D>, CNO_LBFGS_M>(cno::HalfSquaredNormFn<T, D>{}, a);
@@ -199,6 +205,7 @@ typedef int (*launcher_t)(const LaunchArgs&);
 struct Entry {
   int solver, family, dtype, d;
   launcher_t fn;
+  int policy = -1;  // -1 = the default policy of the dtype (fp64: DMMA tree, fp32: butterfly)
 };
 
 // Every (solver, functor, T, D) compiled into this library.
@@ -210,6 +217,7 @@ const Entry kTable[] = {
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock<double, 37>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 64, lbfgs_rosenbrock<double, 64>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock<double, 128>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock_d128_eigen, CNO_POLICY_EIGEN_SSE2},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 2, lbfgs_rosenbrock<float, 2>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 37, lbfgs_rosenbrock<float, 37>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 128, lbfgs_rosenbrock<float, 128>},
@@ -231,8 +239,10 @@ const Entry kTable[] = {
 };
 
 const Entry* find_entry(int solver, const cno_problem_t* p) {
+  const int dflt = (p->dtype == CNO_F64) ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE;
   for (const Entry& e : kTable)
-    if (e.solver == solver && e.family == p->family && e.dtype == p->dtype && e.d == p->d)
+    if (e.solver == solver && e.family == p->family && e.dtype == p->dtype && e.d == p->d &&
+        ((e.policy < 0) ? dflt : e.policy) == p->policy)
       return &e;
   return nullptr;
 }
@@ -242,9 +252,8 @@ int check_args(int solver, const cno_problem_t* p) {
   if (solver < CNO_LBFGS || solver > CNO_NEWTON) return CNO_ERR_INVALID_ARGUMENT;
   if (p->dtype != CNO_F64 && p->dtype != CNO_F32) return CNO_ERR_INVALID_ARGUMENT;
   if (p->d <= 0) return CNO_ERR_INVALID_ARGUMENT;
-  // the reduction policy is compiled into the kernels: fp64 = tensor-core tree, fp32 = butterfly
-  if (p->policy != (p->dtype == CNO_F64 ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE))
-    return CNO_ERR_UNSUPPORTED;
+  // the reduction policy is compiled into the kernels (find_entry matches it):
+  // fp64 = tensor-core tree, fp32 = butterfly, plus the Eigen-SSE2 parity mode where listed
   if (!find_entry(solver, p)) return CNO_ERR_UNSUPPORTED;
   return CNO_OK;
 }

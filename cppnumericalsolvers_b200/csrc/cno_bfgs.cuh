@@ -119,7 +119,7 @@ bfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       // ---- MoreThuente::Search (:111-112); dginit = g.d = phi ----
       T xn[1], gn[1];
       T fn_val;
-      nfev += cvsrch<Fn, T, 1>(fn, ctx, x, f, g, xn, fn_val, gn, alpha_init, dir, phi);
+      nfev += cvsrch<Fn, T, 1>(fn, ctx, RedCtx<T>{nullptr, lane}, x, f, g, xn, fn_val, gn, alpha_init, dir, phi);
 
       // ---- rank-2 update (:122-133) ----
       T s[1], y[1];

@@ -26,9 +26,10 @@ namespace cno {
 
 // Chained Rosenbrock: f = sum_{i<d-1} (1-x_i)^2 + 100 (x_{i+1}-x_i^2)^2.
 // At D = 2 the expressions are exactly src/test/verify.cc:58-69.
-template <class T, int D>
+template <class T, int D, class P = PolicyFast>
 struct RosenbrockFn {
   using Scalar = T;
+  using Policy = P;
   static constexpr int Dim = D;
   static constexpr int Mode = 1;
   static constexpr int E = Shape<D>::E;
@@ -66,7 +67,7 @@ struct RosenbrockFn {
         (*grad)[j] = (i < D) ? gi : T(0);
       }
     }
-    return warp_sum(lane_tree<T, E>(term));
+    return warp_sum_p<P, T, E>(lane_terms_p<P, T, E>(term), RedCtx<T>{static_cast<T*>(c.stage), c.lane});
   }
 };
 

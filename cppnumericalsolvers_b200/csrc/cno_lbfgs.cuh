@@ -32,11 +32,11 @@
 
 namespace cno {
 
-template <class T, int D, int M, int kStage = 0>
+template <class T, int D, int M, int kStage = 0, int kScratchPerLane = 0>
 struct LbfgsSmem {
   static constexpr int E = Shape<D>::E;
   static constexpr int kVec = 32 * E;                        // elements per stored vector
-  static constexpr int kScalars = 2 * M + CNO_MAX_PAST;      // rho[M], alpha[M], f ring
+  static constexpr int kScalars = 2 * M + CNO_MAX_PAST + 32 * kScratchPerLane;  // rho[M], alpha[M], f ring, policy scratch
   // y-history in Tensor Memory (8 columns per stored vector, M*8 <= 128 columns per
   // warp at 16 warps/CTA) when a lane's slice is exactly 4 doubles: this lifts the
   // shared-memory cap on resident warps (11 -> 16 per SM at d = 128 fp64).
@@ -150,7 +150,8 @@ __device__ __forceinline__ void progress_update(ProgressState<T>& p, const StopP
 }
 
 template <class Fn, int M>
-__global__ void __launch_bounds__(LbfgsSmem<typename Fn::Scalar, Fn::Dim, M, StageElems<Fn>::value>::kWarps * 32, 1)
+__global__ void __launch_bounds__(LbfgsSmem<typename Fn::Scalar, Fn::Dim, M, StageElems<Fn>::value,
+                                            PolicyScratch<typename PolicyOf<Fn>::type>::kElemsPerLane>::kWarps * 32, 1)
 lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
                       const long long batch, const StopParams<typename Fn::Scalar> stop,
                       const BatchOut<typename Fn::Scalar> out,
@@ -159,7 +160,8 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   constexpr int D = Fn::Dim;
   constexpr int E = Shape<D>::E;
   constexpr int kStage = StageElems<Fn>::value;
-  using SM = LbfgsSmem<T, D, M, kStage>;
+  using P = typename PolicyOf<Fn>::type;
+  using SM = LbfgsSmem<T, D, M, kStage, PolicyScratch<P>::kElemsPerLane>;
   using SV = SmemVec<T, E>;
   constexpr T eps = Num<T>::eps;
 
@@ -193,7 +195,11 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   typename YHist<T, E, SM::kTmemY>::Pending ypend;
   T* const alpha = rho_s + M;
   T* const ring = alpha + M;
-  void* const stage_ptr = (kStage > 0) ? static_cast<void*>(S + SM::kHistElems) : nullptr;
+  // policy scratch (PolicyEigenSSE2): 16-byte aligned tail of the scalar block; handed to
+  // functors through EvalCtx::stage when they stage nothing themselves
+  T* const red_scratch = (PolicyScratch<P>::kElemsPerLane > 0) ? (ring + CNO_MAX_PAST) : nullptr;
+  const RedCtx<T> rc{red_scratch, lane};
+  void* const stage_ptr = (kStage > 0) ? static_cast<void*>(S + SM::kHistElems) : static_cast<void*>(red_scratch);
   uint32_t stage_parity = 0;
   if constexpr (kStage > 0) fn.init_stage(EvalCtx{lane, 0, stage_ptr});
 
@@ -228,7 +234,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
     // ||x||^2 carried across iterations (the dot the reference recomputes at
     // lbfgs.h:95).
-    T xx = warp_sum(lane_dot<T, E>(x, x));
+    T xx = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(x, x), rc);
 
     do {  // solver.h:196-220
       // ================= Lbfgs::OptimizationStep (lbfgs.h:89-303) =========
@@ -254,11 +260,11 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 #pragma unroll
         for (int i = M - 1; i >= 0; --i) {  // first loop (:157-171): newest pair first
           const int idx_next = (idx == 0) ? M - 1 : idx - 1;
-          const T part = lane_dot<T, E>(sv, q);
+          const auto part = lane_dot_p<P, T, E>(sv, q);
           const T r = rho_s[idx];
           Y.issue(idx, yv, ypend);
           if (i > 0) SV::load(S + idx_next * SM::kVec, lane, sv);
-          const T a = r * warp_sum(part);
+          const T a = r * warp_sum_p<P, T, E>(part, rc);
           if (lane == 0) alpha[i] = a;
           Y.wait(yv, ypend);
 #pragma unroll
@@ -273,12 +279,12 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 #pragma unroll
         for (int i = 0; i < M; ++i) {  // second loop (:185-196): oldest pair first
           const int idx_next = (idx + 1 == M) ? 0 : idx + 1;
-          const T part = lane_dot<T, E>(yv, q);
+          const auto part = lane_dot_p<P, T, E>(yv, q);
           const T r = rho_s[idx];
           const T al = alpha[i];
           SV::load(S + idx * SM::kVec, lane, sv);
           if (i + 1 < M) Y.issue(idx_next, yv, ypend);
-          const T beta = r * warp_sum(part);
+          const T beta = r * warp_sum_p<P, T, E>(part, rc);
           const T coef = al - beta;
 #pragma unroll
           for (int j = 0; j < E; ++j) q[j] = q[j] + sv[j] * coef;
@@ -300,11 +306,11 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   #pragma unroll 1
           for (int i = k - 1; uni(i >= 0); --i) {
             const int idx_next = (idx == 0) ? M - 1 : idx - 1;
-            T part = lane_dot<T, E>(sv, q);
+            const auto part = lane_dot_p<P, T, E>(sv, q);
             T yv[E];
             Y.issue(idx, yv, ypend);
             SV::load(S + idx_next * SM::kVec, lane, sv);  // prefetch (harmless at i == 0)
-            const T a = rho_s[idx] * warp_sum(part);
+            const T a = rho_s[idx] * warp_sum_p<P, T, E>(part, rc);
             Y.wait(yv, ypend);
             if (uni((valid >> idx) & 1u)) {  // lbfgs.h:165 skip
               if (lane == 0) alpha[i] = a;
@@ -327,11 +333,11 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   #pragma unroll 1
           for (int i = 0; uni(i < k); ++i) {
             const int idx_next = (idx + 1 == M) ? 0 : idx + 1;
-            T part = lane_dot<T, E>(yv, q);
+            const auto part = lane_dot_p<P, T, E>(yv, q);
             T sv[E];
             SV::load(S + idx * SM::kVec, lane, sv);
             Y.issue(idx_next, yv, ypend);  // prefetch (harmless past the end: a valid slot)
-            const T beta = rho_s[idx] * warp_sum(part);
+            const T beta = rho_s[idx] * warp_sum_p<P, T, E>(part, rc);
             Y.wait(yv, ypend);
             if (uni((valid >> idx) & 1u)) {  // lbfgs.h:189 skip
               const T coef = alpha[i] - beta;
@@ -345,14 +351,14 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
       // ---- descent test, alpha_init, fallback (:199-224) ----
       T alpha_init = T(1);
-      T gq = lane_dot<T, E>(g, q);
+      T gq;
       if (uni(mem_count == 0)) {  // :208-213 (||q|| only matters without history)
-        T qq = lane_dot<T, E>(q, q);
-        warp_sum2(gq, qq);
+        T qq;
+        warp_sum2_p<P, T, E>(lane_dot_p<P, T, E>(g, q), lane_dot_p<P, T, E>(q, q), rc, gq, qq);
         const T qn = csqrt(qq);
         alpha_init = (qn > eps) ? T(1) / qn : T(1);
       } else {
-        gq = warp_sum(gq);
+        gq = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(g, q), rc);
       }
       const T descent_direction = -gq;
       T dginit = descent_direction;  // = g.(-q), bit for bit
@@ -365,7 +371,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         mem_count = 0;
         mem_pos = 0;
         valid = 0;
-        const T gg = warp_sum(lane_dot<T, E>(g, g));  // :221 (rare path)
+        const T gg = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(g, g), rc);  // :221 (rare path)
         const T gn = csqrt(gg);
         alpha_init = (gn > eps) ? T(1) / gn : T(1);
         dginit = gg;
@@ -377,7 +383,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       // ---- MoreThuente::Search (:231-232) ----
       T xn[E], gn[E];
       T fn_val;
-      nfev += cvsrch<Fn, T, E>(fn, ctx, x, f, g, xn, fn_val, gn, alpha_init, sdir, dginit);
+      nfev += cvsrch<Fn, T, E>(fn, ctx, rc, x, f, g, xn, fn_val, gn, alpha_init, sdir, dginit);
 
       const T prev_value = f;
       T x_delta, gnorm_inf, x_inf;
@@ -391,8 +397,9 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         T sd[E], yd[E];
 #pragma unroll
         for (int j = 0; j < E; ++j) { sd[j] = xn[j] - x[j]; yd[j] = gn[j] - g[j]; }
-        T sy = lane_dot<T, E>(sd, yd), ss = lane_dot<T, E>(sd, sd), yy = lane_dot<T, E>(yd, yd);
-        warp_sum3(sy, ss, yy);
+        T sy, ss, yy;
+        warp_sum3_p<P, T, E>(lane_dot_p<P, T, E>(sd, yd), lane_dot_p<P, T, E>(sd, sd),
+                             lane_dot_p<P, T, E>(yd, yd), rc, sy, ss, yy);
         const T sy_threshold = eps * csqrt(ss) * csqrt(yy);
         if (uni(sy > sy_threshold)) {
           int slot;
@@ -422,7 +429,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         f = fn_val;
         gnorm_inf = warp_max_nonneg(lane_maxabs<T, E>(g));
         x_inf = warp_max_nonneg(lane_maxabs<T, E>(x));
-        xx = warp_sum(lane_dot<T, E>(x, x));
+        xx = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(x, x), rc);
         __syncwarp();
       }
 

@@ -135,9 +135,10 @@ __device__ __forceinline__ int cstep(T& stx, T& fx, T& dx, T& sty, T& fy, T& dy,
 // reference; when dginit >= 0 the search returns at once (:152-156) and
 // x/g/f = x0/g0/f0.  Returns the number of objective evaluations.
 template <class Fn, class T, int E>
-__device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx, const T (&x0)[E],
+__device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc, const T (&x0)[E],
                                       const T f0, const T (&g0)[E], T (&x)[E], T& f,
                                       T (&g)[E], T stp, const T (&s)[E], const T dginit) {
+  using P = typename PolicyOf<Fn>::type;
   int info = 0;
   int infoc = 1;
   const T xtol = T(1e-15);
@@ -186,7 +187,7 @@ __device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx, const T 
     for (int j = 0; j < E; ++j) x[j] = x0[j] + stp * s[j];  // :198
     f = fn(ctx, x, &g);                                      // :199 (already reduced)
     nfev++;
-    const T dg = warp_sum(lane_dot<T, E>(g, s));        // :201
+    const T dg = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(g, s), rc);  // :201
     const T ftest1 = finit + stp * dgtest;
 
     if ((brackt & ((stp <= stmin) | (stp >= stmax))) | (infoc == 0)) info = 6;

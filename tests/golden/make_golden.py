@@ -18,11 +18,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SEED = 12345
 
 CASES = [
-    # name, solver, family, d, dtype, B
+    # name, solver, family, d, dtype, B  (reduction policy = the kernels' default for the dtype,
+    # except names ending in _eigen_sse2: CNO_POLICY_EIGEN_SSE2, the "parity mode")
     ("lbfgs_rosenbrock_d128_f64", ob.LBFGS, ob.FN_ROSENBROCK, 128, np.float64, 48),
     ("lbfgs_rosenbrock_d37_f64", ob.LBFGS, ob.FN_ROSENBROCK, 37, np.float64, 32),
     ("lbfgs_rosenbrock_d2_f64", ob.LBFGS, ob.FN_ROSENBROCK, 2, np.float64, 64),
     ("lbfgs_rosenbrock_d128_f32", ob.LBFGS, ob.FN_ROSENBROCK, 128, np.float32, 32),
+    ("lbfgs_rosenbrock_d128_f64_eigen_sse2", ob.LBFGS, ob.FN_ROSENBROCK, 128, np.float64, 24),
     ("bfgs_rosenbrock_d32_f64", ob.BFGS, ob.FN_ROSENBROCK, 32, np.float64, 48),
     ("bfgs_rosenbrock_d2_f64", ob.BFGS, ob.FN_ROSENBROCK, 2, np.float64, 32),
 ]
@@ -32,10 +34,12 @@ def main():
     assert ob.ref_available(), "oracle/_ref is not built (needs /root/reference)"
     for name, solver, family, d, dtype, B in CASES:
         x0 = ob.fill_uniform((B, d), 0, SEED, -2.0, 2.0, dtype)
-        r = ob.minimize(solver, family, x0, impl="ref")  # policy = the device policy of this dtype
+        policy = ob.POLICY_EIGEN_SSE2 if name.endswith("_eigen_sse2") else None
+        r = ob.minimize(solver, family, x0, impl="ref", policy=policy)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), x0=x0, x=r["x"], value=r["value"],
                             gradient=r["gradient"], num_iterations=r["num_iterations"],
-                            status=r["status"], nfev=r["nfev"], solver=solver, family=family)
+                            status=r["status"], nfev=r["nfev"], solver=solver, family=family,
+                            policy=(policy if policy is not None else ob.device_policy(dtype)))
         print(name, "mean iters", r["num_iterations"].mean())
     # the two verify.cc starts + Dockerfile.test + AL-test half norm (reference code, d = 2)
     pins = {}

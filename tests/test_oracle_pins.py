@@ -174,7 +174,7 @@ def test_oracle_equals_reference_dense_quadratic():
 def test_oracle_reproduces_committed_reference_fixtures(path):
     """Fixtures were produced by oracle/_ref (tests/golden/make_golden.py)."""
     z = np.load(path)
-    r = ob.minimize(int(z["solver"]), int(z["family"]), z["x0"])
+    r = ob.minimize(int(z["solver"]), int(z["family"]), z["x0"], policy=int(z["policy"]))
     for k in ("x", "value", "gradient", "num_iterations", "status", "nfev"):
         assert np.array_equal(r[k].view(np.uint8), z[k].view(np.uint8)), k
 
