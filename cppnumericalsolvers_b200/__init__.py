@@ -6,7 +6,8 @@ the C ABI of include/cno.h.  No CPU fallback.
 """
 from . import _lib  # noqa: F401
 from .function import (BatchedFunctionState, DenseQuadratic, DiagQuadratic,  # noqa: F401
-                       DifferentiabilityMode, Function, HalfSquaredNorm, Logistic, Rosenbrock)
+                       DifferentiabilityMode, Function, HalfSquaredNorm, Logistic, Rosenbrock,
+                       RosenbrockFull)
 from .solver import (BatchedProgress, Bfgs, ConservativeStoppingSolverProgress,  # noqa: F401
                      DefaultStoppingSolverProgress, Lbfgs, NewtonDescent, Progress, Solver,
                      Status, fill_uniform)
@@ -15,5 +16,5 @@ __all__ = [
     "BatchedFunctionState", "BatchedProgress", "Bfgs", "ConservativeStoppingSolverProgress",
     "DefaultStoppingSolverProgress", "DenseQuadratic", "DiagQuadratic", "DifferentiabilityMode",
     "Function", "HalfSquaredNorm", "Lbfgs", "Logistic", "NewtonDescent", "Progress",
-    "Rosenbrock", "Solver", "Status", "fill_uniform",
+    "Rosenbrock", "RosenbrockFull", "Solver", "Status", "fill_uniform",
 ]

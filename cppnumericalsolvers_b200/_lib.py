@@ -34,7 +34,7 @@ class Problem(C.Structure):  # cno_problem_t
     _fields_ = [
         ("family", C.c_int32), ("dtype", C.c_int32), ("d", C.c_int32), ("n", C.c_int32),
         ("param", C.c_double), ("data", C.c_void_p), ("data_stride", C.c_int64),
-        ("policy", C.c_int32), ("reserved", C.c_int32),
+        ("policy", C.c_int32), ("mode", C.c_int32),
     ]
 
 

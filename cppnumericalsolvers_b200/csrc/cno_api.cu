@@ -181,6 +181,13 @@ int lbfgs_rosenbrock_d128_eigen(const LaunchArgs& a) {
   using Fn = cno::RosenbrockFn<double, 128, cno::PolicyEigenSSE2>;
   return launch_lbfgs<Fn, CNO_LBFGS_M>(Fn{}, a);
 }
+// Lbfgs on a Second-mode function: diagonal-preconditioner branch (lbfgs.h:116-139)
+template <class T, int D>
+int lbfgs_rosenbrock_second(const LaunchArgs& a) {
+  using Fn = cno::SecondMode<cno::RosenbrockFn<T, D>>;
+  if (a.stop->condition_hessian > 0) return CNO_ERR_UNSUPPORTED;  // not computed (cno_newton.cuh)
+  return launch_lbfgs<Fn, CNO_LBFGS_M>(Fn{}, a);
+}
 template <class T, int D>
 int lbfgs_half_sq_norm(const LaunchArgs& a) {
   return launch_lbfgs<cno::HalfSquaredNormFn<T, D>, CNO_LBFGS_M>(cno::HalfSquaredNormFn<T, D>{}, a);
@@ -206,6 +213,7 @@ struct Entry {
   int solver, family, dtype, d;
   launcher_t fn;
   int policy = -1;  // -1 = the default policy of the dtype (fp64: DMMA tree, fp32: butterfly)
+  int mode = 0;     // 2 = Lbfgs on a Second-mode function (cno_problem_t::mode)
 };
 
 // Every (solver, functor, T, D) compiled into this library.
@@ -218,6 +226,9 @@ const Entry kTable[] = {
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 64, lbfgs_rosenbrock<double, 64>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock<double, 128>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock_d128_eigen, CNO_POLICY_EIGEN_SSE2},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 2, lbfgs_rosenbrock_second<double, 2>, -1, 2},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock_second<double, 37>, -1, 2},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock_second<double, 128>, -1, 2},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 2, lbfgs_rosenbrock<float, 2>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 37, lbfgs_rosenbrock<float, 37>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 128, lbfgs_rosenbrock<float, 128>},
@@ -242,7 +253,8 @@ const Entry* find_entry(int solver, const cno_problem_t* p) {
   const int dflt = (p->dtype == CNO_F64) ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE;
   for (const Entry& e : kTable)
     if (e.solver == solver && e.family == p->family && e.dtype == p->dtype && e.d == p->d &&
-        ((e.policy < 0) ? dflt : e.policy) == p->policy)
+        ((e.policy < 0) ? dflt : e.policy) == p->policy &&
+        (solver != CNO_LBFGS || (e.mode == 2) == (p->mode == 2)))
       return &e;
   return nullptr;
 }

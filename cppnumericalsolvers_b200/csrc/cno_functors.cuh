@@ -69,6 +69,24 @@ struct RosenbrockFn {
     }
     return warp_sum_p<P, T, E>(lane_terms_p<P, T, E>(term), RedCtx<T>{static_cast<T*>(c.stage), c.lane});
   }
+
+  // Diagonal of the Hessian (Second mode; at D = 2 src/test/verify.cc:93-97 incl. the
+  // reference's "+ 1"): H_ii = [1200 x_i^2 - 400 x_{i+1} + 1]_{i<D-1} (+) [200]_{i>0}.
+  __device__ __forceinline__ void hess_diag(const EvalCtx& c, const T (&x)[E], T (&h)[E]) const {
+    const T x_next_lane = __shfl_down_sync(kFullMask, x[0], 1);
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+      const int i = c.lane * E + j;
+      const T xi = x[j];
+      const T xn = (j + 1 < E) ? x[(j + 1 < E) ? j + 1 : 0] : x_next_lane;
+      const T hii = 1200 * xi * xi - 400 * xn + 1;
+      T v;
+      if (i == 0) v = hii;
+      else if (i == D - 1) v = T(200);
+      else v = T(200) + hii;
+      h[j] = (i < D) ? v : T(1);
+    }
+  }
 };
 
 // Dockerfile.test:21-29: 5 x0^2 + 100 x1^2 + 5 (D = 2).

@@ -161,6 +161,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   constexpr int E = Shape<D>::E;
   constexpr int kStage = StageElems<Fn>::value;
   using P = typename PolicyOf<Fn>::type;
+  constexpr bool kSecond = IsSecondMode<Fn>::value;  // lbfgs.h:116-118 has_diagonal_preconditioner
   using SM = LbfgsSmem<T, D, M, kStage, PolicyScratch<P>::kElemsPerLane>;
   using SV = SmemVec<T, E>;
   constexpr T eps = Num<T>::eps;
@@ -240,6 +241,15 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       // ================= Lbfgs::OptimizationStep (lbfgs.h:89-303) =========
       const T relative_eps = eps * smax(T(1.0), csqrt(xx));  // :93-95
 
+      // Second mode (:129-135): M^-1 = 1 / (|diag H| + eps); the gradient the reference
+      // re-evaluates there is the state's gradient (same function, same x, same bits).
+      T precond[E];
+      if constexpr (kSecond) {
+        fn.hess_diag(ctx, x, precond);
+        nfev++;  // function(current.x, &gradient, &hessian)
+#pragma unroll
+        for (int j = 0; j < E; ++j) precond[j] = T(1) / (cabs(precond[j]) + eps);
+      }
       T q[E];  // search_direction
 #pragma unroll
       for (int j = 0; j < E; ++j) q[j] = g[j];  // :145
@@ -273,7 +283,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         }
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < E; ++j) q[j] = q[j] * gamma;  // H0 scaling (:181)
+        for (int j = 0; j < E; ++j) q[j] = kSecond ? (precond[j] * q[j]) : (q[j] * gamma);  // H0 (:177-182)
         idx = mem_pos;
         // (yv still holds y of the oldest pair: the last pair of loop 1 is the first of loop 2)
 #pragma unroll
@@ -321,9 +331,9 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
           }
         }
         __syncwarp();
-        // ---- H0 scaling (:181) ----
+        // ---- H0 scaling (:177-182) ----
   #pragma unroll
-        for (int j = 0; j < E; ++j) q[j] = q[j] * gamma;
+        for (int j = 0; j < E; ++j) q[j] = kSecond ? (precond[j] * q[j]) : (q[j] * gamma);
         // ---- second loop (:185-196): oldest pair first ----
         if (uni(k > 0)) {
           int idx = mem_pos;
@@ -434,6 +444,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       }
 
       // ================= Progress::Update (progress.h:153-327) ============
+      if constexpr (kSecond) nfev++;  // its Hessian evaluation (progress.h:206-207; value unused)
       progress_update<T>(prog, stop, ring, lane, prev_value, f, x_delta, gnorm_inf, x_inf);
     } while (uni(prog.status == CNO_STATUS_CONTINUE));
 

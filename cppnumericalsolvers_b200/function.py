@@ -52,13 +52,20 @@ class Function:
         policy = self.policy
         if policy is None:
             policy = default_policy(self.ScalarType)
+        mode = 2 if self.Differentiability == DifferentiabilityMode.Second else 0
         return _lib.Problem(self.family, _DTYPES[self.ScalarType], self.Dimension, self.n,
-                            float(self.param), data_ptr, stride, policy, 0)
+                            float(self.param), data_ptr, stride, policy, mode)
 
 
 def Rosenbrock(d: int, dtype: torch.dtype = torch.float64) -> Function:
     """Chained Rosenbrock; d = 2 is src/test/verify.cc:58-69."""
     return Function(d, dtype, DifferentiabilityMode.First, _lib.FN_ROSENBROCK)
+
+
+def RosenbrockFull(d: int, dtype: torch.dtype = torch.float64) -> Function:
+    """Second-mode chained Rosenbrock (src/test/verify.cc:81-99): NewtonDescent, or Lbfgs
+    with its diagonal preconditioner (solver/lbfgs.h:116-139)."""
+    return Function(d, dtype, DifferentiabilityMode.Second, _lib.FN_ROSENBROCK)
 
 
 def DiagQuadratic(dtype: torch.dtype = torch.float64) -> Function:

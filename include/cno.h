@@ -129,7 +129,9 @@ typedef struct cno_problem {
                           for cno_minimize, host ptr for cno_minimize_host/oracle) */
   int64_t data_stride; /* scalars per instance */
   int32_t policy;      /* cno_policy_t */
-  int32_t reserved;
+  int32_t mode;        /* 0/1 = use the functor as a First-mode function; 2 = Second mode:
+                          Lbfgs then takes its diagonal-preconditioner branch
+                          (solver/lbfgs.h:116-139,177-179).  NewtonDescent is always Second. */
 } cno_problem_t;
 
 /* Per-instance outputs.  Any pointer may be NULL (not written).  x, value,

@@ -198,7 +198,10 @@ struct LauncherTraits<Rosenbrock<T, D>> {
 };
 template <class T, int D>
 struct LauncherTraits<RosenbrockFull<T, D>> {
-  template <class E> static void Bind(const RosenbrockFull<T, D>&, E& e) { e.problem = detail_builtin::make<T, D>(CNO_FN_ROSENBROCK); }
+  template <class E> static void Bind(const RosenbrockFull<T, D>&, E& e) {
+    e.problem = detail_builtin::make<T, D>(CNO_FN_ROSENBROCK);
+    e.problem.mode = 2;  // Second mode: Lbfgs takes its diagonal-preconditioner branch (lbfgs.h:116-139)
+  }
 };
 template <class T>
 struct LauncherTraits<DiagQuadratic<T>> {

@@ -41,7 +41,7 @@ class Problem(C.Structure):
     _fields_ = [
         ("family", C.c_int32), ("dtype", C.c_int32), ("d", C.c_int32), ("n", C.c_int32),
         ("param", C.c_double), ("data", C.c_void_p), ("data_stride", C.c_int64),
-        ("policy", C.c_int32), ("reserved", C.c_int32),
+        ("policy", C.c_int32), ("mode", C.c_int32),
     ]
 
 
@@ -89,7 +89,7 @@ def _np_dtype(a):
 
 def minimize(solver: int, family: int, x0: np.ndarray, *, policy: int | None = None, stop: Stop | None = None,
              data: np.ndarray | None = None, n: int = 0, param: float = 0.0, threads: int = 0,
-             impl: str = "oracle") -> dict:
+             impl: str = "oracle", mode: int = 0) -> dict:
     """Runs the CPU oracle ("oracle") or the reference-headers build ("ref")."""
     x0 = np.ascontiguousarray(x0)
     assert x0.dtype in (np.float64, np.float32) and x0.ndim == 2
@@ -101,7 +101,7 @@ def minimize(solver: int, family: int, x0: np.ndarray, *, policy: int | None = N
         data = np.ascontiguousarray(data, dtype=dt)
     p = Problem(family, _np_dtype(x0), d, n, param,
                 data.ctypes.data if data is not None else None,
-                data.shape[1] if data is not None else 0, policy, 0)
+                data.shape[1] if data is not None else 0, policy, mode)
     r = dict(x=np.zeros_like(x0), value=np.zeros(B, dt), gradient=np.zeros_like(x0),
              num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8),
              nfev=np.zeros(B, np.uint32), x_delta=np.zeros(B, dt), f_delta=np.zeros(B, dt),

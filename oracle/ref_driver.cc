@@ -172,7 +172,11 @@ template <class T, template <class, DifferentiabilityMode> class Family>
 void dispatch_solver(int solver, const cno_problem_t* prob, int64_t b,
                      const T* x0, const cno_stop_t* stop,
                      const cno_batch_out_t* out) {
-  if (solver == CNO_LBFGS) {
+  if (solver == CNO_LBFGS && prob->mode == 2) {  // Lbfgs on a Second-mode function (lbfgs.h:116-139)
+    using Fn = Family<T, DifferentiabilityMode::Second>;
+    Fn f;
+    run_one<T, cppoptlib::solver::Lbfgs<Fn>>(f, prob, b, x0, stop, out);
+  } else if (solver == CNO_LBFGS) {
     using Fn = Family<T, DifferentiabilityMode::First>;
     Fn f;
     run_one<T, cppoptlib::solver::Lbfgs<Fn>>(f, prob, b, x0, stop, out);

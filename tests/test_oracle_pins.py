@@ -271,3 +271,14 @@ def test_oracle_logistic_matches_closed_form():
         g_ref = -np.einsum("bn,bnd->bd", y / (1 + np.exp(m)), X) + lam * w
         assert np.allclose(f, f_ref, rtol=tol * 10, atol=tol * 100)
         assert np.allclose(g, g_ref, rtol=0, atol=tol * 500)
+
+
+@pytest.mark.parametrize("d", [2, 8, 37, 128])
+def test_oracle_second_mode_lbfgs_equals_reference_headers(d):
+    """Lbfgs<RosenbrockFull> (Second mode -> diagonal preconditioner, lbfgs.h:116-139)."""
+    if not ob.ref_available():
+        pytest.skip("oracle/_ref not built")
+    x0 = ob.fill_uniform((8, d), 0, 5, -2.0, 2.0)
+    a = ob.minimize(ob.LBFGS, ob.FN_ROSENBROCK, x0, mode=2)
+    b = ob.minimize(ob.LBFGS, ob.FN_ROSENBROCK, x0, mode=2, impl="ref")
+    assert _same(a, b, ("x", "value", "gradient", "num_iterations", "status", "nfev"))
