@@ -278,7 +278,7 @@ def test_oracle_second_mode_lbfgs_equals_reference_headers(d):
     """Lbfgs<RosenbrockFull> (Second mode -> diagonal preconditioner, lbfgs.h:116-139)."""
     if not ob.ref_available():
         pytest.skip("oracle/_ref not built")
-    x0 = ob.fill_uniform((8, d), 0, 5, -2.0, 2.0)
+    x0 = ob.fill_uniform((8 if d < 100 else 2, d), 0, 5, -2.0, 2.0)  # the reference inverts H every iteration
     a = ob.minimize(ob.LBFGS, ob.FN_ROSENBROCK, x0, mode=2)
     b = ob.minimize(ob.LBFGS, ob.FN_ROSENBROCK, x0, mode=2, impl="ref")
     assert _same(a, b, ("x", "value", "gradient", "num_iterations", "status", "nfev"))
