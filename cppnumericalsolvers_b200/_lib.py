@@ -57,6 +57,7 @@ class LaunchInfo(C.Structure):  # cno_launch_info_t
 EXPORTS = (
     "cno_version", "cno_error_string", "cno_last_cuda_error", "cno_default_stop",
     "cno_conservative_stop", "cno_supported", "cno_workspace_bytes", "cno_minimize",
+    "cno_state_bytes", "cno_minimize_steps",
     "cno_minimize_host", "cno_fill_uniform", "cno_done_bitmap", "cno_device_cstep",
 )
 
@@ -94,6 +95,11 @@ def lib() -> C.CDLL:
         L.cno_minimize.argtypes = [
             C.c_int, C.POINTER(Problem), C.c_int64, C.c_void_p, C.POINTER(Stop),
             C.POINTER(BatchOut), C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(LaunchInfo)]
+        L.cno_state_bytes.argtypes = [C.c_int, C.POINTER(Problem), C.c_int64, C.POINTER(C.c_size_t)]
+        L.cno_minimize_steps.argtypes = [
+            C.c_int, C.POINTER(Problem), C.c_int64, C.c_void_p, C.POINTER(Stop),
+            C.POINTER(BatchOut), C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p,
+            C.c_size_t, C.c_void_p, C.POINTER(LaunchInfo)]
         L.cno_minimize_host.argtypes = [
             C.c_int, C.POINTER(Problem), C.c_int64, C.c_void_p, C.POINTER(Stop),
             C.POINTER(BatchOut), C.POINTER(LaunchInfo)]

@@ -51,15 +51,16 @@ struct LaunchArgs {
   void* workspace;
   cudaStream_t stream;
   cno_launch_info_t* info;
+  cno::ResumeArgs resume = cno::ResumeArgs{nullptr, 0, 0, 0};  // stepwise solves only
 };
 
-// One persistent launch of lbfgs_minimize_kernel<Fn, M>.
-template <class Fn, int M>
+// One persistent launch of lbfgs_minimize_kernel<Fn, M[, kResume]>.
+template <class Fn, int M, bool kResume = false>
 int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
   using T = typename Fn::Scalar;
   using SM = cno::LbfgsSmem<T, Fn::Dim, M, cno::StageElems<Fn>::value,
                             cno::PolicyScratch<typename cno::PolicyOf<Fn>::type>::kElemsPerLane>;
-  auto kernel = cno::lbfgs_minimize_kernel<Fn, M>;
+  auto kernel = cno::lbfgs_minimize_kernel<Fn, M, kResume>;
   const size_t smem = SM::kWarpBytes * SM::kWarps;
   CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = 0;
@@ -73,7 +74,7 @@ int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
   const cno::StopParams<T> stop = cno::make_stop<T>(*a.stop);
   const cno::BatchOut<T> out = cno::make_out<T>(*a.out);
   kernel<<<grid, SM::kWarps * 32, smem, a.stream>>>(fn, static_cast<const T*>(a.x0), a.batch,
-                                                    stop, out, queue);
+                                                    stop, out, queue, a.resume);
   CNO_CUDA(cudaGetLastError());
   if (a.info) {
     a.info->kernel_launches += 1;
@@ -197,6 +198,16 @@ int lbfgs_diag_quadratic(const LaunchArgs& a) {
   return launch_lbfgs<cno::DiagQuadraticFn<T>, CNO_LBFGS_M>(cno::DiagQuadraticFn<T>{}, a);
 }
 
+// Stepwise variants (cno_minimize_steps): same kernel with park / un-park code.
+template <class T, int D>
+int lbfgs_rosenbrock_steps(const LaunchArgs& a) {
+  return launch_lbfgs<cno::RosenbrockFn<T, D>, CNO_LBFGS_M, true>(cno::RosenbrockFn<T, D>{}, a);
+}
+template <class T, int D>
+size_t lbfgs_state_stride() {
+  return cno::ResumeLayout<T, cno::Shape<D>::E, CNO_LBFGS_M>::kBytes;
+}
+
 template <class T, int D, int N>
 int lbfgs_logistic(const LaunchArgs& a) {
   const cno_problem_t* p = a.problem;
@@ -214,17 +225,21 @@ struct Entry {
   launcher_t fn;
   int policy = -1;  // -1 = the default policy of the dtype (fp64: DMMA tree, fp32: butterfly)
   int mode = 0;     // 2 = Lbfgs on a Second-mode function (cno_problem_t::mode)
+  launcher_t steps_fn = nullptr;          // stepwise variant (cno_minimize_steps), if instantiated
+  size_t (*state_stride)() = nullptr;     // bytes of one parked instance
 };
 
 // Every (solver, functor, T, D) compiled into this library.
 const Entry kTable[] = {
-    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 2, lbfgs_rosenbrock<double, 2>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 2, lbfgs_rosenbrock<double, 2>, -1, 0,
+     lbfgs_rosenbrock_steps<double, 2>, lbfgs_state_stride<double, 2>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 3, lbfgs_rosenbrock<double, 3>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 8, lbfgs_rosenbrock<double, 8>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 32, lbfgs_rosenbrock<double, 32>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock<double, 37>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 64, lbfgs_rosenbrock<double, 64>},
-    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock<double, 128>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock<double, 128>, -1, 0,
+     lbfgs_rosenbrock_steps<double, 128>, lbfgs_state_stride<double, 128>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock_d128_eigen, CNO_POLICY_EIGEN_SSE2},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 2, lbfgs_rosenbrock_second<double, 2>, -1, 2},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock_second<double, 37>, -1, 2},
@@ -428,6 +443,63 @@ int cno_minimize(int solver, const cno_problem_t* problem, int64_t batch, const 
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     g_last_info = *info;
+  }
+  return CNO_OK;
+}
+
+int cno_state_bytes(int solver, const cno_problem_t* problem, int64_t batch, size_t* bytes) {
+  int rc = check_args(solver, problem);
+  if (rc) return rc;
+  if (!bytes || batch < 0) return CNO_ERR_INVALID_ARGUMENT;
+  const Entry* e = find_entry(solver, problem);
+  if (!e->steps_fn) return CNO_ERR_UNSUPPORTED;
+  *bytes = (size_t)batch * e->state_stride();
+  return CNO_OK;
+}
+
+int cno_minimize_steps(int solver, const cno_problem_t* problem, int64_t batch, const void* x0,
+                       const cno_stop_t* stop, const cno_batch_out_t* out, void* state,
+                       size_t state_bytes, int32_t max_iterations, int32_t first_call,
+                       void* workspace, size_t workspace_bytes, void* stream,
+                       cno_launch_info_t* info) {
+  int rc = check_args(solver, problem);
+  if (rc) return rc;
+  const Entry* e = find_entry(solver, problem);
+  if (!e->steps_fn) return CNO_ERR_UNSUPPORTED;
+  if (batch < 0 || !out || max_iterations <= 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (!out->x || !out->value || !out->gradient || !out->status || !out->num_iterations)
+    return CNO_ERR_INVALID_ARGUMENT;  // the parked state continues from these arrays
+  if (info) memset(info, 0, sizeof(*info));
+  if (batch == 0) return have_device() ? CNO_OK : CNO_ERR_NO_DEVICE;
+  if (!x0 && first_call) return CNO_ERR_INVALID_ARGUMENT;
+  const size_t stride = e->state_stride();
+  if (!state || state_bytes < (size_t)batch * stride || ((uintptr_t)state & 15)) return CNO_ERR_WORKSPACE;
+  if (!workspace || workspace_bytes < kWorkspaceBytes || ((uintptr_t)workspace & 7)) return CNO_ERR_WORKSPACE;
+  if (((uintptr_t)x0 & 15) || ((uintptr_t)out->x & 15) || ((uintptr_t)out->gradient & 15))
+    return CNO_ERR_INVALID_ARGUMENT;
+  cno_stop_t dflt;
+  if (!stop) { cno_default_stop(&dflt); stop = &dflt; }
+  if (stop->past > CNO_MAX_PAST || stop->past < 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (!have_device()) return CNO_ERR_NO_DEVICE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (info) {
+    CNO_CUDA(cudaEventCreate(&e0));
+    CNO_CUDA(cudaEventCreate(&e1));
+    CNO_CUDA(cudaEventRecord(e0, s));
+  }
+  LaunchArgs a{problem, (long long)batch, x0, stop, out, workspace, s, info};
+  a.resume = cno::ResumeArgs{static_cast<unsigned char*>(state), (long long)stride, max_iterations,
+                             first_call ? 1 : 0};
+  rc = e->steps_fn(a);
+  if (rc) return rc;
+  if (info) {
+    CNO_CUDA(cudaEventRecord(e1, s));
+    CNO_CUDA(cudaEventSynchronize(e1));
+    CNO_CUDA(cudaEventElapsedTime(&info->kernel_ms, e0, e1));
+    info->total_ms = info->kernel_ms;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
   }
   return CNO_OK;
 }

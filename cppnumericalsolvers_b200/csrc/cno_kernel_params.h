@@ -70,6 +70,15 @@ inline BatchOut<T> make_out(const cno_batch_out_t& o) {
   return b;
 }
 
+// Stepwise ("resumable") solves: the kernel runs at most max_iterations per call and
+// parks each unfinished instance's solver state in `state` (one record per instance).
+struct ResumeArgs {
+  unsigned char* state;  // [B, stride] bytes
+  long long stride;      // bytes per instance record
+  int max_iterations;    // > 0
+  int first;             // 1 = start from x0, 0 = continue from `state` and the previous outputs
+};
+
 }  // namespace cno
 
 #endif  // CNO_KERNEL_PARAMS_H_

@@ -149,13 +149,28 @@ __device__ __forceinline__ void progress_update(ProgressState<T>& p, const StopP
   p.status = status;
 }
 
-template <class Fn, int M>
+// Record of one parked instance (stepwise solves): S slots, Y slots (lane-major),
+// then scalars.  What Lbfgs keeps as members between OptimizationStep calls
+// (lbfgs.h:305-323) plus the Progress counters (progress.h:87-140).
+template <class T, int E, int M>
+struct ResumeLayout {
+  static constexpr int kVec = 32 * E;
+  static constexpr size_t kS = 0;
+  static constexpr size_t kY = kS + (size_t)M * kVec * sizeof(T);
+  static constexpr size_t kScal = kY + (size_t)M * kVec * sizeof(T);  // rho[M], ring[MAX_PAST], gamma, xx
+  static constexpr int kNumScal = M + CNO_MAX_PAST + 2;
+  static constexpr size_t kInts = kScal + (size_t)kNumScal * sizeof(T);
+  static constexpr int kNumInts = 9;
+  static constexpr size_t kBytes = ((kInts + kNumInts * sizeof(int) + 15) / 16) * 16;
+};
+
+template <class Fn, int M, bool kResume = false>
 __global__ void __launch_bounds__(LbfgsSmem<typename Fn::Scalar, Fn::Dim, M, StageElems<Fn>::value,
                                             PolicyScratch<typename PolicyOf<Fn>::type>::kElemsPerLane>::kWarps * 32, 1)
 lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
                       const long long batch, const StopParams<typename Fn::Scalar> stop,
                       const BatchOut<typename Fn::Scalar> out,
-                      unsigned long long* __restrict__ queue) {
+                      unsigned long long* __restrict__ queue, const ResumeArgs ra = ResumeArgs{}) {
   using T = typename Fn::Scalar;
   constexpr int D = Fn::Dim;
   constexpr int E = Shape<D>::E;
@@ -213,29 +228,74 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     const EvalCtx ctx{lane, (long long)b, stage_ptr};
     if constexpr (kStage > 0) fn.stage(ctx, stage_parity);  // per-instance data -> shared memory (TMA)
 
-    // ---- solver.h:189-192: evaluate once at the start point ----
     T x[E], g[E];
-    load_row<T, D>(x0 + b * D, lane, x);
-    T f = fn(ctx, x, &g);
-    uint32_t nfev = 1;
-
-    // ---- lbfgs.h:72-87 InitializeSolver ----
-    int mem_count = 0, mem_pos = 0;
-    unsigned valid = 0;  // bit idx set <=> !(|s_idx . y_idx| < eps)  (lbfgs.h:165,189)
-    T gamma = T(1);
-
+    T f;
+    uint32_t nfev;
+    int mem_count, mem_pos;
+    unsigned valid;  // bit idx set <=> !(|s_idx . y_idx| < eps)  (lbfgs.h:165,189)
+    T gamma;
+    T xx;            // ||x||^2 carried across iterations (the dot the reference recomputes at lbfgs.h:95)
     ProgressState<T> prog;
-    prog.num_iterations = 0;
-    prog.x_delta_violations = 0;
-    prog.f_delta_violations = 0;
     prog.x_delta = prog.f_delta = prog.gradient_norm = T(0);
-    prog.ring_size = 0;
-    prog.ring_pos = 0;
-    prog.status = CNO_STATUS_NOT_STARTED;
-
-    // ||x||^2 carried across iterations (the dot the reference recomputes at
-    // lbfgs.h:95).
-    T xx = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(x, x), rc);
+    bool resumed = false;
+    using RL = ResumeLayout<T, E, M>;
+    if constexpr (kResume) {
+      if (uni(!ra.first)) {
+        if (uni(out.status[b] != CNO_STATUS_CONTINUE)) continue;  // finished in an earlier call
+        // ---- un-park: state saved by the previous call + its outputs (x, g, f) ----
+        unsigned char* rec = ra.state + (size_t)b * ra.stride;
+        load_row<T, D, false>(out.x + b * D, lane, x);
+        load_row<T, D, false>(out.gradient + b * D, lane, g);
+        f = out.value[b];
+        const T* sc = reinterpret_cast<const T*>(rec + RL::kScal);
+        const int* in = reinterpret_cast<const int*>(rec + RL::kInts);
+        __syncwarp();
+        if (lane < M) rho_s[lane] = sc[lane];
+        if (lane < CNO_MAX_PAST) ring[lane] = sc[M + lane];
+        gamma = sc[M + CNO_MAX_PAST];
+        xx = sc[M + CNO_MAX_PAST + 1];
+        mem_count = in[0];
+        mem_pos = in[1];
+        valid = (unsigned)in[2];
+        prog.num_iterations = (uint32_t)in[3];
+        prog.x_delta_violations = in[4];
+        prog.f_delta_violations = in[5];
+        prog.ring_size = in[6];
+        prog.ring_pos = in[7];
+        nfev = (uint32_t)in[8];
+        prog.status = CNO_STATUS_CONTINUE;
+#pragma unroll 1
+        for (int slot = 0; slot < M; ++slot) {
+          T v[E];
+          load_row<T, 32 * E, false>(reinterpret_cast<const T*>(rec + RL::kS) + slot * 32 * E, lane, v);
+          SV::store(S + slot * SM::kVec, lane, v);
+          load_row<T, 32 * E, false>(reinterpret_cast<const T*>(rec + RL::kY) + slot * 32 * E, lane, v);
+          Y.store(slot, v);
+        }
+        Y.fence_store();
+        __syncwarp();
+        resumed = true;
+      }
+    }
+    if (!kResume || uni(!resumed)) {
+      // ---- solver.h:189-192: evaluate once at the start point ----
+      load_row<T, D>(x0 + b * D, lane, x);
+      f = fn(ctx, x, &g);
+      nfev = 1;
+      // ---- lbfgs.h:72-87 InitializeSolver ----
+      mem_count = 0;
+      mem_pos = 0;
+      valid = 0;
+      gamma = T(1);
+      prog.num_iterations = 0;
+      prog.x_delta_violations = 0;
+      prog.f_delta_violations = 0;
+      prog.ring_size = 0;
+      prog.ring_pos = 0;
+      prog.status = CNO_STATUS_NOT_STARTED;
+      xx = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(x, x), rc);
+    }
+    int local_it = 0;
 
     do {  // solver.h:196-220
       // ================= Lbfgs::OptimizationStep (lbfgs.h:89-303) =========
@@ -446,7 +506,42 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       // ================= Progress::Update (progress.h:153-327) ============
       if constexpr (kSecond) nfev++;  // its Hessian evaluation (progress.h:206-207; value unused)
       progress_update<T>(prog, stop, ring, lane, prev_value, f, x_delta, gnorm_inf, x_inf);
-    } while (uni(prog.status == CNO_STATUS_CONTINUE));
+      local_it++;
+    } while (uni(prog.status == CNO_STATUS_CONTINUE && (!kResume || local_it < ra.max_iterations)));
+
+    if constexpr (kResume) {
+      if (uni(prog.status == CNO_STATUS_CONTINUE)) {
+        // ---- park: the members Lbfgs keeps between OptimizationStep calls ----
+        unsigned char* rec = ra.state + (size_t)b * ra.stride;
+        T* sc = reinterpret_cast<T*>(rec + RL::kScal);
+        int* in = reinterpret_cast<int*>(rec + RL::kInts);
+        __syncwarp();
+        if (lane < M) sc[lane] = rho_s[lane];
+        if (lane < CNO_MAX_PAST) sc[M + lane] = ring[lane];
+        if (lane == 0) {
+          sc[M + CNO_MAX_PAST] = gamma;
+          sc[M + CNO_MAX_PAST + 1] = xx;
+          in[0] = mem_count;
+          in[1] = mem_pos;
+          in[2] = (int)valid;
+          in[3] = (int)prog.num_iterations;
+          in[4] = prog.x_delta_violations;
+          in[5] = prog.f_delta_violations;
+          in[6] = prog.ring_size;
+          in[7] = prog.ring_pos;
+          in[8] = (int)nfev;
+        }
+#pragma unroll 1
+        for (int slot = 0; slot < M; ++slot) {
+          T v[E];
+          SV::load(S + slot * SM::kVec, lane, v);
+          store_row<T, 32 * E>(reinterpret_cast<T*>(rec + RL::kS) + slot * 32 * E, lane, v);
+          Y.issue(slot, v, ypend);
+          Y.wait(v, ypend);
+          store_row<T, 32 * E>(reinterpret_cast<T*>(rec + RL::kY) + slot * 32 * E, lane, v);
+        }
+      }
+    }
 
     // ---- write the returned FunctionState + Progress ----
     if (out.x) store_row<T, D>(out.x + b * D, lane, x);

@@ -15,8 +15,13 @@
 `Minimize(function, state)` returns `(BatchedFunctionState, BatchedProgress)`
 like the reference returns `tuple<State, Progress>`.  All compute happens in
 libcno.so's CUDA kernels; PyTorch only owns device memory and streams.
-Per-iteration `SetCallback` callbacks cannot exist when the whole loop is fused
-on the device; per-instance Progress arrays are returned instead.
+
+`SetCallback(cb, every=K)` (solver/solver.h:163-176): with the whole loop fused on
+the device a host callback cannot run inside it, so Minimize then proceeds in
+rounds of K iterations (`cno_minimize_steps`: the solver's members are parked in
+device memory between rounds) and calls `cb(function, state, progress)` on the
+device-resident snapshot after every round -- bit for bit the same trajectory as
+the one-shot solve.  `every=1` is the reference's per-iteration callback.
 """
 from __future__ import annotations
 
@@ -111,6 +116,19 @@ class Solver:
     def __init__(self, progress: Optional[Progress] = None):
         self.stopping_progress = progress if progress is not None else DefaultStoppingSolverProgress()
         self._workspace: Optional[torch.Tensor] = None
+        self._callback = None
+        self._callback_every = 1
+
+    def SetCallback(self, callback, every: int = 1) -> None:
+        """solver/solver.h:176.  callback(function, BatchedFunctionState, BatchedProgress)
+        runs on the host after every `every` iterations (None removes it)."""
+        self._callback = callback
+        self._callback_every = max(1, int(every))
+
+    def supports_steps(self, function: Function) -> bool:
+        p = function.problem()
+        n = C.c_size_t(0)
+        return _lib.lib().cno_state_bytes(self._solver_id, C.byref(p), 1, C.byref(n)) == _lib.OK
 
     def supported(self, function: Function) -> bool:
         p = function.problem()
@@ -149,6 +167,9 @@ class Solver:
                                 gn.data_ptr())
             stop = self.stopping_progress.to_c()
             info = _lib.LaunchInfo() if timed else None
+            if self._callback is not None:
+                return self._minimize_steps(function, prob, x0, stop, out,
+                                            (x, f, g, it, st, nf, xd, fd, gn))
             _lib.check(L.cno_minimize(
                 self._solver_id, C.byref(prob), B, x0.data_ptr(), C.byref(stop), C.byref(out),
                 self._workspace.data_ptr(), self._workspace.numel(),
@@ -156,6 +177,34 @@ class Solver:
                 C.byref(info) if info is not None else None), "cno_minimize")
         return (BatchedFunctionState(x, f, g),
                 BatchedProgress(it, st, nf, xd, fd, gn, info))
+
+    def _minimize_steps(self, function, prob, x0, stop, out, arrays, stop_test=None):
+        """Rounds of `every` iterations with the host callback (and, if given, a global
+        stop test) in between; the device keeps every instance's solver state parked."""
+        x, f, g, it, st, nf, xd, fd, gn = arrays
+        L = _lib.lib()
+        B, dev = x0.shape[0], x0.device
+        nbytes = C.c_size_t(0)
+        _lib.check(L.cno_state_bytes(self._solver_id, C.byref(prob), B, C.byref(nbytes)), "cno_state_bytes")
+        state = torch.empty(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        first, launches = 1, 0
+        while True:
+            _lib.check(L.cno_minimize_steps(
+                self._solver_id, C.byref(prob), B, x0.data_ptr(), C.byref(stop), C.byref(out),
+                state.data_ptr(), state.numel(), self._callback_every, first,
+                self._workspace.data_ptr(), self._workspace.numel(), stream, None), "cno_minimize_steps")
+            first, launches = 0, launches + 1
+            snapshot_state = BatchedFunctionState(x, f, g)
+            snapshot_prog = BatchedProgress(it, st, nf, xd, fd, gn, None)
+            if self._callback is not None:
+                self._callback(function, snapshot_state, snapshot_prog)
+            done = bool((st != 0).all().item()) if stop_test is None else stop_test(snapshot_prog)
+            if done:
+                break
+        info = _lib.LaunchInfo()
+        info.kernel_launches = launches
+        return snapshot_state, BatchedProgress(it, st, nf, xd, fd, gn, info)
 
     def MinimizeHost(self, function: Function, x0: torch.Tensor
                      ) -> Tuple[BatchedFunctionState, BatchedProgress]:

@@ -19,6 +19,9 @@
  *   solver/progress.h:456-464 Conservative      cno_conservative_stop()
  *   solver/solver.h:181-224   Solver::Minimize  cno_minimize() /
  *                                               cno_minimize_host()
+ *   solver/solver.h:226-228   OptimizationStep  cno_minimize_steps() (K iterations
+ *   solver/solver.h:163-176   SetCallback       per call; the host runs its callback
+ *                                               between calls)
  *   solver/lbfgs.h:40-324     Lbfgs<F,m=10>     solver = CNO_LBFGS
  *   solver/bfgs.h:39-145      Bfgs<F>           solver = CNO_BFGS
  *   solver/newton_descent.h:38-85 NewtonDescent solver = CNO_NEWTON
@@ -186,6 +189,22 @@ int cno_minimize(int solver, const cno_problem_t* problem, int64_t batch,
                  const void* x0, const cno_stop_t* stop,
                  const cno_batch_out_t* out, void* workspace,
                  size_t workspace_bytes, void* stream, cno_launch_info_t* info);
+
+/* Stepwise Minimize = batched OptimizationStep (solver/solver.h:226-228) + the
+ * per-iteration callback hook (solver/solver.h:163-176,197): runs at most
+ * max_iterations iterations of every unfinished instance and parks the solver's
+ * members (lbfgs.h:305-323) and Progress counters in `state`
+ * (cno_state_bytes() bytes, device memory, owned by the caller).  first_call != 0
+ * starts from x0; later calls continue from `state` and the previous outputs
+ * (out->x, value, gradient, status, num_iterations must be the same non-NULL
+ * arrays in every call).  An instance is finished when its status != CONTINUE;
+ * the sequence of calls produces bit for bit what one cno_minimize call does. */
+int cno_state_bytes(int solver, const cno_problem_t* problem, int64_t batch, size_t* bytes);
+int cno_minimize_steps(int solver, const cno_problem_t* problem, int64_t batch, const void* x0,
+                       const cno_stop_t* stop, const cno_batch_out_t* out, void* state,
+                       size_t state_bytes, int32_t max_iterations, int32_t first_call,
+                       void* workspace, size_t workspace_bytes, void* stream,
+                       cno_launch_info_t* info);
 
 /* Same call with HOST pointers (x0, problem->data and every non-NULL member of
  * out): stages through pinned memory, copies H2D, solves, copies D2H.  This is

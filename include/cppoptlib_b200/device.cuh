@@ -23,10 +23,10 @@
 #include "cno_lbfgs.cuh"
 
 namespace cno {
-template <class Fn, class Smem, class Kernel>
+template <class Fn, class Smem, class Kernel, class... Extra>
 inline int launch_user(Kernel kernel, const Fn& fn, int64_t batch, const void* x0,
                        const cno_stop_t* stop, const cno_batch_out_t* out, void* workspace,
-                       size_t workspace_bytes, void* stream, cno_launch_info_t* info) {
+                       size_t workspace_bytes, void* stream, cno_launch_info_t* info, Extra... extra) {
   using T = typename Fn::Scalar;
   if (batch < 0 || !out || !workspace || workspace_bytes < 8) return CNO_ERR_INVALID_ARGUMENT;
   if (info) *info = cno_launch_info_t{};
@@ -47,7 +47,7 @@ inline int launch_user(Kernel kernel, const Fn& fn, int64_t batch, const void* x
   if (info) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
   kernel<<<grid, Smem::kWarps * 32, smem, s>>>(fn, static_cast<const T*>(x0), (long long)batch,
                                                make_stop<T>(*stop), make_out<T>(*out),
-                                               static_cast<unsigned long long*>(workspace));
+                                               static_cast<unsigned long long*>(workspace), extra...);
   if (cudaGetLastError() != cudaSuccess) return CNO_ERR_CUDA;
   if (info) {
     cudaEventRecord(e1, s);
@@ -94,7 +94,7 @@ struct BfgsDispatch<F, true> {
     if (solver == CNO_LBFGS)                                                                        \
       return cno::launch_user<F, cno::LbfgsSmem<typename F::Scalar, F::Dim, CNO_LBFGS_M, cno::StageElems<F>::value>>(          \
           cno::lbfgs_minimize_kernel<F, CNO_LBFGS_M>, fn, batch, x0, stop, out, workspace,          \
-          workspace_bytes, stream, info);                                                           \
+          workspace_bytes, stream, info, cno::ResumeArgs{nullptr, 0, 0, 0});                        \
     if (solver == CNO_BFGS)                                                                         \
       return cno::BfgsDispatch<F>::run(fn, batch, x0, stop, out, workspace, workspace_bytes,        \
                                        stream, info);                                               \
