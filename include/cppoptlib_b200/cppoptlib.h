@@ -29,6 +29,7 @@
 #include <cuda_runtime_api.h>
 
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -309,11 +310,22 @@ class Solver {
   using StateType = function::BatchedFunctionState<ScalarType, FunctionType::Dimension>;
   using ProgressType = Progress<FunctionType, StateType>;
 
+  using CallbackType =
+      std::function<void(const FunctionType&, const StateType&, const BatchedProgress<ScalarType>&)>;
+
   ProgressType stopping_progress;
 
   explicit Solver(const ProgressType& progress = DefaultStoppingSolverProgress<FunctionType, StateType>())
       : stopping_progress(progress) {}
   virtual ~Solver() = default;
+
+  // solver/solver.h:176.  The callback runs on the host after every `every` iterations:
+  // Minimize then proceeds in rounds (cno_minimize_steps, solver state parked on the device
+  // in between) -- the same trajectory, bit for bit, as the fused solve.
+  void SetCallback(CallbackType callback, int every = 1) {
+    step_callback_ = std::move(callback);
+    callback_every_ = every < 1 ? 1 : every;
+  }
 
   // Batched Minimize: returns {state at the solution, per-instance progress}.
   virtual std::tuple<StateType, BatchedProgress<ScalarType>> Minimize(const FunctionType& function,
@@ -352,6 +364,23 @@ class Solver {
     detail::DeviceArray<unsigned char> workspace(256);
     const cno_stop_t stop = stopping_progress.to_c();
     int rc;
+    if (step_callback_ && !expr.raw) {
+      size_t nbytes = 0;
+      detail::check_cno(cno_state_bytes(SolverId, &expr.problem, B, &nbytes), "cno_state_bytes");
+      detail::DeviceArray<unsigned char> state(nbytes < 16 ? 16 : nbytes);
+      for (int first = 1;; first = 0) {
+        detail::check_cno(cno_minimize_steps(SolverId, &expr.problem, B, function_state.x.data(), &stop,
+                                             &out, state.data(), state.size(), callback_every_, first,
+                                             workspace.data(), workspace.size(), stream, nullptr),
+                          "cno_minimize_steps");
+        detail::check_cuda(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+        step_callback_(function, result, prog);
+        bool done = true;
+        for (int8_t s : prog.status.ToHost()) done = done && (s != CNO_STATUS_CONTINUE);
+        if (done) break;
+      }
+      return {std::move(result), std::move(prog)};
+    }
     if (expr.raw) {
       rc = expr.raw(SolverId, expr.pod.data(), B, function_state.x.data(), &stop, &out,
                     workspace.data(), workspace.size(), stream, &prog.launch);
@@ -362,6 +391,10 @@ class Solver {
     detail::check_cno(rc, "Minimize");
     return {std::move(result), std::move(prog)};
   }
+
+ protected:
+  CallbackType step_callback_;
+  int callback_every_ = 1;
 };
 
 template <class F> class Lbfgs : public Solver<F, CNO_LBFGS> { using Solver<F, CNO_LBFGS>::Solver; };

@@ -72,6 +72,19 @@ int main() {
     for (uint32_t it : state.num_iterations.ToHost()) EXPECT_NEAR(26.0, (double)it, 0.0);  // ">" limit, progress.h:212
     for (int8_t s : state.status.ToHost()) EXPECT_NEAR((double)solver::Status::IterationLimit, (double)s, 0.0);
   }
+  {  // SetCallback (solver.h:163-176): rounds of 5 iterations, same answer as the fused solve
+    using F = function::Rosenbrock<double, 2>;
+    solver::Lbfgs<F> fused, stepped;
+    int calls = 0;
+    stepped.SetCallback([&](const F&, const function::BatchedFunctionState<double, 2>&,
+                            const solver::BatchedProgress<double>&) { ++calls; }, 5);
+    auto x0 = function::BatchedFunctionState<double, 2>::FromHost({15.0, 8.0, -1.0, 2.0}, 2);
+    auto [s1, p1] = fused.Minimize(F{}, x0);
+    auto [s2, p2] = stepped.Minimize(F{}, x0);
+    const auto a = s1.x.ToHost(), b = s2.x.ToHost();
+    for (size_t i = 0; i < a.size(); ++i) EXPECT_NEAR(a[i], b[i], 0.0);
+    EXPECT_NEAR(9.0, (double)calls, 0.0);  // ceil(45 / 5) rounds (the Far start takes 45 iterations)
+  }
   if (failures == 0) std::printf("PASS\n");
   return failures != 0;
 }
