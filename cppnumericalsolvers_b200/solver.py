@@ -206,6 +206,38 @@ class Solver:
         info.kernel_launches = launches
         return snapshot_state, BatchedProgress(it, st, nf, xd, fd, gn, info)
 
+    def MinimizeSharded(self, function: Function, state: BatchedFunctionState, global_batch: int,
+                        every: int = 64) -> Tuple[BatchedFunctionState, BatchedProgress]:
+        """Multi-GPU solve with the GLOBAL stop test every `every` iterations:
+        this rank's shard advances `every` iterations (cno_minimize_steps), its convergence
+        bitmap is all-gathered (one NCCL collective per round), and all ranks stop together
+        once every instance of every shard has terminated.  `state.x` is this rank's shard
+        (distributed.shard_range); with one process it degenerates to a local loop."""
+        from . import distributed as cd
+        saved = (self._callback, self._callback_every)
+        self._callback_every = max(1, int(every))
+        x0 = state.x.contiguous()
+        dev, dt, B = x0.device, x0.dtype, x0.shape[0]
+        prob = function.problem()
+        with torch.cuda.device(dev):
+            x, g = torch.empty_like(x0), torch.empty_like(x0)
+            f, xd, fd, gn = (torch.empty(B, dtype=dt, device=dev) for _ in range(4))
+            it, nf = (torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2))
+            st = torch.empty(B, dtype=torch.int8, device=dev)
+            if self._workspace is None or self._workspace.device != dev:
+                self._workspace = torch.empty(256, dtype=torch.uint8, device=dev)
+            out = _lib.BatchOut(x.data_ptr(), f.data_ptr(), g.data_ptr(), it.data_ptr(), st.data_ptr(),
+                                nf.data_ptr(), xd.data_ptr(), fd.data_ptr(), gn.data_ptr())
+            stop = self.stopping_progress.to_c()
+
+            def stop_test(prog):
+                return cd.all_done(cd.gather_done_bitmaps(prog.done_bitmap()), global_batch)
+            try:
+                return self._minimize_steps(function, prob, x0, stop, out,
+                                            (x, f, g, it, st, nf, xd, fd, gn), stop_test=stop_test)
+            finally:
+                self._callback, self._callback_every = saved
+
     def MinimizeHost(self, function: Function, x0: torch.Tensor
                      ) -> Tuple[BatchedFunctionState, BatchedProgress]:
         """Same call with host tensors (pinned for full-speed copies): H2D, solve,
