@@ -247,11 +247,15 @@ class Solver:
         x0 = x0.contiguous()
         B, dt = x0.shape[0], x0.dtype
         pin = x0.is_pinned()
-        mk = lambda *s, dtype=dt: torch.empty(*s, dtype=dtype, pin_memory=pin)
-        x, g = mk(*x0.shape), mk(*x0.shape)
-        f, xd, fd, gn = mk(B), mk(B), mk(B), mk(B)
-        it, nf = mk(B, dtype=torch.int32), mk(B, dtype=torch.int32)
-        st = mk(B, dtype=torch.int8)
+        key = (tuple(x0.shape), dt, pin)
+        if getattr(self, "_host_out_key", None) != key:
+            # (pinned) result buffers are allocated once per shape and reused by later calls:
+            # the tensors a call returns are overwritten by the next MinimizeHost of this solver
+            mk = lambda *s, dtype=dt: torch.empty(*s, dtype=dtype, pin_memory=pin)
+            self._host_out = (mk(*x0.shape), mk(*x0.shape), mk(B), mk(B), mk(B), mk(B),
+                              mk(B, dtype=torch.int32), mk(B, dtype=torch.int32), mk(B, dtype=torch.int8))
+            self._host_out_key = key
+        x, g, f, xd, fd, gn, it, nf, st = self._host_out
         out = _lib.BatchOut(x.data_ptr(), f.data_ptr(), g.data_ptr(), it.data_ptr(),
                             st.data_ptr(), nf.data_ptr(), xd.data_ptr(), fd.data_ptr(),
                             gn.data_ptr())
