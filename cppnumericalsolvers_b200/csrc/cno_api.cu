@@ -59,7 +59,8 @@ template <class Fn, int M, bool kResume = false>
 int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
   using T = typename Fn::Scalar;
   using SM = cno::LbfgsSmem<T, Fn::Dim, M, cno::StageElems<Fn>::value,
-                            cno::PolicyScratch<typename cno::PolicyOf<Fn>::type>::kElemsPerLane>;
+                            cno::PolicyScratch<typename cno::PolicyOf<Fn>::type>::kElemsPerLane,
+                            cno::FnTmemCols<Fn>::value>;
   auto kernel = cno::lbfgs_minimize_kernel<Fn, M, kResume>;
   const size_t smem = SM::kWarpBytes * SM::kWarps;
   CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -32,7 +32,7 @@
 
 namespace cno {
 
-template <class T, int D, int M, int kStage = 0, int kScratchPerLane = 0>
+template <class T, int D, int M, int kStage = 0, int kScratchPerLane = 0, int kFnTmem = 0>
 struct LbfgsSmem {
   static constexpr int E = Shape<D>::E;
   static constexpr int kVec = 32 * E;                        // elements per stored vector
@@ -47,7 +47,10 @@ struct LbfgsSmem {
   // warps per CTA: as many as fit in 227 KB, at most 16 (register budget).
   static constexpr int kMaxSmem = 227 * 1024;
   static constexpr int kWarpsFit = (int)(kMaxSmem / kWarpBytes);
-  static constexpr int kWarps = kWarpsFit > 16 ? 16 : (kWarpsFit < 1 ? 1 : kWarpsFit);
+  // a functor that keeps data in Tensor Memory limits the warps per lane quadrant
+  static constexpr int kTmemWarpCap = kFnTmem > 0 ? 4 * (512 / kFnTmem) : 16;
+  static constexpr int kCap = kTmemWarpCap < 16 ? kTmemWarpCap : 16;
+  static constexpr int kWarps = kWarpsFit > kCap ? kCap : (kWarpsFit < 1 ? 1 : kWarpsFit);
   static constexpr int kTmemColsPerWarp = 128;               // 512 columns / 4 warps per lane quadrant
 };
 
@@ -166,7 +169,8 @@ struct ResumeLayout {
 
 template <class Fn, int M, bool kResume = false>
 __global__ void __launch_bounds__(LbfgsSmem<typename Fn::Scalar, Fn::Dim, M, StageElems<Fn>::value,
-                                            PolicyScratch<typename PolicyOf<Fn>::type>::kElemsPerLane>::kWarps * 32, 1)
+                                            PolicyScratch<typename PolicyOf<Fn>::type>::kElemsPerLane,
+                                            FnTmemCols<Fn>::value>::kWarps * 32, 1)
 lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
                       const long long batch, const StopParams<typename Fn::Scalar> stop,
                       const BatchOut<typename Fn::Scalar> out,
@@ -177,7 +181,8 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   constexpr int kStage = StageElems<Fn>::value;
   using P = typename PolicyOf<Fn>::type;
   constexpr bool kSecond = IsSecondMode<Fn>::value;  // lbfgs.h:116-118 has_diagonal_preconditioner
-  using SM = LbfgsSmem<T, D, M, kStage, PolicyScratch<P>::kElemsPerLane>;
+  constexpr int kFnTmem = FnTmemCols<Fn>::value;
+  using SM = LbfgsSmem<T, D, M, kStage, PolicyScratch<P>::kElemsPerLane, kFnTmem>;
   using SV = SmemVec<T, E>;
   constexpr T eps = Num<T>::eps;
 
@@ -188,7 +193,9 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   T* const Ysm = S + M * SM::kVec;     // (unused when the y-history lives in TMEM)
   T* const rho_s = S + (SM::kTmemY ? 1 : 2) * M * SM::kVec;  // 1 / (s_i . y_i) per slot
   uint32_t tmem_base = 0;
-  if constexpr (SM::kTmemY) {
+  constexpr bool kAllocTmem = SM::kTmemY || (kFnTmem > 0);
+  static_assert(!(SM::kTmemY && kFnTmem > 0), "one Tensor Memory user per kernel");
+  if constexpr (kAllocTmem) {
     __shared__ uint32_t tmem_base_s;
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -217,7 +224,10 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   const RedCtx<T> rc{red_scratch, lane};
   void* const stage_ptr = (kStage > 0) ? static_cast<void*>(S + SM::kHistElems) : static_cast<void*>(red_scratch);
   uint32_t stage_parity = 0;
-  if constexpr (kStage > 0) fn.init_stage(EvalCtx{lane, 0, stage_ptr});
+  const uint32_t fn_tmem = (kFnTmem > 0)
+                               ? tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * kFnTmem)
+                               : 0u;
+  if constexpr (kStage > 0) fn.init_stage(EvalCtx{lane, 0, stage_ptr, fn_tmem});
 
   for (;;) {
     // ---- retire + refill: next instance from the global queue ----
@@ -225,7 +235,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     if (lane == 0) b = atomicAdd(queue, 1ULL);
     b = __shfl_sync(kFullMask, b, 0);
     if (uni(b >= (unsigned long long)batch)) break;
-    const EvalCtx ctx{lane, (long long)b, stage_ptr};
+    const EvalCtx ctx{lane, (long long)b, stage_ptr, fn_tmem};
     if constexpr (kStage > 0) fn.stage(ctx, stage_parity);  // per-instance data -> shared memory (TMA)
 
     T x[E], g[E];
@@ -557,7 +567,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     }
     __syncwarp();
   }
-  if constexpr (SM::kTmemY) {
+  if constexpr (kAllocTmem) {
     __syncthreads();  // every warp is done with its TMEM window
     if (warp == 0)
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));

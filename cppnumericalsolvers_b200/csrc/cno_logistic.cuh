@@ -5,9 +5,13 @@
 // Not in the reference (SURVEY.md 8(d) defines it).  Data block per instance:
 //   [Xt (d x n, feature-major: Xt[i*n + j]) | y (n)]        66,560 B at fp32
 // The block is read twice per evaluation (margins, gradient) and an instance
-// needs ~30 evaluations, so it is staged ONCE per instance (cp.async.bulk +
-// mbarrier) and stays in the warp's shared-memory slice: HBM traffic = one read
-// of the block per instance instead of one per evaluation.
+// needs ~40 evaluations, so it is staged ONCE per instance and stays ON CHIP:
+// HBM traffic = one read of the block per instance instead of one per
+// evaluation.  The block is split over both on-chip stores so more instances are
+// resident per SM (5 warps instead of 3): features 0 .. D/2-1 and y go to the
+// warp's shared-memory slice by TMA bulk copies (cp.async.bulk + mbarrier),
+// features D/2 .. D-1 go to the warp's Tensor Memory window (coalesced loads +
+// tcgen05.st; 8 columns per feature).
 //
 // Lane ownership inside the functor: lane l owns samples 128c + 4l .. 4l+3 of
 // each 128-sample chunk c, so every shared-memory access is a contiguous
@@ -83,33 +87,49 @@ struct LogisticFn {
   static constexpr int E = Shape<D>::E;
   static_assert(N % 128 == 0, "samples come in chunks of 128 (32 lanes x 4)");
   static_assert(sizeof(T) == 4, "LDS.128 = 4 samples; instantiate for float");
+  static_assert(N == 256, "8 samples (= 8 TMEM columns) per lane and feature");
   static constexpr int C = N / 128;             // chunks
-  static constexpr int kBlockElems = D * N + N;  // [Xt | y]
-  static constexpr uint32_t kBlockBytes = (uint32_t)(kBlockElems * sizeof(T));
+  static constexpr int kBlockElems = D * N + N;  // [Xt | y] in global memory
+  static constexpr int DS = D / 2;               // features kept in shared memory
+  static constexpr int DT = D - DS;              // features kept in Tensor Memory
+  static constexpr int kTmemCols = DT * (N / 32);  // 8 columns per feature
+  static constexpr int kSmemElems = DS * N + N;    // [Xt rows 0..DS-1 | y]
   static constexpr int kWvec = ((D + 3) / 4) * 4;
-  // staged block + broadcast copy of w + the mbarrier (8 bytes)
-  static constexpr int kStageElems = ((kBlockElems + kWvec + 8 / (int)sizeof(T) + 3) / 4) * 4;
+  // staged part + broadcast copy of w + the mbarrier (8 bytes)
+  static constexpr int kStageElems = ((kSmemElems + kWvec + 8 / (int)sizeof(T) + 3) / 4) * 4;
 
   const T* data;
   long long stride;
   T lambda;
 
-  // once per instance: TMA bulk copy of the data block into ctx.stage
+  // once per instance: lower features + y -> shared memory (2 TMA bulk copies),
+  // upper features -> Tensor Memory
   __device__ __forceinline__ void stage(const EvalCtx& c, uint32_t& parity) const {
     T* blk = static_cast<T*>(c.stage);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(blk + kBlockElems + kWvec);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(blk + kSmemElems + kWvec);
+    const T* src = data + c.instance * stride;
     __syncwarp();
     if (c.lane == 0) {
       fence_proxy_async();
-      mbar_expect_tx(bar, kBlockBytes);
-      tma_bulk_g2s(blk, data + c.instance * stride, kBlockBytes, bar);
+      mbar_expect_tx(bar, (uint32_t)(kSmemElems * sizeof(T)));
+      tma_bulk_g2s(blk, src, (uint32_t)(DS * N * sizeof(T)), bar);
+      tma_bulk_g2s(blk + DS * N, src + D * N, (uint32_t)(N * sizeof(T)), bar);
     }
+    using P4 = Pack<T, 4>;
+#pragma unroll 4
+    for (int i = 0; i < DT; ++i) {
+      T v[8];
+      P4::get(__ldg(reinterpret_cast<const typename P4::type*>(src + (DS + i) * N + 4 * c.lane)), &v[0]);
+      P4::get(__ldg(reinterpret_cast<const typename P4::type*>(src + (DS + i) * N + 128 + 4 * c.lane)), &v[4]);
+      tmem_st8f(c.tmem + i * 8, v);
+    }
+    tmem_wait_st();
     mbar_wait(bar, parity);
     parity ^= 1u;
   }
   __device__ __forceinline__ void init_stage(const EvalCtx& c) const {
     T* blk = static_cast<T*>(c.stage);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(blk + kBlockElems + kWvec);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(blk + kSmemElems + kWvec);
     if (c.lane == 0) {
       mbar_init(bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -118,8 +138,8 @@ struct LogisticFn {
   }
 
   __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&w)[E], T (*grad)[E]) const {
-    const T* Xt = static_cast<const T*>(c.stage);
-    const T* y = Xt + D * N;
+    const T* Xt = static_cast<const T*>(c.stage);  // features 0 .. DS-1
+    const T* y = Xt + DS * N;
     T* wv = const_cast<T*>(y) + N;
     const int lane = c.lane;
     using P4 = Pack<T, 4>;
@@ -132,7 +152,7 @@ struct LogisticFn {
     // ---- margins z_j = sum_i Xt[i][j] w_i (i ascending), 4C samples per lane ----
     T z[4 * C];
 #pragma unroll 4
-    for (int i = 0; i < D; ++i) {
+    for (int i = 0; i < DS; ++i) {  // shared-memory half
       const T wi = wv[i];
 #pragma unroll
       for (int cc = 0; cc < C; ++cc) {
@@ -140,6 +160,19 @@ struct LogisticFn {
         P4::get(*reinterpret_cast<const typename P4::type*>(Xt + i * N + cc * 128 + 4 * lane), xv);
 #pragma unroll
         for (int t = 0; t < 4; ++t) z[cc * 4 + t] = (i == 0) ? (xv[t] * wi) : (z[cc * 4 + t] + xv[t] * wi);
+      }
+    }
+#pragma unroll 1
+    for (int i0 = 0; i0 < DT; i0 += 4) {  // Tensor Memory half, 4 features in flight
+      uint32_t r[4][8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) tmem_ld4_issue(c.tmem + (i0 + q) * 8, r[q]);
+      tmem_wait_ld_groups<4>(r);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const T wi = wv[DS + i0 + q];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) z[t] = z[t] + __uint_as_float(r[q][t]) * wi;
       }
     }
     // ---- per-sample loss and coefficient ----
@@ -170,14 +203,29 @@ struct LogisticFn {
 #pragma unroll 2
       for (int i0 = 0; i0 < D; i0 += 4) {  // 4 independent butterflies in flight
         T p[4];
+        T xq[4][8];
+        if (i0 < DS) {  // (uniform) shared-memory half
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc)
+              P4::get(*reinterpret_cast<const typename P4::type*>(Xt + (i0 + q) * N + cc * 128 + 4 * lane), &xq[q][cc * 4]);
+        } else {        // Tensor Memory half
+          uint32_t r[4][8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tmem_ld4_issue(c.tmem + (i0 - DS + q) * 8, r[q]);
+          tmem_wait_ld_groups<4>(r);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int t = 0; t < 8; ++t) xq[q][t] = __uint_as_float(r[q][t]);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int i = i0 + q;
           T acc = T(0);
 #pragma unroll
           for (int cc = 0; cc < C; ++cc) {
-            T xv[4];
-            P4::get(*reinterpret_cast<const typename P4::type*>(Xt + i * N + cc * 128 + 4 * lane), xv);
+            const T* xv = &xq[q][cc * 4];
             const T part = (coef[cc * 4 + 0] * xv[0] + coef[cc * 4 + 1] * xv[1]) +
                            (coef[cc * 4 + 2] * xv[2] + coef[cc * 4 + 3] * xv[3]);
             acc = (cc == 0) ? part : (acc + part);

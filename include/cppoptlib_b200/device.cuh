@@ -92,7 +92,9 @@ struct BfgsDispatch<F, true> {
     F fn;                                                                                           \
     memcpy(&fn, functor_bytes, sizeof(F));                                                          \
     if (solver == CNO_LBFGS)                                                                        \
-      return cno::launch_user<F, cno::LbfgsSmem<typename F::Scalar, F::Dim, CNO_LBFGS_M, cno::StageElems<F>::value>>(          \
+      return cno::launch_user<F, cno::LbfgsSmem<typename F::Scalar, F::Dim, CNO_LBFGS_M, cno::StageElems<F>::value,
+                                         cno::PolicyScratch<typename cno::PolicyOf<F>::type>::kElemsPerLane,
+                                         cno::FnTmemCols<F>::value>>(          \
           cno::lbfgs_minimize_kernel<F, CNO_LBFGS_M>, fn, batch, x0, stop, out, workspace,          \
           workspace_bytes, stream, info, cno::ResumeArgs{nullptr, 0, 0, 0});                        \
     if (solver == CNO_BFGS)                                                                         \
