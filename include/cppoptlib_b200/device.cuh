@@ -64,6 +64,11 @@ inline int launch_user(Kernel kernel, const Fn& fn, int64_t batch, const void* x
   }
   return CNO_OK;
 }
+// shared-memory plan of lbfgs_minimize_kernel<F, CNO_LBFGS_M> for a user functor
+template <class F>
+using UserLbfgsSmem = LbfgsSmem<typename F::Scalar, F::Dim, CNO_LBFGS_M, StageElems<F>::value,
+                                PolicyScratch<typename PolicyOf<F>::type>::kElemsPerLane, FnTmemCols<F>::value>;
+
 // BFGS keeps a row of the inverse Hessian in registers: D <= 32 only.
 template <class F, bool Small = (F::Dim <= 32)>
 struct BfgsDispatch {
@@ -92,9 +97,7 @@ struct BfgsDispatch<F, true> {
     F fn;                                                                                           \
     memcpy(&fn, functor_bytes, sizeof(F));                                                          \
     if (solver == CNO_LBFGS)                                                                        \
-      return cno::launch_user<F, cno::LbfgsSmem<typename F::Scalar, F::Dim, CNO_LBFGS_M, cno::StageElems<F>::value,
-                                         cno::PolicyScratch<typename cno::PolicyOf<F>::type>::kElemsPerLane,
-                                         cno::FnTmemCols<F>::value>>(          \
+      return cno::launch_user<F, cno::UserLbfgsSmem<F>>(                                            \
           cno::lbfgs_minimize_kernel<F, CNO_LBFGS_M>, fn, batch, x0, stop, out, workspace,          \
           workspace_bytes, stream, info, cno::ResumeArgs{nullptr, 0, 0, 0});                        \
     if (solver == CNO_BFGS)                                                                         \
