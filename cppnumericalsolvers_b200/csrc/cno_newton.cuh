@@ -128,11 +128,96 @@ struct SmemRowVec {
   }
 };
 
+// ---- the augmented matrix [H | rhs]: shared memory, or shared memory + Tensor Memory ----
+// Column-major, lane l owns rows l*E .. l*E+E-1 of every column.  For D = 64 fp64
+// the matrix alone is 32 KB per instance, which would cap an SM at 6 resident
+// warps; the elimination is a 64-step dependent chain per instance (latency
+// bound), so resident warps are what buys throughput.  Columns D/2 .. D-1 are
+// therefore kept in the warp's Tensor Memory window (a column = this lane's 2
+// doubles = 4 TMEM columns; tcgen05.ld/st .32x32b.x4) and only columns 0 .. D/2-1
+// and the right-hand side stay in shared memory: 17 KB per instance -> 13 warps/SM.
+// An entry of the pivot row is broadcast from shared memory (one LDS) or, for a
+// TMEM column, from the owner lane's registers (SHFL).  The arithmetic and its
+// order are unchanged.
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const double (&v)[2]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr),
+               "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])),
+               "r"(__double2hiint(v[1]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld2_issue(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+template <int NG>
+__device__ __forceinline__ void tmem_ld2_wait(uint32_t (&r)[NG][4], double (&v)[NG][2]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    asm volatile("" : "+r"(r[g][0]), "+r"(r[g][1]), "+r"(r[g][2]), "+r"(r[g][3]));
+    v[g][0] = __hiloint2double((int)r[g][1], (int)r[g][0]);
+    v[g][1] = __hiloint2double((int)r[g][3], (int)r[g][2]);
+  }
+}
+
+template <class T, int D>
+struct AugStore {
+  static constexpr int E = Shape<D>::E;
+  static constexpr bool kSplit = (sizeof(T) == 8 && D == 64);
+  static constexpr int kSm = kSplit ? D / 2 : D;   // matrix columns kept in shared memory
+  static constexpr int kTmemCols = kSplit ? (D - kSm) * 4 : 0;
+  using RV = SmemRowVec<T, D>;
+  T* sm;        // [kSm matrix columns | rhs], each D rows
+  uint32_t tm;  // Tensor Memory window (kSplit)
+  int lane;
+
+  __device__ __forceinline__ T* rhs() const { return sm + kSm * D; }
+  __device__ __forceinline__ T* smcol(int j) const { return sm + j * D; }
+  __device__ __forceinline__ uint32_t tmcol(int j) const { return tm + (uint32_t)((j - kSm) * 4); }
+};
+
 // ---- Second-mode device functors ------------------------------------------------
-// Concept: Scalar, Dim, Mode = 2, plus
-//   stage(ctx, x, aug, bar, parity&)   stage H(x) col-major into aug[0 .. D*D)
-//                                      (and per-instance data behind it)
-//   operator()(ctx, x, grad*, aug, vec) value (+ gradient) using the staged block
+// Concept: Scalar, Dim, Mode = 2, kHessianConstant, plus
+//   stage(ctx, x, A, bar, parity&)      stage H(x) (and per-instance data) into A
+//   operator()(ctx, x, grad*, A, vec)   value (+ gradient) using the staged block
+
+// out_i = sum_j H_ij v_j over the whole staged matrix, j ascending from the first
+// product; v is read from the warp-private shared vector `vec`.
+template <class T, int D>
+__device__ __forceinline__ void aug_gemv(const AugStore<T, D>& A, const T* vec, T (&out)[Shape<D>::E]) {
+  constexpr int E = Shape<D>::E;
+  using AS = AugStore<T, D>;
+  T col[E];
+  AS::RV::load(A.smcol(0), A.lane, col);
+  const T v0 = vec[0];
+#pragma unroll
+  for (int e = 0; e < E; ++e) out[e] = col[e] * v0;
+#pragma unroll 4
+  for (int j = 1; j < AS::kSm; ++j) {
+    AS::RV::load(A.smcol(j), A.lane, col);
+    const T vj = vec[j];
+#pragma unroll
+    for (int e = 0; e < E; ++e) out[e] = out[e] + col[e] * vj;
+  }
+  if constexpr (AS::kSplit) {
+#pragma unroll 1
+    for (int j0 = AS::kSm; j0 < D; j0 += 8) {
+      uint32_t r[8][4];
+      double c2[8][2];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) tmem_ld2_issue(A.tmcol(j0 + t), r[t]);
+      tmem_ld2_wait<8>(r, c2);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const T vj = vec[j0 + t];
+#pragma unroll
+        for (int e = 0; e < E; ++e) out[e] = out[e] + c2[t][e] * vj;
+      }
+    }
+  }
+}
 
 // 0.5 x'Ax - b'x with per-instance [A (d x d col-major, bitwise symmetric) | b].
 // Reference analogue: src/examples/debug.cc:43-65.  (Ax)_i = sum_j A_ij x_j,
@@ -143,36 +228,49 @@ struct DenseQuadraticFn {
   static constexpr int Dim = D;
   static constexpr int Mode = 2;
   static constexpr int E = Shape<D>::E;
-  static constexpr uint32_t kBlockBytes = (uint32_t)((D * D + D) * sizeof(T));
+  using AS = AugStore<T, D>;
   static constexpr bool kHessianConstant = true;
   const T* data;        // [B, stride]
   long long stride;     // scalars per instance (>= D*D + D)
 
-  // one TMA bulk copy of [A | b] into the warp's augmented matrix
-  __device__ __forceinline__ void stage(const EvalCtx& c, const T (&)[E], T* aug, uint64_t* bar,
+  // [A | b] -> the warp's store: shared-memory columns and b by TMA bulk copies
+  // (cp.async.bulk + mbarrier), Tensor Memory columns by coalesced loads + tcgen05.st
+  __device__ __forceinline__ void stage(const EvalCtx& c, const T (&)[E], const AS& A, uint64_t* bar,
                                         uint32_t& parity) const {
-    static_assert(kBlockBytes % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
+    static_assert((AS::kSm * D * sizeof(T)) % 16 == 0 && (D * sizeof(T)) % 16 == 0,
+                  "bulk copy sizes must be multiples of 16 bytes");
+    const T* src = data + c.instance * stride;
     __syncwarp();
     if (c.lane == 0) {
-      fence_proxy_async();  // order prior generic-proxy accesses of aug before the async write
-      mbar_expect_tx(bar, kBlockBytes);
-      tma_bulk_g2s(aug, data + c.instance * stride, kBlockBytes, bar);
+      fence_proxy_async();  // order prior generic-proxy accesses of the store before the async writes
+      mbar_expect_tx(bar, (uint32_t)((AS::kSm * D + D) * sizeof(T)));
+      tma_bulk_g2s(A.sm, src, (uint32_t)(AS::kSm * D * sizeof(T)), bar);
+      tma_bulk_g2s(A.rhs(), src + D * D, (uint32_t)(D * sizeof(T)), bar);
+    }
+    if constexpr (AS::kSplit) {
+#pragma unroll 4
+      for (int j = AS::kSm; j < D; ++j) {
+        T v[E];
+        load_row<T, D>(src + j * D, c.lane, v);
+        tmem_st2(A.tmcol(j), v);
+      }
+      tmem_wait_st();
     }
     mbar_wait(bar, parity);
     parity ^= 1u;
   }
 
-  // value/gradient from the staged (unshifted) A in aug; b = aug column D.
+  // value/gradient from the staged (unshifted) A; b = the rhs column.
   // vec = D scalars of warp-private scratch for the broadcast operand.
   __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&x)[E], T (*grad)[E],
-                                          const T* aug, T* vec) const {
+                                          const AS& A, T* vec) const {
     using SV = SmemRowVec<T, D>;
     __syncwarp();
     SV::store(vec, c.lane, x);
     __syncwarp();
     T Ax[E], bb[E];
-    SV::gemv(aug, vec, c.lane, Ax);
-    SV::load(aug + D * D, c.lane, bb);
+    aug_gemv<T, D>(A, vec, Ax);
+    SV::load(A.rhs(), c.lane, bb);
     if (grad) {
 #pragma unroll
       for (int e = 0; e < E; ++e) (*grad)[e] = (c.lane * E + e < D) ? (Ax[e] - bb[e]) : T(0);
@@ -191,10 +289,12 @@ struct RosenbrockFullFn {
   static constexpr int Dim = D;
   static constexpr int Mode = 2;
   static constexpr int E = Shape<D>::E;
+  using AS = AugStore<T, D>;
   static_assert(D <= 32, "dense Rosenbrock Hessian: D <= 32");
   static constexpr bool kHessianConstant = false;
-  __device__ __forceinline__ void stage(const EvalCtx& c, const T (&x)[E], T* aug, uint64_t*,
+  __device__ __forceinline__ void stage(const EvalCtx& c, const T (&x)[E], const AS& A, uint64_t*,
                                         uint32_t&) const {
+    T* aug = A.sm;
     __syncwarp();
     const int i = c.lane;  // E == 1
     const T xi = x[0];
@@ -214,7 +314,7 @@ struct RosenbrockFullFn {
     __syncwarp();
   }
   __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&x)[E], T (*grad)[E],
-                                          const T*, T*) const {
+                                          const AS&, T*) const {
     return RosenbrockFn<T, D>{}(c, x, grad);
   }
 };
@@ -223,24 +323,145 @@ struct RosenbrockFullFn {
 template <class T, int D>
 struct NewtonSmem {
   static constexpr int E = Shape<D>::E;
-  static constexpr int kAug = D * (D + 1);                       // [H | rhs], col-major
+  using AS = AugStore<T, D>;
+  static constexpr int kAug = D * (AS::kSm + 1);                 // [shared-memory columns | rhs]
   static constexpr int kVecPad = ((D + 3) / 4) * 4;
   // + vec, ring, mbarrier (8 bytes); slice size kept a multiple of 16 bytes so every
-  // warp's aug base stays aligned for 16-byte vector accesses and TMA bulk copies
+  // warp's base stays aligned for 16-byte vector accesses and TMA bulk copies
   static constexpr int kWarpElems = ((kAug + kVecPad + CNO_MAX_PAST + 8 / (int)sizeof(T) + 3) / 4) * 4;
-  static_assert((kAug * sizeof(T)) % 16 == 0 || D % 32 != 0, "aug columns must stay 16-byte aligned");
+  static_assert((kAug * sizeof(T)) % 16 == 0 || D % 32 != 0, "columns must stay 16-byte aligned");
   static constexpr size_t kWarpBytes = (size_t)kWarpElems * sizeof(T);
   static constexpr int kMaxSmem = 227 * 1024;
   static constexpr int kWarpsFit = (int)(kMaxSmem / kWarpBytes);
-  static constexpr int kWarps = kWarpsFit > 8 ? 8 : (kWarpsFit < 1 ? 1 : kWarpsFit);
+  // Tensor Memory: 512 columns per lane quadrant / kTmemCols per warp
+  static constexpr int kCap = AS::kSplit ? 4 * (512 / AS::kTmemCols) : 8;
+  static constexpr int kWarps = kWarpsFit > kCap ? kCap : (kWarpsFit < 1 ? 1 : kWarpsFit);
 };
 
-// delta = (H + shift I)^{-1} rhs by unblocked partial-pivot LU with implicit row
-// exchanges.  aug = [H | rhs] col-major (D rows, D+1 columns), lane owns rows
-// lane*E .. lane*E+E-1.  On return delta holds this lane's slice of the solution.
+// One elimination step's trailing update over the SHARED-MEMORY columns [j0, j1).
 template <class T, int D>
-__device__ __forceinline__ void lu_solve_inplace(T* aug, const int lane, T (&delta)[Shape<D>::E]) {
+__device__ __forceinline__ void lu_update_smem(const AugStore<T, D>& A, int j0, int j1, int prow,
+                                               const T (&l)[Shape<D>::E], const bool (&live)[Shape<D>::E],
+                                               T* rhs_or_null) {
   constexpr int E = Shape<D>::E;
+  using RV = SmemRowVec<T, D>;
+  constexpr int kU = 8;
+  const int lane = A.lane;
+  int j = j0;
+  // Columns are independent; kU of them are loaded before any is stored so the
+  // LDS -> FP64 -> STS chains of different columns overlap.
+#pragma unroll 1
+  for (; j + kU <= j1; j += kU) {
+    T u[kU], cj[kU][E];
+#pragma unroll
+    for (int t = 0; t < kU; ++t) {
+      u[t] = A.smcol(j + t)[prow];  // broadcast
+      RV::load(A.smcol(j + t), lane, cj[t]);
+    }
+    __syncwarp();  // every lane has read the pivot row's entries before its owner rewrites them
+#pragma unroll
+    for (int t = 0; t < kU; ++t) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) cj[t][e] = live[e] ? (cj[t][e] - l[e] * u[t]) : cj[t][e];
+      RV::store(A.smcol(j + t), lane, cj[t]);
+    }
+  }
+#pragma unroll 1
+  for (; j < j1; ++j) {
+    const T u = A.smcol(j)[prow];
+    T cj[E];
+    RV::load(A.smcol(j), lane, cj);
+#pragma unroll
+    for (int e = 0; e < E; ++e) cj[e] = live[e] ? (cj[e] - l[e] * u) : cj[e];
+    __syncwarp();
+    RV::store(A.smcol(j), lane, cj);
+  }
+  if (rhs_or_null) {  // the right-hand side rides along as the last column
+    const T u = rhs_or_null[prow];
+    T cj[E];
+    RV::load(rhs_or_null, lane, cj);
+#pragma unroll
+    for (int e = 0; e < E; ++e) cj[e] = live[e] ? (cj[e] - l[e] * u) : cj[e];
+    __syncwarp();
+    RV::store(rhs_or_null, lane, cj);
+  }
+}
+
+// The same over the TENSOR-MEMORY columns [j0, D): the pivot row's entry comes
+// from its owner lane's registers (SHFL) instead of a shared-memory broadcast.
+template <int D>
+__device__ __forceinline__ void lu_update_tmem(const AugStore<double, D>& A, int j0, int prow,
+                                               const double (&l)[2], const bool (&live)[2]) {
+  constexpr int kU = 8;
+  const int owner = prow >> 1, pe = prow & 1;
+  int j = j0;
+#pragma unroll 1
+  for (; j + kU <= D; j += kU) {
+    uint32_t r[kU][4];
+    double cj[kU][2];
+#pragma unroll
+    for (int t = 0; t < kU; ++t) tmem_ld2_issue(A.tmcol(j + t), r[t]);
+    tmem_ld2_wait<kU>(r, cj);
+#pragma unroll
+    for (int t = 0; t < kU; ++t) {
+      const double u = __shfl_sync(kFullMask, pe ? cj[t][1] : cj[t][0], owner);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) cj[t][e] = live[e] ? (cj[t][e] - l[e] * u) : cj[t][e];
+      tmem_st2(A.tmcol(j + t), cj[t]);
+    }
+  }
+#pragma unroll 1
+  for (; j < D; ++j) {
+    uint32_t r[1][4];
+    double cj[1][2];
+    tmem_ld2_issue(A.tmcol(j), r[0]);
+    tmem_ld2_wait<1>(r, cj);
+    const double u = __shfl_sync(kFullMask, pe ? cj[0][1] : cj[0][0], owner);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) cj[0][e] = live[e] ? (cj[0][e] - l[e] * u) : cj[0][e];
+    tmem_st2(A.tmcol(j), cj[0]);
+  }
+  tmem_wait_st();
+}
+
+// this lane's rows of matrix column k, wherever the column lives
+template <class T, int D>
+__device__ __forceinline__ void aug_load_col(const AugStore<T, D>& A, int k, T (&col)[Shape<D>::E]) {
+  using AS = AugStore<T, D>;
+  if constexpr (AS::kSplit) {
+    if (k >= AS::kSm) {  // uniform
+      uint32_t r[1][4];
+      double c2[1][2];
+      tmem_ld2_issue(A.tmcol(k), r[0]);
+      tmem_ld2_wait<1>(r, c2);
+      col[0] = c2[0][0];
+      col[1] = c2[0][1];
+      return;
+    }
+  }
+  AS::RV::load(A.smcol(k), A.lane, col);
+}
+template <class T, int D>
+__device__ __forceinline__ void aug_store_col(const AugStore<T, D>& A, int k, const T (&col)[Shape<D>::E]) {
+  using AS = AugStore<T, D>;
+  if constexpr (AS::kSplit) {
+    if (k >= AS::kSm) {
+      tmem_st2(A.tmcol(k), col);
+      tmem_wait_st();
+      return;
+    }
+  }
+  AS::RV::store(A.smcol(k), A.lane, col);
+}
+
+// delta = (H + shift I)^{-1} rhs by unblocked partial-pivot LU with implicit row
+// exchanges.  A = [H | rhs] col-major, lane owns rows lane*E .. lane*E+E-1.  On
+// return delta holds this lane's slice of the solution.
+template <class T, int D>
+__device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&delta)[Shape<D>::E]) {
+  constexpr int E = Shape<D>::E;
+  using AS = AugStore<T, D>;
+  const int lane = A.lane;
   int vpos[E];  // virtual row position (what the reference's explicit swaps would give)
 #pragma unroll
   for (int e = 0; e < E; ++e) vpos[e] = lane * E + e;
@@ -249,7 +470,7 @@ __device__ __forceinline__ void lu_solve_inplace(T* aug, const int lane, T (&del
   for (int k = 0; k < D; ++k) {
     // ---- pivot: first maximal |a_ik| over virtual positions >= k ----
     T col[E];
-    SmemRowVec<T, D>::load(aug + k * D, lane, col);
+    aug_load_col<T, D>(A, k, col);
     T best = T(-1);
     int bpos = 0x7fffffff;
 #pragma unroll
@@ -287,51 +508,28 @@ __device__ __forceinline__ void lu_solve_inplace(T* aug, const int lane, T (&del
       l[e] = live[e] ? (col[e] / pivot) : T(0);
       col[e] = live[e] ? l[e] : col[e];
     }
-    SmemRowVec<T, D>::store(aug + k * D, lane, col);
-    // ---- trailing update, columns k+1 .. D (column D = right-hand side) ----
-    // Columns are independent; kU of them are loaded before any is stored so the
-    // LDS -> FP64 -> STS chains of different columns overlap (the compiler cannot
-    // reorder shared-memory loads across stores on its own).
-    constexpr int kU = 8;
-    int j = k + 1;
-#pragma unroll 1
-    for (; j + kU <= D + 1; j += kU) {
-      T u[kU], cj[kU][E];
-#pragma unroll
-      for (int t = 0; t < kU; ++t) {
-        u[t] = aug[prow + (j + t) * D];  // broadcast
-        SmemRowVec<T, D>::load(aug + (j + t) * D, lane, cj[t]);
-      }
-      __syncwarp();  // every lane has read the pivot row's entries before its owner rewrites them
-#pragma unroll
-      for (int t = 0; t < kU; ++t) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) cj[t][e] = live[e] ? (cj[t][e] - l[e] * u[t]) : cj[t][e];
-        SmemRowVec<T, D>::store(aug + (j + t) * D, lane, cj[t]);
-      }
+    aug_store_col<T, D>(A, k, col);
+    // ---- trailing update, columns k+1 .. D-1 and the right-hand side ----
+    if (k + 1 < AS::kSm) {
+      lu_update_smem<T, D>(A, k + 1, AS::kSm, prow, l, live, A.rhs());
+    } else {
+      lu_update_smem<T, D>(A, AS::kSm, AS::kSm, prow, l, live, A.rhs());  // rhs only
     }
-#pragma unroll 1
-    for (; j <= D; ++j) {
-      const T u = aug[prow + j * D];
-      T cj[E];
-      SmemRowVec<T, D>::load(aug + j * D, lane, cj);
-#pragma unroll
-      for (int e = 0; e < E; ++e) cj[e] = live[e] ? (cj[e] - l[e] * u) : cj[e];
-      __syncwarp();
-      SmemRowVec<T, D>::store(aug + j * D, lane, cj);
-    }
+    if constexpr (AS::kSplit) lu_update_tmem<D>(A, (k + 1 > AS::kSm) ? k + 1 : AS::kSm, prow, l, live);
     __syncwarp();
   }
   // ---- back substitution U x = y (pivot order), column oriented ----
+  T* const rhs = A.rhs();
 #pragma unroll 1
   for (int k = D - 1; k >= 0; --k) {
+    T col[E];
+    aug_load_col<T, D>(A, k, col);
     T xk_local = T(0);
     bool mine = false;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       if ((lane * E + e < D) && vpos[e] == k) {
-        const int row = lane * E + e;
-        xk_local = aug[row + D * D] / aug[row + k * D];
+        xk_local = rhs[lane * E + e] / col[e];
         mine = true;
       }
     }
@@ -340,7 +538,7 @@ __device__ __forceinline__ void lu_solve_inplace(T* aug, const int lane, T (&del
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int row = lane * E + e;
-      if ((row < D) && vpos[e] < k) aug[row + D * D] = aug[row + D * D] - aug[row + k * D] * xk;
+      if ((row < D) && vpos[e] < k) rhs[row] = rhs[row] - col[e] * xk;
       if (row == k) delta[e] = xk;  // unknown k belongs to element k
     }
     __syncwarp();
@@ -360,6 +558,7 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   constexpr int D = Fn::Dim;
   constexpr int E = Shape<D>::E;
   using SMN = NewtonSmem<T, D>;
+  using AS = AugStore<T, D>;
   using SV = SmemRowVec<T, D>;
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -370,6 +569,21 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   T* const ring = vec + SMN::kVecPad;
   uint64_t* const bar = reinterpret_cast<uint64_t*>(ring + CNO_MAX_PAST);
   uint32_t parity = 0;
+  uint32_t tmem_base = 0;
+  if constexpr (AS::kSplit) {
+    __shared__ uint32_t tmem_base_s;
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(&tmem_base_s)),
+                   "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    tmem_base = tmem_base_s;
+  }
+  const AS A{aug, tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * AS::kTmemCols), lane};
   if (lane == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -385,8 +599,8 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
     T x[E], g[E];
     load_row<T, D>(x0 + b * D, lane, x);
-    fn.stage(ctx, x, aug, bar, parity);
-    T f = fn(ctx, x, &g, aug, vec);  // solver.h:189-192
+    fn.stage(ctx, x, A, bar, parity);
+    T f = fn(ctx, x, &g, A, vec);  // solver.h:189-192
     uint32_t nfev = 1;
 
     ProgressState<T> prog;
@@ -397,27 +611,45 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     prog.ring_size = 0;
     prog.ring_pos = 0;
     prog.status = CNO_STATUS_NOT_STARTED;
-    bool staged = true;  // aug currently holds the unshifted H(x)
+    bool staged = true;  // the store currently holds the unshifted H(x)
 
     do {  // solver.h:196-220
       // ---- newton_descent.h:73-76 ----
-      if (!staged) fn.stage(ctx, x, aug, bar, parity);
+      if (!staged) fn.stage(ctx, x, A, bar, parity);
       nfev++;  // function(current.x, &gradient, &hessian)
+      // hessian += safe_guard * I ; rhs = -gradient
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const int row = lane * E + e;
         if (row < D) {
-          aug[row + row * D] += T(1e-5);  // hessian += safe_guard * I
-          aug[row + D * D] = -g[e];       // rhs = -gradient
+          A.rhs()[row] = -g[e];
+          if (!AS::kSplit || row < AS::kSm) A.smcol(row)[row] += T(1e-5);
         }
+      }
+      if constexpr (AS::kSplit) {  // diagonal entries held in Tensor Memory
+#pragma unroll 1
+        for (int j0 = AS::kSm; j0 < D; j0 += 8) {
+          uint32_t r8[8][4];
+          double c8[8][2];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) tmem_ld2_issue(A.tmcol(j0 + t), r8[t]);
+          tmem_ld2_wait<8>(r8, c8);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) c8[t][e] = (lane * E + e == j0 + t) ? (c8[t][e] + 1e-5) : c8[t][e];
+            tmem_st2(A.tmcol(j0 + t), c8[t]);
+          }
+        }
+        tmem_wait_st();
       }
       __syncwarp();
       T delta[E];
-      lu_solve_inplace<T, D>(aug, lane, delta);
+      lu_solve_inplace<T, D>(A, delta);
 
       // ---- Armijo<F,2>::Search (armijo.h:82-101) ----
-      fn.stage(ctx, x, aug, bar, parity);  // unshifted H(x) again
-      nfev++;                              // f_in = function(x, &gradient, &hessian)
+      fn.stage(ctx, x, A, bar, parity);  // unshifted H(x) again
+      nfev++;                            // f_in = function(x, &gradient, &hessian)
       const T cc = T(0.2), rho = T(0.9);
       T sd[E], r[E];
       const T half_cc = T(0.5) * cc * cc;
@@ -426,7 +658,7 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       __syncwarp();
       SV::store(vec, lane, sd);
       __syncwarp();
-      SV::gemv(aug, vec, lane, r);  // ((0.5 c^2) d') H, H bitwise symmetric
+      aug_gemv<T, D>(A, vec, r);  // ((0.5 c^2) d') H, H bitwise symmetric
       T p1 = lane_dot<T, E>(g, delta), p2 = lane_dot<T, E>(r, delta);
       warp_sum2(p1, p2);
       const T cache = cc * p1 + p2;
@@ -434,13 +666,13 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       T xt[E], gt[E];
 #pragma unroll
       for (int e = 0; e < E; ++e) xt[e] = x[e] + alpha * delta[e];
-      T ft = fn(ctx, xt, &gt, aug, vec);
+      T ft = fn(ctx, xt, &gt, A, vec);
       nfev++;
       while (uni(ft > f + alpha * cache)) {
         alpha *= rho;
 #pragma unroll
         for (int e = 0; e < E; ++e) xt[e] = x[e] + alpha * delta[e];
-        ft = fn(ctx, xt, &gt, aug, vec);
+        ft = fn(ctx, xt, &gt, A, vec);
         nfev++;
       }
       // ---- x + rate*delta (:80), re-evaluation (solver.h:210-216) = last trial ----
@@ -472,6 +704,11 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       if (out.gradient_norm) out.gradient_norm[b] = prog.gradient_norm;
     }
     __syncwarp();
+  }
+  if constexpr (AS::kSplit) {
+    __syncthreads();  // every warp is done with its TMEM window
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
 
