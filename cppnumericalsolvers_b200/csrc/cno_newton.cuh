@@ -162,6 +162,50 @@ __device__ __forceinline__ void tmem_ld2_wait(uint32_t (&r)[NG][4], double (&v)[
   }
 }
 
+// 8 matrix columns (= 32 TMEM columns) in one instruction
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32], double (&v)[8][2]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    v[t][0] = __hiloint2double((int)r[4 * t + 1], (int)r[4 * t]);
+    v[t][1] = __hiloint2double((int)r[4 * t + 3], (int)r[4 * t + 2]);
+  }
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const double (&v)[8][2]) {
+  uint32_t r[32];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    r[4 * t] = (uint32_t)__double2loint(v[t][0]);
+    r[4 * t + 1] = (uint32_t)__double2hiint(v[t][0]);
+    r[4 * t + 2] = (uint32_t)__double2loint(v[t][1]);
+    r[4 * t + 3] = (uint32_t)__double2hiint(v[t][1]);
+  }
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+      "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
 template <class T, int D>
 struct AugStore {
   static constexpr int E = Shape<D>::E;
@@ -204,11 +248,10 @@ __device__ __forceinline__ void aug_gemv(const AugStore<T, D>& A, const T* vec, 
   if constexpr (AS::kSplit) {
 #pragma unroll 1
     for (int j0 = AS::kSm; j0 < D; j0 += 8) {
-      uint32_t r[8][4];
+      uint32_t r[32];
       double c2[8][2];
-#pragma unroll
-      for (int t = 0; t < 8; ++t) tmem_ld2_issue(A.tmcol(j0 + t), r[t]);
-      tmem_ld2_wait<8>(r, c2);
+      tmem_ld32_issue(A.tmcol(j0), r);
+      tmem_ld32_wait(r, c2);
 #pragma unroll
       for (int t = 0; t < 8; ++t) {
         const T vj = vec[j0 + t];
@@ -248,11 +291,12 @@ struct DenseQuadraticFn {
       tma_bulk_g2s(A.rhs(), src + D * D, (uint32_t)(D * sizeof(T)), bar);
     }
     if constexpr (AS::kSplit) {
-#pragma unroll 4
-      for (int j = AS::kSm; j < D; ++j) {
-        T v[E];
-        load_row<T, D>(src + j * D, c.lane, v);
-        tmem_st2(A.tmcol(j), v);
+#pragma unroll 1
+      for (int j = AS::kSm; j < D; j += 8) {
+        double v[8][2];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) load_row<T, D>(src + (j + t) * D, c.lane, v[t]);
+        tmem_st32(A.tmcol(j), v);
       }
       tmem_wait_st();
     }
@@ -362,7 +406,8 @@ __device__ __forceinline__ void lu_update_smem(const AugStore<T, D>& A, int j0, 
 #pragma unroll
     for (int t = 0; t < kU; ++t) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) cj[t][e] = live[e] ? (cj[t][e] - l[e] * u[t]) : cj[t][e];
+      for (int e = 0; e < E; ++e)
+        if (live[e]) cj[t][e] = cj[t][e] - l[e] * u[t];
       RV::store(A.smcol(j + t), lane, cj[t]);
     }
   }
@@ -372,7 +417,8 @@ __device__ __forceinline__ void lu_update_smem(const AugStore<T, D>& A, int j0, 
     T cj[E];
     RV::load(A.smcol(j), lane, cj);
 #pragma unroll
-    for (int e = 0; e < E; ++e) cj[e] = live[e] ? (cj[e] - l[e] * u) : cj[e];
+    for (int e = 0; e < E; ++e)
+      if (live[e]) cj[e] = cj[e] - l[e] * u;
     __syncwarp();
     RV::store(A.smcol(j), lane, cj);
   }
@@ -381,46 +427,48 @@ __device__ __forceinline__ void lu_update_smem(const AugStore<T, D>& A, int j0, 
     T cj[E];
     RV::load(rhs_or_null, lane, cj);
 #pragma unroll
-    for (int e = 0; e < E; ++e) cj[e] = live[e] ? (cj[e] - l[e] * u) : cj[e];
+    for (int e = 0; e < E; ++e)
+      if (live[e]) cj[e] = cj[e] - l[e] * u;
     __syncwarp();
     RV::store(rhs_or_null, lane, cj);
   }
 }
 
-// The same over the TENSOR-MEMORY columns [j0, D): the pivot row's entry comes
-// from its owner lane's registers (SHFL) instead of a shared-memory broadcast.
-template <int D>
-__device__ __forceinline__ void lu_update_tmem(const AugStore<double, D>& A, int j0, int prow,
+// The same over the TENSOR-MEMORY columns k+1 .. D-1 (and at least kSm): the pivot
+// row's entry comes from its owner lane's registers (SHFL) instead of a
+// shared-memory broadcast.  Columns move in aligned groups of 8 (one
+// tcgen05.ld/st .x32 each); in a group that straddles column k only the columns
+// beyond k are touched.  PE = which of the owner lane's two rows is the pivot row.
+template <int D, int PE, bool kPartial>
+__device__ __forceinline__ void lu_update_tmem_group(const AugStore<double, D>& A, int j, int k, int owner,
+                                                     const double (&l)[2], const bool (&live)[2]) {
+  uint32_t r[32];
+  double cj[8][2];
+  tmem_ld32_issue(A.tmcol(j), r);
+  tmem_ld32_wait(r, cj);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const double u = __shfl_sync(kFullMask, cj[t][PE], owner);
+    const bool on = !kPartial || (j + t > k);
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      if (on && live[e]) cj[t][e] = cj[t][e] - l[e] * u;
+  }
+  tmem_st32(A.tmcol(j), cj);
+}
+template <int D, int PE>
+__device__ __forceinline__ void lu_update_tmem(const AugStore<double, D>& A, int k, int prow,
                                                const double (&l)[2], const bool (&live)[2]) {
-  constexpr int kU = 8;
-  const int owner = prow >> 1, pe = prow & 1;
-  int j = j0;
-#pragma unroll 1
-  for (; j + kU <= D; j += kU) {
-    uint32_t r[kU][4];
-    double cj[kU][2];
-#pragma unroll
-    for (int t = 0; t < kU; ++t) tmem_ld2_issue(A.tmcol(j + t), r[t]);
-    tmem_ld2_wait<kU>(r, cj);
-#pragma unroll
-    for (int t = 0; t < kU; ++t) {
-      const double u = __shfl_sync(kFullMask, pe ? cj[t][1] : cj[t][0], owner);
-#pragma unroll
-      for (int e = 0; e < 2; ++e) cj[t][e] = live[e] ? (cj[t][e] - l[e] * u) : cj[t][e];
-      tmem_st2(A.tmcol(j + t), cj[t]);
-    }
+  constexpr int kSm = AugStore<double, D>::kSm;
+  const int owner = prow >> 1;
+  const int jfirst = (k + 1 > kSm) ? k + 1 : kSm;
+  int j = kSm + ((jfirst - kSm) & ~7);
+  if (j != jfirst) {  // uniform
+    lu_update_tmem_group<D, PE, true>(A, j, k, owner, l, live);
+    j += 8;
   }
 #pragma unroll 1
-  for (; j < D; ++j) {
-    uint32_t r[1][4];
-    double cj[1][2];
-    tmem_ld2_issue(A.tmcol(j), r[0]);
-    tmem_ld2_wait<1>(r, cj);
-    const double u = __shfl_sync(kFullMask, pe ? cj[0][1] : cj[0][0], owner);
-#pragma unroll
-    for (int e = 0; e < 2; ++e) cj[0][e] = live[e] ? (cj[0][e] - l[e] * u) : cj[0][e];
-    tmem_st2(A.tmcol(j), cj[0]);
-  }
+  for (; j < D; j += 8) lu_update_tmem_group<D, PE, false>(A, j, k, owner, l, live);
   tmem_wait_st();
 }
 
@@ -515,7 +563,12 @@ __device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&de
     } else {
       lu_update_smem<T, D>(A, AS::kSm, AS::kSm, prow, l, live, A.rhs());  // rhs only
     }
-    if constexpr (AS::kSplit) lu_update_tmem<D>(A, (k + 1 > AS::kSm) ? k + 1 : AS::kSm, prow, l, live);
+    if constexpr (AS::kSplit) {
+      if (k + 1 < D) {
+        if (prow & 1) lu_update_tmem<D, 1>(A, k, prow, l, live);  // uniform
+        else lu_update_tmem<D, 0>(A, k, prow, l, live);
+      }
+    }
     __syncwarp();
   }
   // ---- back substitution U x = y (pivot order), column oriented ----
@@ -629,17 +682,17 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       if constexpr (AS::kSplit) {  // diagonal entries held in Tensor Memory
 #pragma unroll 1
         for (int j0 = AS::kSm; j0 < D; j0 += 8) {
-          uint32_t r8[8][4];
+          uint32_t r8[32];
           double c8[8][2];
-#pragma unroll
-          for (int t = 0; t < 8; ++t) tmem_ld2_issue(A.tmcol(j0 + t), r8[t]);
-          tmem_ld2_wait<8>(r8, c8);
+          tmem_ld32_issue(A.tmcol(j0), r8);
+          tmem_ld32_wait(r8, c8);
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
 #pragma unroll
-            for (int e = 0; e < E; ++e) c8[t][e] = (lane * E + e == j0 + t) ? (c8[t][e] + 1e-5) : c8[t][e];
-            tmem_st2(A.tmcol(j0 + t), c8[t]);
+            for (int e = 0; e < E; ++e)
+              if (lane * E + e == j0 + t) c8[t][e] = c8[t][e] + 1e-5;
           }
+          tmem_st32(A.tmcol(j0), c8);
         }
         tmem_wait_st();
       }
