@@ -56,7 +56,7 @@ def lbfgs_bytes(w, d, m=10):
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     scale = int(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 0
-    which = args or ["c2", "c3", "c4", "c5"]
+    which = args or ["c2", "c3", "c4", "c5"]  # "gd", "cg": the SURVEY.md 8(f) rank-4 solvers, on request
     gen = torch.Generator(device=DEV)
     gen.manual_seed(0)
     if "c2" in which:  # Rosenbrock d=128 fp64 L-BFGS, B = 2^20
@@ -105,6 +105,20 @@ def main():
         cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
         run("c5 newton dense quadratic d64 f64", cn.NewtonDescent(), cn.DenseQuadratic(data, d), x0,
             lambda it, nf: (8 * (d * d + 3 * d) * it).sum())
+    for tag, solver, limit in (("gd", cn.GradientDescent, 200), ("cg", cn.ConjugatedGradientDescent, 100)):
+        if tag not in which:
+            continue
+        # Rosenbrock d=128 fp64, B = 2^18, iteration limit `limit` (these solvers crawl on Rosenbrock:
+        # the limit fixes the work per instance).  Algorithmic bytes as in SURVEY.md 8(d): every
+        # evaluation the kernel makes reads x and writes g; an iteration touches x, g, d once more.
+        B, d = (1 << 18) >> scale, 128
+        x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
+        cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
+        prog = cn.DefaultStoppingSolverProgress()
+        prog.num_iterations = limit
+        run(f"{tag} rosenbrock d128 f64 (iteration limit {limit})", solver(prog), cn.Rosenbrock(d), x0,
+            lambda it, nf: (8 * d * (2 * (nf - 3 * it) + 6 * it)).sum())
+        del x0
 
 
 if __name__ == "__main__":

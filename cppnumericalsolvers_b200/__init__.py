@@ -1,6 +1,7 @@
 """cppnumericalsolvers_b200 -- B200-native batched unconstrained minimisation.
 
-Host-side mirror of cppoptlib's solver::{Lbfgs,Bfgs,NewtonDescent}::Minimize
+Host-side mirror of cppoptlib's solver::{Lbfgs,Bfgs,NewtonDescent,GradientDescent,
+ConjugatedGradientDescent}::Minimize
 with a batch axis; the compute is hand-written sm_100a CUDA in libcno.so behind
 the C ABI of include/cno.h.  No CPU fallback.
 """
@@ -8,12 +9,13 @@ from . import _lib  # noqa: F401
 from .function import (BatchedFunctionState, DenseQuadratic, DiagQuadratic,  # noqa: F401
                        DifferentiabilityMode, Function, HalfSquaredNorm, Logistic, Rosenbrock,
                        RosenbrockFull)
-from .solver import (BatchedProgress, Bfgs, ConservativeStoppingSolverProgress,  # noqa: F401
-                     DefaultStoppingSolverProgress, Lbfgs, NewtonDescent, Progress, Solver,
-                     Status, fill_uniform)
+from .solver import (BatchedProgress, Bfgs, ConjugatedGradientDescent,  # noqa: F401
+                     ConservativeStoppingSolverProgress, DefaultStoppingSolverProgress,
+                     GradientDescent, Lbfgs, NewtonDescent, Progress, Solver, Status, fill_uniform)
 
 __all__ = [
-    "BatchedFunctionState", "BatchedProgress", "Bfgs", "ConservativeStoppingSolverProgress",
+    "BatchedFunctionState", "BatchedProgress", "Bfgs", "ConjugatedGradientDescent",
+    "ConservativeStoppingSolverProgress", "GradientDescent",
     "DefaultStoppingSolverProgress", "DenseQuadratic", "DiagQuadratic", "DifferentiabilityMode",
     "Function", "HalfSquaredNorm", "Lbfgs", "Logistic", "NewtonDescent", "Progress",
     "Rosenbrock", "RosenbrockFull", "Solver", "Status", "fill_uniform",

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcno.so")
 
 # enums of include/cno.h
-LBFGS, BFGS, NEWTON = 0, 1, 2
+LBFGS, BFGS, NEWTON, GRADIENT_DESCENT, CONJUGATED_GRADIENT_DESCENT = 0, 1, 2, 3, 4
 F64, F32 = 0, 1
 FN_ROSENBROCK, FN_DIAG_QUADRATIC, FN_HALF_SQUARED_NORM, FN_LOGISTIC, FN_DENSE_QUADRATIC = range(5)
 POLICY_WARP_TREE, POLICY_EIGEN_SSE2, POLICY_DMMA_TREE = 0, 1, 2

@@ -16,6 +16,7 @@
 #include "cno_kernel_params.h"
 #include "cno_lbfgs.cuh"
 #include "cno_bfgs.cuh"
+#include "cno_descent.cuh"
 #include "cno_newton.cuh"
 #include "cno_logistic.cuh"
 
@@ -116,6 +117,36 @@ int launch_bfgs(const Fn& fn, const LaunchArgs& a) {
   return CNO_OK;
 }
 
+// One persistent launch of descent_minimize_kernel<Fn, kConjugate>
+// (GradientDescent / ConjugatedGradientDescent).
+template <class Fn, bool kConjugate>
+int launch_descent(const Fn& fn, const LaunchArgs& a) {
+  using T = typename Fn::Scalar;
+  using SM = cno::DescentSmem<T>;
+  auto kernel = cno::descent_minimize_kernel<Fn, kConjugate>;
+  const size_t smem = SM::kWarpBytes * SM::kWarps;
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  long long ctas = (a.batch + SM::kWarps - 1) / SM::kWarps;
+  const int grid = (int)(ctas < sms ? (ctas < 1 ? 1 : ctas) : sms);
+  unsigned long long* queue = static_cast<unsigned long long*>(a.workspace);
+  CNO_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), a.stream));
+  const cno::StopParams<T> stop = cno::make_stop<T>(*a.stop);
+  const cno::BatchOut<T> out = cno::make_out<T>(*a.out);
+  kernel<<<grid, SM::kWarps * 32, smem, a.stream>>>(fn, static_cast<const T*>(a.x0), a.batch,
+                                                    stop, out, queue);
+  CNO_CUDA(cudaGetLastError());
+  if (a.info) {
+    a.info->kernel_launches += 1;
+    a.info->grid = grid;
+    a.info->block = SM::kWarps * 32;
+    a.info->warps_per_cta = SM::kWarps;
+    a.info->dynamic_smem = (int64_t)smem;
+  }
+  return CNO_OK;
+}
+
 // One persistent launch of newton_minimize_kernel<Fn>.
 template <class Fn>
 int launch_newton(const Fn& fn, const LaunchArgs& a) {
@@ -172,6 +203,15 @@ int bfgs_half_sq_norm(const LaunchArgs& a) {
 template <class T>
 int bfgs_diag_quadratic(const LaunchArgs& a) {
   return launch_bfgs<cno::DiagQuadraticFn<T>>(cno::DiagQuadraticFn<T>{}, a);
+}
+
+template <class T, int D, bool kConjugate>
+int descent_rosenbrock(const LaunchArgs& a) {
+  return launch_descent<cno::RosenbrockFn<T, D>, kConjugate>(cno::RosenbrockFn<T, D>{}, a);
+}
+template <class T, bool kConjugate>
+int descent_diag_quadratic(const LaunchArgs& a) {
+  return launch_descent<cno::DiagQuadraticFn<T>, kConjugate>(cno::DiagQuadraticFn<T>{}, a);
 }
 
 template <class T, int D>
@@ -263,6 +303,17 @@ const Entry kTable[] = {
     {CNO_NEWTON, CNO_FN_DENSE_QUADRATIC, CNO_F32, 64, newton_dense_quadratic<float, 64>},
     {CNO_NEWTON, CNO_FN_ROSENBROCK, CNO_F64, 2, newton_rosenbrock<double, 2>},
     {CNO_NEWTON, CNO_FN_ROSENBROCK, CNO_F64, 8, newton_rosenbrock<double, 8>},
+    {CNO_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F64, 2, descent_rosenbrock<double, 2, false>},
+    {CNO_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F64, 8, descent_rosenbrock<double, 8, false>},
+    {CNO_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F64, 37, descent_rosenbrock<double, 37, false>},
+    {CNO_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F64, 128, descent_rosenbrock<double, 128, false>},
+    {CNO_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F32, 37, descent_rosenbrock<float, 37, false>},
+    {CNO_GRADIENT_DESCENT, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, descent_diag_quadratic<double, false>},
+    {CNO_CONJUGATED_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F64, 2, descent_rosenbrock<double, 2, true>},
+    {CNO_CONJUGATED_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F64, 8, descent_rosenbrock<double, 8, true>},
+    {CNO_CONJUGATED_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F64, 37, descent_rosenbrock<double, 37, true>},
+    {CNO_CONJUGATED_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F64, 128, descent_rosenbrock<double, 128, true>},
+    {CNO_CONJUGATED_GRADIENT_DESCENT, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, descent_diag_quadratic<double, true>},
 };
 
 const Entry* find_entry(int solver, const cno_problem_t* p) {
@@ -270,14 +321,14 @@ const Entry* find_entry(int solver, const cno_problem_t* p) {
   for (const Entry& e : kTable)
     if (e.solver == solver && e.family == p->family && e.dtype == p->dtype && e.d == p->d &&
         ((e.policy < 0) ? dflt : e.policy) == p->policy &&
-        (solver != CNO_LBFGS || (e.mode == 2) == (p->mode == 2)))
+        ((solver == CNO_BFGS || solver == CNO_NEWTON) || (e.mode == 2) == (p->mode == 2)))
       return &e;
   return nullptr;
 }
 
 int check_args(int solver, const cno_problem_t* p) {
   if (!p) return CNO_ERR_INVALID_ARGUMENT;
-  if (solver < CNO_LBFGS || solver > CNO_NEWTON) return CNO_ERR_INVALID_ARGUMENT;
+  if (solver < CNO_LBFGS || solver > CNO_CONJUGATED_GRADIENT_DESCENT) return CNO_ERR_INVALID_ARGUMENT;
   if (p->dtype != CNO_F64 && p->dtype != CNO_F32) return CNO_ERR_INVALID_ARGUMENT;
   if (p->d <= 0) return CNO_ERR_INVALID_ARGUMENT;
   // the reduction policy is compiled into the kernels (find_entry matches it):

@@ -283,6 +283,16 @@ class NewtonDescent(Solver):
     _solver_id = _lib.NEWTON
 
 
+class GradientDescent(Solver):
+    """solver/gradient_descent.h:37-75 (LineSearch = MoreThuente, the reference's default)."""
+    _solver_id = _lib.GRADIENT_DESCENT
+
+
+class ConjugatedGradientDescent(Solver):
+    """solver/conjugated_gradient_descent.h:38-92 (Fletcher-Reeves, Armijo<F,1>); fp64 only."""
+    _solver_id = _lib.CONJUGATED_GRADIENT_DESCENT
+
+
 def fill_uniform(t: torch.Tensor, first: int, seed: int, lo: float, hi: float) -> torch.Tensor:
     """Counter-based start generator on the device."""
     assert t.is_cuda and t.is_contiguous()

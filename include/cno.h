@@ -25,6 +25,10 @@
  *   solver/lbfgs.h:40-324     Lbfgs<F,m=10>     solver = CNO_LBFGS
  *   solver/bfgs.h:39-145      Bfgs<F>           solver = CNO_BFGS
  *   solver/newton_descent.h:38-85 NewtonDescent solver = CNO_NEWTON
+ *   solver/gradient_descent.h:37-75 GradientDescent (MoreThuente)
+ *                                               solver = CNO_GRADIENT_DESCENT
+ *   solver/conjugated_gradient_descent.h:38-92 ConjugatedGradientDescent
+ *                                               solver = CNO_CONJUGATED_GRADIENT_DESCENT
  *   function_base.h:96-126    FunctionCRTP      cno_problem_t names a functor
  *                                               that was compiled for the
  *                                               device
@@ -73,7 +77,10 @@ typedef enum cno_error {
 typedef enum cno_solver {
   CNO_LBFGS = 0,  /* solver/lbfgs.h, m = 10, MoreThuente */
   CNO_BFGS = 1,   /* solver/bfgs.h, MoreThuente */
-  CNO_NEWTON = 2  /* solver/newton_descent.h, Armijo<F,2> */
+  CNO_NEWTON = 2, /* solver/newton_descent.h, Armijo<F,2> */
+  CNO_GRADIENT_DESCENT = 3,            /* solver/gradient_descent.h, MoreThuente */
+  CNO_CONJUGATED_GRADIENT_DESCENT = 4  /* solver/conjugated_gradient_descent.h, Armijo<F,1>;
+                                          fp64 only (the reference computes beta in double) */
 } cno_solver_t;
 
 typedef enum cno_dtype { CNO_F64 = 0, CNO_F32 = 1 } cno_dtype_t;

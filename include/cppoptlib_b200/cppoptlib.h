@@ -404,6 +404,16 @@ template <class F> class NewtonDescent : public Solver<F, CNO_NEWTON> {
                 "NewtonDescent only supports second-order differentiable functions");
   using Solver<F, CNO_NEWTON>::Solver;
 };
+// solver/gradient_descent.h:37-75 (LineSearch = MoreThuente, the reference's default policy)
+template <class F> class GradientDescent : public Solver<F, CNO_GRADIENT_DESCENT> {
+  using Solver<F, CNO_GRADIENT_DESCENT>::Solver;
+};
+// solver/conjugated_gradient_descent.h:38-92 (Fletcher-Reeves beta, Armijo<F,1>)
+template <class F> class ConjugatedGradientDescent : public Solver<F, CNO_CONJUGATED_GRADIENT_DESCENT> {
+  static_assert(sizeof(typename F::ScalarType) == 8,
+                "ConjugatedGradientDescent: fp64 only (the reference computes beta in double)");
+  using Solver<F, CNO_CONJUGATED_GRADIENT_DESCENT>::Solver;
+};
 
 }  // namespace solver
 }  // namespace cppoptlib

@@ -12,13 +12,14 @@
 //   CNO_INSTANTIATE_FUNCTION(myf, MyF)    // device side: defines the symbols
 //
 // This is the "thin extern-C layer": one symbol per instantiated functor
-// (SURVEY.md 8(b)), behind which Lbfgs<MyF>/Bfgs<MyF>::Minimize launch the same
+// (SURVEY.md 8(b)), behind which Lbfgs/Bfgs/GradientDescent/ConjugatedGradientDescent<MyF>::Minimize launch the same
 // persistent kernels as the built-in families.
 #ifndef CPPOPTLIB_B200_DEVICE_CUH_
 #define CPPOPTLIB_B200_DEVICE_CUH_
 
 #include "cppoptlib.h"
 #include "cno_bfgs.cuh"
+#include "cno_descent.cuh"
 #include "cno_device.cuh"
 #include "cno_lbfgs.cuh"
 
@@ -103,6 +104,14 @@ struct BfgsDispatch<F, true> {
     if (solver == CNO_BFGS)                                                                         \
       return cno::BfgsDispatch<F>::run(fn, batch, x0, stop, out, workspace, workspace_bytes,        \
                                        stream, info);                                               \
+    if (solver == CNO_GRADIENT_DESCENT)                                                             \
+      return cno::launch_user<F, cno::DescentSmem<typename F::Scalar>>(                             \
+          cno::descent_minimize_kernel<F, false>, fn, batch, x0, stop, out, workspace,              \
+          workspace_bytes, stream, info);                                                           \
+    if (solver == CNO_CONJUGATED_GRADIENT_DESCENT)                                                  \
+      return cno::launch_user<F, cno::DescentSmem<typename F::Scalar>>(                             \
+          cno::descent_minimize_kernel<F, true>, fn, batch, x0, stop, out, workspace,               \
+          workspace_bytes, stream, info);                                                           \
     return CNO_ERR_UNSUPPORTED;                                                                     \
   }
 

@@ -67,7 +67,7 @@ static void oracle_default_stop(cno_stop_t* s) {
 
 static int check_problem(int solver, const cno_problem_t* p) {
   if (!p || p->d <= 0 || p->d > CNO_MAX_D) return CNO_ERR_INVALID_ARGUMENT;
-  if (solver < CNO_LBFGS || solver > CNO_NEWTON) return CNO_ERR_INVALID_ARGUMENT;
+  if (solver < CNO_LBFGS || solver > CNO_CONJUGATED_GRADIENT_DESCENT) return CNO_ERR_INVALID_ARGUMENT;
   if (p->dtype != CNO_F64 && p->dtype != CNO_F32) return CNO_ERR_INVALID_ARGUMENT;
   switch (p->family) {
     case CNO_FN_ROSENBROCK:

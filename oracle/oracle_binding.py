@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_LIB = os.path.join(HERE, "libcno_oracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "libcno_ref.so")
 
-LBFGS, BFGS, NEWTON = 0, 1, 2
+LBFGS, BFGS, NEWTON, GRADIENT_DESCENT, CONJUGATED_GRADIENT_DESCENT = 0, 1, 2, 3, 4
 FN_ROSENBROCK, FN_DIAG_QUADRATIC, FN_HALF_SQUARED_NORM, FN_LOGISTIC, FN_DENSE_QUADRATIC = range(5)
 POLICY_WARP_TREE, POLICY_EIGEN_SSE2, POLICY_DMMA_TREE = 0, 1, 2
 
@@ -35,6 +35,18 @@ class Stop(C.Structure):
         ("condition_hessian", C.c_double), ("past", C.c_int32),
         ("past_delta", C.c_double),
     ]
+
+
+def default_stop() -> "Stop":
+    """solver/progress.h:353-431 (DefaultStoppingSolverProgress)."""
+    return Stop(10000, 1e-9, 1, 0.0, 1, 0, 1e-5, 1, 0.0, 3, 1e-6)
+
+
+def conservative_stop() -> "Stop":
+    """solver/progress.h:456-464 (ConservativeStoppingSolverProgress)."""
+    s = default_stop()
+    s.gradient_norm, s.past, s.past_delta = 5e-6, 5, 1e-10
+    return s
 
 
 class Problem(C.Structure):

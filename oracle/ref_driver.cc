@@ -4,12 +4,14 @@
 //
 // Linear algebra comes from oracle/ref_shim (an Eigen-API shim, NOT Eigen; see
 // its header for what that does and does not pin).  The control flow --
-// Solver::Minimize, Lbfgs/Bfgs/NewtonDescent::OptimizationStep,
-// MoreThuente::cvsrch/cstep, Armijo<F,2>, Progress::Update and the default
+// Solver::Minimize, Lbfgs/Bfgs/NewtonDescent/GradientDescent/
+// ConjugatedGradientDescent::OptimizationStep,
+// MoreThuente::cvsrch/cstep, Armijo<F,1> and <F,2>, Progress::Update and the default
 // stopping preset -- is the reference's own code.
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <type_traits>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -17,6 +19,8 @@
 #include "cno_oracle.h"
 #include "cppoptlib/function.h"
 #include "cppoptlib/solver/bfgs.h"
+#include "cppoptlib/solver/conjugated_gradient_descent.h"
+#include "cppoptlib/solver/gradient_descent.h"
 #include "cppoptlib/solver/lbfgs.h"
 #include "cppoptlib/solver/newton_descent.h"
 
@@ -184,6 +188,17 @@ void dispatch_solver(int solver, const cno_problem_t* prob, int64_t b,
     using Fn = Family<T, DifferentiabilityMode::First>;
     Fn f;
     run_one<T, cppoptlib::solver::Bfgs<Fn>>(f, prob, b, x0, stop, out);
+  } else if (solver == CNO_GRADIENT_DESCENT) {
+    using Fn = Family<T, DifferentiabilityMode::First>;
+    Fn f;
+    run_one<T, cppoptlib::solver::GradientDescent<Fn>>(f, prob, b, x0, stop, out);
+  } else if (solver == CNO_CONJUGATED_GRADIENT_DESCENT) {
+    // fp64 only: the reference mixes a `double beta` into ScalarType vectors (:76-78)
+    if constexpr (std::is_same_v<T, double>) {
+      using Fn = Family<T, DifferentiabilityMode::First>;
+      Fn f;
+      run_one<T, cppoptlib::solver::ConjugatedGradientDescent<Fn>>(f, prob, b, x0, stop, out);
+    }
   } else {
     using Fn = Family<T, DifferentiabilityMode::Second>;
     Fn f;

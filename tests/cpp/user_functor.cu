@@ -1,7 +1,8 @@
 // tests/cpp/user_functor.cu -- a USER objective written against the public
 // headers: derives from FunctionCRTP like with the reference (README.md:21-28),
 // is compiled for the device by CNO_INSTANTIATE_FUNCTION, and is minimised by
-// the same persistent kernels through solver::Lbfgs / solver::Bfgs.
+// the same persistent kernels through solver::Lbfgs / Bfgs / GradientDescent /
+// ConjugatedGradientDescent.
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -59,6 +60,8 @@ int main() {
   bad += run<cppoptlib::solver::Lbfgs<Bowl64>, Bowl64, 64>("Lbfgs<Bowl<64>>", 0.75);
   bad += run<cppoptlib::solver::Lbfgs<Bowl16>, Bowl16, 16>("Lbfgs<Bowl<16>>", -2.5);
   bad += run<cppoptlib::solver::Bfgs<Bowl16>, Bowl16, 16>("Bfgs<Bowl<16>>", -2.5);
+  bad += run<cppoptlib::solver::GradientDescent<Bowl16>, Bowl16, 16>("GradientDescent<Bowl<16>>", -2.5);
+  bad += run<cppoptlib::solver::ConjugatedGradientDescent<Bowl64>, Bowl64, 64>("ConjugatedGradientDescent<Bowl<64>>", 0.75);
   if (!bad) std::printf("PASS\n");
   return bad;
 }

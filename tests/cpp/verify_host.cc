@@ -41,12 +41,29 @@ void solve_far_near() {
   }
 }
 
+// SOLVE_PROBLEM_CONSERVATIVE of verify.cc:138-154 (conservative stopping preset).
+template <template <class> class Sol, class Function>
+void solve_far_near_conservative() {
+  using Solver = Sol<Function>;
+  using StateType = cppoptlib::function::BatchedFunctionState<double, 2>;
+  Function f;
+  auto initial_state = StateType::FromHost({15.0, 8.0, -1.0, 2.0}, 2);
+  auto progress = cppoptlib::solver::ConservativeStoppingSolverProgress<Function, StateType>();
+  Solver solver(progress);
+  auto [solution, solver_state] = solver.Minimize(f, initial_state);
+  const std::vector<double> x = solution.x.ToHost();
+  for (int b = 0; b < 2; ++b) EXPECT_NEAR(0.0, rosen2(&x[2 * b]), PRECISION);
+}
+
 int main() {
   using namespace cppoptlib;
   // SOLVER_SETUP(Bfgs, RosenbrockGradient), (Lbfgs, ...), (NewtonDescent, RosenbrockFull): verify.cc:187-192
   solve_far_near<solver::Lbfgs, function::Rosenbrock<double, 2>>();
   solve_far_near<solver::Bfgs, function::Rosenbrock<double, 2>>();
   solve_far_near<solver::NewtonDescent, function::RosenbrockFull<double, 2>>();
+  // SOLVER_SETUP_CONSERVATIVE(GradientDescent, ...), SOLVER_SETUP(ConjugatedGradientDescent, ...): verify.cc:185-186
+  solve_far_near_conservative<solver::GradientDescent, function::Rosenbrock<double, 2>>();
+  solve_far_near<solver::ConjugatedGradientDescent, function::Rosenbrock<double, 2>>();
 
   {  // Dockerfile.test:30-45
     function::DiagQuadratic<double> f;

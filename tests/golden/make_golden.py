@@ -3,7 +3,8 @@
 container.  /root/reference does not exist on the GPU box, so the vectors are
 committed; rerun this script here to regenerate them:
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # everything
+    python tests/golden/make_golden.py gd_ cg_    # only the cases whose name starts with gd_ / cg_
 """
 import os
 import sys
@@ -27,12 +28,19 @@ CASES = [
     ("lbfgs_rosenbrock_d128_f64_eigen_sse2", ob.LBFGS, ob.FN_ROSENBROCK, 128, np.float64, 24),
     ("bfgs_rosenbrock_d32_f64", ob.BFGS, ob.FN_ROSENBROCK, 32, np.float64, 48),
     ("bfgs_rosenbrock_d2_f64", ob.BFGS, ob.FN_ROSENBROCK, 2, np.float64, 32),
+    ("gd_rosenbrock_d8_f64", ob.GRADIENT_DESCENT, ob.FN_ROSENBROCK, 8, np.float64, 16),
+    ("gd_rosenbrock_d37_f32", ob.GRADIENT_DESCENT, ob.FN_ROSENBROCK, 37, np.float32, 8),
+    ("cg_rosenbrock_d8_f64", ob.CONJUGATED_GRADIENT_DESCENT, ob.FN_ROSENBROCK, 8, np.float64, 16),
+    ("cg_rosenbrock_d2_f64", ob.CONJUGATED_GRADIENT_DESCENT, ob.FN_ROSENBROCK, 2, np.float64, 32),
 ]
 
 
 def main():
     assert ob.ref_available(), "oracle/_ref is not built (needs /root/reference)"
+    only = tuple(sys.argv[1:])
     for name, solver, family, d, dtype, B in CASES:
+        if only and not name.startswith(only):
+            continue
         x0 = ob.fill_uniform((B, d), 0, SEED, -2.0, 2.0, dtype)
         policy = ob.POLICY_EIGEN_SSE2 if name.endswith("_eigen_sse2") else None
         r = ob.minimize(solver, family, x0, impl="ref", policy=policy)
@@ -41,6 +49,8 @@ def main():
                             status=r["status"], nfev=r["nfev"], solver=solver, family=family,
                             policy=(policy if policy is not None else ob.device_policy(dtype)))
         print(name, "mean iters", r["num_iterations"].mean())
+    if only and "pins" not in only:
+        return
     # the two verify.cc starts + Dockerfile.test + AL-test half norm (reference code, d = 2)
     pins = {}
     for tag, solver, family, x0 in [
@@ -52,6 +62,10 @@ def main():
         ("newton_near", ob.NEWTON, ob.FN_ROSENBROCK, [-1.0, 2.0]),
         ("lbfgs_quadratic", ob.LBFGS, ob.FN_DIAG_QUADRATIC, [-10.0, 2.0]),
         ("lbfgs_halfnorm", ob.LBFGS, ob.FN_HALF_SQUARED_NORM, [5.0, 5.0]),
+        ("gd_far", ob.GRADIENT_DESCENT, ob.FN_ROSENBROCK, [15.0, 8.0]),
+        ("gd_near", ob.GRADIENT_DESCENT, ob.FN_ROSENBROCK, [-1.0, 2.0]),
+        ("cg_far", ob.CONJUGATED_GRADIENT_DESCENT, ob.FN_ROSENBROCK, [15.0, 8.0]),
+        ("cg_near", ob.CONJUGATED_GRADIENT_DESCENT, ob.FN_ROSENBROCK, [-1.0, 2.0]),
     ]:
         r = ob.minimize(solver, family, np.array([x0]), impl="ref")
         pins[tag + "_x"] = r["x"][0]

@@ -105,6 +105,24 @@ def test_verify_cc_rosenbrock_far_near(impl, solver, x0):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("x0", [[15.0, 8.0], [-1.0, 2.0]])
+def test_verify_cc_gradient_descent_far_near(impl, x0):
+    """SOLVER_SETUP_CONSERVATIVE(GradientDescent, RosenbrockGradient), verify.cc:185."""
+    r = ob.minimize(ob.GRADIENT_DESCENT, ob.FN_ROSENBROCK, np.array([x0]), impl=impl,
+                    stop=ob.conservative_stop())
+    assert abs(_rosen2(r["x"][0])) < PRECISION
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("x0", [[15.0, 8.0], [-1.0, 2.0]])
+def test_verify_cc_conjugated_gradient_descent_far_near(impl, x0):
+    """SOLVER_SETUP(ConjugatedGradientDescent, RosenbrockGradient), verify.cc:186."""
+    r = ob.minimize(ob.CONJUGATED_GRADIENT_DESCENT, ob.FN_ROSENBROCK, np.array([x0]), impl=impl)
+    assert abs(_rosen2(r["x"][0])) < PRECISION
+    assert r["status"][0] != 1
+
+
+@pytest.mark.parametrize("impl", IMPLS)
 def test_dockerfile_quadratic(impl):  # Dockerfile.test:35-42
     r = ob.minimize(ob.LBFGS, ob.FN_DIAG_QUADRATIC, np.array([[-10.0, 2.0]]), impl=impl)
     assert abs(r["x"][0, 0]) < 1e-4 and abs(r["x"][0, 1]) < 1e-4
@@ -152,6 +170,24 @@ def test_oracle_equals_reference_headers(dtype, policy, solver, d):
     assert _same(a, b)
 
 
+@pytest.mark.parametrize("policy", [ob.POLICY_WARP_TREE, ob.POLICY_EIGEN_SSE2, ob.POLICY_DMMA_TREE])
+@pytest.mark.parametrize("solver,dtype,d", [
+    (ob.GRADIENT_DESCENT, np.float64, 2), (ob.GRADIENT_DESCENT, np.float64, 8),
+    (ob.GRADIENT_DESCENT, np.float64, 37), (ob.GRADIENT_DESCENT, np.float32, 37),
+    (ob.CONJUGATED_GRADIENT_DESCENT, np.float64, 2), (ob.CONJUGATED_GRADIENT_DESCENT, np.float64, 8),
+    (ob.CONJUGATED_GRADIENT_DESCENT, np.float64, 37)])
+def test_oracle_descent_solvers_equal_reference_headers(policy, solver, dtype, d):
+    """gradient_descent.h / conjugated_gradient_descent.h / armijo.h:52-68 compiled from the reference."""
+    if not ob.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    x0 = ob.fill_uniform((8, d), 77 * d, 5, -2.0, 2.0, dtype)
+    stop = ob.default_stop()
+    stop.num_iterations = 400  # bounded: these solvers crawl on Rosenbrock
+    a = ob.minimize(solver, ob.FN_ROSENBROCK, x0, policy=policy, impl="oracle", stop=stop)
+    b = ob.minimize(solver, ob.FN_ROSENBROCK, x0, policy=policy, impl="ref", stop=stop)
+    assert _same(a, b)
+
+
 def test_oracle_equals_reference_dense_quadratic():
     if not ob.ref_available():
         pytest.skip("oracle/_ref not built")
@@ -170,7 +206,7 @@ def test_oracle_equals_reference_dense_quadratic():
         assert np.allclose(a["x"], xs, atol=1e-4)
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*_rosenbrock_*.npz"))))
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*_rosenbrock_*.npz"))))  # incl. gd_*, cg_*
 def test_oracle_reproduces_committed_reference_fixtures(path):
     """Fixtures were produced by oracle/_ref (tests/golden/make_golden.py)."""
     z = np.load(path)
