@@ -34,6 +34,24 @@ thread_local cno_launch_info_t g_last_info;
     }                                        \
   } while (0)
 
+// Owners for the CUDA objects the entry points create, so that every early return
+// (CNO_CUDA, a failing launcher) releases them.
+struct EventOwner {
+  cudaEvent_t e = nullptr;
+  ~EventOwner() { if (e) cudaEventDestroy(e); }
+  cudaError_t create() { return cudaEventCreate(&e); }
+};
+struct StreamOwner {
+  cudaStream_t s = nullptr;
+  ~StreamOwner() { if (s) cudaStreamDestroy(s); }
+  cudaError_t create() { return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); }
+};
+struct DeviceBuffer {
+  void* p = nullptr;
+  ~DeviceBuffer() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+};
+
 int device_sm_count(int* sms) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -478,22 +496,20 @@ int cno_minimize(int solver, const cno_problem_t* problem, int64_t batch, const 
   if (batch == 0) return CNO_OK;
 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  EventOwner e0, e1;
   if (info) {
-    CNO_CUDA(cudaEventCreate(&e0));
-    CNO_CUDA(cudaEventCreate(&e1));
-    CNO_CUDA(cudaEventRecord(e0, s));
+    CNO_CUDA(e0.create());
+    CNO_CUDA(e1.create());
+    CNO_CUDA(cudaEventRecord(e0.e, s));
   }
   const LaunchArgs a{problem, (long long)batch, x0, stop, out, workspace, s, info};
   rc = find_entry(solver, problem)->fn(a);
   if (rc) return rc;
   if (info) {
-    CNO_CUDA(cudaEventRecord(e1, s));
-    CNO_CUDA(cudaEventSynchronize(e1));
-    CNO_CUDA(cudaEventElapsedTime(&info->kernel_ms, e0, e1));
+    CNO_CUDA(cudaEventRecord(e1.e, s));
+    CNO_CUDA(cudaEventSynchronize(e1.e));
+    CNO_CUDA(cudaEventElapsedTime(&info->kernel_ms, e0.e, e1.e));
     info->total_ms = info->kernel_ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     g_last_info = *info;
   }
   return CNO_OK;
@@ -534,11 +550,11 @@ int cno_minimize_steps(int solver, const cno_problem_t* problem, int64_t batch, 
   if (stop->past > CNO_MAX_PAST || stop->past < 0) return CNO_ERR_INVALID_ARGUMENT;
   if (!have_device()) return CNO_ERR_NO_DEVICE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  EventOwner e0, e1;
   if (info) {
-    CNO_CUDA(cudaEventCreate(&e0));
-    CNO_CUDA(cudaEventCreate(&e1));
-    CNO_CUDA(cudaEventRecord(e0, s));
+    CNO_CUDA(e0.create());
+    CNO_CUDA(e1.create());
+    CNO_CUDA(cudaEventRecord(e0.e, s));
   }
   LaunchArgs a{problem, (long long)batch, x0, stop, out, workspace, s, info};
   a.resume = cno::ResumeArgs{static_cast<unsigned char*>(state), (long long)stride, max_iterations,
@@ -546,12 +562,10 @@ int cno_minimize_steps(int solver, const cno_problem_t* problem, int64_t batch, 
   rc = e->steps_fn(a);
   if (rc) return rc;
   if (info) {
-    CNO_CUDA(cudaEventRecord(e1, s));
-    CNO_CUDA(cudaEventSynchronize(e1));
-    CNO_CUDA(cudaEventElapsedTime(&info->kernel_ms, e0, e1));
+    CNO_CUDA(cudaEventRecord(e1.e, s));
+    CNO_CUDA(cudaEventSynchronize(e1.e));
+    CNO_CUDA(cudaEventElapsedTime(&info->kernel_ms, e0.e, e1.e));
     info->total_ms = info->kernel_ms;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
   }
   return CNO_OK;
 }
@@ -566,15 +580,23 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, c
   cno_launch_info_t local;
   memset(&local, 0, sizeof(local));
   if (batch == 0) { if (info) *info = local; return CNO_OK; }
+  cno_stop_t dflt;
+  if (!stop) { cno_default_stop(&dflt); stop = &dflt; }
+  if (stop->past > CNO_MAX_PAST || stop->past < 0) return CNO_ERR_INVALID_ARGUMENT;
 
   const size_t ts = problem->dtype == CNO_F64 ? 8 : 4;
   const size_t d = (size_t)problem->d;
   const size_t vec_bytes = (size_t)batch * d * ts, sc_bytes = (size_t)batch * ts;
-  cudaStream_t s = nullptr;
-  CNO_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  cudaEvent_t e0, e1;
-  CNO_CUDA(cudaEventCreate(&e0));
-  CNO_CUDA(cudaEventCreate(&e1));
+  // declared before the arena: destroyed after it (cudaFree waits for the device)
+  StreamOwner so, so2;
+  EventOwner eo0, eo1, eo_join;
+  CNO_CUDA(so.create());
+  CNO_CUDA(so2.create());
+  CNO_CUDA(eo0.create());
+  CNO_CUDA(eo1.create());
+  CNO_CUDA(eo_join.create());
+  const cudaStream_t s = so.s, s2 = so2.s;
+  const cudaEvent_t e0 = eo0.e, e1 = eo1.e, e_start2 = eo_join.e;
 
   // One device arena: x0 | x | g | value | x_delta | f_delta | gnorm | iters | nfev | status | ws | data
   const size_t data_bytes = problem->data ? (size_t)batch * (size_t)problem->data_stride * ts : 0;
@@ -592,21 +614,18 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, c
   const size_t o_st = off; off += out->status ? up((size_t)batch) : 0;
   const size_t o_ws = off; off += kWorkspaceBytes;  // one 16-byte queue slot per chunk
   const size_t o_data = off; off += up(data_bytes);
-  unsigned char* arena = nullptr;
-  CNO_CUDA(cudaMalloc(&arena, off));
+  DeviceBuffer arena_owner;
+  CNO_CUDA(arena_owner.alloc(off));
+  unsigned char* const arena = static_cast<unsigned char*>(arena_owner.p);
 
   // Chunked pipeline on two streams: H2D of chunk c+1 and D2H of chunk c-1 overlap
   // the solve of chunk c, so only ~1/kChunks of the copy time is exposed.
-  cudaStream_t s2 = nullptr;
-  CNO_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
   cudaStream_t streams[2] = {s, s2};
   const int64_t min_chunk = 16384;
   int chunks = (int)((batch + min_chunk - 1) / min_chunk);
   if (chunks > 8) chunks = 8;
   if (chunks < 1) chunks = 1;
   const int64_t per = (batch + chunks - 1) / chunks;
-  cudaEvent_t e_start2;
-  CNO_CUDA(cudaEventCreate(&e_start2));
   CNO_CUDA(cudaEventRecord(e0, s));
   CNO_CUDA(cudaStreamWaitEvent(s2, e0, 0));  // both streams start after e0
   cno_launch_info_t kinfo;
@@ -638,14 +657,10 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, c
     dout.num_iterations = out->num_iterations ? (uint32_t*)(arena + o_it) + lo : nullptr;
     dout.nfev = out->nfev ? (uint32_t*)(arena + o_nf) + lo : nullptr;
     dout.status = out->status ? (int8_t*)(arena + o_st) + lo : nullptr;
-    cno_stop_t dflt;
-    const cno_stop_t* stp = stop;
-    if (!stp) { cno_default_stop(&dflt); stp = &dflt; }
-    if (stp->past > CNO_MAX_PAST || stp->past < 0) { cudaFree(arena); return CNO_ERR_INVALID_ARGUMENT; }
-    const LaunchArgs a{&dprob, (long long)n, arena + o_x0 + vlo, stp, &dout,
+    const LaunchArgs a{&dprob, (long long)n, arena + o_x0 + vlo, stop, &dout,
                        arena + o_ws + (size_t)c * 16, st, &kinfo};
     rc = find_entry(solver, problem)->fn(a);
-    if (rc) { cudaFree(arena); return rc; }
+    if (rc) return rc;
     auto down = [&](void* host, size_t o, size_t off, size_t bytes) -> cudaError_t {
       if (!host) return cudaSuccess;
       local.d2h_bytes += (int64_t)bytes;
@@ -673,12 +688,6 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, c
   local.d2h_bytes = d2h;
   local.total_ms = ms;
   local.kernel_ms = ms;
-  cudaFree(arena);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaEventDestroy(e_start2);
-  cudaStreamDestroy(s);
-  cudaStreamDestroy(s2);
   if (info) *info = local;
   g_last_info = local;
   return CNO_OK;
@@ -715,10 +724,11 @@ int cno_done_bitmap(const int8_t* status, int64_t batch, uint32_t* words, void* 
 int cno_device_cstep(double io[11], int* brackt, int* info, int* ret) {
   if (!io || !brackt || !info || !ret) return CNO_ERR_INVALID_ARGUMENT;
   if (!have_device()) return CNO_ERR_NO_DEVICE;
-  double* dio = nullptr;
-  int* dfl = nullptr;
-  CNO_CUDA(cudaMalloc(&dio, 11 * sizeof(double)));
-  CNO_CUDA(cudaMalloc(&dfl, 3 * sizeof(int)));
+  DeviceBuffer bio, bfl;
+  CNO_CUDA(bio.alloc(11 * sizeof(double)));
+  CNO_CUDA(bfl.alloc(3 * sizeof(int)));
+  double* const dio = static_cast<double*>(bio.p);
+  int* const dfl = static_cast<int*>(bfl.p);
   int fl[3] = {*brackt, *info, 0};
   CNO_CUDA(cudaMemcpy(dio, io, 11 * sizeof(double), cudaMemcpyHostToDevice));
   CNO_CUDA(cudaMemcpy(dfl, fl, sizeof(fl), cudaMemcpyHostToDevice));
@@ -726,8 +736,6 @@ int cno_device_cstep(double io[11], int* brackt, int* info, int* ret) {
   CNO_CUDA(cudaGetLastError());
   CNO_CUDA(cudaMemcpy(io, dio, 11 * sizeof(double), cudaMemcpyDeviceToHost));
   CNO_CUDA(cudaMemcpy(fl, dfl, sizeof(fl), cudaMemcpyDeviceToHost));
-  cudaFree(dio);
-  cudaFree(dfl);
   *brackt = fl[0];
   *info = fl[1];
   *ret = fl[2];

@@ -44,24 +44,28 @@ inline int launch_user(Kernel kernel, const Fn& fn, int64_t batch, const void* x
   const int grid = (int)(ctas < sms ? ctas : sms);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaMemsetAsync(workspace, 0, 8, s);
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (info) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, s); }
+  struct Event {  // released on every return path
+    cudaEvent_t e = nullptr;
+    ~Event() { if (e) cudaEventDestroy(e); }
+  } e0, e1;
+  if (info) {
+    if (cudaEventCreate(&e0.e) != cudaSuccess || cudaEventCreate(&e1.e) != cudaSuccess) return CNO_ERR_CUDA;
+    cudaEventRecord(e0.e, s);
+  }
   kernel<<<grid, Smem::kWarps * 32, smem, s>>>(fn, static_cast<const T*>(x0), (long long)batch,
                                                make_stop<T>(*stop), make_out<T>(*out),
                                                static_cast<unsigned long long*>(workspace), extra...);
   if (cudaGetLastError() != cudaSuccess) return CNO_ERR_CUDA;
   if (info) {
-    cudaEventRecord(e1, s);
-    cudaEventSynchronize(e1);
-    cudaEventElapsedTime(&info->kernel_ms, e0, e1);
+    cudaEventRecord(e1.e, s);
+    if (cudaEventSynchronize(e1.e) != cudaSuccess) return CNO_ERR_CUDA;
+    cudaEventElapsedTime(&info->kernel_ms, e0.e, e1.e);
     info->total_ms = info->kernel_ms;
     info->kernel_launches = 1;
     info->grid = grid;
     info->block = Smem::kWarps * 32;
     info->warps_per_cta = Smem::kWarps;
     info->dynamic_smem = (int64_t)smem;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
   }
   return CNO_OK;
 }
