@@ -15,6 +15,7 @@
 #include <omp.h>
 #endif
 
+#include "cno_al_oracle.h"
 #include "cno_oracle.h"
 
 /* ---- double ---- */
@@ -119,7 +120,7 @@ int cno_oracle_minimize(int solver, const cno_problem_t* problem, int64_t batch,
   for (int64_t b = 0; b < batch; ++b) {
     if (problem->dtype == CNO_F64) {
       minimize_one_f64(
-          solver, problem, b, (const double*)x0 + b * d, stop,
+          solver, problem, NULL, b, (const double*)x0 + b * d, stop,
           out->x ? (double*)out->x + b * d : NULL,
           out->value ? (double*)out->value + b : NULL,
           out->gradient ? (double*)out->gradient + b * d : NULL,
@@ -130,7 +131,7 @@ int cno_oracle_minimize(int solver, const cno_problem_t* problem, int64_t batch,
           out->gradient_norm ? (double*)out->gradient_norm + b : NULL);
     } else {
       minimize_one_f32(
-          solver, problem, b, (const float*)x0 + b * d, stop,
+          solver, problem, NULL, b, (const float*)x0 + b * d, stop,
           out->x ? (float*)out->x + b * d : NULL,
           out->value ? (float*)out->value + b : NULL,
           out->gradient ? (float*)out->gradient + b * d : NULL,
@@ -151,13 +152,13 @@ int cno_oracle_evaluate(const cno_problem_t* problem, int64_t batch,
   const int d = problem->d;
   for (int64_t b = 0; b < batch; ++b) {
     if (problem->dtype == CNO_F64) {
-      fnctx_t_f64 c = {problem, b, 0};
+      fnctx_t_f64 c = {problem, b, 0, NULL};
       double v = eval_f64(&c, (const double*)x + b * d,
                           g ? (double*)g + b * d : NULL,
                           H ? (double*)H + b * d * d : NULL);
       if (f) ((double*)f)[b] = v;
     } else {
-      fnctx_t_f32 c = {problem, b, 0};
+      fnctx_t_f32 c = {problem, b, 0, NULL};
       float v = eval_f32(&c, (const float*)x + b * d,
                          g ? (float*)g + b * d : NULL,
                          H ? (float*)H + b * d * d : NULL);
@@ -210,7 +211,122 @@ int cno_oracle_cstep(double io[11], int* brackt, int* info, int* ret) {
 int cno_oracle_cvsrch_f64(const cno_problem_t* problem, int64_t instance,
                           double* x, double* f, double* g, double* stp,
                           const double* s) {
-  fnctx_t_f64 c = {problem, instance, 0};
+  fnctx_t_f64 c = {problem, instance, 0, NULL};
   cvsrch_f64(&c, x, f, g, stp, s);
   return (int)c.nfev;
+}
+
+/* ---- AugmentedLagrangian (cno_al_oracle.h) ------------------------------- */
+void cno_al_oracle_default_config(cno_al_config_t* c) { /* augmented_lagrangian.h:63-239 */
+  memset(c, 0, sizeof(*c));
+  c->penalty_growth_factor = 10;
+  c->violation_shrink_ratio = 0.25;
+  c->auto_scale_initial_penalty = 1;
+  c->penalty_auto_objective_scale = 10;
+  c->penalty_auto_min = 1e-8;
+  c->penalty_auto_max = 1e8;
+  c->warmup_max_inner_iterations = 10;
+  c->warmup_inner_gradient_tolerance = 1e-2;
+  c->multiplier_max = 1e20;
+  c->kkt_gradient_tolerance = 1e-4;
+}
+
+void cno_al_oracle_default_stop(cno_al_stop_t* s) { /* progress.h:126, 353-431 */
+  s->num_iterations = 10000;
+  s->constraint_threshold = 1e-5;
+  s->kkt_stationarity_threshold = 1e-4;
+}
+
+static int check_constraints(const cno_problem_t* p, const cno_constraints_t* k) {
+  if (!k || k->n_eq < 0 || k->n_ineq < 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (k->n_eq > CNO_AL_MAX_CON || k->n_ineq > CNO_AL_MAX_CON) return CNO_ERR_UNSUPPORTED;
+  if (k->n_eq + k->n_ineq > 0 && (!k->kinds || !k->data)) return CNO_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < k->n_eq + k->n_ineq; ++i)
+    if (k->kinds[i] != CNO_CON_AFFINE && k->kinds[i] != CNO_CON_SQNORM) return CNO_ERR_INVALID_ARGUMENT;
+  if (p->mode == 2) return CNO_ERR_UNSUPPORTED; /* First-mode composite only */
+  return CNO_OK;
+}
+
+int cno_al_oracle_minimize(const cno_problem_t* objective, const cno_constraints_t* constraints,
+                           int64_t batch, const void* x0, const void* eq0, const void* ineq0,
+                           const void* penalty0, const cno_stop_t* inner_stop,
+                           const cno_al_stop_t* outer_stop, const cno_al_config_t* config,
+                           const cno_al_out_t* out, int threads) {
+  int rc = check_problem(CNO_LBFGS, objective);
+  if (rc) return rc;
+  rc = check_constraints(objective, constraints);
+  if (rc) return rc;
+  if (batch < 0 || !x0 || !out) return CNO_ERR_INVALID_ARGUMENT;
+  cno_stop_t idflt;
+  if (!inner_stop) { oracle_default_stop(&idflt); inner_stop = &idflt; }
+  if (inner_stop->past > CNO_MAX_PAST) return CNO_ERR_INVALID_ARGUMENT;
+  cno_al_stop_t odflt;
+  if (!outer_stop) { cno_al_oracle_default_stop(&odflt); outer_stop = &odflt; }
+  cno_al_config_t cdflt;
+  if (!config) { cno_al_oracle_default_config(&cdflt); config = &cdflt; }
+  const int d = objective->d, ne = constraints->n_eq, ni = constraints->n_ineq;
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#else
+  threads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (int64_t b = 0; b < batch; ++b) {
+#define CNO_AL_RUN(REAL_T, SUF)                                                                   \
+  do {                                                                                            \
+    alstate_t_##SUF* r = (alstate_t_##SUF*)malloc(sizeof(alstate_t_##SUF));                       \
+    REAL_T xd = 0, fd = 0, gn = 0;                                                                \
+    al_minimize_one_##SUF(objective, constraints, b, (const REAL_T*)x0 + b * d,                   \
+                          eq0 ? (const REAL_T*)eq0 + b * ne : NULL,                               \
+                          ineq0 ? (const REAL_T*)ineq0 + b * ni : NULL,                           \
+                          penalty0 ? ((const REAL_T*)penalty0)[b] : (REAL_T)0, inner_stop,        \
+                          outer_stop, config, r, out->num_iterations ? out->num_iterations + b : NULL, \
+                          out->status ? out->status + b : NULL, out->nfev ? out->nfev + b : NULL, \
+                          &xd, &fd, &gn);                                                         \
+    if (out->x) memcpy((REAL_T*)out->x + b * d, r->x, sizeof(REAL_T) * d);                        \
+    if (out->equality_multipliers)                                                                \
+      memcpy((REAL_T*)out->equality_multipliers + b * ne, r->lambda, sizeof(REAL_T) * ne);        \
+    if (out->inequality_multipliers)                                                              \
+      memcpy((REAL_T*)out->inequality_multipliers + b * ni, r->mu, sizeof(REAL_T) * ni);          \
+    if (out->penalty) ((REAL_T*)out->penalty)[b] = r->penalty;                                    \
+    if (out->max_violation) ((REAL_T*)out->max_violation)[b] = r->max_violation;                  \
+    if (out->max_lagrangian_gradient)                                                             \
+      ((REAL_T*)out->max_lagrangian_gradient)[b] = r->max_lagrangian_gradient;                    \
+    if (out->x_delta) ((REAL_T*)out->x_delta)[b] = xd;                                            \
+    if (out->f_delta) ((REAL_T*)out->f_delta)[b] = fd;                                            \
+    if (out->gradient_norm) ((REAL_T*)out->gradient_norm)[b] = gn;                                \
+    free(r);                                                                                      \
+  } while (0)
+    if (objective->dtype == CNO_F64) CNO_AL_RUN(double, f64);
+    else CNO_AL_RUN(float, f32);
+#undef CNO_AL_RUN
+  }
+  return CNO_OK;
+}
+
+int cno_al_oracle_evaluate(const cno_problem_t* objective, const cno_constraints_t* constraints,
+                           int64_t batch, const void* x, const void* eq, const void* ineq,
+                           const void* penalty, void* value, void* grad) {
+  int rc = check_problem(CNO_LBFGS, objective);
+  if (rc) return rc;
+  rc = check_constraints(objective, constraints);
+  if (rc) return rc;
+  if (batch < 0 || !x || !penalty) return CNO_ERR_INVALID_ARGUMENT;
+  const int d = objective->d, ne = constraints->n_eq, ni = constraints->n_ineq;
+  for (int64_t b = 0; b < batch; ++b) {
+    if (objective->dtype == CNO_F64) {
+      const alctx_t_f64 al = {constraints, eq ? (const double*)eq + b * ne : NULL,
+                              ineq ? (const double*)ineq + b * ni : NULL, ((const double*)penalty)[b]};
+      fnctx_t_f64 c = {objective, b, 0, &al};
+      const double v = eval_f64(&c, (const double*)x + b * d, grad ? (double*)grad + b * d : NULL, NULL);
+      if (value) ((double*)value)[b] = v;
+    } else {
+      const alctx_t_f32 al = {constraints, eq ? (const float*)eq + b * ne : NULL,
+                              ineq ? (const float*)ineq + b * ni : NULL, ((const float*)penalty)[b]};
+      fnctx_t_f32 c = {objective, b, 0, &al};
+      const float v = eval_f32(&c, (const float*)x + b * d, grad ? (float*)grad + b * d : NULL, NULL);
+      if (value) ((float*)value)[b] = v;
+    }
+  }
+  return CNO_OK;
 }

@@ -175,3 +175,126 @@ def cstep(io, brackt: int, info: int = 0, impl: str = "oracle"):
 
 def num_threads() -> int:
     return oracle_lib().cno_oracle_num_threads()
+
+
+# ---- AugmentedLagrangian oracle (cno_al_oracle.h; SURVEY.md 8(f) rank 1, no device path yet) ----
+CON_AFFINE, CON_SQNORM = 0, 1
+
+
+class Constraints(C.Structure):
+    _fields_ = [("n_eq", C.c_int32), ("n_ineq", C.c_int32), ("kinds", C.c_void_p),
+                ("data", C.c_void_p), ("data_stride", C.c_int64)]
+
+
+class AlConfig(C.Structure):
+    _fields_ = [("penalty_growth_factor", C.c_double), ("violation_shrink_ratio", C.c_double),
+                ("auto_scale_initial_penalty", C.c_int32), ("penalty_auto_objective_scale", C.c_double),
+                ("penalty_auto_min", C.c_double), ("penalty_auto_max", C.c_double),
+                ("warmup_max_inner_iterations", C.c_int32),
+                ("warmup_inner_gradient_tolerance", C.c_double), ("multiplier_max", C.c_double),
+                ("kkt_gradient_tolerance", C.c_double)]
+
+
+class AlStop(C.Structure):
+    _fields_ = [("num_iterations", C.c_uint64), ("constraint_threshold", C.c_double),
+                ("kkt_stationarity_threshold", C.c_double)]
+
+
+class AlOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "x", "equality_multipliers", "inequality_multipliers", "penalty", "max_violation",
+        "max_lagrangian_gradient", "num_iterations", "status", "nfev", "x_delta", "f_delta",
+        "gradient_norm")]
+
+
+def al_default_config() -> AlConfig:
+    c = AlConfig()
+    oracle_lib().cno_al_oracle_default_config(C.byref(c))
+    return c
+
+
+def al_default_stop() -> AlStop:
+    s = AlStop()
+    oracle_lib().cno_al_oracle_default_stop(C.byref(s))
+    return s
+
+
+def _constraints(kinds, rows, n_eq, dt, B, d):
+    """rows: [n_con, d+1] shared by the batch, or [B, n_con, d+1] per instance."""
+    kinds = np.ascontiguousarray(kinds, dtype=np.int32)
+    rows = np.ascontiguousarray(rows, dtype=dt)
+    n_con = kinds.shape[0]
+    assert rows.shape[-2:] == (n_con, d + 1) or n_con == 0
+    stride = 0 if rows.ndim == 2 else n_con * (d + 1)
+    assert rows.ndim == 2 or rows.shape[0] == B
+    k = Constraints(n_eq, n_con - n_eq, kinds.ctypes.data if n_con else None,
+                    rows.ctypes.data if n_con else None, stride)
+    return k, (kinds, rows)
+
+
+def al_minimize(family: int, x0: np.ndarray, kinds, rows, n_eq: int, *, eq0=None, ineq0=None,
+                penalty0=None, inner_stop: Stop | None = None, outer_stop: AlStop | None = None,
+                config: AlConfig | None = None, policy: int | None = None, data=None, threads: int = 0,
+                impl: str = "oracle") -> dict:
+    """AugmentedLagrangian<Problem, Lbfgs>::Minimize per instance: the C restatement ("oracle")
+    or the reference's own headers on the Eigen-API shim ("ref")."""
+    x0 = np.ascontiguousarray(x0)
+    B, d = x0.shape
+    dt = x0.dtype
+    if policy is None:
+        policy = device_policy(dt)
+    if data is not None:
+        data = np.ascontiguousarray(data, dtype=dt)
+    p = Problem(family, _np_dtype(x0), d, 0, 0.0, data.ctypes.data if data is not None else None,
+                data.shape[1] if data is not None else 0, policy, 0)
+    k, keep = _constraints(kinds, rows, n_eq, dt, B, d)
+    ne, ni = k.n_eq, k.n_ineq
+    arr = lambda a, n: None if a is None else np.ascontiguousarray(np.broadcast_to(np.asarray(a, dt), (B, n)))  # noqa: E731
+    eq0, ineq0 = arr(eq0, ne), arr(ineq0, ni)
+    pen = None if penalty0 is None else np.ascontiguousarray(np.broadcast_to(np.asarray(penalty0, dt), (B,)))
+    r = dict(x=np.zeros_like(x0), equality_multipliers=np.zeros((B, ne), dt),
+             inequality_multipliers=np.zeros((B, ni), dt), penalty=np.zeros(B, dt),
+             max_violation=np.zeros(B, dt), max_lagrangian_gradient=np.zeros(B, dt),
+             num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8),
+             nfev=np.zeros(B, np.uint32), x_delta=np.zeros(B, dt), f_delta=np.zeros(B, dt),
+             gradient_norm=np.zeros(B, dt))
+    o = AlOut(*[r[n].ctypes.data for n, _ in AlOut._fields_])
+    fn = oracle_lib().cno_al_oracle_minimize if impl == "oracle" else ref_lib().cno_ref_al_minimize
+    ptr = lambda a: None if a is None else C.c_void_p(a.ctypes.data)  # noqa: E731
+    t0 = time.perf_counter()
+    rc = fn(C.byref(p), C.byref(k), C.c_int64(B), C.c_void_p(x0.ctypes.data), ptr(eq0), ptr(ineq0), ptr(pen),
+            C.byref(inner_stop) if inner_stop is not None else None,
+            C.byref(outer_stop) if outer_stop is not None else None,
+            C.byref(config) if config is not None else None, C.byref(o), threads)
+    r["seconds"] = time.perf_counter() - t0
+    del keep
+    if rc != 0:
+        raise RuntimeError(f"al minimize failed: {rc}")
+    return r
+
+
+def al_evaluate(family: int, x: np.ndarray, kinds, rows, n_eq: int, eq, ineq, penalty, *,
+                policy: int | None = None, data=None):
+    """ToAugmentedLagrangian(problem, multipliers, penalty)(x, &grad) -> (value [B], grad [B,d])."""
+    x = np.ascontiguousarray(x)
+    B, d = x.shape
+    dt = x.dtype
+    if policy is None:
+        policy = device_policy(dt)
+    if data is not None:
+        data = np.ascontiguousarray(data, dtype=dt)
+    p = Problem(family, _np_dtype(x), d, 0, 0.0, data.ctypes.data if data is not None else None,
+                data.shape[1] if data is not None else 0, policy, 0)
+    k, keep = _constraints(kinds, rows, n_eq, dt, B, d)
+    eq = np.ascontiguousarray(np.broadcast_to(np.asarray(eq, dt), (B, k.n_eq)))
+    ineq = np.ascontiguousarray(np.broadcast_to(np.asarray(ineq, dt), (B, k.n_ineq)))
+    pen = np.ascontiguousarray(np.broadcast_to(np.asarray(penalty, dt), (B,)))
+    v, g = np.zeros(B, dt), np.zeros_like(x)
+    rc = oracle_lib().cno_al_oracle_evaluate(C.byref(p), C.byref(k), C.c_int64(B), C.c_void_p(x.ctypes.data),
+                                             C.c_void_p(eq.ctypes.data), C.c_void_p(ineq.ctypes.data),
+                                             C.c_void_p(pen.ctypes.data), C.c_void_p(v.ctypes.data),
+                                             C.c_void_p(g.ctypes.data))
+    del keep
+    if rc != 0:
+        raise RuntimeError(f"al evaluate failed: {rc}")
+    return v, g

@@ -16,8 +16,10 @@
 #include <omp.h>
 #endif
 
+#include "cno_al_oracle.h"
 #include "cno_oracle.h"
 #include "cppoptlib/function.h"
+#include "cppoptlib/solver/augmented_lagrangian.h"
 #include "cppoptlib/solver/bfgs.h"
 #include "cppoptlib/solver/conjugated_gradient_descent.h"
 #include "cppoptlib/solver/gradient_descent.h"
@@ -36,6 +38,8 @@ struct Payload {
   const cno_problem_t* p = nullptr;
   int64_t instance = 0;
   mutable uint32_t nfev = 0;
+  uint32_t* shared_nfev = nullptr;  // set when the functor is cloned into expression trees
+  void count() const { if (shared_nfev) ++*shared_nfev; else ++nfev; }
 };
 
 // Chained Rosenbrock; at d = 2 the expressions are src/test/verify.cc:58-69
@@ -48,7 +52,7 @@ struct Rosenbrock : FunctionCRTP<Rosenbrock<T, Mode>, T, Mode>, Payload<T> {
   using typename Base::VectorType;
   T operator()(const VectorType& x, VectorType* gradient = nullptr,
                MatrixType* hessian = nullptr) const {
-    this->nfev++;
+    this->count();
     const int d = static_cast<int>(x.size());
     VectorType term = VectorType::Zero(d);
     if (gradient) *gradient = VectorType::Zero(d);
@@ -83,7 +87,7 @@ struct DiagQuadratic : FunctionCRTP<DiagQuadratic<T, Mode>, T, Mode>, Payload<T>
   using typename Base::VectorType;
   T operator()(const VectorType& x, VectorType* grad = nullptr,
                MatrixType* hess = nullptr) const {
-    this->nfev++;
+    this->count();
     if (grad) {
       *grad = VectorType::Zero(2);
       (*grad)[0] = 10 * x[0];
@@ -106,7 +110,7 @@ struct HalfSquaredNorm : FunctionCRTP<HalfSquaredNorm<T, Mode>, T, Mode>, Payloa
   using typename Base::VectorType;
   T operator()(const VectorType& x, VectorType* grad = nullptr,
                MatrixType* hess = nullptr) const {
-    this->nfev++;
+    this->count();
     if (grad) *grad = x;
     if (hess) *hess = MatrixType::Identity(x.size(), x.size());
     return T(0.5) * x.squaredNorm();
@@ -121,7 +125,7 @@ struct DenseQuadratic : FunctionCRTP<DenseQuadratic<T, Mode>, T, Mode>, Payload<
   using typename Base::VectorType;
   T operator()(const VectorType& x, VectorType* grad = nullptr,
                MatrixType* hess = nullptr) const {
-    this->nfev++;
+    this->count();
     const int d = this->p->d;
     const T* Ap = static_cast<const T*>(this->p->data) + this->instance * this->p->data_stride;
     MatrixType A(d, d);
@@ -219,6 +223,126 @@ int dispatch_family(int solver, const cno_problem_t* prob, int64_t b,
   }
 }
 
+// ---- AugmentedLagrangian: the reference's own
+// augmented_lagrangian.h / function_penalty.h / function_expressions.h ----------
+// One constraint functor; row = [a (d) | t] (cno_al_oracle.h).
+template <class T>
+struct Constraint : FunctionCRTP<Constraint<T>, T, DifferentiabilityMode::First> {
+  using Base = FunctionCRTP<Constraint<T>, T, DifferentiabilityMode::First>;
+  using typename Base::VectorType;
+  int kind = 0;
+  int d = 0;
+  const T* row = nullptr;
+  T operator()(const VectorType& x, VectorType* grad = nullptr) const {
+    const T t = row[d];
+    if (kind == CNO_CON_AFFINE) {
+      VectorType a(d);
+      for (int i = 0; i < d; ++i) a[i] = row[i];
+      if (grad) *grad = a;
+      return x.dot(a) - t;
+    }
+    if (grad) *grad = T(-2) * x;
+    return t - x.squaredNorm();
+  }
+};
+
+template <class T, template <class, DifferentiabilityMode> class Family>
+void al_run_one(const cno_problem_t* prob, const cno_constraints_t* cons, int64_t b, const T* x0,
+                const T* eq0, const T* ineq0, T penalty0, const cno_stop_t* inner_stop,
+                const cno_al_stop_t* ostop, const cno_al_config_t* cfg, const cno_al_out_t* out) {
+  constexpr auto Mode = DifferentiabilityMode::First;
+  using Obj = Family<T, Mode>;
+  using Expr = cppoptlib::function::FunctionExpr<T, Mode, Obj::Dimension>;
+  using Problem = cppoptlib::function::ConstrainedOptimizationProblem<T, Mode, Obj::Dimension>;
+  using Inner = cppoptlib::solver::Lbfgs<Expr>;
+  using State = cppoptlib::solver::AugmentedLagrangeState<T, Obj::Dimension>;
+  const int d = prob->d, ne = cons->n_eq, ni = cons->n_ineq;
+  uint32_t counter = 0;
+  Obj f;
+  f.p = prob;
+  f.instance = b;
+  f.shared_nfev = &counter;
+  std::vector<Expr> eqs, ineqs;
+  for (int i = 0; i < ne + ni; ++i) {
+    Constraint<T> c;
+    c.kind = cons->kinds[i];
+    c.d = d;
+    c.row = static_cast<const T*>(cons->data) + static_cast<size_t>(b) * cons->data_stride +
+            static_cast<size_t>(i) * (d + 1);
+    (i < ne ? eqs : ineqs).push_back(Expr(c));
+  }
+  Problem problem(Expr(f), eqs, ineqs);
+
+  Inner inner;  // DefaultStoppingSolverProgress (progress.h:353)
+  if (inner_stop) {
+    auto& p = inner.stopping_progress;
+    p.num_iterations = inner_stop->num_iterations;
+    p.x_delta = static_cast<T>(inner_stop->x_delta);
+    p.x_delta_violations = inner_stop->x_delta_violations;
+    p.f_delta = static_cast<T>(inner_stop->f_delta);
+    p.f_delta_violations = inner_stop->f_delta_violations;
+    p.f_delta_relative = inner_stop->f_delta_relative != 0;
+    p.gradient_norm = static_cast<T>(inner_stop->gradient_norm);
+    p.gradient_norm_relative = inner_stop->gradient_norm_relative != 0;
+    p.condition_hessian = static_cast<T>(inner_stop->condition_hessian);
+    p.past = inner_stop->past;
+    p.past_delta = static_cast<T>(inner_stop->past_delta);
+  }
+  cppoptlib::solver::AugmentedLagrangianConfig<T> config;
+  config.penalty_growth_factor = static_cast<T>(cfg->penalty_growth_factor);
+  config.violation_shrink_ratio = static_cast<T>(cfg->violation_shrink_ratio);
+  config.auto_scale_initial_penalty = cfg->auto_scale_initial_penalty != 0;
+  config.penalty_auto_objective_scale = static_cast<T>(cfg->penalty_auto_objective_scale);
+  config.penalty_auto_min = static_cast<T>(cfg->penalty_auto_min);
+  config.penalty_auto_max = static_cast<T>(cfg->penalty_auto_max);
+  config.warmup_max_inner_iterations = cfg->warmup_max_inner_iterations;
+  config.warmup_inner_gradient_tolerance = static_cast<T>(cfg->warmup_inner_gradient_tolerance);
+  config.multiplier_max = static_cast<T>(cfg->multiplier_max);
+  config.kkt_gradient_tolerance = static_cast<T>(cfg->kkt_gradient_tolerance);
+  cppoptlib::solver::AugmentedLagrangian<Problem, Inner> solver(problem, inner, config);
+  solver.stopping_progress.num_iterations = ostop->num_iterations;
+  solver.stopping_progress.constraint_threshold = static_cast<T>(ostop->constraint_threshold);
+  solver.stopping_progress.kkt_stationarity_threshold = static_cast<T>(ostop->kkt_stationarity_threshold);
+
+  typename Obj::VectorType x(d);
+  for (int i = 0; i < d; ++i) x[i] = x0[i];
+  State state(x, static_cast<size_t>(ne), static_cast<size_t>(ni), penalty0);
+  for (int i = 0; i < ne; ++i) state.multiplier_state.equality_multipliers[i] = eq0 ? eq0[i] : T(0);
+  for (int j = 0; j < ni; ++j) state.multiplier_state.inequality_multipliers[j] = ineq0 ? ineq0[j] : T(0);
+  auto [sol, prog] = solver.Minimize(problem, state);
+
+  if (out->x) for (int i = 0; i < d; ++i) static_cast<T*>(out->x)[b * d + i] = sol.x[i];
+  if (out->equality_multipliers)
+    for (int i = 0; i < ne; ++i)
+      static_cast<T*>(out->equality_multipliers)[b * ne + i] = sol.multiplier_state.equality_multipliers[i];
+  if (out->inequality_multipliers)
+    for (int j = 0; j < ni; ++j)
+      static_cast<T*>(out->inequality_multipliers)[b * ni + j] = sol.multiplier_state.inequality_multipliers[j];
+  if (out->penalty) static_cast<T*>(out->penalty)[b] = sol.penalty_state.penalty;
+  if (out->max_violation) static_cast<T*>(out->max_violation)[b] = sol.max_violation;
+  if (out->max_lagrangian_gradient) static_cast<T*>(out->max_lagrangian_gradient)[b] = sol.max_lagrangian_gradient;
+  if (out->num_iterations) out->num_iterations[b] = static_cast<uint32_t>(prog.num_iterations);
+  if (out->status) out->status[b] = static_cast<int8_t>(prog.status);
+  if (out->nfev) out->nfev[b] = counter;
+  if (out->x_delta) static_cast<T*>(out->x_delta)[b] = prog.x_delta;
+  if (out->f_delta) static_cast<T*>(out->f_delta)[b] = prog.f_delta;
+  if (out->gradient_norm) static_cast<T*>(out->gradient_norm)[b] = prog.gradient_norm;
+}
+
+template <class T>
+int al_dispatch_family(const cno_problem_t* prob, const cno_constraints_t* cons, int64_t b,
+                       const T* x0, const T* eq0, const T* ineq0, T penalty0,
+                       const cno_stop_t* inner_stop, const cno_al_stop_t* ostop,
+                       const cno_al_config_t* cfg, const cno_al_out_t* out) {
+  switch (prob->family) {
+    case CNO_FN_ROSENBROCK: al_run_one<T, Rosenbrock>(prob, cons, b, x0, eq0, ineq0, penalty0, inner_stop, ostop, cfg, out); return 0;
+    case CNO_FN_DIAG_QUADRATIC: al_run_one<T, DiagQuadratic>(prob, cons, b, x0, eq0, ineq0, penalty0, inner_stop, ostop, cfg, out); return 0;
+    case CNO_FN_HALF_SQUARED_NORM: al_run_one<T, HalfSquaredNorm>(prob, cons, b, x0, eq0, ineq0, penalty0, inner_stop, ostop, cfg, out); return 0;
+    case CNO_FN_DENSE_QUADRATIC: al_run_one<T, DenseQuadratic>(prob, cons, b, x0, eq0, ineq0, penalty0, inner_stop, ostop, cfg, out); return 0;
+    default: return CNO_ERR_UNSUPPORTED;
+  }
+}
+
 struct ScalarStub : FunctionCRTP<ScalarStub, double, DifferentiabilityMode::First> {
   double operator()(const VectorType&, VectorType* = nullptr) const { return 0.0; }
 };
@@ -246,6 +370,48 @@ int cno_ref_minimize(int solver, const cno_problem_t* problem, int64_t batch,
     int r = problem->dtype == CNO_F64
                 ? dispatch_family<double>(solver, problem, b, static_cast<const double*>(x0) + b * d, stop, out)
                 : dispatch_family<float>(solver, problem, b, static_cast<const float*>(x0) + b * d, stop, out);
+    if (r) rc = r;
+  }
+  return rc;
+}
+
+// Same contract as cno_al_oracle_minimize, executed by the reference's own
+// AugmentedLagrangian<ConstrainedOptimizationProblem, Lbfgs<FunctionExpr>>.
+int cno_ref_al_minimize(const cno_problem_t* objective, const cno_constraints_t* constraints,
+                        int64_t batch, const void* x0, const void* eq0, const void* ineq0,
+                        const void* penalty0, const cno_stop_t* inner_stop,
+                        const cno_al_stop_t* outer_stop, const cno_al_config_t* config,
+                        const cno_al_out_t* out, int threads) {
+  if (!objective || !constraints || !x0 || !out) return CNO_ERR_INVALID_ARGUMENT;
+  if (objective->family == CNO_FN_LOGISTIC) return CNO_ERR_UNSUPPORTED;
+  cno_al_stop_t odflt;
+  if (!outer_stop) { cno_al_oracle_default_stop(&odflt); outer_stop = &odflt; }
+  cno_al_config_t cdflt;
+  if (!config) { cno_al_oracle_default_config(&cdflt); config = &cdflt; }
+  Eigen::cno_policy_ref() = objective->policy;
+  const int d = objective->d, ne = constraints->n_eq, ni = constraints->n_ineq;
+  int rc = 0;
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#else
+  threads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (int64_t b = 0; b < batch; ++b) {
+    int r;
+    if (objective->dtype == CNO_F64) {
+      const double* e = eq0 ? static_cast<const double*>(eq0) + b * ne : nullptr;
+      const double* q = ineq0 ? static_cast<const double*>(ineq0) + b * ni : nullptr;
+      r = al_dispatch_family<double>(objective, constraints, b, static_cast<const double*>(x0) + b * d, e, q,
+                                     penalty0 ? static_cast<const double*>(penalty0)[b] : 0.0, inner_stop,
+                                     outer_stop, config, out);
+    } else {
+      const float* e = eq0 ? static_cast<const float*>(eq0) + b * ne : nullptr;
+      const float* q = ineq0 ? static_cast<const float*>(ineq0) + b * ni : nullptr;
+      r = al_dispatch_family<float>(objective, constraints, b, static_cast<const float*>(x0) + b * d, e, q,
+                                    penalty0 ? static_cast<const float*>(penalty0)[b] : 0.0f, inner_stop,
+                                    outer_stop, config, out);
+    }
     if (r) rc = r;
   }
   return rc;
