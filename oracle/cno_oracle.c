@@ -101,7 +101,17 @@ int cno_oracle_num_threads(void) {
 int cno_oracle_minimize(int solver, const cno_problem_t* problem, int64_t batch,
                         const void* x0, const cno_stop_t* stop,
                         const cno_batch_out_t* out, int threads) {
+  return cno_oracle_minimize_ls(solver, problem, batch, x0, stop, out, threads, CNO_LS_MORE_THUENTE);
+}
+
+int cno_oracle_minimize_ls(int solver, const cno_problem_t* problem, int64_t batch,
+                           const void* x0, const cno_stop_t* stop,
+                           const cno_batch_out_t* out, int threads, int linesearch) {
   int rc = check_problem(solver, problem);
+  if (linesearch != CNO_LS_MORE_THUENTE && linesearch != CNO_LS_HAGER_ZHANG) return CNO_ERR_INVALID_ARGUMENT;
+  if (linesearch == CNO_LS_HAGER_ZHANG && solver != CNO_LBFGS && solver != CNO_BFGS &&
+      solver != CNO_GRADIENT_DESCENT)
+    return CNO_ERR_UNSUPPORTED; /* the solvers with a LineSearch template parameter */
   if (rc) return rc;
   if (batch < 0 || !x0 || !out) return CNO_ERR_INVALID_ARGUMENT;
   cno_stop_t dflt;
@@ -120,7 +130,7 @@ int cno_oracle_minimize(int solver, const cno_problem_t* problem, int64_t batch,
   for (int64_t b = 0; b < batch; ++b) {
     if (problem->dtype == CNO_F64) {
       minimize_one_f64(
-          solver, problem, NULL, b, (const double*)x0 + b * d, stop,
+          solver, problem, NULL, linesearch, b, (const double*)x0 + b * d, stop,
           out->x ? (double*)out->x + b * d : NULL,
           out->value ? (double*)out->value + b : NULL,
           out->gradient ? (double*)out->gradient + b * d : NULL,
@@ -131,7 +141,7 @@ int cno_oracle_minimize(int solver, const cno_problem_t* problem, int64_t batch,
           out->gradient_norm ? (double*)out->gradient_norm + b : NULL);
     } else {
       minimize_one_f32(
-          solver, problem, NULL, b, (const float*)x0 + b * d, stop,
+          solver, problem, NULL, linesearch, b, (const float*)x0 + b * d, stop,
           out->x ? (float*)out->x + b * d : NULL,
           out->value ? (float*)out->value + b : NULL,
           out->gradient ? (float*)out->gradient + b * d : NULL,
@@ -152,13 +162,13 @@ int cno_oracle_evaluate(const cno_problem_t* problem, int64_t batch,
   const int d = problem->d;
   for (int64_t b = 0; b < batch; ++b) {
     if (problem->dtype == CNO_F64) {
-      fnctx_t_f64 c = {problem, b, 0, NULL};
+      fnctx_t_f64 c = {problem, b, 0, NULL, 0};
       double v = eval_f64(&c, (const double*)x + b * d,
                           g ? (double*)g + b * d : NULL,
                           H ? (double*)H + b * d * d : NULL);
       if (f) ((double*)f)[b] = v;
     } else {
-      fnctx_t_f32 c = {problem, b, 0, NULL};
+      fnctx_t_f32 c = {problem, b, 0, NULL, 0};
       float v = eval_f32(&c, (const float*)x + b * d,
                          g ? (float*)g + b * d : NULL,
                          H ? (float*)H + b * d * d : NULL);
@@ -211,9 +221,33 @@ int cno_oracle_cstep(double io[11], int* brackt, int* info, int* ret) {
 int cno_oracle_cvsrch_f64(const cno_problem_t* problem, int64_t instance,
                           double* x, double* f, double* g, double* stp,
                           const double* s) {
-  fnctx_t_f64 c = {problem, instance, 0, NULL};
+  fnctx_t_f64 c = {problem, instance, 0, NULL, 0};
   cvsrch_f64(&c, x, f, g, stp, s);
   return (int)c.nfev;
+}
+
+/* HagerZhang<F,1>::Search(x, f0, g0, s, f, alpha_init, &x_out, &f_out, &g_out)
+ * (hager_zhang.h:80-96) on the 1-D quartic of src/test/hager_zhang_test.cc with s = 1. */
+int cno_oracle_hz_search_poly(const double coef[5], double x0, double alpha_init,
+                              double* alpha, double* f_out, double* x_out, int* nfev) {
+  cno_problem_t p;
+  memset(&p, 0, sizeof(p));
+  p.family = CNO_ORACLE_FN_POLY1D;
+  p.dtype = CNO_F64;
+  p.d = 1;
+  p.data = coef;
+  p.policy = CNO_POLICY_WARP_TREE;
+  fnctx_t_f64 c = {&p, 0, 0, NULL, 1};
+  double x = x0, g = 0, s = 1.0;
+  double f = eval_f64(&c, &x, &g, NULL);
+  double a = alpha_init;
+  const uint32_t before = c.nfev;
+  hzls_f64(&c, &x, &f, &g, &a, &s);
+  if (alpha) *alpha = a;
+  if (f_out) *f_out = f;
+  if (x_out) *x_out = x;
+  if (nfev) *nfev = (int)(c.nfev - before);
+  return CNO_OK;
 }
 
 /* ---- AugmentedLagrangian (cno_al_oracle.h) ------------------------------- */
@@ -317,13 +351,13 @@ int cno_al_oracle_evaluate(const cno_problem_t* objective, const cno_constraints
     if (objective->dtype == CNO_F64) {
       const alctx_t_f64 al = {constraints, eq ? (const double*)eq + b * ne : NULL,
                               ineq ? (const double*)ineq + b * ni : NULL, ((const double*)penalty)[b]};
-      fnctx_t_f64 c = {objective, b, 0, &al};
+      fnctx_t_f64 c = {objective, b, 0, &al, 0};
       const double v = eval_f64(&c, (const double*)x + b * d, grad ? (double*)grad + b * d : NULL, NULL);
       if (value) ((double*)value)[b] = v;
     } else {
       const alctx_t_f32 al = {constraints, eq ? (const float*)eq + b * ne : NULL,
                               ineq ? (const float*)ineq + b * ni : NULL, ((const float*)penalty)[b]};
-      fnctx_t_f32 c = {objective, b, 0, &al};
+      fnctx_t_f32 c = {objective, b, 0, &al, 0};
       const float v = eval_f32(&c, (const float*)x + b * d, grad ? (float*)grad + b * d : NULL, NULL);
       if (value) ((float*)value)[b] = v;
     }

@@ -32,6 +32,19 @@ int cno_oracle_minimize(int solver, const cno_problem_t* problem, int64_t batch,
                         const void* x0, const cno_stop_t* stop,
                         const cno_batch_out_t* out, int threads);
 
+/* The LineSearch template parameter of Lbfgs / Bfgs / GradientDescent (lbfgs.h:41,
+ * bfgs.h:40, gradient_descent.h:38).  HagerZhang (linesearch/hager_zhang.h:54-552) is
+ * restated and pinned here, not on the device yet. */
+typedef enum cno_oracle_linesearch { CNO_LS_MORE_THUENTE = 0, CNO_LS_HAGER_ZHANG = 1 } cno_oracle_linesearch_t;
+int cno_oracle_minimize_ls(int solver, const cno_problem_t* problem, int64_t batch,
+                           const void* x0, const cno_stop_t* stop,
+                           const cno_batch_out_t* out, int threads, int linesearch);
+
+/* HagerZhang<F,1>::Search on the 1-D quartic (((c4 v + c3) v + c2) v + c1) v + c0 of
+ * src/test/hager_zhang_test.cc (Quadratic, Cubic, FlatQuartic) along s = +1 from x0. */
+int cno_oracle_hz_search_poly(const double coef[5], double x0, double alpha_init,
+                              double* alpha, double* f_out, double* x_out, int* nfev);
+
 /* Objective evaluation only: f[B], g[B,d] (nullable), H[B,d,d] col-major
  * (nullable; Second-mode families only). */
 int cno_oracle_evaluate(const cno_problem_t* problem, int64_t batch,

@@ -99,10 +99,14 @@ def _np_dtype(a):
     return 0 if a.dtype == np.float64 else 1
 
 
+LS_MORE_THUENTE, LS_HAGER_ZHANG = 0, 1
+
+
 def minimize(solver: int, family: int, x0: np.ndarray, *, policy: int | None = None, stop: Stop | None = None,
              data: np.ndarray | None = None, n: int = 0, param: float = 0.0, threads: int = 0,
-             impl: str = "oracle", mode: int = 0) -> dict:
-    """Runs the CPU oracle ("oracle") or the reference-headers build ("ref")."""
+             impl: str = "oracle", mode: int = 0, linesearch: int = LS_MORE_THUENTE) -> dict:
+    """Runs the CPU oracle ("oracle") or the reference-headers build ("ref").  linesearch = the
+    LineSearch template parameter of Lbfgs / Bfgs / GradientDescent (HagerZhang: oracle only)."""
     x0 = np.ascontiguousarray(x0)
     assert x0.dtype in (np.float64, np.float32) and x0.ndim == 2
     B, d = x0.shape
@@ -121,10 +125,10 @@ def minimize(solver: int, family: int, x0: np.ndarray, *, policy: int | None = N
     o = BatchOut(*[r[k].ctypes.data for k in (
         "x", "value", "gradient", "num_iterations", "status", "nfev", "x_delta", "f_delta",
         "gradient_norm")])
-    fn = oracle_lib().cno_oracle_minimize if impl == "oracle" else ref_lib().cno_ref_minimize
+    fn = oracle_lib().cno_oracle_minimize_ls if impl == "oracle" else ref_lib().cno_ref_minimize_ls
     t0 = time.perf_counter()
     rc = fn(solver, C.byref(p), C.c_int64(B), C.c_void_p(x0.ctypes.data),
-            C.byref(stop) if stop is not None else None, C.byref(o), threads)
+            C.byref(stop) if stop is not None else None, C.byref(o), threads, linesearch)
     r["seconds"] = time.perf_counter() - t0
     if rc != 0:
         raise RuntimeError(f"oracle minimize failed: {rc}")
@@ -298,3 +302,13 @@ def al_evaluate(family: int, x: np.ndarray, kinds, rows, n_eq: int, eq, ineq, pe
     if rc != 0:
         raise RuntimeError(f"al evaluate failed: {rc}")
     return v, g
+
+
+def hz_search_poly(coef, x0: float, alpha_init: float, impl: str = "oracle"):
+    """HagerZhang<F,1>::Search on the quartic (((c4 v + c3) v + c2) v + c1) v + c0 along s = +1
+    (RunSearch of src/test/hager_zhang_test.cc:87-99).  Returns (alpha, f_at, x_at, nfev)."""
+    k = (C.c_double * 5)(*[float(v) for v in coef])
+    a, f, x, n = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int(0)
+    fn = oracle_lib().cno_oracle_hz_search_poly if impl == "oracle" else ref_lib().cno_ref_hz_search_poly
+    fn(k, C.c_double(x0), C.c_double(alpha_init), C.byref(a), C.byref(f), C.byref(x), C.byref(n))
+    return a.value, f.value, x.value, n.value

@@ -19,6 +19,7 @@
 #include "cno_al_oracle.h"
 #include "cno_oracle.h"
 #include "cppoptlib/function.h"
+#include "cppoptlib/linesearch/hager_zhang.h"
 #include "cppoptlib/solver/augmented_lagrangian.h"
 #include "cppoptlib/solver/bfgs.h"
 #include "cppoptlib/solver/conjugated_gradient_descent.h"
@@ -176,6 +177,30 @@ void run_one(Fn& f, const cno_problem_t* prob, int64_t b, const T* x0,
   if (out->gradient_norm) static_cast<T*>(out->gradient_norm)[b] = state.gradient_norm;
 }
 
+// The LineSearch template parameter (lbfgs.h:41, bfgs.h:40, gradient_descent.h:38).
+template <class T, template <class, DifferentiabilityMode> class Family>
+void dispatch_solver_hager_zhang(int solver, const cno_problem_t* prob, int64_t b, const T* x0,
+                                 const cno_stop_t* stop, const cno_batch_out_t* out) {
+  namespace ls = cppoptlib::solver::linesearch;
+  if (solver == CNO_LBFGS && prob->mode == 2) {
+    using Fn = Family<T, DifferentiabilityMode::Second>;
+    Fn f;
+    run_one<T, cppoptlib::solver::Lbfgs<Fn, 10, ls::HagerZhang>>(f, prob, b, x0, stop, out);
+  } else if (solver == CNO_LBFGS) {
+    using Fn = Family<T, DifferentiabilityMode::First>;
+    Fn f;
+    run_one<T, cppoptlib::solver::Lbfgs<Fn, 10, ls::HagerZhang>>(f, prob, b, x0, stop, out);
+  } else if (solver == CNO_BFGS) {
+    using Fn = Family<T, DifferentiabilityMode::First>;
+    Fn f;
+    run_one<T, cppoptlib::solver::Bfgs<Fn, ls::HagerZhang>>(f, prob, b, x0, stop, out);
+  } else {
+    using Fn = Family<T, DifferentiabilityMode::First>;
+    Fn f;
+    run_one<T, cppoptlib::solver::GradientDescent<Fn, ls::HagerZhang>>(f, prob, b, x0, stop, out);
+  }
+}
+
 template <class T, template <class, DifferentiabilityMode> class Family>
 void dispatch_solver(int solver, const cno_problem_t* prob, int64_t b,
                      const T* x0, const cno_stop_t* stop,
@@ -213,7 +238,15 @@ void dispatch_solver(int solver, const cno_problem_t* prob, int64_t b,
 template <class T>
 int dispatch_family(int solver, const cno_problem_t* prob, int64_t b,
                     const T* x0, const cno_stop_t* stop,
-                    const cno_batch_out_t* out) {
+                    const cno_batch_out_t* out, int linesearch = CNO_LS_MORE_THUENTE) {
+  if (linesearch == CNO_LS_HAGER_ZHANG) {
+    switch (prob->family) {
+      case CNO_FN_ROSENBROCK: dispatch_solver_hager_zhang<T, Rosenbrock>(solver, prob, b, x0, stop, out); return 0;
+      case CNO_FN_DIAG_QUADRATIC: dispatch_solver_hager_zhang<T, DiagQuadratic>(solver, prob, b, x0, stop, out); return 0;
+      case CNO_FN_HALF_SQUARED_NORM: dispatch_solver_hager_zhang<T, HalfSquaredNorm>(solver, prob, b, x0, stop, out); return 0;
+      default: return CNO_ERR_UNSUPPORTED;
+    }
+  }
   switch (prob->family) {
     case CNO_FN_ROSENBROCK: dispatch_solver<T, Rosenbrock>(solver, prob, b, x0, stop, out); return 0;
     case CNO_FN_DIAG_QUADRATIC: dispatch_solver<T, DiagQuadratic>(solver, prob, b, x0, stop, out); return 0;
@@ -343,6 +376,21 @@ int al_dispatch_family(const cno_problem_t* prob, const cno_constraints_t* cons,
   }
 }
 
+// The 1-D quartic of src/test/hager_zhang_test.cc:40-85, Horner form (cno_oracle_hz_search_poly).
+struct Poly1D : FunctionCRTP<Poly1D, double, DifferentiabilityMode::First, 1> {
+  double c4 = 0, c3 = 0, c2 = 0, c1 = 0, c0 = 0;
+  mutable int nfev = 0;
+  double operator()(const VectorType& x, VectorType* grad = nullptr) const {
+    ++nfev;
+    const double v = x[0];
+    if (grad) {
+      grad->resize(1);
+      (*grad)[0] = ((4.0 * c4 * v + 3.0 * c3) * v + 2.0 * c2) * v + c1;
+    }
+    return (((c4 * v + c3) * v + c2) * v + c1) * v + c0;
+  }
+};
+
 struct ScalarStub : FunctionCRTP<ScalarStub, double, DifferentiabilityMode::First> {
   double operator()(const VectorType&, VectorType* = nullptr) const { return 0.0; }
 };
@@ -351,11 +399,44 @@ struct ScalarStub : FunctionCRTP<ScalarStub, double, DifferentiabilityMode::Firs
 
 extern "C" {
 
+int cno_ref_minimize_ls(int solver, const cno_problem_t* problem, int64_t batch, const void* x0,
+                        const cno_stop_t* stop, const cno_batch_out_t* out, int threads, int linesearch);
+
 // Same contract as cno_oracle_minimize, executed by the reference's own code.
 int cno_ref_minimize(int solver, const cno_problem_t* problem, int64_t batch,
                      const void* x0, const cno_stop_t* stop,
                      const cno_batch_out_t* out, int threads) {
+  return cno_ref_minimize_ls(solver, problem, batch, x0, stop, out, threads, CNO_LS_MORE_THUENTE);
+}
+
+// RunSearch of src/test/hager_zhang_test.cc:87-99 on the quartic.
+int cno_ref_hz_search_poly(const double coef[5], double x0, double alpha_init, double* alpha,
+                           double* f_out, double* x_out, int* nfev) {
+  Poly1D phi;
+  phi.c4 = coef[0]; phi.c3 = coef[1]; phi.c2 = coef[2]; phi.c1 = coef[3]; phi.c0 = coef[4];
+  using Line1D = Eigen::Matrix<double, 1, 1>;
+  Line1D x, s, xo, g0, go;
+  x[0] = x0;
+  s[0] = 1.0;
+  double fo = 0.0;
+  const double f0 = phi(x, &g0);
+  const int before = phi.nfev;
+  const double a = cppoptlib::solver::linesearch::HagerZhang<Poly1D, 1>::Search(x, f0, g0, s, phi, alpha_init,
+                                                                                &xo, &fo, &go);
+  if (alpha) *alpha = a;
+  if (f_out) *f_out = fo;
+  if (x_out) *x_out = xo[0];
+  if (nfev) *nfev = phi.nfev - before;
+  return 0;
+}
+
+// Same contract as cno_oracle_minimize_ls.
+int cno_ref_minimize_ls(int solver, const cno_problem_t* problem, int64_t batch, const void* x0,
+                        const cno_stop_t* stop, const cno_batch_out_t* out, int threads, int linesearch) {
   if (!problem || !x0 || !out) return CNO_ERR_INVALID_ARGUMENT;
+  if (linesearch == CNO_LS_HAGER_ZHANG && solver != CNO_LBFGS && solver != CNO_BFGS &&
+      solver != CNO_GRADIENT_DESCENT)
+    return CNO_ERR_UNSUPPORTED;
   if (problem->family == CNO_FN_LOGISTIC) return CNO_ERR_UNSUPPORTED;
   Eigen::cno_policy_ref() = problem->policy;
   const int d = problem->d;
@@ -368,8 +449,8 @@ int cno_ref_minimize(int solver, const cno_problem_t* problem, int64_t batch,
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
   for (int64_t b = 0; b < batch; ++b) {
     int r = problem->dtype == CNO_F64
-                ? dispatch_family<double>(solver, problem, b, static_cast<const double*>(x0) + b * d, stop, out)
-                : dispatch_family<float>(solver, problem, b, static_cast<const float*>(x0) + b * d, stop, out);
+                ? dispatch_family<double>(solver, problem, b, static_cast<const double*>(x0) + b * d, stop, out, linesearch)
+                : dispatch_family<float>(solver, problem, b, static_cast<const float*>(x0) + b * d, stop, out, linesearch);
     if (r) rc = r;
   }
   return rc;
