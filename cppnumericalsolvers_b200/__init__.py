@@ -11,12 +11,13 @@ from .function import (BatchedFunctionState, DenseQuadratic, DiagQuadratic,  # n
                        RosenbrockFull)
 from .solver import (BatchedProgress, Bfgs, ConjugatedGradientDescent,  # noqa: F401
                      ConservativeStoppingSolverProgress, DefaultStoppingSolverProgress,
-                     GradientDescent, Lbfgs, NewtonDescent, Progress, Solver, Status, fill_uniform)
+                     GradientDescent, Lbfgs, NewtonDescent, PrintProgressCallback, Progress, Solver,
+                     Status, fill_uniform)
 
 __all__ = [
     "BatchedFunctionState", "BatchedProgress", "Bfgs", "ConjugatedGradientDescent",
     "ConservativeStoppingSolverProgress", "GradientDescent",
     "DefaultStoppingSolverProgress", "DenseQuadratic", "DiagQuadratic", "DifferentiabilityMode",
-    "Function", "HalfSquaredNorm", "Lbfgs", "Logistic", "NewtonDescent", "Progress",
+    "Function", "HalfSquaredNorm", "Lbfgs", "Logistic", "NewtonDescent", "PrintProgressCallback", "Progress",
     "Rosenbrock", "RosenbrockFull", "Solver", "Status", "fill_uniform",
 ]

@@ -293,6 +293,46 @@ class ConjugatedGradientDescent(Solver):
     _solver_id = _lib.CONJUGATED_GRADIENT_DESCENT
 
 
+def _eigen_row(v) -> str:
+    """`stream << vector.transpose()` with Eigen's default IOFormat on a default stream: every
+    coefficient printed with 6 significant digits, right-aligned to the widest one, one space apart."""
+    cells = ["%g" % float(c) for c in v]
+    width = max((len(c) for c in cells), default=0)
+    return " ".join(c.rjust(width) for c in cells)
+
+
+def PrintProgressCallback(output_stream=None, instance: int = 0):
+    """solver/solver.h:59-130 with a batch axis: prints the reference's per-iteration block for
+    ONE instance of the batch (`instance`), followed by one line summarising the whole batch.
+    Use with `solver.SetCallback(PrintProgressCallback(sys.stdout), every=K)`; each call costs a
+    device->host read of that instance's row."""
+    import sys
+    out = output_stream if output_stream is not None else sys.stdout
+    label_width, num_width = 18, 15
+
+    def callback(function, state, progress):
+        i = instance
+        num = lambda v: ("%.6f" % float(v)).rjust(num_width)  # noqa: E731  std::fixed << setprecision(6)
+        lines = ["--- Iteration: %5d ---" % int(progress.num_iterations[i])]
+        if state.value is not None:
+            lines.append("  Value:".ljust(label_width) + num(state.value[i]))
+        lines.append("  X:".ljust(label_width) + " " + _eigen_row(state.x[i].tolist()))
+        if state.gradient is not None:
+            lines.append("  Gradient:".ljust(label_width) + " " + _eigen_row(state.gradient[i].tolist()))
+            lines.append("  Gradient Norm:".ljust(label_width) + num(progress.gradient_norm[i]))
+        lines.append("  X Delta:".ljust(label_width) + num(progress.x_delta[i]))
+        lines.append("  F Delta:".ljust(label_width) + num(progress.f_delta[i]))
+        if function.Differentiability == 2:
+            lines.append("  Hessian Cond.:".ljust(label_width) + "N/A".rjust(num_width))  # not computed (DESIGN.md 2.3)
+        running = int((progress.status == int(Status.Continue)).sum())
+        lines.append("  Batch:".ljust(label_width) + " %d of %d instances still running" % (running, state.x.shape[0]))
+        lines.append("-------------------------")
+        out.write("\n".join(lines) + "\n")
+        out.flush()
+
+    return callback
+
+
 def fill_uniform(t: torch.Tensor, first: int, seed: int, lo: float, hi: float) -> torch.Tensor:
     """Counter-based start generator on the device."""
     assert t.is_cuda and t.is_contiguous()

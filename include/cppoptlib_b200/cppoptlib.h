@@ -29,8 +29,12 @@
 #include <cuda_runtime_api.h>
 
 #include <cstdint>
+#include <cstdio>
 #include <functional>
+#include <iomanip>
 #include <memory>
+#include <ostream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -78,6 +82,14 @@ class DeviceArray {
   std::vector<T> ToHost() const {
     std::vector<T> h(n_);
     if (n_) check_cuda(cudaMemcpy(h.data(), p_, n_ * sizeof(T), cudaMemcpyDeviceToHost), "D2H");
+    return h;
+  }
+  // elements [first, first + count) only
+  std::vector<T> ToHost(size_t first, size_t count) const {
+    if (first + count > n_) throw std::out_of_range("DeviceArray::ToHost: range");
+    std::vector<T> h(count);
+    if (count)
+      check_cuda(cudaMemcpy(h.data(), static_cast<const T*>(p_) + first, count * sizeof(T), cudaMemcpyDeviceToHost), "D2H");
     return h;
   }
   T* data() const { return static_cast<T*>(p_); }
@@ -396,6 +408,61 @@ class Solver {
   CallbackType step_callback_;
   int callback_every_ = 1;
 };
+
+// solver/solver.h:59-130 with a batch axis: prints the reference's per-iteration block (label
+// width 18, numeric width 15, fixed 6 decimals; vectors through Eigen's default IOFormat) for ONE
+// instance of the batch and a line summarising the batch.  Use with
+//   solver.SetCallback(PrintProgressCallback<F>(std::cout), /*every=*/K);
+// each call reads that instance's row and the status array back from the device.
+template <class FunctionType>
+auto PrintProgressCallback(std::ostream& output_stream, int64_t instance = 0) {
+  using T = typename FunctionType::ScalarType;
+  using StateType = function::BatchedFunctionState<T, FunctionType::Dimension>;
+  return [&output_stream, instance](const FunctionType&, const StateType& state,
+                                    const BatchedProgress<T>& progress) {
+    constexpr int label_width = 18, num_width = 15, precision = 6;
+    constexpr size_t D = FunctionType::Dimension;
+    const size_t i = static_cast<size_t>(instance);
+    auto eigen_row = [](const std::vector<T>& v) {  // `ss << vector.transpose()`, default stream
+      std::vector<std::string> cells;
+      size_t width = 0;
+      for (T c : v) {
+        char buf[64];
+        std::snprintf(buf, sizeof(buf), "%g", static_cast<double>(c));
+        cells.emplace_back(buf);
+        if (cells.back().size() > width) width = cells.back().size();
+      }
+      std::string row;
+      for (size_t k = 0; k < cells.size(); ++k)
+        row += (k ? " " : "") + std::string(width - cells[k].size(), ' ') + cells[k];
+      return row;
+    };
+    std::ostream& os = output_stream;
+    os << std::fixed << std::setprecision(precision);
+    os << "--- Iteration: " << std::setw(5) << std::right << progress.num_iterations.ToHost(i, 1)[0] << " ---\n";
+    if (state.value.size() > i)
+      os << std::left << std::setw(label_width) << "  Value:" << std::right << std::setw(num_width)
+         << state.value.ToHost(i, 1)[0] << "\n";
+    os << std::left << std::setw(label_width) << "  X:" << " " << eigen_row(state.x.ToHost(i * D, D)) << "\n";
+    if (state.gradient.size() >= (i + 1) * D) {
+      os << std::left << std::setw(label_width) << "  Gradient:" << " " << eigen_row(state.gradient.ToHost(i * D, D)) << "\n";
+      os << std::left << std::setw(label_width) << "  Gradient Norm:" << std::right << std::setw(num_width)
+         << progress.gradient_norm.ToHost(i, 1)[0] << "\n";
+    }
+    os << std::left << std::setw(label_width) << "  X Delta:" << std::right << std::setw(num_width)
+       << progress.x_delta.ToHost(i, 1)[0] << "\n";
+    os << std::left << std::setw(label_width) << "  F Delta:" << std::right << std::setw(num_width)
+       << progress.f_delta.ToHost(i, 1)[0] << "\n";
+    if (FunctionType::Differentiability == function::DifferentiabilityMode::Second)
+      os << std::left << std::setw(label_width) << "  Hessian Cond.:" << std::right << std::setw(num_width) << "N/A"
+         << "\n";  // not computed
+    size_t running = 0;
+    for (int8_t st : progress.status.ToHost()) running += (st == static_cast<int8_t>(Status::Continue));
+    os << std::left << std::setw(label_width) << "  Batch:" << " " << running << " of " << progress.batch
+       << " instances still running\n";
+    os << "-------------------------" << std::endl;
+  };
+}
 
 template <class F> class Lbfgs : public Solver<F, CNO_LBFGS> { using Solver<F, CNO_LBFGS>::Solver; };
 template <class F> class Bfgs : public Solver<F, CNO_BFGS> { using Solver<F, CNO_BFGS>::Solver; };

@@ -4,6 +4,8 @@
 // Plain g++ translation unit: no nvcc, links libcno.so + libcudart.
 #include <cmath>
 #include <cstdio>
+#include <sstream>
+#include <string>
 #include <vector>
 
 #include "cppoptlib_b200/cppoptlib.h"
@@ -101,6 +103,16 @@ int main() {
     const auto a = s1.x.ToHost(), b = s2.x.ToHost();
     for (size_t i = 0; i < a.size(); ++i) EXPECT_NEAR(a[i], b[i], 0.0);
     EXPECT_NEAR(9.0, (double)calls, 0.0);  // ceil(45 / 5) rounds (the Far start takes 45 iterations)
+  }
+  {  // PrintProgressCallback (solver.h:59-130): the reference's block for one instance of the batch
+    using F = function::Rosenbrock<double, 2>;
+    solver::Lbfgs<F> s;
+    std::ostringstream log;
+    s.SetCallback(solver::PrintProgressCallback<F>(log, /*instance=*/1), 20);
+    auto [sol, prog] = s.Minimize(F{}, function::BatchedFunctionState<double, 2>::FromHost({15.0, 8.0, -1.0, 2.0}, 2));
+    const std::string text = log.str();
+    EXPECT_NEAR(0.0, (double)text.rfind("--- Iteration:    20 ---", 0), 0.0);  // first block: after 20 iterations
+    EXPECT_NEAR(1.0, text.find("  Gradient Norm:") != std::string::npos ? 1.0 : 0.0, 0.0);
   }
   if (failures == 0) std::printf("PASS\n");
   return failures != 0;
