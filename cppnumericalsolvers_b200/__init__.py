@@ -11,12 +11,13 @@ from .function import (BatchedFunctionState, DenseQuadratic, DiagQuadratic,  # n
                        RosenbrockFull)
 from .solver import (BatchedProgress, Bfgs, ConjugatedGradientDescent,  # noqa: F401
                      ConservativeStoppingSolverProgress, DefaultStoppingSolverProgress,
-                     GradientDescent, Lbfgs, NewtonDescent, PrintProgressCallback, Progress, Solver,
+                     GradientDescent, HagerZhang, Lbfgs, MoreThuente, NewtonDescent, PrintProgressCallback,
+                     Progress, Solver,
                      Status, fill_uniform)
 
 __all__ = [
     "BatchedFunctionState", "BatchedProgress", "Bfgs", "ConjugatedGradientDescent",
-    "ConservativeStoppingSolverProgress", "GradientDescent",
+    "ConservativeStoppingSolverProgress", "GradientDescent", "HagerZhang", "MoreThuente",
     "DefaultStoppingSolverProgress", "DenseQuadratic", "DiagQuadratic", "DifferentiabilityMode",
     "Function", "HalfSquaredNorm", "Lbfgs", "Logistic", "NewtonDescent", "PrintProgressCallback", "Progress",
     "Rosenbrock", "RosenbrockFull", "Solver", "Status", "fill_uniform",

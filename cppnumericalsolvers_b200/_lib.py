@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libcno.so")
 
 # enums of include/cno.h
 LBFGS, BFGS, NEWTON, GRADIENT_DESCENT, CONJUGATED_GRADIENT_DESCENT = 0, 1, 2, 3, 4
+LBFGS_HAGER_ZHANG, BFGS_HAGER_ZHANG, GRADIENT_DESCENT_HAGER_ZHANG = 5, 6, 7
 F64, F32 = 0, 1
 FN_ROSENBROCK, FN_DIAG_QUADRATIC, FN_HALF_SQUARED_NORM, FN_LOGISTIC, FN_DENSE_QUADRATIC = range(5)
 POLICY_WARP_TREE, POLICY_EIGEN_SSE2, POLICY_DMMA_TREE = 0, 1, 2

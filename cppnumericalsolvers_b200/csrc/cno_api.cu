@@ -74,13 +74,13 @@ struct LaunchArgs {
 };
 
 // One persistent launch of lbfgs_minimize_kernel<Fn, M[, kResume]>.
-template <class Fn, int M, bool kResume = false>
+template <class Fn, int M, bool kResume = false, class LS = cno::LsMoreThuente>
 int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
   using T = typename Fn::Scalar;
   using SM = cno::LbfgsSmem<T, Fn::Dim, M, cno::StageElems<Fn>::value,
                             cno::PolicyScratch<typename cno::PolicyOf<Fn>::type>::kElemsPerLane,
                             cno::FnTmemCols<Fn>::value>;
-  auto kernel = cno::lbfgs_minimize_kernel<Fn, M, kResume>;
+  auto kernel = cno::lbfgs_minimize_kernel<Fn, M, kResume, LS>;
   const size_t smem = SM::kWarpBytes * SM::kWarps;
   CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = 0;
@@ -107,11 +107,11 @@ int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
 }
 
 // One persistent launch of bfgs_minimize_kernel<Fn>.
-template <class Fn>
+template <class Fn, class LS = cno::LsMoreThuente>
 int launch_bfgs(const Fn& fn, const LaunchArgs& a) {
   using T = typename Fn::Scalar;
   using SM = cno::BfgsSmem<T, Fn::Dim>;
-  auto kernel = cno::bfgs_minimize_kernel<Fn>;
+  auto kernel = cno::bfgs_minimize_kernel<Fn, LS>;
   const size_t smem = SM::kWarpBytes * SM::kWarps;
   int sms = 0;
   int rc = device_sm_count(&sms);
@@ -137,11 +137,11 @@ int launch_bfgs(const Fn& fn, const LaunchArgs& a) {
 
 // One persistent launch of descent_minimize_kernel<Fn, kConjugate>
 // (GradientDescent / ConjugatedGradientDescent).
-template <class Fn, bool kConjugate>
+template <class Fn, bool kConjugate, class LS = cno::LsMoreThuente>
 int launch_descent(const Fn& fn, const LaunchArgs& a) {
   using T = typename Fn::Scalar;
   using SM = cno::DescentSmem<T>;
-  auto kernel = cno::descent_minimize_kernel<Fn, kConjugate>;
+  auto kernel = cno::descent_minimize_kernel<Fn, kConjugate, LS>;
   const size_t smem = SM::kWarpBytes * SM::kWarps;
   int sms = 0;
   int rc = device_sm_count(&sms);
@@ -221,6 +221,20 @@ int bfgs_half_sq_norm(const LaunchArgs& a) {
 template <class T>
 int bfgs_diag_quadratic(const LaunchArgs& a) {
   return launch_bfgs<cno::DiagQuadraticFn<T>>(cno::DiagQuadraticFn<T>{}, a);
+}
+
+// LineSearch = HagerZhang variants (CNO_*_HAGER_ZHANG)
+template <class T, int D>
+int lbfgs_rosenbrock_hz(const LaunchArgs& a) {
+  return launch_lbfgs<cno::RosenbrockFn<T, D>, CNO_LBFGS_M, false, cno::LsHagerZhang>(cno::RosenbrockFn<T, D>{}, a);
+}
+template <class T, int D>
+int bfgs_rosenbrock_hz(const LaunchArgs& a) {
+  return launch_bfgs<cno::RosenbrockFn<T, D>, cno::LsHagerZhang>(cno::RosenbrockFn<T, D>{}, a);
+}
+template <class T, int D>
+int gd_rosenbrock_hz(const LaunchArgs& a) {
+  return launch_descent<cno::RosenbrockFn<T, D>, false, cno::LsHagerZhang>(cno::RosenbrockFn<T, D>{}, a);
 }
 
 template <class T, int D, bool kConjugate>
@@ -332,6 +346,14 @@ const Entry kTable[] = {
     {CNO_CONJUGATED_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F64, 37, descent_rosenbrock<double, 37, true>},
     {CNO_CONJUGATED_GRADIENT_DESCENT, CNO_FN_ROSENBROCK, CNO_F64, 128, descent_rosenbrock<double, 128, true>},
     {CNO_CONJUGATED_GRADIENT_DESCENT, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, descent_diag_quadratic<double, true>},
+    {CNO_LBFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 2, lbfgs_rosenbrock_hz<double, 2>},
+    {CNO_LBFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock_hz<double, 37>},
+    {CNO_LBFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock_hz<double, 128>},
+    {CNO_LBFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F32, 37, lbfgs_rosenbrock_hz<float, 37>},
+    {CNO_BFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 8, bfgs_rosenbrock_hz<double, 8>},
+    {CNO_BFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 32, bfgs_rosenbrock_hz<double, 32>},
+    {CNO_GRADIENT_DESCENT_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 8, gd_rosenbrock_hz<double, 8>},
+    {CNO_GRADIENT_DESCENT_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 37, gd_rosenbrock_hz<double, 37>},
 };
 
 const Entry* find_entry(int solver, const cno_problem_t* p) {
@@ -346,7 +368,7 @@ const Entry* find_entry(int solver, const cno_problem_t* p) {
 
 int check_args(int solver, const cno_problem_t* p) {
   if (!p) return CNO_ERR_INVALID_ARGUMENT;
-  if (solver < CNO_LBFGS || solver > CNO_CONJUGATED_GRADIENT_DESCENT) return CNO_ERR_INVALID_ARGUMENT;
+  if (solver < CNO_LBFGS || solver > CNO_GRADIENT_DESCENT_HAGER_ZHANG) return CNO_ERR_INVALID_ARGUMENT;
   if (p->dtype != CNO_F64 && p->dtype != CNO_F32) return CNO_ERR_INVALID_ARGUMENT;
   if (p->d <= 0) return CNO_ERR_INVALID_ARGUMENT;
   // the reduction policy is compiled into the kernels (find_entry matches it):

@@ -46,7 +46,7 @@ __device__ __forceinline__ T gemv_row(const T (&Hrow)[D], const T* __restrict__ 
   return acc;
 }
 
-template <class Fn>
+template <class Fn, class LS = LsMoreThuente>
 __global__ void __launch_bounds__(BfgsSmem<typename Fn::Scalar, Fn::Dim>::kWarps * 32, 1)
 bfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
                      const long long batch, const StopParams<typename Fn::Scalar> stop,
@@ -119,7 +119,7 @@ bfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       // ---- MoreThuente::Search (:111-112); dginit = g.d = phi ----
       T xn[1], gn[1];
       T fn_val;
-      nfev += cvsrch<Fn, T, 1>(fn, ctx, RedCtx<T>{nullptr, lane}, x, f, g, xn, fn_val, gn, alpha_init, dir, phi);
+      nfev += LS::template search<Fn, T, 1>(fn, ctx, RedCtx<T>{nullptr, lane}, x, f, g, xn, fn_val, gn, alpha_init, dir, phi);
 
       // ---- rank-2 update (:122-133) ----
       T s[1], y[1];

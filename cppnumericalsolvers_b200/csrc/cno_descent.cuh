@@ -37,7 +37,7 @@ struct DescentSmem {
 };
 
 // kConjugate = false: GradientDescent (MoreThuente); true: ConjugatedGradientDescent (Armijo<F,1>)
-template <class Fn, bool kConjugate>
+template <class Fn, bool kConjugate, class LS = LsMoreThuente>
 __global__ void __launch_bounds__(DescentSmem<typename Fn::Scalar>::kWarps * 32, 1)
 descent_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0, const long long batch,
                         const StopParams<typename Fn::Scalar> stop,
@@ -92,7 +92,7 @@ descent_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         for (int e = 0; e < E; ++e) dir[e] = -g[e];
         nfev++;  // MoreThuente::Search evaluates (f, g) at x (more_thuente.h:69)
         // dginit = g.(-g) = -(g.g), bit for bit
-        nfev += cvsrch<Fn, T, E>(fn, ctx, RedCtx<T>{nullptr, lane}, x, f, g, xn, fn_val, gn, T(1), dir, -gg);
+        nfev += LS::template search<Fn, T, E>(fn, ctx, RedCtx<T>{nullptr, lane}, x, f, g, xn, fn_val, gn, T(1), dir, -gg);
       } else {
         // ---- conjugated_gradient_descent.h:70-84 ----
         if (uni(prog.num_iterations == 0)) {

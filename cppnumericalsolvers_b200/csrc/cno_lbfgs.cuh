@@ -167,7 +167,7 @@ struct ResumeLayout {
   static constexpr size_t kBytes = ((kInts + kNumInts * sizeof(int) + 15) / 16) * 16;
 };
 
-template <class Fn, int M, bool kResume = false>
+template <class Fn, int M, bool kResume = false, class LS = LsMoreThuente>
 __global__ void __launch_bounds__(LbfgsSmem<typename Fn::Scalar, Fn::Dim, M, StageElems<Fn>::value,
                                             PolicyScratch<typename PolicyOf<Fn>::type>::kElemsPerLane,
                                             FnTmemCols<Fn>::value>::kWarps * 32, 1)
@@ -463,7 +463,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       // ---- MoreThuente::Search (:231-232) ----
       T xn[E], gn[E];
       T fn_val;
-      nfev += cvsrch<Fn, T, E>(fn, ctx, rc, x, f, g, xn, fn_val, gn, alpha_init, sdir, dginit);
+      nfev += LS::template search<Fn, T, E>(fn, ctx, rc, x, f, g, xn, fn_val, gn, alpha_init, sdir, dginit);
 
       const T prev_value = f;
       T x_delta, gnorm_inf, x_inf;

@@ -225,6 +225,254 @@ __device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx, const Re
   }
 }
 
+// ---- HagerZhang (linesearch/hager_zhang.h:54-552), the alternative LineSearch policy ----
+//
+// The reference keeps every sample (alpha, phi, dphi) in a std::vector and passes
+// indices around.  Only three samples are ever live -- the bracket ends a, b and the
+// newest one -- plus, during the bracket phase, "the most recent earlier sample with
+// phi <= phi_lim" (what the backward scan at :366-371 finds).  They are kept here as
+// value tuples in registers, each carrying the index it would have in the reference's
+// vector so that the index comparisons of Secant2 (:253-254) stay exact.  Control flow
+// is warp-uniform (every lane holds the same scalars) and voted through uni().
+// State: the last evaluated point (xa, gx) and the best-sample copy (best_x, best_g)
+// of :318-329, E registers per lane each.
+template <class T>
+struct HzSample {
+  T alpha, phi, dphi;
+  int id;
+};
+
+template <class Fn, class T, int E>
+struct HzSearch {
+  using P = typename PolicyOf<Fn>::type;
+  const Fn& fn;
+  const EvalCtx& ctx;
+  const RedCtx<T>& rc;
+  const T (&x0)[E];
+  const T (&s)[E];
+  T (&xa)[E];  // last evaluated point
+  T (&gx)[E];  // its gradient
+  T phi_0, dphi_0, phi_lim, delta, sigma;
+  int n;     // history.size()
+  int nfev;
+
+  // PhiDphi (:152-159) + history.push_back
+  __device__ __forceinline__ HzSample<T> eval(T alpha) {
+    HzSample<T> r;
+#pragma unroll
+    for (int j = 0; j < E; ++j) xa[j] = x0[j] + alpha * s[j];
+    r.alpha = alpha;
+    r.phi = fn(ctx, xa, &gx);
+    r.dphi = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(gx, s), rc);
+    r.id = -1;
+    nfev++;
+    return r;
+  }
+  __device__ __forceinline__ void push(HzSample<T>& r) { r.id = n++; }
+
+  // SatisfiesWolfe (:137-146)
+  __device__ __forceinline__ bool wolfe(const HzSample<T>& r) const {
+    const bool w1 = (delta * dphi_0 >= (r.phi - phi_0) / r.alpha) & (r.dphi >= sigma * dphi_0);
+    const bool w2 = ((T(2) * delta - T(1)) * dphi_0 >= r.dphi) & (r.dphi >= sigma * dphi_0) & (r.phi <= phi_lim);
+    return w1 | w2;
+  }
+  __device__ __forceinline__ static T secant(T a, T b, T da, T db) {  // :148-151
+    return (a * db - b * da) / (db - da);
+  }
+
+  // Bisect (:189-218): returns wolfe_hit; A / B updated like the returned indices
+  __device__ __forceinline__ bool bisect(HzSample<T>& A, HzSample<T>& B) {
+    T a = A.alpha, b = B.alpha;
+    while (uni(b - a > Num<T>::eps * b)) {
+      const T dd = (a + b) / T(2);
+      HzSample<T> r = eval(dd);
+      push(r);
+      if (uni(wolfe(r))) { B = r; return true; }
+      if (uni(r.dphi >= T(0))) { B = r; return false; }
+      if (uni(r.phi <= phi_lim)) { a = dd; A = r; }
+      else { b = dd; B = r; }
+    }
+    return false;
+  }
+
+  // Update (:165-187) with the new sample C
+  __device__ __forceinline__ bool update(HzSample<T>& A, HzSample<T>& B, const HzSample<T>& C) {
+    if (uni((C.alpha < A.alpha) | (C.alpha > B.alpha))) return false;  // U0
+    if (uni(C.dphi >= T(0))) { B = C; return false; }                   // U1
+    if (uni(C.phi <= phi_lim)) { A = C; return false; }                 // U2
+    B = C;                                                              // U3
+    return bisect(A, B);
+  }
+
+  // Secant2 (:222-283): returns wolfe_hit with the accepted sample in A (= B); else the new bracket
+  __device__ __forceinline__ bool secant2(HzSample<T>& A, HzSample<T>& B) {
+    const HzSample<T> a0 = A, b0 = B;
+    T cc = secant(a0.alpha, b0.alpha, a0.dphi, b0.dphi);  // S1
+    if (uni(!cfinite(cc))) cc = (a0.alpha + b0.alpha) / T(2);
+    HzSample<T> c1 = eval(cc);
+    push(c1);
+    if (uni(wolfe(c1))) { A = B = c1; return true; }
+    if (update(A, B, c1)) { A = B; return true; }  // S2
+    T c2 = cc;  // S3
+    const bool moved_b = (B.id == c1.id), moved_a = (A.id == c1.id);
+    if (uni(moved_b)) c2 = secant(b0.alpha, B.alpha, b0.dphi, B.dphi);
+    else if (uni(moved_a)) c2 = secant(a0.alpha, A.alpha, a0.dphi, A.dphi);
+    if (uni((moved_a | moved_b) & (A.alpha <= c2) & (c2 <= B.alpha))) {
+      HzSample<T> r2 = eval(c2);
+      push(r2);
+      if (uni(wolfe(r2))) { A = B = r2; return true; }
+      if (update(A, B, r2)) { A = B; return true; }  // S4
+    }
+    return false;
+  }
+};
+
+// hzls (:290-548).  Same contract as cvsrch: returns the number of evaluations; (x, f, g)
+// is the accepted state, or the start state when the search fails (return -1 there).
+template <class Fn, class T, int E>
+__device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc, const T (&x0)[E],
+                                 const T f0, const T (&g0)[E], T (&x)[E], T& f, T (&g)[E], T stp,
+                                 const T (&s)[E], const T dginit) {
+  const T epsilon_k = T(1e-6), gamma = T(0.66), rho = T(5), psi3 = T(0.1);
+  const int maxlinesearch = 50, iterfinitemax = 60;
+  // x / g double as the PhiDphi workspaces (xa, gx); they hold the start state until the
+  // first evaluation and the accepted state on success
+#pragma unroll
+  for (int j = 0; j < E; ++j) { x[j] = x0[j]; g[j] = g0[j]; }
+  f = f0;
+  if (uni(dginit >= T(0))) return 0;  // :316
+
+  HzSearch<Fn, T, E> z{fn, ctx, rc, x0, s, x, g, f0, dginit, T(0), T(1) / T(10), T(9) / T(10), 1, 0};
+  z.phi_lim = f0 + epsilon_k * cabs(f0);
+  const HzSample<T> origin{T(0), f0, dginit, 0};
+  T best_alpha = T(0), best_phi = f0;
+  T best_x[E], best_g[E];
+#pragma unroll
+  for (int j = 0; j < E; ++j) { best_x[j] = x0[j]; best_g[j] = g0[j]; }
+
+  // the three ways out (:338-341 etc.)
+  auto update_best = [&](const HzSample<T>& r) {
+    if (uni((r.alpha > T(0)) & (r.phi < best_phi))) {
+      best_alpha = r.alpha;
+      best_phi = r.phi;
+#pragma unroll
+      for (int j = 0; j < E; ++j) { best_x[j] = x[j]; best_g[j] = g[j]; }
+    }
+  };
+  auto fail = [&]() {  // state untouched
+#pragma unroll
+    for (int j = 0; j < E; ++j) { x[j] = x0[j]; g[j] = g0[j]; }
+    f = f0;
+  };
+  auto best_or_fail = [&]() {
+    if (uni(best_alpha > T(0))) {
+#pragma unroll
+      for (int j = 0; j < E; ++j) { x[j] = best_x[j]; g[j] = best_g[j]; }
+      f = best_phi;
+    } else {
+      fail();
+    }
+  };
+
+  T cc = stp;  // :330
+  if (uni(!(cc > T(0)))) cc = T(1);
+  HzSample<T> ec = z.eval(cc);
+  int iterfinite = 0;
+  while (uni(!(cfinite(ec.phi) & cfinite(ec.dphi)) & (iterfinite < iterfinitemax))) {
+    cc *= psi3;
+    ec = z.eval(cc);
+    ++iterfinite;
+  }
+  if (uni(!(cfinite(ec.phi) & cfinite(ec.dphi)))) { fail(); return z.nfev; }
+  z.push(ec);
+  update_best(ec);
+  if (uni(z.wolfe(ec))) { f = ec.phi; return z.nfev; }  // (x, g) already hold the accepted point
+
+  bool bracketed = false;
+  HzSample<T> A = origin, B = ec;
+  HzSample<T> last = ec;      // history.back()
+  HzSample<T> cand = origin;  // most recent sample before `last` with phi <= phi_lim (else the origin: ia stays 0)
+  int iter = 1;
+  while (uni(!bracketed & (iter < maxlinesearch))) {  // bracket phase, :361-437
+    if (uni(last.dphi >= T(0))) {
+      B = last;
+      A = cand;
+      bracketed = true;
+    } else if (uni(last.phi > z.phi_lim)) {
+      B = last;
+      A = origin;
+      if (z.bisect(A, B)) { f = B.phi; return z.nfev; }
+      bracketed = true;
+    } else {
+      cc *= rho;
+      ec = z.eval(cc);
+      iterfinite = 0;
+      while (uni(!(cfinite(ec.phi) & cfinite(ec.dphi)) & (iterfinite < iterfinitemax))) {
+        cc = (last.alpha + cc) / T(2);
+        ec = z.eval(cc);
+        ++iterfinite;
+      }
+      if (uni(!(cfinite(ec.phi) & cfinite(ec.dphi)))) { best_or_fail(); return z.nfev; }
+      if (uni(last.phi <= z.phi_lim)) cand = last;
+      z.push(ec);
+      last = ec;
+      update_best(ec);
+      if (uni(z.wolfe(ec))) { f = ec.phi; return z.nfev; }
+    }
+    ++iter;
+  }
+  if (uni(!bracketed)) { best_or_fail(); return z.nfev; }
+
+  while (uni(iter < maxlinesearch)) {  // secant phase, :449-538
+    const T a = A.alpha, b = B.alpha;
+    if (uni(b - a <= Num<T>::eps * b)) {
+      if (uni(a > T(0))) {
+        ec = z.eval(a);
+        f = ec.phi;
+        return z.nfev;
+      }
+      best_or_fail();
+      return z.nfev;
+    }
+    HzSample<T> nA = A, nB = B;
+    if (z.secant2(nA, nB)) { f = nA.phi; return z.nfev; }
+    if (uni(nB.alpha - nA.alpha < gamma * (b - a))) {
+      A = nA;
+      B = nB;
+    } else {
+      const T cm = (nA.alpha + nB.alpha) / T(2);
+      HzSample<T> rm = z.eval(cm);
+      z.push(rm);
+      update_best(rm);
+      if (uni(z.wolfe(rm))) { f = rm.phi; return z.nfev; }
+      if (z.update(nA, nB, rm)) { f = nB.phi; return z.nfev; }
+      A = nA;
+      B = nB;
+    }
+    ++iter;
+  }
+  best_or_fail();
+  return z.nfev;
+}
+
+// The LineSearch template parameter of the solvers (lbfgs.h:41, bfgs.h:40, gradient_descent.h:38).
+struct LsMoreThuente {
+  template <class Fn, class T, int E>
+  __device__ __forceinline__ static int search(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc,
+                                               const T (&x0)[E], const T f0, const T (&g0)[E], T (&x)[E],
+                                               T& f, T (&g)[E], T stp, const T (&s)[E], const T dginit) {
+    return cvsrch<Fn, T, E>(fn, ctx, rc, x0, f0, g0, x, f, g, stp, s, dginit);
+  }
+};
+struct LsHagerZhang {
+  template <class Fn, class T, int E>
+  __device__ __forceinline__ static int search(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc,
+                                               const T (&x0)[E], const T f0, const T (&g0)[E], T (&x)[E],
+                                               T& f, T (&g)[E], T stp, const T (&s)[E], const T dginit) {
+    return hzls<Fn, T, E>(fn, ctx, rc, x0, f0, g0, x, f, g, stp, s, dginit);
+  }
+};
+
 }  // namespace cno
 
 #endif  // CNO_LINESEARCH_CUH_

@@ -268,14 +268,37 @@ class Solver:
         return (BatchedFunctionState(x, f, g), BatchedProgress(it, st, nf, xd, fd, gn, info))
 
 
-class Lbfgs(Solver):
-    """solver/lbfgs.h:40-324 (m = 10, MoreThuente)."""
+class MoreThuente:
+    """linesearch/more_thuente.h: the default LineSearch policy."""
+
+
+class HagerZhang:
+    """linesearch/hager_zhang.h:54-552: the alternative LineSearch policy."""
+
+
+class _LineSearchSolver(Solver):
+    """Solvers with a LineSearch template parameter (lbfgs.h:41, bfgs.h:40, gradient_descent.h:38):
+    `Lbfgs(progress, linesearch=HagerZhang)` mirrors `Lbfgs<F, 10, linesearch::HagerZhang>`."""
+    _solver_ids = {}
+
+    def __init__(self, progress: Optional[Progress] = None, linesearch=MoreThuente):
+        super().__init__(progress)
+        if linesearch not in self._solver_ids:
+            raise ValueError("linesearch must be MoreThuente or HagerZhang")
+        self.linesearch = linesearch
+        self._solver_id = self._solver_ids[linesearch]
+
+
+class Lbfgs(_LineSearchSolver):
+    """solver/lbfgs.h:40-324 (m = 10; LineSearch = MoreThuente unless given)."""
     _solver_id = _lib.LBFGS
+    _solver_ids = {MoreThuente: _lib.LBFGS, HagerZhang: _lib.LBFGS_HAGER_ZHANG}
 
 
-class Bfgs(Solver):
-    """solver/bfgs.h:39-145 (MoreThuente)."""
+class Bfgs(_LineSearchSolver):
+    """solver/bfgs.h:39-145 (LineSearch = MoreThuente unless given)."""
     _solver_id = _lib.BFGS
+    _solver_ids = {MoreThuente: _lib.BFGS, HagerZhang: _lib.BFGS_HAGER_ZHANG}
 
 
 class NewtonDescent(Solver):
@@ -283,9 +306,10 @@ class NewtonDescent(Solver):
     _solver_id = _lib.NEWTON
 
 
-class GradientDescent(Solver):
-    """solver/gradient_descent.h:37-75 (LineSearch = MoreThuente, the reference's default)."""
+class GradientDescent(_LineSearchSolver):
+    """solver/gradient_descent.h:37-75 (LineSearch = MoreThuente, the reference's default, unless given)."""
     _solver_id = _lib.GRADIENT_DESCENT
+    _solver_ids = {MoreThuente: _lib.GRADIENT_DESCENT, HagerZhang: _lib.GRADIENT_DESCENT_HAGER_ZHANG}
 
 
 class ConjugatedGradientDescent(Solver):

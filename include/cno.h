@@ -79,8 +79,13 @@ typedef enum cno_solver {
   CNO_BFGS = 1,   /* solver/bfgs.h, MoreThuente */
   CNO_NEWTON = 2, /* solver/newton_descent.h, Armijo<F,2> */
   CNO_GRADIENT_DESCENT = 3,            /* solver/gradient_descent.h, MoreThuente */
-  CNO_CONJUGATED_GRADIENT_DESCENT = 4  /* solver/conjugated_gradient_descent.h, Armijo<F,1>;
+  CNO_CONJUGATED_GRADIENT_DESCENT = 4, /* solver/conjugated_gradient_descent.h, Armijo<F,1>;
                                           fp64 only (the reference computes beta in double) */
+  /* the same solvers with LineSearch = linesearch::HagerZhang (linesearch/hager_zhang.h:54-552;
+   * the template parameter at lbfgs.h:41, bfgs.h:40, gradient_descent.h:38) */
+  CNO_LBFGS_HAGER_ZHANG = 5,
+  CNO_BFGS_HAGER_ZHANG = 6,
+  CNO_GRADIENT_DESCENT_HAGER_ZHANG = 7
 } cno_solver_t;
 
 typedef enum cno_dtype { CNO_F64 = 0, CNO_F32 = 1 } cno_dtype_t;
