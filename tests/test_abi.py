@@ -80,7 +80,7 @@ def test_no_device_fails_loudly_no_cpu_fallback():
 def test_invalid_arguments():
     L = _lib.lib()
     prob = cn.Rosenbrock(128).problem()
-    assert L.cno_minimize_host(7, C.byref(prob), 4, None, None, None, None) == _lib.ERR_INVALID_ARGUMENT
+    assert L.cno_minimize_host(99, C.byref(prob), 4, None, None, None, None) == _lib.ERR_INVALID_ARGUMENT
     bad = cn.Rosenbrock(129).problem()
     assert L.cno_supported(_lib.LBFGS, C.byref(bad)) == _lib.ERR_UNSUPPORTED
     n = C.c_size_t()
