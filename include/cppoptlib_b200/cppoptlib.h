@@ -464,16 +464,41 @@ auto PrintProgressCallback(std::ostream& output_stream, int64_t instance = 0) {
   };
 }
 
-template <class F> class Lbfgs : public Solver<F, CNO_LBFGS> { using Solver<F, CNO_LBFGS>::Solver; };
-template <class F> class Bfgs : public Solver<F, CNO_BFGS> { using Solver<F, CNO_BFGS>::Solver; };
+// The LineSearch policies (linesearch/more_thuente.h, linesearch/hager_zhang.h:54-552).  The
+// reference takes them as `template <class, int> class LineSearch`; here they are tags that
+// select the kernel compiled with that search (C ABI solver ids CNO_*_HAGER_ZHANG).
+namespace linesearch {
+struct MoreThuente {
+  static constexpr int solver_id(int base) { return base; }
+};
+struct HagerZhang {
+  static constexpr int solver_id(int base) {
+    return base == CNO_LBFGS ? CNO_LBFGS_HAGER_ZHANG
+                             : (base == CNO_BFGS ? CNO_BFGS_HAGER_ZHANG : CNO_GRADIENT_DESCENT_HAGER_ZHANG);
+  }
+};
+}  // namespace linesearch
+
+// solver/lbfgs.h:40-42: Lbfgs<F, m = 10, LineSearch = MoreThuente>
+template <class F, int m = CNO_LBFGS_M, class LineSearch = linesearch::MoreThuente>
+class Lbfgs : public Solver<F, LineSearch::solver_id(CNO_LBFGS)> {
+  static_assert(m == CNO_LBFGS_M, "the kernels are compiled for m = 10 (the reference's default)");
+  using Solver<F, LineSearch::solver_id(CNO_LBFGS)>::Solver;
+};
+// solver/bfgs.h:39-41: Bfgs<F, LineSearch = MoreThuente>
+template <class F, class LineSearch = linesearch::MoreThuente>
+class Bfgs : public Solver<F, LineSearch::solver_id(CNO_BFGS)> {
+  using Solver<F, LineSearch::solver_id(CNO_BFGS)>::Solver;
+};
 template <class F> class NewtonDescent : public Solver<F, CNO_NEWTON> {
   static_assert(F::Differentiability == function::DifferentiabilityMode::Second,
                 "NewtonDescent only supports second-order differentiable functions");
   using Solver<F, CNO_NEWTON>::Solver;
 };
 // solver/gradient_descent.h:37-75 (LineSearch = MoreThuente, the reference's default policy)
-template <class F> class GradientDescent : public Solver<F, CNO_GRADIENT_DESCENT> {
-  using Solver<F, CNO_GRADIENT_DESCENT>::Solver;
+template <class F, class LineSearch = linesearch::MoreThuente>
+class GradientDescent : public Solver<F, LineSearch::solver_id(CNO_GRADIENT_DESCENT)> {
+  using Solver<F, LineSearch::solver_id(CNO_GRADIENT_DESCENT)>::Solver;
 };
 // solver/conjugated_gradient_descent.h:38-92 (Fletcher-Reeves beta, Armijo<F,1>)
 template <class F> class ConjugatedGradientDescent : public Solver<F, CNO_CONJUGATED_GRADIENT_DESCENT> {

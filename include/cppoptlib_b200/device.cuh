@@ -75,20 +75,20 @@ using UserLbfgsSmem = LbfgsSmem<typename F::Scalar, F::Dim, CNO_LBFGS_M, StageEl
                                 PolicyScratch<typename PolicyOf<F>::type>::kElemsPerLane, FnTmemCols<F>::value>;
 
 // BFGS keeps a row of the inverse Hessian in registers: D <= 32 only.
-template <class F, bool Small = (F::Dim <= 32)>
+template <class F, class LS = LsMoreThuente, bool Small = (F::Dim <= 32)>
 struct BfgsDispatch {
   static int run(const F&, int64_t, const void*, const cno_stop_t*, const cno_batch_out_t*, void*,
                  size_t, void*, cno_launch_info_t*) {
     return CNO_ERR_UNSUPPORTED;
   }
 };
-template <class F>
-struct BfgsDispatch<F, true> {
+template <class F, class LS>
+struct BfgsDispatch<F, LS, true> {
   static int run(const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop,
                  const cno_batch_out_t* out, void* workspace, size_t workspace_bytes, void* stream,
                  cno_launch_info_t* info) {
     return launch_user<F, BfgsSmem<typename F::Scalar, F::Dim>>(
-        bfgs_minimize_kernel<F>, fn, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
+        bfgs_minimize_kernel<F, LS>, fn, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
   }
 };
 }  // namespace cno
@@ -108,6 +108,17 @@ struct BfgsDispatch<F, true> {
     if (solver == CNO_BFGS)                                                                         \
       return cno::BfgsDispatch<F>::run(fn, batch, x0, stop, out, workspace, workspace_bytes,        \
                                        stream, info);                                               \
+    if (solver == CNO_LBFGS_HAGER_ZHANG)                                                            \
+      return cno::launch_user<F, cno::UserLbfgsSmem<F>>(                                            \
+          cno::lbfgs_minimize_kernel<F, CNO_LBFGS_M, false, cno::LsHagerZhang>, fn, batch, x0,      \
+          stop, out, workspace, workspace_bytes, stream, info, cno::ResumeArgs{nullptr, 0, 0, 0});  \
+    if (solver == CNO_BFGS_HAGER_ZHANG)                                                             \
+      return cno::BfgsDispatch<F, cno::LsHagerZhang>::run(fn, batch, x0, stop, out, workspace,      \
+                                                          workspace_bytes, stream, info);           \
+    if (solver == CNO_GRADIENT_DESCENT_HAGER_ZHANG)                                                 \
+      return cno::launch_user<F, cno::DescentSmem<typename F::Scalar>>(                             \
+          cno::descent_minimize_kernel<F, false, cno::LsHagerZhang>, fn, batch, x0, stop, out,      \
+          workspace, workspace_bytes, stream, info);                                                \
     if (solver == CNO_GRADIENT_DESCENT)                                                             \
       return cno::launch_user<F, cno::DescentSmem<typename F::Scalar>>(                             \
           cno::descent_minimize_kernel<F, false>, fn, batch, x0, stop, out, workspace,              \

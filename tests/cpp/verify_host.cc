@@ -66,6 +66,13 @@ int main() {
   // SOLVER_SETUP_CONSERVATIVE(GradientDescent, ...), SOLVER_SETUP(ConjugatedGradientDescent, ...): verify.cc:185-186
   solve_far_near_conservative<solver::GradientDescent, function::Rosenbrock<double, 2>>();
   solve_far_near<solver::ConjugatedGradientDescent, function::Rosenbrock<double, 2>>();
+  {  // the alternative LineSearch policy: Lbfgs<F, 10, linesearch::HagerZhang> (lbfgs.h:40-42)
+    using F = function::Rosenbrock<double, 2>;
+    solver::Lbfgs<F, 10, solver::linesearch::HagerZhang> s;
+    auto [sol, prog] = s.Minimize(F{}, function::BatchedFunctionState<double, 2>::FromHost({15.0, 8.0, -1.0, 2.0}, 2));
+    const std::vector<double> x = sol.x.ToHost();
+    for (int b = 0; b < 2; ++b) EXPECT_NEAR(0.0, rosen2(&x[2 * b]), PRECISION);
+  }
 
   {  // Dockerfile.test:30-45
     function::DiagQuadratic<double> f;
