@@ -6,6 +6,8 @@ with a batch axis; the compute is hand-written sm_100a CUDA in libcno.so behind
 the C ABI of include/cno.h.  No CPU fallback.
 """
 from . import _lib  # noqa: F401
+from .constrained import (AugmentedLagrangeState, AugmentedLagrangian,  # noqa: F401
+                          AugmentedLagrangianConfig, ConstrainedOptimizationProblem, ConstrainedStop)
 from .function import (BatchedFunctionState, DenseQuadratic, DiagQuadratic,  # noqa: F401
                        DifferentiabilityMode, Function, HalfSquaredNorm, Logistic, Rosenbrock,
                        RosenbrockFull)
@@ -16,6 +18,8 @@ from .solver import (BatchedProgress, Bfgs, ConjugatedGradientDescent,  # noqa: 
                      Status, fill_uniform)
 
 __all__ = [
+    "AugmentedLagrangeState", "AugmentedLagrangian", "AugmentedLagrangianConfig",
+    "ConstrainedOptimizationProblem", "ConstrainedStop",
     "BatchedFunctionState", "BatchedProgress", "Bfgs", "ConjugatedGradientDescent",
     "ConservativeStoppingSolverProgress", "GradientDescent", "HagerZhang", "MoreThuente",
     "DefaultStoppingSolverProgress", "DenseQuadratic", "DiagQuadratic", "DifferentiabilityMode",

@@ -54,8 +54,38 @@ class LaunchInfo(C.Structure):  # cno_launch_info_t
     ]
 
 
-# every symbol include/cno.h declares
+class Constraints(C.Structure):  # cno_constraints_t (include/cno_al.h)
+    _fields_ = [("n_eq", C.c_int32), ("n_ineq", C.c_int32), ("kinds", C.c_void_p),
+                ("data", C.c_void_p), ("data_stride", C.c_int64)]
+
+
+class AlConfig(C.Structure):  # cno_al_config_t
+    _fields_ = [("penalty_growth_factor", C.c_double), ("violation_shrink_ratio", C.c_double),
+                ("auto_scale_initial_penalty", C.c_int32), ("penalty_auto_objective_scale", C.c_double),
+                ("penalty_auto_min", C.c_double), ("penalty_auto_max", C.c_double),
+                ("warmup_max_inner_iterations", C.c_int32),
+                ("warmup_inner_gradient_tolerance", C.c_double), ("multiplier_max", C.c_double),
+                ("kkt_gradient_tolerance", C.c_double)]
+
+
+class AlStop(C.Structure):  # cno_al_stop_t
+    _fields_ = [("num_iterations", C.c_uint64), ("constraint_threshold", C.c_double),
+                ("kkt_stationarity_threshold", C.c_double)]
+
+
+class AlOut(C.Structure):  # cno_al_out_t
+    _fields_ = [(n, C.c_void_p) for n in (
+        "x", "equality_multipliers", "inequality_multipliers", "penalty", "max_violation",
+        "max_lagrangian_gradient", "num_iterations", "status", "nfev", "x_delta", "f_delta",
+        "gradient_norm")]
+
+
+CON_AFFINE, CON_SQNORM = 0, 1
+
+# every symbol include/*.h declares
 EXPORTS = (
+    "cno_al_default_config", "cno_al_default_stop", "cno_al_supported", "cno_al_workspace_bytes",
+    "cno_al_minimize",
     "cno_version", "cno_error_string", "cno_last_cuda_error", "cno_default_stop",
     "cno_conservative_stop", "cno_supported", "cno_workspace_bytes", "cno_minimize",
     "cno_state_bytes", "cno_minimize_steps",

@@ -19,6 +19,8 @@
 #include "cno_descent.cuh"
 #include "cno_newton.cuh"
 #include "cno_logistic.cuh"
+#include "cno_auglag.cuh"
+#include "../../include/cno_al.h"
 
 namespace {
 
@@ -424,6 +426,205 @@ __global__ void cstep_kernel(double* io, int* flags) {
   flags[2] = ret;
 }
 
+// ---- AugmentedLagrangian (include/cno_al.h; csrc/cno_auglag.cuh) -----------------
+struct AlArgs {
+  const cno_problem_t* objective;
+  const cno_constraints_t* constraints;
+  long long batch;
+  const void* x0;
+  const void* eq0;
+  const void* ineq0;
+  const void* penalty0;
+  const cno_stop_t* inner_stop;
+  const cno_al_stop_t* outer_stop;
+  const cno_al_config_t* config;
+  const cno_al_out_t* out;
+  unsigned char* workspace;
+  cudaStream_t stream;
+  cno_launch_info_t* info;
+};
+
+inline size_t al_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// Scratch layout behind `workspace` (every region 256-byte aligned).
+struct AlLayout {
+  size_t queue, remaining, x_work, prev_penalty, inner_nfev, best_recorded, best_x, best_lambda, best_mu,
+      best_penalty, best_objective, best_violation, best_kkt, total;
+  AlLayout(size_t B, size_t d, size_t ne, size_t ni, size_t ts) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += al_up(bytes ? bytes : 1); return o; };
+    queue = take(256);
+    remaining = take(sizeof(int));
+    x_work = take(B * d * ts);
+    prev_penalty = take(B * ts);
+    inner_nfev = take(B * 4);
+    best_recorded = take(B);
+    best_x = take(B * d * ts);
+    best_lambda = take(B * ne * ts);
+    best_mu = take(B * ni * ts);
+    best_penalty = take(B * ts);
+    best_objective = take(B * ts);
+    best_violation = take(B * ts);
+    best_kkt = take(B * ts);
+    total = off;
+  }
+};
+
+template <class Obj>
+int al_run(const Obj& obj, const AlArgs& A) {
+  using T = typename Obj::Scalar;
+  constexpr int D = Obj::Dim;
+  const long long B = A.batch;
+  const int ne = A.constraints->n_eq, ni = A.constraints->n_ineq;
+  const cno_al_out_t& o = *A.out;
+  const AlLayout L((size_t)B, D, (size_t)ne, (size_t)ni, sizeof(T));
+  unsigned char* ws = A.workspace;
+  cudaStream_t s = A.stream;
+
+  cno::AlArrays<T> a{};
+  a.x = static_cast<T*>(o.x);
+  a.x_work = reinterpret_cast<T*>(ws + L.x_work);
+  a.lambda = static_cast<T*>(o.equality_multipliers);
+  a.mu = static_cast<T*>(o.inequality_multipliers);
+  a.penalty = static_cast<T*>(o.penalty);
+  a.prev_penalty = reinterpret_cast<T*>(ws + L.prev_penalty);
+  a.max_violation = static_cast<T*>(o.max_violation);
+  a.max_lagrangian_gradient = static_cast<T*>(o.max_lagrangian_gradient);
+  a.num_iterations = o.num_iterations;
+  a.status = o.status;
+  a.nfev = o.nfev;
+  a.inner_nfev = reinterpret_cast<uint32_t*>(ws + L.inner_nfev);
+  a.x_delta = static_cast<T*>(o.x_delta);
+  a.f_delta = static_cast<T*>(o.f_delta);
+  a.gradient_norm = static_cast<T*>(o.gradient_norm);
+  a.best_recorded = reinterpret_cast<int8_t*>(ws + L.best_recorded);
+  a.best_x = reinterpret_cast<T*>(ws + L.best_x);
+  a.best_lambda = reinterpret_cast<T*>(ws + L.best_lambda);
+  a.best_mu = reinterpret_cast<T*>(ws + L.best_mu);
+  a.best_penalty = reinterpret_cast<T*>(ws + L.best_penalty);
+  a.best_objective = reinterpret_cast<T*>(ws + L.best_objective);
+  a.best_violation = reinterpret_cast<T*>(ws + L.best_violation);
+  a.best_kkt = reinterpret_cast<T*>(ws + L.best_kkt);
+  a.remaining = reinterpret_cast<int*>(ws + L.remaining);
+
+  // ---- initial AugmentedLagrangeState (augmented_lagrangian.h:241-276) + ResetBestIterateTracker ----
+  auto init = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    return src ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s) : cudaMemsetAsync(dst, 0, bytes, s);
+  };
+  CNO_CUDA(init(a.x, A.x0, (size_t)B * D * sizeof(T)));
+  CNO_CUDA(init(a.lambda, A.eq0, (size_t)B * ne * sizeof(T)));
+  CNO_CUDA(init(a.mu, A.ineq0, (size_t)B * ni * sizeof(T)));
+  CNO_CUDA(init(a.penalty, A.penalty0, (size_t)B * sizeof(T)));
+  CNO_CUDA(cudaMemcpyAsync(a.prev_penalty, a.penalty, (size_t)B * sizeof(T), cudaMemcpyDeviceToDevice, s));
+  CNO_CUDA(cudaMemsetAsync(a.max_violation, 0, (size_t)B * sizeof(T), s));
+  CNO_CUDA(cudaMemsetAsync(a.max_lagrangian_gradient, 0, (size_t)B * sizeof(T), s));
+  CNO_CUDA(cudaMemsetAsync(a.num_iterations, 0, (size_t)B * 4, s));
+  CNO_CUDA(cudaMemsetAsync(a.nfev, 0, (size_t)B * 4, s));
+  CNO_CUDA(cudaMemsetAsync(a.status, 0xFF, (size_t)B, s));  // CNO_STATUS_NOT_STARTED
+  CNO_CUDA(cudaMemsetAsync(a.best_recorded, 0, (size_t)B, s));
+
+  cno::AlView<T> view{};
+  view.rows = static_cast<const T*>(A.constraints->data);
+  view.row_stride = (long long)A.constraints->data_stride;
+  view.kinds = reinterpret_cast<const int*>(A.constraints->kinds);
+  view.n_eq = ne;
+  view.n_ineq = ni;
+  view.lambda = a.lambda;
+  view.mu = a.mu;
+  view.penalty = a.penalty;
+  view.status = a.status;
+
+  cno::AlParams<T> p{};
+  p.penalty_growth_factor = (T)A.config->penalty_growth_factor;
+  p.violation_shrink_ratio = (T)A.config->violation_shrink_ratio;
+  p.auto_scale_initial_penalty = A.config->auto_scale_initial_penalty;
+  p.penalty_auto_objective_scale = (T)A.config->penalty_auto_objective_scale;
+  p.penalty_auto_min = (T)A.config->penalty_auto_min;
+  p.penalty_auto_max = (T)A.config->penalty_auto_max;
+  p.multiplier_max = (T)A.config->multiplier_max;
+  p.num_iterations = A.outer_stop->num_iterations;
+  p.constraint_threshold = (T)A.outer_stop->constraint_threshold;
+  p.kkt_stationarity_threshold = A.outer_stop->kkt_stationarity_threshold;
+
+  const cno::AugLagFn<Obj> composite{obj, view};
+  cno_batch_out_t inner_out{};
+  inner_out.x = a.x_work;
+  inner_out.nfev = const_cast<uint32_t*>(a.inner_nfev);
+  const int blocks = (int)((B + cno::kAlWarps - 1) / cno::kAlWarps);
+  const int threads = cno::kAlWarps * 32;
+  int launches = 0;
+
+  for (unsigned long long outer = 1;; ++outer) {
+    if (outer == 1 && A.config->auto_scale_initial_penalty) {  // augmented_lagrangian.h:312-318
+      cno::al_autoscale_kernel<Obj><<<blocks, threads, 0, s>>>(obj, view, B, p, a);
+      CNO_CUDA(cudaGetLastError());
+      ++launches;
+    }
+    cno_stop_t inner = *A.inner_stop;  // working copy of the template (:347), ConfigureInnerSubproblem (:477-490)
+    inner.f_delta = 0;
+    if (outer == 1 && (ne > 0 || ni > 0) && A.config->warmup_max_inner_iterations > 0) {
+      inner.num_iterations = (uint64_t)A.config->warmup_max_inner_iterations;
+      inner.gradient_norm = (double)(T)A.config->warmup_inner_gradient_tolerance;
+    }
+    cno_launch_info_t inner_info{};
+    const LaunchArgs la{A.objective, B, a.x, &inner, &inner_out, ws + L.queue, s, &inner_info};
+    int rc = launch_lbfgs<cno::AugLagFn<Obj>, CNO_LBFGS_M>(composite, la);
+    if (rc) return rc;
+    ++launches;
+    CNO_CUDA(cudaMemsetAsync(a.remaining, 0, sizeof(int), s));
+    cno::al_outer_step_kernel<Obj><<<blocks, threads, 0, s>>>(obj, view, B, p, a);
+    CNO_CUDA(cudaGetLastError());
+    ++launches;
+    int remaining = 0;
+    CNO_CUDA(cudaMemcpyAsync(&remaining, a.remaining, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CNO_CUDA(cudaStreamSynchronize(s));
+    if (remaining == 0) break;
+  }
+  cno::al_finalize_kernel<T, D><<<blocks, threads, 0, s>>>(B, ne, ni, a);  // Minimize (:436-449)
+  CNO_CUDA(cudaGetLastError());
+  ++launches;
+  if (A.info) A.info->kernel_launches = launches;
+  return CNO_OK;
+}
+
+template <class T, int D>
+int al_rosenbrock(const AlArgs& a) { return al_run(cno::RosenbrockFn<T, D>{}, a); }
+template <class T, int D>
+int al_half_sq_norm(const AlArgs& a) { return al_run(cno::HalfSquaredNormFn<T, D>{}, a); }
+
+struct AlEntry {
+  int family, dtype, d;
+  int (*fn)(const AlArgs&);
+};
+const AlEntry kAlTable[] = {
+    {CNO_FN_ROSENBROCK, CNO_F64, 2, al_rosenbrock<double, 2>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 8, al_rosenbrock<double, 8>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 37, al_rosenbrock<double, 37>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 128, al_rosenbrock<double, 128>},
+    {CNO_FN_ROSENBROCK, CNO_F32, 8, al_rosenbrock<float, 8>},
+    {CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, al_half_sq_norm<double, 2>},
+    {CNO_FN_HALF_SQUARED_NORM, CNO_F64, 8, al_half_sq_norm<double, 8>},
+};
+
+const AlEntry* al_find(const cno_problem_t* p) {
+  const int dflt = (p->dtype == CNO_F64) ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE;
+  if (p->policy != dflt || p->mode == 2) return nullptr;
+  for (const AlEntry& e : kAlTable)
+    if (e.family == p->family && e.dtype == p->dtype && e.d == p->d) return &e;
+  return nullptr;
+}
+
+int al_check(const cno_problem_t* p, const cno_constraints_t* k) {
+  if (!p || !k) return CNO_ERR_INVALID_ARGUMENT;
+  if (p->dtype != CNO_F64 && p->dtype != CNO_F32) return CNO_ERR_INVALID_ARGUMENT;
+  if (k->n_eq < 0 || k->n_ineq < 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (k->n_eq > cno::kAlMaxCon || k->n_ineq > cno::kAlMaxCon) return CNO_ERR_UNSUPPORTED;
+  if (k->n_eq + k->n_ineq > 0 && (!k->kinds || !k->data)) return CNO_ERR_INVALID_ARGUMENT;
+  if (!al_find(p)) return CNO_ERR_UNSUPPORTED;
+  return CNO_OK;
+}
+
 bool have_device() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -761,6 +962,93 @@ int cno_device_cstep(double io[11], int* brackt, int* info, int* ret) {
   *brackt = fl[0];
   *info = fl[1];
   *ret = fl[2];
+  return CNO_OK;
+}
+
+void cno_al_default_config(cno_al_config_t* c) {  // augmented_lagrangian.h:63-239
+  if (!c) return;
+  memset(c, 0, sizeof(*c));
+  c->penalty_growth_factor = 10;
+  c->violation_shrink_ratio = 0.25;
+  c->auto_scale_initial_penalty = 1;
+  c->penalty_auto_objective_scale = 10;
+  c->penalty_auto_min = 1e-8;
+  c->penalty_auto_max = 1e8;
+  c->warmup_max_inner_iterations = 10;
+  c->warmup_inner_gradient_tolerance = 1e-2;
+  c->multiplier_max = 1e20;
+  c->kkt_gradient_tolerance = 1e-4;
+}
+
+void cno_al_default_stop(cno_al_stop_t* s) {  // progress.h:126, 353-431
+  if (!s) return;
+  s->num_iterations = 10000;
+  s->constraint_threshold = 1e-5;
+  s->kkt_stationarity_threshold = 1e-4;
+}
+
+int cno_al_supported(const cno_problem_t* objective, const cno_constraints_t* constraints) {
+  return al_check(objective, constraints);
+}
+
+int cno_al_workspace_bytes(const cno_problem_t* objective, const cno_constraints_t* constraints,
+                           int64_t batch, size_t* bytes) {
+  int rc = al_check(objective, constraints);
+  if (rc) return rc;
+  if (!bytes || batch < 0) return CNO_ERR_INVALID_ARGUMENT;
+  const size_t ts = objective->dtype == CNO_F64 ? 8 : 4;
+  *bytes = AlLayout((size_t)batch, (size_t)objective->d, (size_t)constraints->n_eq,
+                    (size_t)constraints->n_ineq, ts).total;
+  return CNO_OK;
+}
+
+int cno_al_minimize(const cno_problem_t* objective, const cno_constraints_t* constraints,
+                    int64_t batch, const void* x0, const void* eq0, const void* ineq0,
+                    const void* penalty0, const cno_stop_t* inner_stop,
+                    const cno_al_stop_t* outer_stop, const cno_al_config_t* config,
+                    const cno_al_out_t* out, void* workspace, size_t workspace_bytes, void* stream,
+                    cno_launch_info_t* info) {
+  int rc = al_check(objective, constraints);
+  if (rc) return rc;
+  if (batch < 0 || !out) return CNO_ERR_INVALID_ARGUMENT;
+  if (info) memset(info, 0, sizeof(*info));
+  if (batch == 0) return have_device() ? CNO_OK : CNO_ERR_NO_DEVICE;
+  if (!x0 || !out->x || !out->penalty || !out->max_violation || !out->max_lagrangian_gradient ||
+      !out->num_iterations || !out->status || !out->nfev)
+    return CNO_ERR_INVALID_ARGUMENT;  // they are the solver's state between outer iterations
+  if ((constraints->n_eq > 0 && !out->equality_multipliers) ||
+      (constraints->n_ineq > 0 && !out->inequality_multipliers))
+    return CNO_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)x0 & 15) || ((uintptr_t)out->x & 15)) return CNO_ERR_INVALID_ARGUMENT;
+  const size_t ts = objective->dtype == CNO_F64 ? 8 : 4;
+  const AlLayout L((size_t)batch, (size_t)objective->d, (size_t)constraints->n_eq,
+                   (size_t)constraints->n_ineq, ts);
+  if (!workspace || workspace_bytes < L.total || ((uintptr_t)workspace & 255)) return CNO_ERR_WORKSPACE;
+  cno_stop_t idflt;
+  if (!inner_stop) { cno_default_stop(&idflt); inner_stop = &idflt; }
+  if (inner_stop->past > CNO_MAX_PAST || inner_stop->past < 0) return CNO_ERR_INVALID_ARGUMENT;
+  cno_al_stop_t odflt;
+  if (!outer_stop) { cno_al_default_stop(&odflt); outer_stop = &odflt; }
+  cno_al_config_t cdflt;
+  if (!config) { cno_al_default_config(&cdflt); config = &cdflt; }
+  if (!have_device()) return CNO_ERR_NO_DEVICE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  EventOwner e0, e1;
+  if (info) {
+    CNO_CUDA(e0.create());
+    CNO_CUDA(e1.create());
+    CNO_CUDA(cudaEventRecord(e0.e, s));
+  }
+  const AlArgs a{objective, constraints, (long long)batch, x0, eq0, ineq0, penalty0, inner_stop,
+                 outer_stop, config, out, static_cast<unsigned char*>(workspace), s, info};
+  rc = al_find(objective)->fn(a);
+  if (rc) return rc;
+  if (info) {
+    CNO_CUDA(cudaEventRecord(e1.e, s));
+    CNO_CUDA(cudaEventSynchronize(e1.e));
+    CNO_CUDA(cudaEventElapsedTime(&info->total_ms, e0.e, e1.e));
+    info->kernel_ms = info->total_ms;
+  }
   return CNO_OK;
 }
 

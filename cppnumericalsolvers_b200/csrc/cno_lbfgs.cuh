@@ -235,6 +235,9 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     if (lane == 0) b = atomicAdd(queue, 1ULL);
     b = __shfl_sync(kFullMask, b, 0);
     if (uni(b >= (unsigned long long)batch)) break;
+    if constexpr (FnSkipsInstances<Fn>::value) {  // e.g. AugLagFn: the instance's outer loop has finished
+      if (uni(!fn.active((long long)b))) continue;
+    }
     const EvalCtx ctx{lane, (long long)b, stage_ptr, fn_tmem};
     if constexpr (kStage > 0) fn.stage(ctx, stage_parity);  // per-instance data -> shared memory (TMA)
 

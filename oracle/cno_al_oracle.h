@@ -1,9 +1,8 @@
 /*
  * cno_al_oracle.h -- CPU ORACLE for the NEXT row of the scope table (SURVEY.md
  * 8(f) rank 1): solver::AugmentedLagrangian driving Lbfgs as its inner solver,
- * with a batch axis.  TEST INFRASTRUCTURE ONLY, like cno_oracle.h; there is no
- * device counterpart yet (round-2 plan), so nothing here is part
- * of the product ABI.  The structs below are the draft of that boundary.
+ * with a batch axis.  TEST INFRASTRUCTURE ONLY, like cno_oracle.h.  The device
+ * counterpart is cno_al_minimize (include/cno_al.h, which also owns the structs).
  *
  * Reference (include/cppoptlib/...):
  *   solver/augmented_lagrangian.h:295-434   OptimizationStep (auto-scaled penalty,
@@ -27,64 +26,14 @@
 #ifndef CNO_AL_ORACLE_H_
 #define CNO_AL_ORACLE_H_
 
+#include "../include/cno_al.h"
 #include "cno_oracle.h"
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-/* Constraint families.  A constraint row is d + 1 scalars [a (d) | t]. */
-typedef enum cno_constraint_kind {
-  CNO_CON_AFFINE = 0, /* c(x) = a.x - t,  grad = a   (a.x: products reduced under the policy) */
-  CNO_CON_SQNORM = 1  /* c(x) = t - x.x,  grad = -2 x (a unused) */
-} cno_constraint_kind_t;
-
-/* function_problem.h:38-60: equality constraints c(x) == 0 first, then inequality
- * constraints c(x) >= 0. */
-typedef struct cno_constraints {
-  int32_t n_eq, n_ineq;
-  const int32_t* kinds; /* [n_eq + n_ineq] */
-  const void* data;     /* rows [a | t], (n_eq + n_ineq) rows per instance, dtype of the problem */
-  int64_t data_stride;  /* scalars between instances; 0 = one set shared by the whole batch */
-} cno_constraints_t;
-
-/* solver/augmented_lagrangian.h:63-239 (AugmentedLagrangianConfig), same defaults. */
-typedef struct cno_al_config {
-  double penalty_growth_factor;           /* 10 */
-  double violation_shrink_ratio;          /* 0.25 */
-  int32_t auto_scale_initial_penalty;     /* 1 */
-  double penalty_auto_objective_scale;    /* 10 */
-  double penalty_auto_min;                /* 1e-8 */
-  double penalty_auto_max;                /* 1e8 */
-  int32_t warmup_max_inner_iterations;    /* 10 */
-  double warmup_inner_gradient_tolerance; /* 1e-2 */
-  double multiplier_max;                  /* 1e20 */
-  double kkt_gradient_tolerance;          /* 1e-4 (carried, unused by the reference's loop) */
-} cno_al_config_t;
-
-/* The fields of the OUTER solver's stopping_progress the constrained branch of
- * Progress::Update reads (progress.h:212-252). */
-typedef struct cno_al_stop {
-  uint64_t num_iterations;           /* 0 = unlimited */
-  double constraint_threshold;       /* 1e-5 in both presets (progress.h:378,416) */
-  double kkt_stationarity_threshold; /* 1e-4 (progress.h:126); <= 0 disables */
-} cno_al_stop_t;
-
-/* Per-instance results (all nullable). */
-typedef struct cno_al_out {
-  void* x;                       /* [B, d]     AugmentedLagrangeState::x (best iterate) */
-  void* equality_multipliers;    /* [B, n_eq] */
-  void* inequality_multipliers;  /* [B, n_ineq] */
-  void* penalty;                 /* [B] */
-  void* max_violation;           /* [B] */
-  void* max_lagrangian_gradient; /* [B] */
-  uint32_t* num_iterations;      /* [B] outer iterations */
-  int8_t* status;                /* [B] cno_status_t of the outer loop */
-  uint32_t* nfev;                /* [B] evaluations of the OBJECTIVE functor, all uses */
-  void* x_delta;                 /* [B] outer Progress values (composite of prev / cur state) */
-  void* f_delta;
-  void* gradient_norm;
-} cno_al_out_t;
+/* cno_constraints_t, cno_al_config_t, cno_al_stop_t, cno_al_out_t: include/cno_al.h */
 
 void cno_al_oracle_default_config(cno_al_config_t* c);
 void cno_al_oracle_default_stop(cno_al_stop_t* s);

@@ -1,5 +1,5 @@
 """C-ABI checks that need no GPU: libcno.so loads, exports every symbol that
-include/cno.h declares, presets match the reference, and compute entry points
+include/cno.h and include/cno_al.h declare, presets match the reference, and compute entry points
 fail loudly (CNO_ERR_NO_DEVICE) instead of falling back to the CPU."""
 import ctypes as C
 import os
@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_header_symbols_all_exported():
-    hdr = open(os.path.join(ROOT, "include", "cno.h")).read()
+    hdr = "".join(open(os.path.join(ROOT, "include", h)).read() for h in ("cno.h", "cno_al.h"))
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)  # declarations only, not comments
     declared = set(re.findall(r"\b(cno_[a-z0-9_]+)\s*\(", hdr))
     assert declared == set(_lib.EXPORTS)
@@ -56,7 +56,9 @@ def test_supported_table():
 
 def test_struct_layouts_match_oracle_binding():
     from oracle import oracle_binding as ob
-    for a, b in ((ob.Stop, _lib.Stop), (ob.Problem, _lib.Problem), (ob.BatchOut, _lib.BatchOut)):
+    for a, b in ((ob.Stop, _lib.Stop), (ob.Problem, _lib.Problem), (ob.BatchOut, _lib.BatchOut),
+                 (ob.Constraints, _lib.Constraints), (ob.AlConfig, _lib.AlConfig), (ob.AlStop, _lib.AlStop),
+                 (ob.AlOut, _lib.AlOut)):
         assert C.sizeof(a) == C.sizeof(b)
         assert [f[0] for f in a._fields_] == [f[0] for f in b._fields_]
 
