@@ -49,6 +49,15 @@ int cno_al_oracle_minimize(const cno_problem_t* objective, const cno_constraints
                            const cno_al_stop_t* outer_stop, const cno_al_config_t* config,
                            const cno_al_out_t* out, int threads);
 
+/* One inner solve of the outer loop: Lbfgs::Minimize on ToAugmentedLagrangian(problem, eq, ineq,
+ * penalty) from x0 under `inner_stop` as given (the caller applies ConfigureInnerSubproblem).
+ * x_out [B,d], nfev_out [B] (objective evaluations).  Used by tests/test_al_emulated.py to stand
+ * in for the fused device L-BFGS kernel, whose parity with this restatement is validated on the GPU. */
+int cno_al_oracle_inner_minimize(const cno_problem_t* objective, const cno_constraints_t* constraints,
+                                 int64_t batch, const void* x0, const void* eq, const void* ineq,
+                                 const void* penalty, const cno_stop_t* inner_stop, void* x_out,
+                                 uint32_t* nfev_out, int threads);
+
 /* ToAugmentedLagrangian(problem, multipliers, penalty)(x, &grad): value[B], grad[B,d]. */
 int cno_al_oracle_evaluate(const cno_problem_t* objective, const cno_constraints_t* constraints,
                            int64_t batch, const void* x, const void* eq, const void* ineq,

@@ -338,6 +338,40 @@ int cno_al_oracle_minimize(const cno_problem_t* objective, const cno_constraints
   return CNO_OK;
 }
 
+int cno_al_oracle_inner_minimize(const cno_problem_t* objective, const cno_constraints_t* constraints,
+                                 int64_t batch, const void* x0, const void* eq, const void* ineq,
+                                 const void* penalty, const cno_stop_t* inner_stop, void* x_out,
+                                 uint32_t* nfev_out, int threads) {
+  int rc = check_problem(CNO_LBFGS, objective);
+  if (rc) return rc;
+  rc = check_constraints(objective, constraints);
+  if (rc) return rc;
+  if (batch < 0 || !x0 || !penalty || !inner_stop || !x_out) return CNO_ERR_INVALID_ARGUMENT;
+  const int d = objective->d, ne = constraints->n_eq, ni = constraints->n_ineq;
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#else
+  threads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (int64_t b = 0; b < batch; ++b) {
+    if (objective->dtype == CNO_F64) {
+      const alctx_t_f64 al = {constraints, eq ? (const double*)eq + b * ne : NULL,
+                              ineq ? (const double*)ineq + b * ni : NULL, ((const double*)penalty)[b]};
+      minimize_one_f64(CNO_LBFGS, objective, &al, 0, b, (const double*)x0 + b * d, inner_stop,
+                       (double*)x_out + b * d, NULL, NULL, NULL, NULL, nfev_out ? nfev_out + b : NULL, NULL,
+                       NULL, NULL);
+    } else {
+      const alctx_t_f32 al = {constraints, eq ? (const float*)eq + b * ne : NULL,
+                              ineq ? (const float*)ineq + b * ni : NULL, ((const float*)penalty)[b]};
+      minimize_one_f32(CNO_LBFGS, objective, &al, 0, b, (const float*)x0 + b * d, inner_stop,
+                       (float*)x_out + b * d, NULL, NULL, NULL, NULL, nfev_out ? nfev_out + b : NULL, NULL,
+                       NULL, NULL);
+    }
+  }
+  return CNO_OK;
+}
+
 int cno_al_oracle_evaluate(const cno_problem_t* objective, const cno_constraints_t* constraints,
                            int64_t batch, const void* x, const void* eq, const void* ineq,
                            const void* penalty, void* value, void* grad) {

@@ -1,0 +1,129 @@
+// tests/emu/emu_auglag.cc -- runs the DEVICE SOURCE of the AugmentedLagrangian path
+// (csrc/cno_auglag.cuh: AugLagFn, al_autoscale_kernel, al_outer_step_kernel,
+// al_finalize_kernel, on top of csrc/cno_functors.cuh) on the CPU under the warp
+// emulation of warp_emu.h.  TEST INFRASTRUCTURE ONLY: the first GPU run of this path is
+// still pending, so this is how its logic is checked against the oracle meanwhile
+// (tests/test_al_emulated.py).  Built by tests/emu/Makefile into libcno_emu.so.
+#include "cno_functors.cuh"
+#include "cno_auglag.cuh"
+
+namespace {
+
+template <class F>
+void launch(long long batch, F&& body) {  // grid of ceil(batch / kAlWarps) blocks x kAlWarps warps
+  const int blocks = (int)((batch + cno::kAlWarps - 1) / cno::kAlWarps);
+  for (int blk = 0; blk < blocks; ++blk)
+    for (int w = 0; w < cno::kAlWarps; ++w)
+      emu::run_warp([&](int lane) {
+        blockIdx.x = (unsigned)blk;
+        threadIdx.x = (unsigned)(w * 32 + lane);
+        body();
+      });
+}
+
+struct EmuArrays {  // mirrors cno::AlArrays<T> with untyped pointers
+  void *x, *x_work, *lambda, *mu, *penalty, *prev_penalty, *max_violation, *max_lagrangian_gradient;
+  uint32_t* num_iterations;
+  int8_t* status;
+  uint32_t* nfev;
+  const uint32_t* inner_nfev;
+  void *x_delta, *f_delta, *gradient_norm;
+  int8_t* best_recorded;
+  void *best_x, *best_lambda, *best_mu, *best_penalty, *best_objective, *best_violation, *best_kkt;
+  int* remaining;
+};
+
+template <class T>
+cno::AlArrays<T> arrays(const EmuArrays& e) {
+  cno::AlArrays<T> a{};
+  a.x = (T*)e.x; a.x_work = (T*)e.x_work; a.lambda = (T*)e.lambda; a.mu = (T*)e.mu;
+  a.penalty = (T*)e.penalty; a.prev_penalty = (T*)e.prev_penalty; a.max_violation = (T*)e.max_violation;
+  a.max_lagrangian_gradient = (T*)e.max_lagrangian_gradient; a.num_iterations = e.num_iterations;
+  a.status = e.status; a.nfev = e.nfev; a.inner_nfev = e.inner_nfev; a.x_delta = (T*)e.x_delta;
+  a.f_delta = (T*)e.f_delta; a.gradient_norm = (T*)e.gradient_norm; a.best_recorded = e.best_recorded;
+  a.best_x = (T*)e.best_x; a.best_lambda = (T*)e.best_lambda; a.best_mu = (T*)e.best_mu;
+  a.best_penalty = (T*)e.best_penalty; a.best_objective = (T*)e.best_objective;
+  a.best_violation = (T*)e.best_violation; a.best_kkt = (T*)e.best_kkt; a.remaining = e.remaining;
+  return a;
+}
+
+template <class T>
+cno::AlView<T> view(const cno_constraints_t* k, const EmuArrays& e) {
+  cno::AlView<T> v{};
+  v.rows = (const T*)k->data;
+  v.row_stride = (long long)k->data_stride;
+  v.kinds = (const int*)k->kinds;
+  v.n_eq = k->n_eq;
+  v.n_ineq = k->n_ineq;
+  v.lambda = (const T*)e.lambda;
+  v.mu = (const T*)e.mu;
+  v.penalty = (const T*)e.penalty;
+  v.status = e.status;
+  return v;
+}
+
+template <class T>
+cno::AlParams<T> params(const cno_al_config_t* c, const cno_al_stop_t* s) {  // as al_run (csrc/cno_api.cu)
+  cno::AlParams<T> p{};
+  p.penalty_growth_factor = (T)c->penalty_growth_factor;
+  p.violation_shrink_ratio = (T)c->violation_shrink_ratio;
+  p.auto_scale_initial_penalty = c->auto_scale_initial_penalty;
+  p.penalty_auto_objective_scale = (T)c->penalty_auto_objective_scale;
+  p.penalty_auto_min = (T)c->penalty_auto_min;
+  p.penalty_auto_max = (T)c->penalty_auto_max;
+  p.multiplier_max = (T)c->multiplier_max;
+  p.num_iterations = s->num_iterations;
+  p.constraint_threshold = (T)s->constraint_threshold;
+  p.kkt_stationarity_threshold = s->kkt_stationarity_threshold;
+  return p;
+}
+
+enum Op { kComposite = 0, kAutoscale = 1, kOuterStep = 2, kFinalize = 3 };
+
+template <class Obj>
+int run(int op, const cno_constraints_t* k, long long B, const EmuArrays& e, const cno_al_config_t* cfg,
+        const cno_al_stop_t* stop, const void* x_in, void* value_out, void* grad_out) {
+  using T = typename Obj::Scalar;
+  constexpr int D = Obj::Dim;
+  constexpr int E = cno::Shape<D>::E;
+  const Obj obj{};
+  const cno::AlView<T> v = view<T>(k, e);
+  if (op == kComposite) {  // AugLagFn::operator() at x_in under (lambda, mu, penalty)
+    const cno::AugLagFn<Obj> fn{obj, v};
+    for (long long b = 0; b < B; ++b)
+      emu::run_warp([&](int lane) {
+        const cno::EvalCtx ctx{lane, b, nullptr};
+        T x[E], g[E];
+        cno::al_load<T, D>((const T*)x_in + b * D, lane, x);
+        const T f = fn(ctx, x, &g);
+        cno::al_store<T, D>((T*)grad_out + b * D, lane, g);
+        if (lane == 0) ((T*)value_out)[b] = f;
+      });
+    return 0;
+  }
+  const cno::AlArrays<T> a = arrays<T>(e);
+  const cno::AlParams<T> p = params<T>(cfg, stop);
+  if (op == kAutoscale) launch(B, [&] { cno::al_autoscale_kernel<Obj>(obj, v, B, p, a); });
+  else if (op == kOuterStep) launch(B, [&] { cno::al_outer_step_kernel<Obj>(obj, v, B, p, a); });
+  else launch(B, [&] { cno::al_finalize_kernel<T, D>(B, k->n_eq, k->n_ineq, a); });
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int emu_al(int op, const cno_problem_t* objective, const cno_constraints_t* constraints, long long batch,
+                      const EmuArrays* arrays_, const cno_al_config_t* config, const cno_al_stop_t* stop,
+                      const void* x_in, void* value_out, void* grad_out) {
+#define CASE(FAM, DT, TY, DIM, FN)                                                                  \
+  if (objective->family == FAM && objective->dtype == DT && objective->d == DIM)                    \
+    return run<cno::FN<TY, DIM>>(op, constraints, batch, *arrays_, config, stop, x_in, value_out, grad_out);
+  CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 2, RosenbrockFn)
+  CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 8, RosenbrockFn)
+  CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 37, RosenbrockFn)
+  CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 128, RosenbrockFn)
+  CASE(CNO_FN_ROSENBROCK, CNO_F32, float, 8, RosenbrockFn)
+  CASE(CNO_FN_HALF_SQUARED_NORM, CNO_F64, double, 2, HalfSquaredNormFn)
+  CASE(CNO_FN_HALF_SQUARED_NORM, CNO_F64, double, 8, HalfSquaredNormFn)
+#undef CASE
+  return CNO_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,203 @@
+"""The DEVICE SOURCE of the AugmentedLagrangian path, executed on the CPU (no GPU needed).
+
+csrc/cno_auglag.cuh (the composite functor AugLagFn and the auto-scale / outer-step / finalize
+kernels) is compiled by g++ against tests/emu/warp_emu.h -- 32 lock-step threads per warp, the
+warp intrinsics as publish/barrier/read, the FP64 tensor-core reduction restated with the arithmetic
+measured on B200 -- and driven through the outer loop of csrc/cno_api.cu::al_run, restated here in
+numpy.  The inner solve is the oracle's L-BFGS on the composite (the fused device L-BFGS kernel
+itself needs Tensor Memory and is validated against that oracle on the GPU).  Everything must equal
+the AugmentedLagrangian oracle -- which equals the reference's own headers -- bit for bit.
+
+This is what stands in for the pending first GPU run of this path (tests/test_al_gpu_pending.py)."""
+import ctypes as C
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_binding as ob
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+GOLDEN = os.path.join(HERE, "golden")
+KEYS = ("num_iterations", "status", "nfev", "x", "equality_multipliers", "inequality_multipliers", "penalty",
+        "max_violation", "max_lagrangian_gradient", "x_delta", "f_delta", "gradient_norm")
+COMPOSITE, AUTOSCALE, OUTER_STEP, FINALIZE = range(4)
+
+
+class EmuArrays(C.Structure):  # tests/emu/emu_auglag.cc
+    _fields_ = [(n, C.c_void_p) for n in (
+        "x", "x_work", "lam", "mu", "penalty", "prev_penalty", "max_violation", "max_lagrangian_gradient",
+        "num_iterations", "status", "nfev", "inner_nfev", "x_delta", "f_delta", "gradient_norm", "best_recorded",
+        "best_x", "best_lambda", "best_mu", "best_penalty", "best_objective", "best_violation", "best_kkt",
+        "remaining")]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    return C.CDLL(os.path.join(EMU_DIR, "libcno_emu.so"))
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None and a.size else None
+
+
+def _problem(family, x0, policy=None):
+    return ob.Problem(family, ob._np_dtype(x0), x0.shape[1], 0, 0.0, None, 0,
+                      ob.device_policy(x0.dtype) if policy is None else policy, 0)
+
+
+def emulated_al_minimize(emu, family, x0, kinds, rows, n_eq, *, outer_stop=None, config=None, inner_stop=None,
+                         eq0=None, ineq0=None, penalty0=None):
+    """csrc/cno_api.cu::al_run with the kernels of csrc/cno_auglag.cuh run under the warp emulation."""
+    x0 = np.ascontiguousarray(x0)
+    B, d = x0.shape
+    dt = x0.dtype
+    prob = _problem(family, x0)
+    k, keep = ob._constraints(kinds, rows, n_eq, dt, B, d)
+    ne, ni = k.n_eq, k.n_ineq
+    cfg = config if config is not None else ob.al_default_config()
+    ostop = outer_stop if outer_stop is not None else ob.al_default_stop()
+    istop = inner_stop if inner_stop is not None else ob.default_stop()
+    full = lambda v, n: np.ascontiguousarray(np.broadcast_to(np.asarray(0.0 if v is None else v, dt), (B, n)))  # noqa: E731
+    s = dict(x=x0.copy(), x_work=np.zeros_like(x0), lam=full(eq0, ne).copy(), mu=full(ineq0, ni).copy(),
+             penalty=np.ascontiguousarray(np.broadcast_to(np.asarray(0.0 if penalty0 is None else penalty0, dt), (B,))).copy(),
+             max_violation=np.zeros(B, dt), max_lagrangian_gradient=np.zeros(B, dt),
+             num_iterations=np.zeros(B, np.uint32), status=np.full(B, -1, np.int8), nfev=np.zeros(B, np.uint32),
+             inner_nfev=np.zeros(B, np.uint32), x_delta=np.zeros(B, dt), f_delta=np.zeros(B, dt),
+             gradient_norm=np.zeros(B, dt), best_recorded=np.zeros(B, np.int8), best_x=np.zeros_like(x0),
+             best_lambda=np.zeros((B, ne), dt), best_mu=np.zeros((B, ni), dt), best_penalty=np.zeros(B, dt),
+             best_objective=np.zeros(B, dt), best_violation=np.zeros(B, dt), best_kkt=np.zeros(B, dt),
+             remaining=np.zeros(1, np.int32))
+    s["prev_penalty"] = s["penalty"].copy()
+    arr = EmuArrays(*[_ptr(s[n]) for n, _ in EmuArrays._fields_])
+
+    def kernel(op):
+        rc = emu.emu_al(op, C.byref(prob), C.byref(k), C.c_longlong(B), C.byref(arr), C.byref(cfg), C.byref(ostop),
+                        None, None, None)
+        assert rc == 0
+
+    outer = 0
+    while True:
+        outer += 1
+        if outer == 1 and cfg.auto_scale_initial_penalty:
+            kernel(AUTOSCALE)
+        inner = ob.Stop.from_buffer_copy(istop)  # working copy of the template, ConfigureInnerSubproblem
+        inner.f_delta = 0.0
+        if outer == 1 and (ne > 0 or ni > 0) and cfg.warmup_max_inner_iterations > 0:
+            inner.num_iterations = cfg.warmup_max_inner_iterations
+            inner.gradient_norm = float(dt.type(cfg.warmup_inner_gradient_tolerance))
+        active = (s["status"] == 0) | (s["status"] == -1)  # AugLagFn::active: the inner kernel skips the rest
+        idx = np.nonzero(active)[0]
+        if idx.size:
+            xw = np.zeros((idx.size, d), dt)
+            nf = np.zeros(idx.size, np.uint32)
+            rows_a = np.ascontiguousarray(keep[1][idx]) if keep[1].ndim == 3 else keep[1]
+            ka, keep_a = ob._constraints(keep[0], rows_a, n_eq, dt, idx.size, d)
+            xa, la, ma, pa = (np.ascontiguousarray(s[n][idx]) for n in ("x", "lam", "mu", "penalty"))  # kept alive
+            rc = ob.oracle_lib().cno_al_oracle_inner_minimize(
+                C.byref(prob), C.byref(ka), C.c_int64(idx.size), C.c_void_p(xa.ctypes.data),
+                C.c_void_p(_ptr(la)), C.c_void_p(_ptr(ma)), C.c_void_p(pa.ctypes.data), C.byref(inner),
+                C.c_void_p(xw.ctypes.data), C.c_void_p(nf.ctypes.data), 0)
+            assert rc == 0
+            s["x_work"][idx] = xw
+            s["inner_nfev"][idx] = nf
+            del keep_a
+        s["remaining"][0] = 0
+        kernel(OUTER_STEP)
+        if s["remaining"][0] == 0:
+            break
+    kernel(FINALIZE)
+    return dict(x=s["x"], equality_multipliers=s["lam"], inequality_multipliers=s["mu"], penalty=s["penalty"],
+                max_violation=s["max_violation"], max_lagrangian_gradient=s["max_lagrangian_gradient"],
+                num_iterations=s["num_iterations"], status=s["status"], nfev=s["nfev"], x_delta=s["x_delta"],
+                f_delta=s["f_delta"], gradient_norm=s["gradient_norm"])
+
+
+def _assert_same(a, b):
+    for key in KEYS:
+        assert np.array_equal(a[key].view(np.uint8), b[key].view(np.uint8)), f"{key} differs"
+
+
+@pytest.mark.parametrize("family,dtype,d", [(ob.FN_ROSENBROCK, np.float64, 8), (ob.FN_ROSENBROCK, np.float64, 37),
+                                            (ob.FN_ROSENBROCK, np.float64, 128), (ob.FN_ROSENBROCK, np.float32, 8),
+                                            (ob.FN_HALF_SQUARED_NORM, np.float64, 8)])
+def test_device_composite_functor_equals_oracle(emu, family, dtype, d):
+    """AugLagFn::operator() == ToAugmentedLagrangian(...)(x, &grad) of the oracle: value and gradient, all bits;
+    zero / positive / inactive-side multipliers, penalty 0 (no penalty and no inequality part) and > 0."""
+    rng = np.random.default_rng(d)
+    B = 12
+    x = rng.uniform(-1.5, 1.5, (B, d)).astype(dtype)
+    kinds = [ob.CON_AFFINE, ob.CON_SQNORM, ob.CON_AFFINE, ob.CON_SQNORM]
+    rows = rng.uniform(-1, 1, (B, 4, d + 1)).astype(dtype)
+    rows[:, 3, d] = d / 2.0  # t - x.x > mu / rho for some instances (inactive side), not for others
+    lam = rng.uniform(-1, 1, (B, 2)).astype(dtype)
+    lam[::3, 0] = 0.0  # the MulExpression c == 0 short cut
+    mu = rng.uniform(0, 2, (B, 2)).astype(dtype)
+    rho = rng.uniform(0.5, 3, B).astype(dtype)
+    rho[1::4] = 0.0
+    prob = _problem(family, x)
+    k, keep = ob._constraints(kinds, rows, 2, x.dtype, B, d)
+    arr = EmuArrays()
+    arr.lam, arr.mu, arr.penalty = lam.ctypes.data, mu.ctypes.data, rho.ctypes.data
+    v, g = np.zeros(B, dtype), np.zeros_like(x)
+    cfg, stop = ob.al_default_config(), ob.al_default_stop()
+    assert emu.emu_al(COMPOSITE, C.byref(prob), C.byref(k), C.c_longlong(B), C.byref(arr), C.byref(cfg), C.byref(stop),
+                      C.c_void_p(x.ctypes.data), C.c_void_p(v.ctypes.data), C.c_void_p(g.ctypes.data)) == 0
+    vo, go = ob.al_evaluate(family, x, kinds, rows, 2, lam, mu, rho)
+    assert np.array_equal(v.view(np.uint8), vo.view(np.uint8))
+    assert np.array_equal(g.view(np.uint8), go.view(np.uint8))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "al_*.npz"))))
+def test_emulated_device_loop_matches_reference_fixtures(emu, path):
+    """The committed outputs of the reference's own headers (tests/golden/make_golden_al.py)."""
+    z = np.load(path)
+    n = min(4, z["x0"].shape[0])  # the emulation runs 32 threads per warp: keep it to a few instances
+    stop = ob.al_default_stop()
+    stop.num_iterations = int(z["outer_limit"])
+    r = emulated_al_minimize(emu, int(z["family"]), z["x0"][:n], z["kinds"], z["rows"][:n], int(z["n_eq"]), outer_stop=stop)
+    for key in KEYS:
+        assert np.array_equal(r[key].view(np.uint8), z[key][:n].view(np.uint8)), key
+
+
+@pytest.mark.parametrize("family,dtype,d,n_eq,per_instance", [
+    (ob.FN_ROSENBROCK, np.float64, 2, 1, False), (ob.FN_ROSENBROCK, np.float64, 8, 3, True),
+    (ob.FN_ROSENBROCK, np.float64, 37, 0, True), (ob.FN_ROSENBROCK, np.float32, 8, 1, True),
+    (ob.FN_HALF_SQUARED_NORM, np.float64, 8, 2, False)])
+def test_emulated_device_loop_equals_oracle(emu, family, dtype, d, n_eq, per_instance):
+    B = 5
+    rng = np.random.default_rng(200 + d)
+    x0 = ob.fill_uniform((B, d), 0, 31 + d, -1.5, 1.5, dtype)
+    kinds = [ob.CON_AFFINE, ob.CON_SQNORM, ob.CON_AFFINE]
+    shape = (B, 3, d + 1) if per_instance else (3, d + 1)
+    rows = rng.uniform(-1, 1, shape).astype(dtype)
+    rows[..., 1, d] = 2.0 + rng.uniform(0, 1, shape[:-2])
+    stop = ob.al_default_stop()
+    stop.num_iterations = 8
+    _assert_same(emulated_al_minimize(emu, family, x0, kinds, rows, n_eq, outer_stop=stop),
+                 ob.al_minimize(family, x0, kinds, rows, n_eq, outer_stop=stop))
+    # user-set multipliers / penalty (no auto-scaling), non-default config and inner preset
+    cfg = ob.al_default_config()
+    cfg.warmup_max_inner_iterations, cfg.violation_shrink_ratio, cfg.multiplier_max = 0, 0.5, 5.0
+    kw = dict(outer_stop=stop, config=cfg, inner_stop=ob.conservative_stop(), eq0=0.25, ineq0=0.5, penalty0=2.0)
+    _assert_same(emulated_al_minimize(emu, family, x0, kinds, rows, n_eq, **kw),
+                 ob.al_minimize(family, x0, kinds, rows, n_eq, **kw))
+
+
+def test_emulated_device_loop_known_answers(emu):
+    """augmented_lagrangian_test.cc:492-539 (EqualityOnlyQuadratic), :627-692 (FeasibleStart, NoConstraints)."""
+    r = emulated_al_minimize(emu, ob.FN_HALF_SQUARED_NORM, np.array([[5.0, 5.0]]), [ob.CON_AFFINE], [[1.0, 0.0, 1.0]], 1,
+                             penalty0=1.0)
+    assert abs(r["x"][0, 0] - 1.0) <= 1e-3 and abs(r["x"][0, 1]) <= 1e-3
+    assert abs(r["equality_multipliers"][0, 0] + 1.0) <= 1e-2
+    _assert_same(r, ob.al_minimize(ob.FN_HALF_SQUARED_NORM, np.array([[5.0, 5.0]]), [ob.CON_AFFINE], [[1.0, 0.0, 1.0]], 1,
+                                   penalty0=1.0))
+    r = emulated_al_minimize(emu, ob.FN_HALF_SQUARED_NORM, np.array([[0.0, 0.0]]), [ob.CON_AFFINE], [[0.0, 0.0, 0.0]], 1,
+                             penalty0=1.0)
+    assert r["status"][0] == 6 and r["num_iterations"][0] <= 5
+    r = emulated_al_minimize(emu, ob.FN_HALF_SQUARED_NORM, np.array([[5.0, 5.0]]), [], np.zeros((0, 3)), 0, penalty0=1.0)
+    assert r["status"][0] == 6 and np.all(np.abs(r["x"][0]) <= 1e-3)
