@@ -58,7 +58,7 @@ bfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   using SMB = BfgsSmem<T, D>;
   constexpr T eps = Num<T>::eps;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CNO_DYNAMIC_SMEM(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   T* const va = reinterpret_cast<T*>(smem_raw) + (size_t)warp * SMB::kWarpElems;  // broadcast vec A

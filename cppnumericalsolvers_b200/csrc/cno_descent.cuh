@@ -48,7 +48,7 @@ descent_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   constexpr int E = Shape<D>::E;
   using SMD = DescentSmem<T>;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CNO_DYNAMIC_SMEM(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   T* const ring = reinterpret_cast<T*>(smem_raw) + (size_t)warp * SMD::kWarpElems;

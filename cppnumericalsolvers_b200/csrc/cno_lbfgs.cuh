@@ -186,7 +186,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   using SV = SmemVec<T, E>;
   constexpr T eps = Num<T>::eps;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CNO_DYNAMIC_SMEM(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   T* const S = reinterpret_cast<T*>(smem_raw) + (size_t)warp * SM::kWarpElems;

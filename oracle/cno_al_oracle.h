@@ -51,7 +51,7 @@ int cno_al_oracle_minimize(const cno_problem_t* objective, const cno_constraints
 
 /* One inner solve of the outer loop: Lbfgs::Minimize on ToAugmentedLagrangian(problem, eq, ineq,
  * penalty) from x0 under `inner_stop` as given (the caller applies ConfigureInnerSubproblem).
- * x_out [B,d], nfev_out [B] (objective evaluations).  Used by tests/test_al_emulated.py to stand
+ * x_out [B,d], nfev_out [B] (objective evaluations).  Used by tests/test_device_emulated.py to stand
  * in for the fused device L-BFGS kernel, whose parity with this restatement is validated on the GPU. */
 int cno_al_oracle_inner_minimize(const cno_problem_t* objective, const cno_constraints_t* constraints,
                                  int64_t batch, const void* x0, const void* eq, const void* ineq,

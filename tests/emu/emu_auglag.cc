@@ -3,9 +3,12 @@
 // al_finalize_kernel, on top of csrc/cno_functors.cuh) on the CPU under the warp
 // emulation of warp_emu.h.  TEST INFRASTRUCTURE ONLY: the first GPU run of this path is
 // still pending, so this is how its logic is checked against the oracle meanwhile
-// (tests/test_al_emulated.py).  Built by tests/emu/Makefile into libcno_emu.so.
+// (tests/test_device_emulated.py).  Built by tests/emu/Makefile into libcno_emu.so.
 #include "cno_functors.cuh"
 #include "cno_auglag.cuh"
+#include "cno_lbfgs.cuh"
+#include "cno_bfgs.cuh"
+#include "cno_descent.cuh"
 
 namespace {
 
@@ -78,7 +81,7 @@ cno::AlParams<T> params(const cno_al_config_t* c, const cno_al_stop_t* s) {  // 
   return p;
 }
 
-enum Op { kComposite = 0, kAutoscale = 1, kOuterStep = 2, kFinalize = 3 };
+enum Op { kComposite = 0, kAutoscale = 1, kOuterStep = 2, kFinalize = 3, kInner = 4 };
 
 template <class Obj>
 int run(int op, const cno_constraints_t* k, long long B, const EmuArrays& e, const cno_al_config_t* cfg,
@@ -102,6 +105,29 @@ int run(int op, const cno_constraints_t* k, long long B, const EmuArrays& e, con
     return 0;
   }
   const cno::AlArrays<T> a = arrays<T>(e);
+  if (op == kInner) {
+    // the fused inner solve: lbfgs_minimize_kernel<AugLagFn<Obj>> exactly as al_run launches it
+    // (x0 = state x, out.x = x_work, out.nfev = inner_nfev), one emulated warp draining the queue.
+    // Shapes whose y-history lives in Tensor Memory (fp64, d = 128) cannot run here.
+    if constexpr (sizeof(T) == 8 && E == 4) {
+      return CNO_ERR_UNSUPPORTED;
+    } else {
+      const cno::AugLagFn<Obj> fn{obj, v};
+      const cno_stop_t* inner = static_cast<const cno_stop_t*>(x_in);
+      cno_batch_out_t o{};
+      o.x = a.x_work;
+      o.nfev = const_cast<uint32_t*>(a.inner_nfev);
+      unsigned long long queue = 0;
+      emu::run_warp([&](int lane) {
+        blockIdx.x = 0;
+        threadIdx.x = (unsigned)lane;
+        cno::lbfgs_minimize_kernel<cno::AugLagFn<Obj>, CNO_LBFGS_M>(fn, a.x, B, cno::make_stop<T>(*inner),
+                                                                   cno::make_out<T>(o), &queue,
+                                                                   cno::ResumeArgs{nullptr, 0, 0, 0});
+      });
+      return 0;
+    }
+  }
   const cno::AlParams<T> p = params<T>(cfg, stop);
   if (op == kAutoscale) launch(B, [&] { cno::al_autoscale_kernel<Obj>(obj, v, B, p, a); });
   else if (op == kOuterStep) launch(B, [&] { cno::al_outer_step_kernel<Obj>(obj, v, B, p, a); });
@@ -110,6 +136,52 @@ int run(int op, const cno_constraints_t* k, long long B, const EmuArrays& e, con
 }
 
 }  // namespace
+
+// ---- the unconstrained solver kernels under emulation (one warp draining the queue) ----
+template <class Fn, class LS>
+int run_solver(int solver, long long B, const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out) {
+  using T = typename Fn::Scalar;
+  constexpr int E = cno::Shape<Fn::Dim>::E;
+  const Fn fn{};
+  unsigned long long queue = 0;
+  int rc = 0;
+  emu::run_warp([&](int lane) {
+    blockIdx.x = 0;
+    threadIdx.x = (unsigned)lane;
+    const auto sp = cno::make_stop<T>(*stop);
+    const auto bo = cno::make_out<T>(*out);
+    if (solver == CNO_LBFGS) {
+      if constexpr (sizeof(T) == 8 && E == 4) rc = CNO_ERR_UNSUPPORTED;  // y-history in Tensor Memory
+      else cno::lbfgs_minimize_kernel<Fn, CNO_LBFGS_M, false, LS>(fn, (const T*)x0, B, sp, bo, &queue, cno::ResumeArgs{nullptr, 0, 0, 0});
+    } else if (solver == CNO_BFGS) {
+      if constexpr (Fn::Dim <= 32) cno::bfgs_minimize_kernel<Fn, LS>(fn, (const T*)x0, B, sp, bo, &queue);
+      else rc = CNO_ERR_UNSUPPORTED;
+    } else if (solver == CNO_GRADIENT_DESCENT) {
+      cno::descent_minimize_kernel<Fn, false, LS>(fn, (const T*)x0, B, sp, bo, &queue);
+    } else if (solver == CNO_CONJUGATED_GRADIENT_DESCENT) {
+      cno::descent_minimize_kernel<Fn, true, LS>(fn, (const T*)x0, B, sp, bo, &queue);
+    } else {
+      rc = CNO_ERR_UNSUPPORTED;
+    }
+  });
+  return rc;
+}
+
+// solver: CNO_LBFGS / CNO_BFGS / CNO_GRADIENT_DESCENT / CNO_CONJUGATED_GRADIENT_DESCENT; hager_zhang selects
+// the LineSearch policy.  Host pointers.
+extern "C" int emu_minimize(int solver, int hager_zhang, const cno_problem_t* p, long long batch, const void* x0,
+                            const cno_stop_t* stop, const cno_batch_out_t* out) {
+#define SOLVER_CASE(DT, TY, DIM)                                                                         \
+  if (p->family == CNO_FN_ROSENBROCK && p->dtype == DT && p->d == DIM)                                   \
+    return hager_zhang ? run_solver<cno::RosenbrockFn<TY, DIM>, cno::LsHagerZhang>(solver, batch, x0, stop, out) \
+                       : run_solver<cno::RosenbrockFn<TY, DIM>, cno::LsMoreThuente>(solver, batch, x0, stop, out);
+  SOLVER_CASE(CNO_F64, double, 2)
+  SOLVER_CASE(CNO_F64, double, 8)
+  SOLVER_CASE(CNO_F64, double, 37)
+  SOLVER_CASE(CNO_F32, float, 37)
+#undef SOLVER_CASE
+  return CNO_ERR_UNSUPPORTED;
+}
 
 extern "C" int emu_al(int op, const cno_problem_t* objective, const cno_constraints_t* constraints, long long batch,
                       const EmuArrays* arrays_, const cno_al_config_t* config, const cno_al_stop_t* stop,

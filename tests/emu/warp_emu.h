@@ -17,6 +17,7 @@
 #include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstddef>
 #include <cstring>
 #include <functional>
 #include <thread>
@@ -133,6 +134,8 @@ inline unsigned __reduce_min_sync(unsigned, unsigned v) {
   return m;
 }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::sync(); }
+inline void __syncthreads() {}  // only reached from Tensor-Memory paths, which the emulation does not run
+inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 template <class T> inline T __ldg(const T* p) { return *p; }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {

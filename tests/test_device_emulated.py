@@ -1,12 +1,14 @@
-"""The DEVICE SOURCE of the AugmentedLagrangian path, executed on the CPU (no GPU needed).
+"""DEVICE SOURCE executed on the CPU (no GPU needed).
 
 csrc/cno_auglag.cuh (the composite functor AugLagFn and the auto-scale / outer-step / finalize
-kernels) is compiled by g++ against tests/emu/warp_emu.h -- 32 lock-step threads per warp, the
-warp intrinsics as publish/barrier/read, the FP64 tensor-core reduction restated with the arithmetic
-measured on B200 -- and driven through the outer loop of csrc/cno_api.cu::al_run, restated here in
-numpy.  The inner solve is the oracle's L-BFGS on the composite (the fused device L-BFGS kernel
-itself needs Tensor Memory and is validated against that oracle on the GPU).  Everything must equal
-the AugmentedLagrangian oracle -- which equals the reference's own headers -- bit for bit.
+kernels) and the solver kernels (csrc/cno_lbfgs.cuh, cno_bfgs.cuh, cno_descent.cuh with
+cno_linesearch.cuh) are compiled by g++ against tests/emu/warp_emu.h -- 32 lock-step threads per
+warp, the warp intrinsics as publish/barrier/read, the FP64 tensor-core reduction restated with the
+arithmetic measured on B200 -- and driven through the outer loop of csrc/cno_api.cu::al_run,
+restated here in numpy.  The inner solve is either the oracle's L-BFGS on the composite or the fused
+device kernel itself under emulation.  Everything must equal the oracle -- which equals the
+reference's own headers -- bit for bit; the GPU-validated kernels are run too, to show that the
+emulation reproduces what the B200 computes.
 
 This is what stands in for the pending first GPU run of this path (tests/test_al_gpu_pending.py)."""
 import ctypes as C
@@ -24,7 +26,7 @@ EMU_DIR = os.path.join(HERE, "emu")
 GOLDEN = os.path.join(HERE, "golden")
 KEYS = ("num_iterations", "status", "nfev", "x", "equality_multipliers", "inequality_multipliers", "penalty",
         "max_violation", "max_lagrangian_gradient", "x_delta", "f_delta", "gradient_norm")
-COMPOSITE, AUTOSCALE, OUTER_STEP, FINALIZE = range(4)
+COMPOSITE, AUTOSCALE, OUTER_STEP, FINALIZE, INNER = range(5)
 
 
 class EmuArrays(C.Structure):  # tests/emu/emu_auglag.cc
@@ -51,7 +53,7 @@ def _problem(family, x0, policy=None):
 
 
 def emulated_al_minimize(emu, family, x0, kinds, rows, n_eq, *, outer_stop=None, config=None, inner_stop=None,
-                         eq0=None, ineq0=None, penalty0=None):
+                         eq0=None, ineq0=None, penalty0=None, device_inner=False):
     """csrc/cno_api.cu::al_run with the kernels of csrc/cno_auglag.cuh run under the warp emulation."""
     x0 = np.ascontiguousarray(x0)
     B, d = x0.shape
@@ -92,7 +94,10 @@ def emulated_al_minimize(emu, family, x0, kinds, rows, n_eq, *, outer_stop=None,
             inner.gradient_norm = float(dt.type(cfg.warmup_inner_gradient_tolerance))
         active = (s["status"] == 0) | (s["status"] == -1)  # AugLagFn::active: the inner kernel skips the rest
         idx = np.nonzero(active)[0]
-        if idx.size:
+        if device_inner:  # the fused L-BFGS kernel itself on the composite, incl. its active() skip hook
+            assert emu.emu_al(INNER, C.byref(prob), C.byref(k), C.c_longlong(B), C.byref(arr), C.byref(cfg),
+                              C.byref(ostop), C.byref(inner), None, None) == 0
+        elif idx.size:
             xw = np.zeros((idx.size, d), dt)
             nf = np.zeros(idx.size, np.uint32)
             rows_a = np.ascontiguousarray(keep[1][idx]) if keep[1].ndim == 3 else keep[1]
@@ -201,3 +206,50 @@ def test_emulated_device_loop_known_answers(emu):
     assert r["status"][0] == 6 and r["num_iterations"][0] <= 5
     r = emulated_al_minimize(emu, ob.FN_HALF_SQUARED_NORM, np.array([[5.0, 5.0]]), [], np.zeros((0, 3)), 0, penalty0=1.0)
     assert r["status"][0] == 6 and np.all(np.abs(r["x"][0]) <= 1e-3)
+
+
+# ---- the fused inner kernel too: the whole device path of the row under emulation ----------------
+@pytest.mark.parametrize("family,dtype,d,n_eq", [(ob.FN_ROSENBROCK, np.float64, 8, 1), (ob.FN_ROSENBROCK, np.float64, 37, 2),
+                                                 (ob.FN_ROSENBROCK, np.float32, 8, 1), (ob.FN_HALF_SQUARED_NORM, np.float64, 8, 1)])
+def test_emulated_device_loop_with_the_device_inner_kernel(emu, family, dtype, d, n_eq):
+    """lbfgs_minimize_kernel<AugLagFn<Obj>> (with its active() skip of finished instances) + the outer-loop
+    kernels, all device source, all under emulation == the oracle, bit for bit."""
+    B = 2  # 32 lock-step threads per warp: a few instances keep this to seconds
+    rng = np.random.default_rng(300 + d)
+    x0 = ob.fill_uniform((B, d), 0, 57 + d, -1.5, 1.5, dtype)
+    kinds = [ob.CON_AFFINE, ob.CON_SQNORM, ob.CON_AFFINE]
+    rows = rng.uniform(-1, 1, (B, 3, d + 1)).astype(dtype)
+    rows[:, 1, d] = 2.0 + rng.uniform(0, 1, B)
+    stop = ob.al_default_stop()
+    stop.num_iterations = 3 if (d > 8 or dtype == np.float32) else 6
+    _assert_same(emulated_al_minimize(emu, family, x0, kinds, rows, n_eq, outer_stop=stop, device_inner=True),
+                 ob.al_minimize(family, x0, kinds, rows, n_eq, outer_stop=stop))
+
+
+# ---- fidelity of the emulation itself: GPU-validated kernels under emulation == oracle --------------
+SOLVER_KEYS = ("num_iterations", "status", "nfev", "x", "value", "gradient", "x_delta", "f_delta", "gradient_norm")
+
+
+@pytest.mark.parametrize("solver,hz,dtype,d,limit", [
+    (ob.LBFGS, 0, np.float64, 2, 10000), (ob.LBFGS, 0, np.float64, 37, 40), (ob.LBFGS, 0, np.float32, 37, 20),
+    (ob.LBFGS, 1, np.float64, 8, 10000), (ob.BFGS, 0, np.float64, 8, 10000), (ob.BFGS, 1, np.float64, 2, 10000),
+    (ob.GRADIENT_DESCENT, 0, np.float64, 8, 40), (ob.GRADIENT_DESCENT, 1, np.float64, 8, 40),
+    (ob.CONJUGATED_GRADIENT_DESCENT, 0, np.float64, 8, 8)])
+def test_emulation_reproduces_gpu_validated_kernels(emu, solver, hz, dtype, d, limit):
+    """The L-BFGS / BFGS / descent kernels (MoreThuente and HagerZhang) are bit-identical to the oracle on the
+    B200; run under the emulation they must be too -- that is what makes the emulated AugmentedLagrangian
+    results above evidence about the device code rather than about the emulator."""
+    B = 2
+    x0 = ob.fill_uniform((B, d), 0, 900 + d, -2.0, 2.0, dtype)
+    stop = ob.default_stop()
+    stop.num_iterations = limit
+    prob = _problem(ob.FN_ROSENBROCK, x0)
+    r = dict(x=np.zeros_like(x0), value=np.zeros(B, dtype), gradient=np.zeros_like(x0),
+             num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32),
+             x_delta=np.zeros(B, dtype), f_delta=np.zeros(B, dtype), gradient_norm=np.zeros(B, dtype))
+    out = ob.BatchOut(*[r[n].ctypes.data for n, _ in ob.BatchOut._fields_])
+    assert emu.emu_minimize(solver, hz, C.byref(prob), C.c_longlong(B), C.c_void_p(x0.ctypes.data), C.byref(stop),
+                            C.byref(out)) == 0
+    o = ob.minimize(solver, ob.FN_ROSENBROCK, x0, stop=stop, linesearch=hz)
+    for key in SOLVER_KEYS:
+        assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
