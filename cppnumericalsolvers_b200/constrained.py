@@ -101,6 +101,8 @@ class AugmentedLagrangian:
         d = fn.Dimension
         kinds = torch.tensor(list(p.kinds), dtype=torch.int32, device=p.rows.device)
         rows = p.rows.contiguous()
+        if rows.dtype != fn.ScalarType:
+            raise ValueError("constraint rows must have the objective's scalar type")
         n_con = len(p.kinds)
         if n_con and rows.shape[-2:] != (n_con, d + 1):
             raise ValueError("rows must be [n_con, d+1] or [B, n_con, d+1]")

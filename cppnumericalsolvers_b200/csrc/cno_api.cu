@@ -509,7 +509,7 @@ int al_run(const Obj& obj, const AlArgs& A) {
 
   // ---- initial AugmentedLagrangeState (augmented_lagrangian.h:241-276) + ResetBestIterateTracker ----
   auto init = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
-    if (!bytes) return cudaSuccess;
+    if (!bytes || src == dst) return cudaSuccess;  // (a caller may pass its state arrays as the initial values)
     return src ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s) : cudaMemsetAsync(dst, 0, bytes, s);
   };
   CNO_CUDA(init(a.x, A.x0, (size_t)B * D * sizeof(T)));
