@@ -92,7 +92,21 @@ descent_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         for (int e = 0; e < E; ++e) dir[e] = -g[e];
         nfev++;  // MoreThuente::Search evaluates (f, g) at x (more_thuente.h:69)
         // dginit = g.(-g) = -(g.g), bit for bit
-        nfev += LS::template search<Fn, T, E>(fn, ctx, RedCtx<T>{nullptr, lane}, x, f, g, xn, fn_val, gn, T(1), dir, -gg);
+        if constexpr (!LS::kStateMayDifferFromStep) {
+          nfev += LS::template search<Fn, T, E>(fn, ctx, RedCtx<T>{nullptr, lane}, x, f, g, xn, fn_val, gn, T(1), dir, -gg);
+        } else {
+          // gradient_descent.h:72 builds the next point from the step width alone: after a failed
+          // search that is x - 0 * g (NaN where g is not finite) or x - 1 * g, not the start state
+          T rate;
+          bool ls_ok;
+          nfev += LS::template search_with_step<Fn, T, E>(fn, ctx, RedCtx<T>{nullptr, lane}, x, f, g, xn, fn_val, gn, T(1),
+                                                          dir, -gg, rate, ls_ok);
+          if (uni(!ls_ok)) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) xn[e] = x[e] - rate * g[e];
+            fn_val = fn(ctx, xn, &gn);  // = the driver's re-evaluation, counted below
+          }
+        }
       } else {
         // ---- conjugated_gradient_descent.h:70-84 ----
         if (uni(prog.num_iterations == 0)) {

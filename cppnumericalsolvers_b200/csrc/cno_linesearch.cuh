@@ -329,10 +329,13 @@ struct HzSearch {
 
 // hzls (:290-548).  Same contract as cvsrch: returns the number of evaluations; (x, f, g)
 // is the accepted state, or the start state when the search fails (return -1 there).
+// stp_out / ok = the reference's `*stp` on return and `return value == 0`: GradientDescent rebuilds
+// its next point from the step width alone (gradient_descent.h:72), which differs from the
+// returned state exactly when the search failed.
 template <class Fn, class T, int E>
 __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc, const T (&x0)[E],
                                  const T f0, const T (&g0)[E], T (&x)[E], T& f, T (&g)[E], T stp,
-                                 const T (&s)[E], const T dginit) {
+                                 const T (&s)[E], const T dginit, T& stp_out, bool& ok) {
   const T epsilon_k = T(1e-6), gamma = T(0.66), rho = T(5), psi3 = T(0.1);
   const int maxlinesearch = 50, iterfinitemax = 60;
   // x / g double as the PhiDphi workspaces (xa, gx); they hold the start state until the
@@ -340,7 +343,9 @@ __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedC
 #pragma unroll
   for (int j = 0; j < E; ++j) { x[j] = x0[j]; g[j] = g0[j]; }
   f = f0;
-  if (uni(dginit >= T(0))) return 0;  // :316
+  stp_out = stp;
+  ok = false;
+  if (uni(dginit >= T(0))) return 0;  // :316 (the step is left at its initial value)
 
   HzSearch<Fn, T, E> z{fn, ctx, rc, x0, s, x, g, f0, dginit, T(0), T(1) / T(10), T(9) / T(10), 1, 0};
   z.phi_lim = f0 + epsilon_k * cabs(f0);
@@ -359,16 +364,23 @@ __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedC
       for (int j = 0; j < E; ++j) { best_x[j] = x[j]; best_g[j] = g[j]; }
     }
   };
-  auto fail = [&]() {  // state untouched
+  auto fail = [&]() {  // state untouched, *stp = 0
 #pragma unroll
     for (int j = 0; j < E; ++j) { x[j] = x0[j]; g[j] = g0[j]; }
     f = f0;
+    stp_out = T(0);
+    ok = false;
+  };
+  auto accept = [&](const T phi, const T alpha) {  // (x, g) already hold the accepted point
+    f = phi;
+    stp_out = alpha;
+    ok = true;
   };
   auto best_or_fail = [&]() {
     if (uni(best_alpha > T(0))) {
 #pragma unroll
       for (int j = 0; j < E; ++j) { x[j] = best_x[j]; g[j] = best_g[j]; }
-      f = best_phi;
+      accept(best_phi, best_alpha);
     } else {
       fail();
     }
@@ -386,7 +398,7 @@ __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedC
   if (uni(!(cfinite(ec.phi) & cfinite(ec.dphi)))) { fail(); return z.nfev; }
   z.push(ec);
   update_best(ec);
-  if (uni(z.wolfe(ec))) { f = ec.phi; return z.nfev; }  // (x, g) already hold the accepted point
+  if (uni(z.wolfe(ec))) { accept(ec.phi, cc); return z.nfev; }
 
   bool bracketed = false;
   HzSample<T> A = origin, B = ec;
@@ -401,7 +413,7 @@ __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedC
     } else if (uni(last.phi > z.phi_lim)) {
       B = last;
       A = origin;
-      if (z.bisect(A, B)) { f = B.phi; return z.nfev; }
+      if (z.bisect(A, B)) { accept(B.phi, B.alpha); return z.nfev; }
       bracketed = true;
     } else {
       cc *= rho;
@@ -417,7 +429,7 @@ __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedC
       z.push(ec);
       last = ec;
       update_best(ec);
-      if (uni(z.wolfe(ec))) { f = ec.phi; return z.nfev; }
+      if (uni(z.wolfe(ec))) { accept(ec.phi, cc); return z.nfev; }
     }
     ++iter;
   }
@@ -428,14 +440,14 @@ __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedC
     if (uni(b - a <= Num<T>::eps * b)) {
       if (uni(a > T(0))) {
         ec = z.eval(a);
-        f = ec.phi;
+        accept(ec.phi, a);
         return z.nfev;
       }
       best_or_fail();
       return z.nfev;
     }
     HzSample<T> nA = A, nB = B;
-    if (z.secant2(nA, nB)) { f = nA.phi; return z.nfev; }
+    if (z.secant2(nA, nB)) { accept(nA.phi, nA.alpha); return z.nfev; }
     if (uni(nB.alpha - nA.alpha < gamma * (b - a))) {
       A = nA;
       B = nB;
@@ -444,8 +456,8 @@ __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedC
       HzSample<T> rm = z.eval(cm);
       z.push(rm);
       update_best(rm);
-      if (uni(z.wolfe(rm))) { f = rm.phi; return z.nfev; }
-      if (z.update(nA, nB, rm)) { f = nB.phi; return z.nfev; }
+      if (uni(z.wolfe(rm))) { accept(rm.phi, cm); return z.nfev; }
+      if (z.update(nA, nB, rm)) { accept(nB.phi, nB.alpha); return z.nfev; }
       A = nA;
       B = nB;
     }
@@ -457,6 +469,8 @@ __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedC
 
 // The LineSearch template parameter of the solvers (lbfgs.h:41, bfgs.h:40, gradient_descent.h:38).
 struct LsMoreThuente {
+  // cvsrch always evaluates at the step it returns: the returned state IS x0 + stp * s
+  static constexpr bool kStateMayDifferFromStep = false;
   template <class Fn, class T, int E>
   __device__ __forceinline__ static int search(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc,
                                                const T (&x0)[E], const T f0, const T (&g0)[E], T (&x)[E],
@@ -465,11 +479,22 @@ struct LsMoreThuente {
   }
 };
 struct LsHagerZhang {
+  // a failed hzls leaves the state at the start point and the step at 0 (or at its initial value)
+  static constexpr bool kStateMayDifferFromStep = true;
   template <class Fn, class T, int E>
   __device__ __forceinline__ static int search(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc,
                                                const T (&x0)[E], const T f0, const T (&g0)[E], T (&x)[E],
                                                T& f, T (&g)[E], T stp, const T (&s)[E], const T dginit) {
-    return hzls<Fn, T, E>(fn, ctx, rc, x0, f0, g0, x, f, g, stp, s, dginit);
+    T stp_out;
+    bool ok;
+    return hzls<Fn, T, E>(fn, ctx, rc, x0, f0, g0, x, f, g, stp, s, dginit, stp_out, ok);
+  }
+  template <class Fn, class T, int E>
+  __device__ __forceinline__ static int search_with_step(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc,
+                                                         const T (&x0)[E], const T f0, const T (&g0)[E],
+                                                         T (&x)[E], T& f, T (&g)[E], T stp, const T (&s)[E],
+                                                         const T dginit, T& stp_out, bool& ok) {
+    return hzls<Fn, T, E>(fn, ctx, rc, x0, f0, g0, x, f, g, stp, s, dginit, stp_out, ok);
   }
 };
 

@@ -253,3 +253,30 @@ def test_emulation_reproduces_gpu_validated_kernels(emu, solver, hz, dtype, d, l
     o = ob.minimize(solver, ob.FN_ROSENBROCK, x0, stop=stop, linesearch=hz)
     for key in SOLVER_KEYS:
         assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
+
+
+def test_gradient_descent_hager_zhang_failed_search_rebuilds_point_from_step(emu):
+    """Found by sweeping the emulated kernels against the oracle: when HagerZhang fails (non-finite
+    evaluations) GradientDescent's next point is x - rate * g with rate = 0 (gradient_descent.h:72), i.e. NaN
+    wherever g is not finite -- not the start state the search leaves behind.  NaN / Inf / huge starts."""
+    x0 = np.array([[np.nan, 1.0, -0.5, 2.0, 0.3, -1.2, 0.8, 0.1], [0.4, -0.7, 1.1, 0.2, -0.9, 0.6, 1.3, np.inf],
+                   [3e5, -2e5, 1e5, 4e5, -3e5, 2e5, -1e5, 5e5]])
+    B, d = x0.shape
+    stop = ob.default_stop()
+    stop.num_iterations = 10
+    prob = _problem(ob.FN_ROSENBROCK, x0)
+    r = dict(x=np.zeros_like(x0), value=np.zeros(B), gradient=np.zeros_like(x0),
+             num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32),
+             x_delta=np.zeros(B), f_delta=np.zeros(B), gradient_norm=np.zeros(B))
+    out = ob.BatchOut(*[r[n].ctypes.data for n, _ in ob.BatchOut._fields_])
+    assert emu.emu_minimize(ob.GRADIENT_DESCENT, 1, C.byref(prob), C.c_longlong(B), C.c_void_p(x0.ctypes.data),
+                            C.byref(stop), C.byref(out)) == 0
+    o = ob.minimize(ob.GRADIENT_DESCENT, ob.FN_ROSENBROCK, x0, stop=stop, linesearch=ob.LS_HAGER_ZHANG)
+    for key in SOLVER_KEYS:
+        u, v = r[key], o[key]
+        if u.dtype.kind == "f":  # a NaN must be a NaN in both; its sign / payload is not part of the contract
+            nan = np.isnan(u)
+            assert np.array_equal(nan, np.isnan(v)), key
+            u, v = np.where(nan, 0, u), np.where(nan, 0, v)
+        assert np.array_equal(u.view(np.uint8), v.view(np.uint8)), key
+    assert np.isnan(o["x"][0]).sum() > 1  # the oracle (= reference) really spreads the NaN through 0 * g
