@@ -56,7 +56,7 @@ def lbfgs_bytes(w, d, m=10):
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     scale = int(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 0
-    which = args or ["c2", "c3", "c4", "c5"]  # "gd", "cg": the SURVEY.md 8(f) rank-4 solvers, on request
+    which = args or ["c2", "c3", "c4", "c5"]  # "gd", "cg", "hz", "al": the SURVEY.md 8(f) rows, on request
     gen = torch.Generator(device=DEV)
     gen.manual_seed(0)
     if "c2" in which:  # Rosenbrock d=128 fp64 L-BFGS, B = 2^20
@@ -119,6 +119,35 @@ def main():
         run(f"{tag} rosenbrock d128 f64 (iteration limit {limit})", solver(prog), cn.Rosenbrock(d), x0,
             lambda it, nf: (8 * d * (2 * (nf - 3 * it) + 6 * it)).sum())
         del x0
+    if "hz" in which:  # Lbfgs<F, 10, HagerZhang>, same workload as c2 (not yet timed on a GPU: DESIGN.md 9)
+        B = (1 << 18) >> scale
+        x0 = torch.empty(B, 128, dtype=torch.float64, device=DEV)
+        cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
+        run("hz lbfgs(HagerZhang) rosenbrock d128 f64", cn.Lbfgs(linesearch=cn.HagerZhang), cn.Rosenbrock(128), x0,
+            lbfgs_bytes(8, 128))
+        del x0
+    if "al" in which:  # AugmentedLagrangian (GPU validation pending: DESIGN.md 8): Rosenbrock d=128 on a ball + halfspace
+        B, d = (1 << 15) >> scale, 128
+        x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
+        cn.fill_uniform(x0, 0, 12345, -1.5, 1.5)
+        rows = torch.zeros(2, d + 1, dtype=torch.float64, device=DEV)
+        rows[0, d] = 16.0           # t - x.x = 0  (equality: on the sphere of radius 4)
+        rows[1, :d] = 1.0           # sum(x) + 1 >= 0
+        rows[1, d] = -1.0
+        problem = cn.ConstrainedOptimizationProblem(cn.Rosenbrock(d), [1, 0], rows, 1)
+        solver = cn.AugmentedLagrangian(problem)
+        solver.stopping_progress.num_iterations = 20
+        ms = []
+        for _ in range(3):
+            st, pr = solver.Minimize(cn.AugmentedLagrangeState(x0))
+            ms.append(pr.launch.total_ms)
+        print(json.dumps({"config": "al rosenbrock d128 f64 sphere+halfspace (outer limit 20)", "batch": B,
+                          "total_ms": float(np.mean(ms[1:])), "instances_per_s": B / float(np.mean(ms[1:])) * 1e3,
+                          "kernel_launches": pr.launch.kernel_launches,
+                          "mean_outer_iterations": float(pr.num_iterations.float().mean()),
+                          "mean_objective_evaluations": float(pr.nfev.float().mean()),
+                          "status_histogram": np.bincount(pr.status.cpu().numpy().astype(np.int64) + 1).tolist(),
+                          "max_violation_max": float(st.max_violation.max())}), flush=True)
 
 
 if __name__ == "__main__":
