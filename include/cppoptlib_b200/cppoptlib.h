@@ -43,6 +43,7 @@
 #include <vector>
 
 #include "../cno.h"
+#include "../cno_al.h"
 
 namespace cppoptlib {
 
@@ -505,6 +506,165 @@ template <class F> class ConjugatedGradientDescent : public Solver<F, CNO_CONJUG
   static_assert(sizeof(typename F::ScalarType) == 8,
                 "ConjugatedGradientDescent: fp64 only (the reference computes beta in double)");
   using Solver<F, CNO_CONJUGATED_GRADIENT_DESCENT>::Solver;
+};
+
+
+// ---- the constrained caller of the path (solver/augmented_lagrangian.h, function_problem.h) ----
+// STATUS: like include/cno_al.h -- written against the pinned CPU oracle and checked under the CPU warp
+// emulation; its first GPU run is pending.
+}  // namespace solver
+
+namespace function {
+// function_problem.h:38-60 with the two device constraint families (include/cno_al.h):
+// a constraint is a row [a (d) | t]; AFFINE c(x) = a.x - t, SQNORM c(x) = t - x.x; equalities
+// (c == 0) first, then inequalities (c >= 0).  `rows` is one set shared by the batch
+// ([n_con][d+1]) or per instance ([B][n_con][d+1]).
+template <class Objective>
+struct ConstrainedOptimizationProblem {
+  using ScalarType = typename Objective::ScalarType;
+  static constexpr int Dimension = Objective::Dimension;
+  static constexpr DifferentiabilityMode Differentiability = Objective::Differentiability;
+  Objective objective;
+  std::vector<int32_t> kinds;
+  std::vector<ScalarType> rows;
+  int n_eq = 0;
+  bool per_instance = false;
+  int n_ineq() const { return static_cast<int>(kinds.size()) - n_eq; }
+};
+}  // namespace function
+
+namespace solver {
+
+template <class TScalar>
+struct AugmentedLagrangianConfig {  // solver/augmented_lagrangian.h:63-239, same names and defaults
+  TScalar penalty_growth_factor = TScalar{10};
+  TScalar violation_shrink_ratio = TScalar{0.25};
+  bool auto_scale_initial_penalty = true;
+  TScalar penalty_auto_objective_scale = TScalar{10};
+  TScalar penalty_auto_min = TScalar{1e-8};
+  TScalar penalty_auto_max = TScalar{1e8};
+  int warmup_max_inner_iterations = 10;
+  TScalar warmup_inner_gradient_tolerance = TScalar{1e-2};
+  TScalar multiplier_max = TScalar{1e20};
+  TScalar kkt_gradient_tolerance = TScalar{1e-4};
+};
+
+// AugmentedLagrangeState (solver/augmented_lagrangian.h:241-276), one row per instance.
+template <class TScalar, int TDimension>
+struct BatchedAugmentedLagrangeState {
+  static constexpr bool IsConstrained = true;
+  int64_t batch = 0;
+  detail::DeviceArray<TScalar> x, equality_multipliers, inequality_multipliers, penalty, max_violation,
+      max_lagrangian_gradient;
+  // (x, num_eq, num_ineq, penalty = 0): zero multipliers; penalty 0 = auto-scale (:263-275, 312-318)
+  static BatchedAugmentedLagrangeState FromHost(const std::vector<TScalar>& x_host, int64_t batch, size_t num_eq,
+                                                size_t num_ineq, TScalar penalty = TScalar(0)) {
+    if (static_cast<int64_t>(x_host.size()) != batch * TDimension) throw std::invalid_argument("x0 must be [B, d]");
+    BatchedAugmentedLagrangeState s;
+    s.batch = batch;
+    s.x = detail::DeviceArray<TScalar>::FromHost(x_host);
+    s.equality_multipliers = detail::DeviceArray<TScalar>::FromHost(std::vector<TScalar>(batch * num_eq, TScalar(0)));
+    s.inequality_multipliers = detail::DeviceArray<TScalar>::FromHost(std::vector<TScalar>(batch * num_ineq, TScalar(0)));
+    s.penalty = detail::DeviceArray<TScalar>::FromHost(std::vector<TScalar>(batch, penalty));
+    return s;
+  }
+};
+
+// AugmentedLagrangian<Problem, Lbfgs<...>> (solver/augmented_lagrangian.h:278-449).
+template <class ProblemType, class solver_t>
+class AugmentedLagrangian {
+ public:
+  using ScalarType = typename ProblemType::ScalarType;
+  using StateType = BatchedAugmentedLagrangeState<ScalarType, ProblemType::Dimension>;
+  // the fields of the outer stopping_progress the constrained branch of Progress::Update reads
+  struct OuterProgress {
+    size_t num_iterations = 10000;
+    ScalarType constraint_threshold = ScalarType(1e-5);
+    ScalarType kkt_stationarity_threshold = ScalarType(1e-4);
+  } stopping_progress;
+
+  AugmentedLagrangian(const ProblemType& problem, const solver_t& unconstrained_solver,
+                      AugmentedLagrangianConfig<ScalarType> config = {})
+      : problem_(problem), unconstrained_solver_template_(unconstrained_solver), config_(config) {}
+
+  std::tuple<StateType, BatchedProgress<ScalarType>> Minimize(const StateType& state, cudaStream_t stream = nullptr) {
+    using T = ScalarType;
+    constexpr int D = ProblemType::Dimension;
+    const int64_t B = state.batch;
+    const int ne = problem_.n_eq, ni = problem_.n_ineq();
+    function::FunctionExpr<T, ProblemType::Differentiability, D> expr(problem_.objective);
+    if (expr.raw) throw std::runtime_error("AugmentedLagrangian: built-in objective families only");
+    auto kinds = detail::DeviceArray<int32_t>::FromHost(problem_.kinds);
+    auto rows = detail::DeviceArray<T>::FromHost(problem_.rows);
+    cno_constraints_t k{};
+    k.n_eq = ne;
+    k.n_ineq = ni;
+    k.kinds = kinds.data();
+    k.data = rows.data();
+    k.data_stride = problem_.per_instance ? static_cast<int64_t>(problem_.kinds.size()) * (D + 1) : 0;
+
+    StateType result;
+    result.batch = B;
+    result.x = detail::DeviceArray<T>(B * D);
+    result.equality_multipliers = detail::DeviceArray<T>(B * ne);
+    result.inequality_multipliers = detail::DeviceArray<T>(B * ni);
+    result.penalty = detail::DeviceArray<T>(B);
+    result.max_violation = detail::DeviceArray<T>(B);
+    result.max_lagrangian_gradient = detail::DeviceArray<T>(B);
+    BatchedProgress<T> prog;
+    prog.batch = B;
+    prog.num_iterations = detail::DeviceArray<uint32_t>(B);
+    prog.nfev = detail::DeviceArray<uint32_t>(B);
+    prog.status = detail::DeviceArray<int8_t>(B);
+    prog.x_delta = detail::DeviceArray<T>(B);
+    prog.f_delta = detail::DeviceArray<T>(B);
+    prog.gradient_norm = detail::DeviceArray<T>(B);
+    cno_al_out_t out{};
+    out.x = result.x.data();
+    out.equality_multipliers = result.equality_multipliers.data();
+    out.inequality_multipliers = result.inequality_multipliers.data();
+    out.penalty = result.penalty.data();
+    out.max_violation = result.max_violation.data();
+    out.max_lagrangian_gradient = result.max_lagrangian_gradient.data();
+    out.num_iterations = prog.num_iterations.data();
+    out.status = prog.status.data();
+    out.nfev = prog.nfev.data();
+    out.x_delta = prog.x_delta.data();
+    out.f_delta = prog.f_delta.data();
+    out.gradient_norm = prog.gradient_norm.data();
+
+    size_t nbytes = 0;
+    detail::check_cno(cno_al_workspace_bytes(&expr.problem, &k, B, &nbytes), "cno_al_workspace_bytes");
+    detail::DeviceArray<unsigned char> workspace(nbytes < 256 ? 256 : nbytes);
+    const cno_stop_t inner = unconstrained_solver_template_.stopping_progress.to_c();
+    cno_al_stop_t outer{};
+    outer.num_iterations = stopping_progress.num_iterations;
+    outer.constraint_threshold = stopping_progress.constraint_threshold;
+    outer.kkt_stationarity_threshold = stopping_progress.kkt_stationarity_threshold;
+    cno_al_config_t cfg{};
+    cfg.penalty_growth_factor = config_.penalty_growth_factor;
+    cfg.violation_shrink_ratio = config_.violation_shrink_ratio;
+    cfg.auto_scale_initial_penalty = config_.auto_scale_initial_penalty;
+    cfg.penalty_auto_objective_scale = config_.penalty_auto_objective_scale;
+    cfg.penalty_auto_min = config_.penalty_auto_min;
+    cfg.penalty_auto_max = config_.penalty_auto_max;
+    cfg.warmup_max_inner_iterations = config_.warmup_max_inner_iterations;
+    cfg.warmup_inner_gradient_tolerance = config_.warmup_inner_gradient_tolerance;
+    cfg.multiplier_max = config_.multiplier_max;
+    cfg.kkt_gradient_tolerance = config_.kkt_gradient_tolerance;
+    detail::check_cno(
+        cno_al_minimize(&expr.problem, &k, B, state.x.data(),
+                        ne ? state.equality_multipliers.data() : nullptr,
+                        ni ? state.inequality_multipliers.data() : nullptr, state.penalty.data(), &inner, &outer, &cfg,
+                        &out, workspace.data(), workspace.size(), stream, &prog.launch),
+        "cno_al_minimize");
+    return {std::move(result), std::move(prog)};
+  }
+
+ private:
+  ProblemType problem_;
+  solver_t unconstrained_solver_template_;
+  AugmentedLagrangianConfig<ScalarType> config_;
 };
 
 }  // namespace solver

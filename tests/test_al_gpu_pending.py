@@ -105,3 +105,14 @@ def test_al_reference_known_answers_and_user_state():
                       ineq0=0.5, penalty0=2.0, config=cfg, inner=cn.Lbfgs(cn.ConservativeStoppingSolverProgress())),
                  ob.al_minimize(ob.FN_ROSENBROCK, x0, [ob.CON_AFFINE, ob.CON_SQNORM], rows, 1, outer_stop=stop,
                                 config=ocfg, inner_stop=ob.conservative_stop(), eq0=0.25, ineq0=0.5, penalty0=2.0))
+
+
+def test_al_cpp_mirror_equality_only_quadratic():
+    """tests/cpp/al_host_pending.cc: the C++ mirror (cppoptlib::solver::AugmentedLagrangian) on
+    augmented_lagrangian_test.cc:492-539."""
+    import subprocess
+    from cppnumericalsolvers_b200 import build
+    build.build_cpp_tests()
+    exe = os.path.join(os.path.dirname(__file__), "cpp", "build", "al_host_pending")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
