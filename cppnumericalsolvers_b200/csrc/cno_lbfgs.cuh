@@ -196,6 +196,9 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   constexpr bool kAllocTmem = SM::kTmemY || (kFnTmem > 0);
   static_assert(!(SM::kTmemY && kFnTmem > 0), "one Tensor Memory user per kernel");
   if constexpr (kAllocTmem) {
+#ifdef CNO_WARP_EMULATION  // tests/emu: the emulated warp's Tensor Memory window starts at column 0
+    tmem_base = 0;
+#else
     __shared__ uint32_t tmem_base_s;
     if (warp == 0) {
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -207,6 +210,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     tmem_base = tmem_base_s;
+#endif
   }
   YHist<T, E, SM::kTmemY> Y;
   if constexpr (SM::kTmemY) {
@@ -570,11 +574,13 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     }
     __syncwarp();
   }
+#ifndef CNO_WARP_EMULATION
   if constexpr (kAllocTmem) {
     __syncthreads();  // every warp is done with its TMEM window
     if (warp == 0)
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
+#endif
 }
 
 }  // namespace cno

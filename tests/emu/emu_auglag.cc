@@ -108,10 +108,8 @@ int run(int op, const cno_constraints_t* k, long long B, const EmuArrays& e, con
   if (op == kInner) {
     // the fused inner solve: lbfgs_minimize_kernel<AugLagFn<Obj>> exactly as al_run launches it
     // (x0 = state x, out.x = x_work, out.nfev = inner_nfev), one emulated warp draining the queue.
-    // Shapes whose y-history lives in Tensor Memory (fp64, d = 128) cannot run here.
-    if constexpr (sizeof(T) == 8 && E == 4) {
-      return CNO_ERR_UNSUPPORTED;
-    } else {
+    // (shapes whose y-history lives in Tensor Memory -- fp64, d = 128 -- use the host array of warp_emu.h)
+    {
       const cno::AugLagFn<Obj> fn{obj, v};
       const cno_stop_t* inner = static_cast<const cno_stop_t*>(x_in);
       cno_batch_out_t o{};
@@ -141,7 +139,6 @@ int run(int op, const cno_constraints_t* k, long long B, const EmuArrays& e, con
 template <class Fn, class LS>
 int run_solver(int solver, long long B, const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out) {
   using T = typename Fn::Scalar;
-  constexpr int E = cno::Shape<Fn::Dim>::E;
   const Fn fn{};
   unsigned long long queue = 0;
   int rc = 0;
@@ -151,8 +148,7 @@ int run_solver(int solver, long long B, const void* x0, const cno_stop_t* stop, 
     const auto sp = cno::make_stop<T>(*stop);
     const auto bo = cno::make_out<T>(*out);
     if (solver == CNO_LBFGS) {
-      if constexpr (sizeof(T) == 8 && E == 4) rc = CNO_ERR_UNSUPPORTED;  // y-history in Tensor Memory
-      else cno::lbfgs_minimize_kernel<Fn, CNO_LBFGS_M, false, LS>(fn, (const T*)x0, B, sp, bo, &queue, cno::ResumeArgs{nullptr, 0, 0, 0});
+      cno::lbfgs_minimize_kernel<Fn, CNO_LBFGS_M, false, LS>(fn, (const T*)x0, B, sp, bo, &queue, cno::ResumeArgs{nullptr, 0, 0, 0});
     } else if (solver == CNO_BFGS) {
       if constexpr (Fn::Dim <= 32) cno::bfgs_minimize_kernel<Fn, LS>(fn, (const T*)x0, B, sp, bo, &queue);
       else rc = CNO_ERR_UNSUPPORTED;
@@ -178,6 +174,7 @@ extern "C" int emu_minimize(int solver, int hager_zhang, const cno_problem_t* p,
   SOLVER_CASE(CNO_F64, double, 2)
   SOLVER_CASE(CNO_F64, double, 8)
   SOLVER_CASE(CNO_F64, double, 37)
+  SOLVER_CASE(CNO_F64, double, 128)
   SOLVER_CASE(CNO_F32, float, 37)
 #undef SOLVER_CASE
   return CNO_ERR_UNSUPPORTED;

@@ -20,6 +20,7 @@
 #include <cstddef>
 #include <cstring>
 #include <functional>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -46,6 +47,7 @@ struct Warp {
   std::barrier<> bar{32};
   uint64_t slot[32];
   double dslot[32];
+  uint32_t tmem[32][512];  // Tensor Memory window of the emulated warp: [lane][column], 32-bit cells
 };
 inline thread_local int tl_lane = 0;
 inline thread_local Warp* tl_warp = nullptr;
@@ -80,9 +82,21 @@ inline void dmma_ones(double& d0, double& d1, double b) {
   sync();
 }
 
+// tcgen05.st / tcgen05.ld .32x32b.xN: lane l moves N consecutive 32-bit columns of its own TMEM lane
+inline void tmem_store(uint32_t taddr, const uint32_t* w, int n) {
+  const uint32_t col = taddr & 0xffffu;
+  for (int i = 0; i < n; ++i) tl_warp->tmem[tl_lane][col + i] = w[i];
+}
+inline void tmem_load(uint32_t taddr, uint32_t* w, int n) {
+  const uint32_t col = taddr & 0xffffu;
+  for (int i = 0; i < n; ++i) w[i] = tl_warp->tmem[tl_lane][col + i];
+}
+
 // Runs f(lane) on 32 lock-step threads = one warp.
 inline void run_warp(const std::function<void(int)>& f) {
-  Warp w;
+  static Warp w_storage;  // (one emulated warp at a time; too large for the stack)
+  Warp& w = w_storage;
+  new (&w) Warp();
   std::vector<std::thread> ts;
   for (int l = 0; l < 32; ++l)
     ts.emplace_back([&, l] {

@@ -210,10 +210,12 @@ def test_emulated_device_loop_known_answers(emu):
 
 # ---- the fused inner kernel too: the whole device path of the row under emulation ----------------
 @pytest.mark.parametrize("family,dtype,d,n_eq", [(ob.FN_ROSENBROCK, np.float64, 8, 1), (ob.FN_ROSENBROCK, np.float64, 37, 2),
+                                                 (ob.FN_ROSENBROCK, np.float64, 128, 1),
                                                  (ob.FN_ROSENBROCK, np.float32, 8, 1), (ob.FN_HALF_SQUARED_NORM, np.float64, 8, 1)])
 def test_emulated_device_loop_with_the_device_inner_kernel(emu, family, dtype, d, n_eq):
     """lbfgs_minimize_kernel<AugLagFn<Obj>> (with its active() skip of finished instances) + the outer-loop
-    kernels, all device source, all under emulation == the oracle, bit for bit."""
+    kernels, all device source, all under emulation == the oracle, bit for bit (d = 128: the y-history of
+    the inner kernel lives in the emulated Tensor Memory)."""
     B = 2  # 32 lock-step threads per warp: a few instances keep this to seconds
     rng = np.random.default_rng(300 + d)
     x0 = ob.fill_uniform((B, d), 0, 57 + d, -1.5, 1.5, dtype)
@@ -232,6 +234,7 @@ SOLVER_KEYS = ("num_iterations", "status", "nfev", "x", "value", "gradient", "x_
 
 @pytest.mark.parametrize("solver,hz,dtype,d,limit", [
     (ob.LBFGS, 0, np.float64, 2, 10000), (ob.LBFGS, 0, np.float64, 37, 40), (ob.LBFGS, 0, np.float32, 37, 20),
+    (ob.LBFGS, 0, np.float64, 128, 100), (ob.LBFGS, 1, np.float64, 128, 60),  # the headline shape: y-history in (emulated) Tensor Memory
     (ob.LBFGS, 1, np.float64, 8, 10000), (ob.BFGS, 0, np.float64, 8, 10000), (ob.BFGS, 1, np.float64, 2, 10000),
     (ob.GRADIENT_DESCENT, 0, np.float64, 8, 40), (ob.GRADIENT_DESCENT, 1, np.float64, 8, 40),
     (ob.CONJUGATED_GRADIENT_DESCENT, 0, np.float64, 8, 8)])
