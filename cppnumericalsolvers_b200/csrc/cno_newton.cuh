@@ -38,6 +38,15 @@
 namespace cno {
 
 // ---- TMA bulk copy + mbarrier (one barrier per warp) ---------------------------
+#ifdef CNO_WARP_EMULATION  // tests/emu: the bulk copy is a memcpy by the issuing lane; the vote in mbar_wait is the barrier
+__device__ __forceinline__ void mbar_init(uint64_t*, int) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) { (void)uni(true); }
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t*) {
+  std::memcpy(dst_smem, src_gmem, bytes);
+}
+__device__ __forceinline__ void fence_proxy_async() {}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -79,6 +88,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+
+#endif  // CNO_WARP_EMULATION
 
 // ---- plain-layout shared-memory vectors/columns (element i at index i) ----------
 // Lane l owns elements l*E .. l*E+E-1 (a contiguous chunk, so an access by the
@@ -139,6 +150,38 @@ struct SmemRowVec {
 // An entry of the pivot row is broadcast from shared memory (one LDS) or, for a
 // TMEM column, from the owner lane's registers (SHFL).  The arithmetic and its
 // order are unchanged.
+#ifdef CNO_WARP_EMULATION  // tests/emu: Tensor Memory as a host array of the emulated warp
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const double (&v)[2]) {
+  const uint32_t w[4] = {(uint32_t)__double2loint(v[0]), (uint32_t)__double2hiint(v[0]), (uint32_t)__double2loint(v[1]),
+                         (uint32_t)__double2hiint(v[1])};
+  emu::tmem_store(taddr, w, 4);
+}
+__device__ __forceinline__ void tmem_ld2_issue(uint32_t taddr, uint32_t (&r)[4]) { emu::tmem_load(taddr, r, 4); }
+template <int NG>
+__device__ __forceinline__ void tmem_ld2_wait(uint32_t (&r)[NG][4], double (&v)[NG][2]) {
+  for (int g = 0; g < NG; ++g) {
+    v[g][0] = __hiloint2double((int)r[g][1], (int)r[g][0]);
+    v[g][1] = __hiloint2double((int)r[g][3], (int)r[g][2]);
+  }
+}
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) { emu::tmem_load(taddr, r, 32); }
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32], double (&v)[8][2]) {
+  for (int t = 0; t < 8; ++t) {
+    v[t][0] = __hiloint2double((int)r[4 * t + 1], (int)r[4 * t]);
+    v[t][1] = __hiloint2double((int)r[4 * t + 3], (int)r[4 * t + 2]);
+  }
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const double (&v)[8][2]) {
+  uint32_t r[32];
+  for (int t = 0; t < 8; ++t) {
+    r[4 * t] = (uint32_t)__double2loint(v[t][0]);
+    r[4 * t + 1] = (uint32_t)__double2hiint(v[t][0]);
+    r[4 * t + 2] = (uint32_t)__double2loint(v[t][1]);
+    r[4 * t + 3] = (uint32_t)__double2hiint(v[t][1]);
+  }
+  emu::tmem_store(taddr, r, 32);
+}
+#else
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, const double (&v)[2]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr),
                "r"(__double2loint(v[0])), "r"(__double2hiint(v[0])), "r"(__double2loint(v[1])),
@@ -205,6 +248,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const double (&v)[8][2
       "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+
+#endif  // CNO_WARP_EMULATION
 
 template <class T, int D>
 struct AugStore {
@@ -521,17 +566,22 @@ __device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&de
     aug_load_col<T, D>(A, k, col);
     T best = T(-1);
     int bpos = 0x7fffffff;
+    bool k_is_nan = false;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int row = lane * E + e;
       const T v = cabs(col[e]);
       const bool cand = (row < D) && (vpos[e] >= k);
       if (cand && (v > best || (v == best && vpos[e] < bpos))) { best = v; bpos = vpos[e]; }
+      k_is_nan = k_is_nan || ((row < D) && (vpos[e] == k) && (v != v));
     }
-    // warp arg-max: larger |v|, ties -> smaller virtual position
+    // warp arg-max: larger |v|, ties -> smaller virtual position.  A NaN at virtual position k stays the
+    // pivot: the sequential scan of the specification starts from it and no comparison with a NaN is
+    // true (oracle lu_solve); that also keeps the pivot position valid when every candidate is NaN.
     const T bmax = warp_max_nonneg(best < T(0) ? T(0) : best);
     const unsigned mypos = (best == bmax) ? (unsigned)bpos : 0xffffffffu;
-    const int ppos = (int)__reduce_min_sync(kFullMask, mypos);
+    const int pmax = (int)__reduce_min_sync(kFullMask, mypos);
+    const int ppos = uni(k_is_nan) ? k : pmax;
     // the row at virtual position k and the pivot row exchange virtual positions
     T pivot_local = T(0);
     int prow_local = -1;
@@ -614,7 +664,7 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   using AS = AugStore<T, D>;
   using SV = SmemRowVec<T, D>;
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CNO_DYNAMIC_SMEM(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   T* const aug = reinterpret_cast<T*>(smem_raw) + (size_t)warp * SMN::kWarpElems;
@@ -623,6 +673,7 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   uint64_t* const bar = reinterpret_cast<uint64_t*>(ring + CNO_MAX_PAST);
   uint32_t parity = 0;
   uint32_t tmem_base = 0;
+#ifndef CNO_WARP_EMULATION  // (tests/emu: the emulated warp's Tensor Memory window starts at column 0)
   if constexpr (AS::kSplit) {
     __shared__ uint32_t tmem_base_s;
     if (warp == 0) {
@@ -636,10 +687,13 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     asm volatile("tcgen05.fence::after_thread_sync;");
     tmem_base = tmem_base_s;
   }
+#endif
   const AS A{aug, tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * AS::kTmemCols), lane};
   if (lane == 0) {
     mbar_init(bar, 1);
+#ifndef CNO_WARP_EMULATION
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
   }
   __syncwarp();
 
@@ -758,11 +812,13 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     }
     __syncwarp();
   }
+#ifndef CNO_WARP_EMULATION
   if constexpr (AS::kSplit) {
     __syncthreads();  // every warp is done with its TMEM window
     if (warp == 0)
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
+#endif
 }
 
 }  // namespace cno

@@ -9,6 +9,7 @@
 #include "cno_lbfgs.cuh"
 #include "cno_bfgs.cuh"
 #include "cno_descent.cuh"
+#include "cno_newton.cuh"
 
 namespace {
 
@@ -177,6 +178,38 @@ extern "C" int emu_minimize(int solver, int hager_zhang, const cno_problem_t* p,
   SOLVER_CASE(CNO_F64, double, 128)
   SOLVER_CASE(CNO_F32, float, 37)
 #undef SOLVER_CASE
+  return CNO_ERR_UNSUPPORTED;
+}
+
+// NewtonDescent (csrc/cno_newton.cuh) under emulation: the TMA bulk copy is a memcpy, Tensor Memory a host array.
+template <class Fn>
+int run_newton(const Fn& fn, long long B, const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out) {
+  using T = typename Fn::Scalar;
+  unsigned long long queue = 0;
+  emu::run_warp([&](int lane) {
+    blockIdx.x = 0;
+    threadIdx.x = (unsigned)lane;
+    cno::newton_minimize_kernel<Fn>(fn, (const T*)x0, B, cno::make_stop<T>(*stop), cno::make_out<T>(*out), &queue);
+  });
+  return 0;
+}
+
+extern "C" int emu_newton(const cno_problem_t* p, long long batch, const void* x0, const cno_stop_t* stop,
+                          const cno_batch_out_t* out) {
+  if (p->family == CNO_FN_DENSE_QUADRATIC) {
+#define NEWTON_CASE(DT, TY, DIM)                                                                   \
+  if (p->dtype == DT && p->d == DIM)                                                               \
+    return run_newton(cno::DenseQuadraticFn<TY, DIM>{static_cast<const TY*>(p->data), (long long)p->data_stride}, \
+                      batch, x0, stop, out);
+    NEWTON_CASE(CNO_F64, double, 64)
+    NEWTON_CASE(CNO_F64, double, 12)
+    NEWTON_CASE(CNO_F32, float, 64)
+#undef NEWTON_CASE
+  }
+  if (p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64 && p->d == 2)
+    return run_newton(cno::RosenbrockFullFn<double, 2>{}, batch, x0, stop, out);
+  if (p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64 && p->d == 8)
+    return run_newton(cno::RosenbrockFullFn<double, 8>{}, batch, x0, stop, out);
   return CNO_ERR_UNSUPPORTED;
 }
 

@@ -147,6 +147,7 @@ inline unsigned __reduce_min_sync(unsigned, unsigned v) {
   emu::sync();
   return m;
 }
+inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::sync(); }
 inline void __syncthreads() {}  // only reached from Tensor-Memory paths, which the emulation does not run
 inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }

@@ -283,3 +283,33 @@ def test_gradient_descent_hager_zhang_failed_search_rebuilds_point_from_step(emu
             u, v = np.where(nan, 0, u), np.where(nan, 0, v)
         assert np.array_equal(u.view(np.uint8), v.view(np.uint8)), key
     assert np.isnan(o["x"][0]).sum() > 1  # the oracle (= reference) really spreads the NaN through 0 * g
+
+
+def _spd_data(B, d, seed, dtype=np.float64):
+    rng = np.random.default_rng(seed)
+    M = rng.uniform(-1, 1, (B, d, d))
+    A = np.einsum("bij,bkj->bik", M, M) / d + np.eye(d)
+    A = (A + A.transpose(0, 2, 1)) / 2
+    b = rng.uniform(-1, 1, (B, d))
+    return np.concatenate([A.transpose(0, 2, 1).reshape(B, -1), b], 1).astype(dtype)
+
+
+@pytest.mark.parametrize("family,dtype,d", [(ob.FN_DENSE_QUADRATIC, np.float64, 64), (ob.FN_DENSE_QUADRATIC, np.float32, 64),
+                                            (ob.FN_DENSE_QUADRATIC, np.float64, 12), (ob.FN_ROSENBROCK, np.float64, 2)])
+def test_emulation_reproduces_the_newton_kernel(emu, family, dtype, d):
+    """newton_minimize_kernel under emulation (the TMA bulk copy as a memcpy, the Tensor Memory half of the d = 64
+    fp64 matrix as a host array) == the oracle, as on the B200."""
+    B = 2
+    x0 = ob.fill_uniform((B, d), 0, 5, -2.0, 2.0, dtype)
+    data = _spd_data(B, d, 9, dtype) if family == ob.FN_DENSE_QUADRATIC else None
+    prob = ob.Problem(family, ob._np_dtype(x0), d, 0, 0.0, data.ctypes.data if data is not None else None,
+                      data.shape[1] if data is not None else 0, ob.device_policy(x0.dtype), 0)
+    stop = ob.default_stop()
+    r = dict(x=np.zeros_like(x0), value=np.zeros(B, dtype), gradient=np.zeros_like(x0),
+             num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32),
+             x_delta=np.zeros(B, dtype), f_delta=np.zeros(B, dtype), gradient_norm=np.zeros(B, dtype))
+    out = ob.BatchOut(*[r[n].ctypes.data for n, _ in ob.BatchOut._fields_])
+    assert emu.emu_newton(C.byref(prob), C.c_longlong(B), C.c_void_p(x0.ctypes.data), C.byref(stop), C.byref(out)) == 0
+    o = ob.minimize(ob.NEWTON, family, x0, data=data, stop=stop)
+    for key in SOLVER_KEYS:
+        assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
