@@ -132,7 +132,9 @@ struct LogisticFn {
     uint64_t* bar = reinterpret_cast<uint64_t*>(blk + kSmemElems + kWvec);
     if (c.lane == 0) {
       mbar_init(bar, 1);
+#ifndef CNO_WARP_EMULATION
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
     }
     __syncwarp();
   }

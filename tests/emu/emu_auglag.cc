@@ -10,6 +10,7 @@
 #include "cno_bfgs.cuh"
 #include "cno_descent.cuh"
 #include "cno_newton.cuh"
+#include "cno_logistic.cuh"
 
 namespace {
 
@@ -211,6 +212,23 @@ extern "C" int emu_newton(const cno_problem_t* p, long long batch, const void* x
   if (p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64 && p->d == 8)
     return run_newton(cno::RosenbrockFullFn<double, 8>{}, batch, x0, stop, out);
   return CNO_ERR_UNSUPPORTED;
+}
+
+// L-BFGS on the logistic-regression functor (csrc/cno_logistic.cuh: per-instance data staged by TMA into shared
+// memory and by tcgen05.st into Tensor Memory) under emulation.
+extern "C" int emu_logistic(const cno_problem_t* p, long long batch, const void* x0, const cno_stop_t* stop,
+                            const cno_batch_out_t* out) {
+  if (!(p->family == CNO_FN_LOGISTIC && p->dtype == CNO_F32 && p->d == 64 && p->n == 256)) return CNO_ERR_UNSUPPORTED;
+  using Fn = cno::LogisticFn<float, 64, 256>;
+  const Fn fn{static_cast<const float*>(p->data), (long long)p->data_stride, (float)p->param};
+  unsigned long long queue = 0;
+  emu::run_warp([&](int lane) {
+    blockIdx.x = 0;
+    threadIdx.x = (unsigned)lane;
+    cno::lbfgs_minimize_kernel<Fn, CNO_LBFGS_M>(fn, (const float*)x0, batch, cno::make_stop<float>(*stop),
+                                                cno::make_out<float>(*out), &queue, cno::ResumeArgs{nullptr, 0, 0, 0});
+  });
+  return 0;
 }
 
 extern "C" int emu_al(int op, const cno_problem_t* objective, const cno_constraints_t* constraints, long long batch,

@@ -313,3 +313,27 @@ def test_emulation_reproduces_the_newton_kernel(emu, family, dtype, d):
     o = ob.minimize(ob.NEWTON, family, x0, data=data, stop=stop)
     for key in SOLVER_KEYS:
         assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
+
+
+def test_emulation_reproduces_the_logistic_kernel(emu):
+    """L-BFGS on the logistic-regression functor (csrc/cno_logistic.cuh): per-instance data staged by TMA bulk
+    copies into shared memory and by tcgen05.st into Tensor Memory -- under emulation a memcpy and a host array."""
+    B, n, d, lam = 1, 256, 64, 1e-2
+    rng = np.random.default_rng(3)
+    X = rng.uniform(-1, 1, (B, n, d)).astype(np.float32)
+    wstar = rng.normal(size=(B, d)).astype(np.float32)
+    y = np.sign(np.einsum("bnd,bd->bn", X, wstar) + 0.1 * rng.normal(size=(B, n))).astype(np.float32)
+    y[y == 0] = 1
+    data = np.ascontiguousarray(np.concatenate([X.transpose(0, 2, 1).reshape(B, -1), y], axis=1))
+    x0 = np.zeros((B, d), np.float32)
+    prob = ob.Problem(ob.FN_LOGISTIC, ob._np_dtype(x0), d, n, lam, data.ctypes.data, data.shape[1],
+                      ob.device_policy(x0.dtype), 0)
+    stop = ob.default_stop()
+    r = dict(x=np.zeros_like(x0), value=np.zeros(B, np.float32), gradient=np.zeros_like(x0),
+             num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32),
+             x_delta=np.zeros(B, np.float32), f_delta=np.zeros(B, np.float32), gradient_norm=np.zeros(B, np.float32))
+    out = ob.BatchOut(*[r[k].ctypes.data for k, _ in ob.BatchOut._fields_])
+    assert emu.emu_logistic(C.byref(prob), C.c_longlong(B), C.c_void_p(x0.ctypes.data), C.byref(stop), C.byref(out)) == 0
+    o = ob.minimize(ob.LBFGS, ob.FN_LOGISTIC, x0, data=data, n=n, param=lam)
+    for key in SOLVER_KEYS:
+        assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
