@@ -87,3 +87,40 @@ def test_invalid_arguments():
     assert L.cno_supported(_lib.LBFGS, C.byref(bad)) == _lib.ERR_UNSUPPORTED
     n = C.c_size_t()
     assert L.cno_workspace_bytes(_lib.LBFGS, C.byref(prob), 10, C.byref(n)) == 0 and n.value >= 8
+
+
+def test_al_entry_points_without_a_device():
+    """include/cno_al.h: argument checking and the scratch-size contract need no GPU; the solve itself
+    fails loudly (CNO_ERR_NO_DEVICE) instead of falling back to the CPU."""
+    L = _lib.lib()
+    prob = cn.Rosenbrock(8).problem()
+    kinds = np.array([0, 1], np.int32)
+    rows = np.zeros((2, 9))
+    k = _lib.Constraints(1, 1, kinds.ctypes.data, rows.ctypes.data, 0)
+    assert L.cno_al_supported(C.byref(prob), C.byref(k)) == _lib.OK
+    assert L.cno_al_supported(C.byref(cn.Rosenbrock(64).problem()), C.byref(k)) == _lib.ERR_UNSUPPORTED
+    assert L.cno_al_supported(C.byref(cn.RosenbrockFull(2).problem()), C.byref(k)) == _lib.ERR_UNSUPPORTED  # First mode only
+    too_many = _lib.Constraints(33, 0, kinds.ctypes.data, rows.ctypes.data, 0)
+    assert L.cno_al_supported(C.byref(prob), C.byref(too_many)) == _lib.ERR_UNSUPPORTED
+    no_rows = _lib.Constraints(1, 0, kinds.ctypes.data, None, 0)
+    assert L.cno_al_supported(C.byref(prob), C.byref(no_rows)) == _lib.ERR_INVALID_ARGUMENT
+    sizes = []
+    for B in (1, 1000, 4096):
+        n = C.c_size_t(0)
+        assert L.cno_al_workspace_bytes(C.byref(prob), C.byref(k), C.c_int64(B), C.byref(n)) == _lib.OK
+        # x_work + best_x (2 B d) + 5 scalars per instance + best multipliers, every region 256-byte aligned
+        assert n.value % 256 == 0 and n.value >= B * 8 * (2 * 8 + 5 + 2)
+        sizes.append(n.value)
+    assert sizes == sorted(sizes)
+    cfg, stop = _lib.AlConfig(), _lib.AlStop()
+    L.cno_al_default_config(C.byref(cfg))
+    L.cno_al_default_stop(C.byref(stop))
+    assert (cfg.penalty_growth_factor, cfg.violation_shrink_ratio, cfg.auto_scale_initial_penalty) == (10.0, 0.25, 1)
+    assert (cfg.warmup_max_inner_iterations, cfg.warmup_inner_gradient_tolerance, cfg.multiplier_max) == (10, 1e-2, 1e20)
+    assert (stop.num_iterations, stop.constraint_threshold, stop.kkt_stationarity_threshold) == (10000, 1e-5, 1e-4)
+    out = _lib.AlOut()
+    assert L.cno_al_minimize(C.byref(prob), C.byref(k), C.c_int64(4), None, None, None, None, None, None, None,
+                             C.byref(out), None, C.c_size_t(0), None, None) == _lib.ERR_INVALID_ARGUMENT
+    if not torch.cuda.is_available():
+        assert L.cno_al_minimize(C.byref(prob), C.byref(k), C.c_int64(0), None, None, None, None, None, None, None,
+                                 C.byref(out), None, C.c_size_t(0), None, None) == _lib.ERR_NO_DEVICE
