@@ -20,6 +20,7 @@
 #include "cno_newton.cuh"
 #include "cno_logistic.cuh"
 #include "cno_auglag.cuh"
+#include "cno_auglag_host.h"
 #include "../../include/cno_al.h"
 
 namespace {
@@ -444,29 +445,56 @@ struct AlArgs {
   cno_launch_info_t* info;
 };
 
-inline size_t al_up(size_t v) { return (v + 255) & ~(size_t)255; }
+using cno::AlLayout;
 
-// Scratch layout behind `workspace` (every region 256-byte aligned).
-struct AlLayout {
-  size_t queue, remaining, x_work, prev_penalty, inner_nfev, best_recorded, best_x, best_lambda, best_mu,
-      best_penalty, best_objective, best_violation, best_kkt, total;
-  AlLayout(size_t B, size_t d, size_t ne, size_t ni, size_t ts) {
-    size_t off = 0;
-    auto take = [&](size_t bytes) { const size_t o = off; off += al_up(bytes ? bytes : 1); return o; };
-    queue = take(256);
-    remaining = take(sizeof(int));
-    x_work = take(B * d * ts);
-    prev_penalty = take(B * ts);
-    inner_nfev = take(B * 4);
-    best_recorded = take(B);
-    best_x = take(B * d * ts);
-    best_lambda = take(B * ne * ts);
-    best_mu = take(B * ni * ts);
-    best_penalty = take(B * ts);
-    best_objective = take(B * ts);
-    best_violation = take(B * ts);
-    best_kkt = take(B * ts);
-    total = off;
+// The CUDA backend of cno::al_outer_loop (csrc/cno_auglag_host.h).
+template <class Obj>
+struct AlCudaBackend {
+  using T = typename Obj::Scalar;
+  const Obj& obj;
+  const AlArgs& A;
+  cno::AlArrays<T> a;
+  cno::AlView<T> view;
+  cno::AlParams<T> p;
+  unsigned char* queue;
+  cudaStream_t s;
+  int blocks, threads;
+
+  int copy_or_zero(void* dst, const void* src, size_t bytes) {
+    if (!bytes || src == dst) return CNO_OK;  // (a caller may pass its state arrays as the initial values)
+    CNO_CUDA(src ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s) : cudaMemsetAsync(dst, 0, bytes, s));
+    return CNO_OK;
+  }
+  int fill(void* dst, int byte, size_t bytes) {
+    if (bytes) CNO_CUDA(cudaMemsetAsync(dst, byte, bytes, s));
+    return CNO_OK;
+  }
+  int autoscale() {
+    cno::al_autoscale_kernel<Obj><<<blocks, threads, 0, s>>>(obj, view, A.batch, p, a);
+    CNO_CUDA(cudaGetLastError());
+    return CNO_OK;
+  }
+  int inner(const cno_stop_t& stop) {
+    const cno::AugLagFn<Obj> composite{obj, view};
+    cno_batch_out_t inner_out{};
+    inner_out.x = a.x_work;
+    inner_out.nfev = const_cast<uint32_t*>(a.inner_nfev);
+    cno_launch_info_t inner_info{};
+    const LaunchArgs la{A.objective, A.batch, a.x, &stop, &inner_out, queue, s, &inner_info};
+    return launch_lbfgs<cno::AugLagFn<Obj>, CNO_LBFGS_M>(composite, la);
+  }
+  int outer_step(int* remaining) {
+    CNO_CUDA(cudaMemsetAsync(a.remaining, 0, sizeof(int), s));
+    cno::al_outer_step_kernel<Obj><<<blocks, threads, 0, s>>>(obj, view, A.batch, p, a);
+    CNO_CUDA(cudaGetLastError());
+    CNO_CUDA(cudaMemcpyAsync(remaining, a.remaining, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CNO_CUDA(cudaStreamSynchronize(s));
+    return CNO_OK;
+  }
+  int finalize() {
+    cno::al_finalize_kernel<T, Obj::Dim><<<blocks, threads, 0, s>>>(A.batch, view.n_eq, view.n_ineq, a);
+    CNO_CUDA(cudaGetLastError());
+    return CNO_OK;
   }
 };
 
@@ -474,116 +502,16 @@ template <class Obj>
 int al_run(const Obj& obj, const AlArgs& A) {
   using T = typename Obj::Scalar;
   constexpr int D = Obj::Dim;
-  const long long B = A.batch;
   const int ne = A.constraints->n_eq, ni = A.constraints->n_ineq;
-  const cno_al_out_t& o = *A.out;
-  const AlLayout L((size_t)B, D, (size_t)ne, (size_t)ni, sizeof(T));
-  unsigned char* ws = A.workspace;
-  cudaStream_t s = A.stream;
-
-  cno::AlArrays<T> a{};
-  a.x = static_cast<T*>(o.x);
-  a.x_work = reinterpret_cast<T*>(ws + L.x_work);
-  a.lambda = static_cast<T*>(o.equality_multipliers);
-  a.mu = static_cast<T*>(o.inequality_multipliers);
-  a.penalty = static_cast<T*>(o.penalty);
-  a.prev_penalty = reinterpret_cast<T*>(ws + L.prev_penalty);
-  a.max_violation = static_cast<T*>(o.max_violation);
-  a.max_lagrangian_gradient = static_cast<T*>(o.max_lagrangian_gradient);
-  a.num_iterations = o.num_iterations;
-  a.status = o.status;
-  a.nfev = o.nfev;
-  a.inner_nfev = reinterpret_cast<uint32_t*>(ws + L.inner_nfev);
-  a.x_delta = static_cast<T*>(o.x_delta);
-  a.f_delta = static_cast<T*>(o.f_delta);
-  a.gradient_norm = static_cast<T*>(o.gradient_norm);
-  a.best_recorded = reinterpret_cast<int8_t*>(ws + L.best_recorded);
-  a.best_x = reinterpret_cast<T*>(ws + L.best_x);
-  a.best_lambda = reinterpret_cast<T*>(ws + L.best_lambda);
-  a.best_mu = reinterpret_cast<T*>(ws + L.best_mu);
-  a.best_penalty = reinterpret_cast<T*>(ws + L.best_penalty);
-  a.best_objective = reinterpret_cast<T*>(ws + L.best_objective);
-  a.best_violation = reinterpret_cast<T*>(ws + L.best_violation);
-  a.best_kkt = reinterpret_cast<T*>(ws + L.best_kkt);
-  a.remaining = reinterpret_cast<int*>(ws + L.remaining);
-
-  // ---- initial AugmentedLagrangeState (augmented_lagrangian.h:241-276) + ResetBestIterateTracker ----
-  auto init = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
-    if (!bytes || src == dst) return cudaSuccess;  // (a caller may pass its state arrays as the initial values)
-    return src ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s) : cudaMemsetAsync(dst, 0, bytes, s);
-  };
-  CNO_CUDA(init(a.x, A.x0, (size_t)B * D * sizeof(T)));
-  CNO_CUDA(init(a.lambda, A.eq0, (size_t)B * ne * sizeof(T)));
-  CNO_CUDA(init(a.mu, A.ineq0, (size_t)B * ni * sizeof(T)));
-  CNO_CUDA(init(a.penalty, A.penalty0, (size_t)B * sizeof(T)));
-  CNO_CUDA(cudaMemcpyAsync(a.prev_penalty, a.penalty, (size_t)B * sizeof(T), cudaMemcpyDeviceToDevice, s));
-  CNO_CUDA(cudaMemsetAsync(a.max_violation, 0, (size_t)B * sizeof(T), s));
-  CNO_CUDA(cudaMemsetAsync(a.max_lagrangian_gradient, 0, (size_t)B * sizeof(T), s));
-  CNO_CUDA(cudaMemsetAsync(a.num_iterations, 0, (size_t)B * 4, s));
-  CNO_CUDA(cudaMemsetAsync(a.nfev, 0, (size_t)B * 4, s));
-  CNO_CUDA(cudaMemsetAsync(a.status, 0xFF, (size_t)B, s));  // CNO_STATUS_NOT_STARTED
-  CNO_CUDA(cudaMemsetAsync(a.best_recorded, 0, (size_t)B, s));
-
-  cno::AlView<T> view{};
-  view.rows = static_cast<const T*>(A.constraints->data);
-  view.row_stride = (long long)A.constraints->data_stride;
-  view.kinds = reinterpret_cast<const int*>(A.constraints->kinds);
-  view.n_eq = ne;
-  view.n_ineq = ni;
-  view.lambda = a.lambda;
-  view.mu = a.mu;
-  view.penalty = a.penalty;
-  view.status = a.status;
-
-  cno::AlParams<T> p{};
-  p.penalty_growth_factor = (T)A.config->penalty_growth_factor;
-  p.violation_shrink_ratio = (T)A.config->violation_shrink_ratio;
-  p.auto_scale_initial_penalty = A.config->auto_scale_initial_penalty;
-  p.penalty_auto_objective_scale = (T)A.config->penalty_auto_objective_scale;
-  p.penalty_auto_min = (T)A.config->penalty_auto_min;
-  p.penalty_auto_max = (T)A.config->penalty_auto_max;
-  p.multiplier_max = (T)A.config->multiplier_max;
-  p.num_iterations = A.outer_stop->num_iterations;
-  p.constraint_threshold = (T)A.outer_stop->constraint_threshold;
-  p.kkt_stationarity_threshold = A.outer_stop->kkt_stationarity_threshold;
-
-  const cno::AugLagFn<Obj> composite{obj, view};
-  cno_batch_out_t inner_out{};
-  inner_out.x = a.x_work;
-  inner_out.nfev = const_cast<uint32_t*>(a.inner_nfev);
-  const int blocks = (int)((B + cno::kAlWarps - 1) / cno::kAlWarps);
-  const int threads = cno::kAlWarps * 32;
+  const AlLayout L((size_t)A.batch, D, (size_t)ne, (size_t)ni, sizeof(T));
+  AlCudaBackend<Obj> be{obj, A, cno::al_make_arrays<T>(*A.out, A.workspace, L), {}, {}, A.workspace + L.queue, A.stream,
+                        (int)((A.batch + cno::kAlWarps - 1) / cno::kAlWarps), cno::kAlWarps * 32};
+  be.view = cno::al_make_view<T>(*A.constraints, be.a);
+  be.p = cno::al_make_params<T>(*A.config, *A.outer_stop);
   int launches = 0;
-
-  for (unsigned long long outer = 1;; ++outer) {
-    if (outer == 1 && A.config->auto_scale_initial_penalty) {  // augmented_lagrangian.h:312-318
-      cno::al_autoscale_kernel<Obj><<<blocks, threads, 0, s>>>(obj, view, B, p, a);
-      CNO_CUDA(cudaGetLastError());
-      ++launches;
-    }
-    cno_stop_t inner = *A.inner_stop;  // working copy of the template (:347), ConfigureInnerSubproblem (:477-490)
-    inner.f_delta = 0;
-    if (outer == 1 && (ne > 0 || ni > 0) && A.config->warmup_max_inner_iterations > 0) {
-      inner.num_iterations = (uint64_t)A.config->warmup_max_inner_iterations;
-      inner.gradient_norm = (double)(T)A.config->warmup_inner_gradient_tolerance;
-    }
-    cno_launch_info_t inner_info{};
-    const LaunchArgs la{A.objective, B, a.x, &inner, &inner_out, ws + L.queue, s, &inner_info};
-    int rc = launch_lbfgs<cno::AugLagFn<Obj>, CNO_LBFGS_M>(composite, la);
-    if (rc) return rc;
-    ++launches;
-    CNO_CUDA(cudaMemsetAsync(a.remaining, 0, sizeof(int), s));
-    cno::al_outer_step_kernel<Obj><<<blocks, threads, 0, s>>>(obj, view, B, p, a);
-    CNO_CUDA(cudaGetLastError());
-    ++launches;
-    int remaining = 0;
-    CNO_CUDA(cudaMemcpyAsync(&remaining, a.remaining, sizeof(int), cudaMemcpyDeviceToHost, s));
-    CNO_CUDA(cudaStreamSynchronize(s));
-    if (remaining == 0) break;
-  }
-  cno::al_finalize_kernel<T, D><<<blocks, threads, 0, s>>>(B, ne, ni, a);  // Minimize (:436-449)
-  CNO_CUDA(cudaGetLastError());
-  ++launches;
+  const int rc = cno::al_outer_loop<T>(be, be.a, A.batch, D, ne, ni, A.x0, A.eq0, A.ineq0, A.penalty0, *A.inner_stop,
+                                       *A.config, &launches);
+  if (rc) return rc;
   if (A.info) A.info->kernel_launches = launches;
   return CNO_OK;
 }

@@ -6,6 +6,7 @@
 // (tests/test_device_emulated.py).  Built by tests/emu/Makefile into libcno_emu.so.
 #include "cno_functors.cuh"
 #include "cno_auglag.cuh"
+#include "cno_auglag_host.h"
 #include "cno_lbfgs.cuh"
 #include "cno_bfgs.cuh"
 #include "cno_descent.cuh"
@@ -229,6 +230,80 @@ extern "C" int emu_logistic(const cno_problem_t* p, long long batch, const void*
                                                 cno::make_out<float>(*out), &queue, cno::ResumeArgs{nullptr, 0, 0, 0});
   });
   return 0;
+}
+
+// ---- cno::al_outer_loop (csrc/cno_auglag_host.h: the host side of cno_al_minimize) with an emulation backend ----
+template <class Obj>
+struct AlEmuBackend {
+  using T = typename Obj::Scalar;
+  Obj obj;
+  long long B;
+  cno::AlArrays<T> a;
+  cno::AlView<T> view;
+  cno::AlParams<T> p;
+  int copy_or_zero(void* dst, const void* src, size_t bytes) {
+    if (!bytes || src == dst) return 0;
+    if (src) std::memcpy(dst, src, bytes); else std::memset(dst, 0, bytes);
+    return 0;
+  }
+  int fill(void* dst, int byte, size_t bytes) { if (bytes) std::memset(dst, byte, bytes); return 0; }
+  int autoscale() { launch(B, [&] { cno::al_autoscale_kernel<Obj>(obj, view, B, p, a); }); return 0; }
+  int inner(const cno_stop_t& stop) {
+    const cno::AugLagFn<Obj> fn{obj, view};
+    cno_batch_out_t o{};
+    o.x = a.x_work;
+    o.nfev = const_cast<uint32_t*>(a.inner_nfev);
+    unsigned long long queue = 0;
+    emu::run_warp([&](int lane) {
+      blockIdx.x = 0;
+      threadIdx.x = (unsigned)lane;
+      cno::lbfgs_minimize_kernel<cno::AugLagFn<Obj>, CNO_LBFGS_M>(fn, a.x, B, cno::make_stop<T>(stop), cno::make_out<T>(o),
+                                                                 &queue, cno::ResumeArgs{nullptr, 0, 0, 0});
+    });
+    return 0;
+  }
+  int outer_step(int* remaining) {
+    *a.remaining = 0;
+    launch(B, [&] { cno::al_outer_step_kernel<Obj>(obj, view, B, p, a); });
+    *remaining = *a.remaining;
+    return 0;
+  }
+  int finalize() { launch(B, [&] { cno::al_finalize_kernel<T, Obj::Dim>(B, view.n_eq, view.n_ineq, a); }); return 0; }
+};
+
+template <class Obj>
+int run_al_minimize(const cno_constraints_t* k, long long B, const void* x0, const void* eq0, const void* ineq0,
+                    const void* penalty0, const cno_stop_t* inner_stop, const cno_al_stop_t* outer_stop,
+                    const cno_al_config_t* config, const cno_al_out_t* out, int* launches) {
+  using T = typename Obj::Scalar;
+  const cno::AlLayout L((size_t)B, Obj::Dim, (size_t)k->n_eq, (size_t)k->n_ineq, sizeof(T));
+  std::vector<unsigned char> storage(L.total + 256);
+  unsigned char* ws = storage.data() + (256 - ((uintptr_t)storage.data() & 255)) % 256;
+  AlEmuBackend<Obj> be{Obj{}, B, cno::al_make_arrays<T>(*out, ws, L), {}, {}};
+  be.view = cno::al_make_view<T>(*k, be.a);
+  be.p = cno::al_make_params<T>(*config, *outer_stop);
+  return cno::al_outer_loop<T>(be, be.a, B, Obj::Dim, k->n_eq, k->n_ineq, x0, eq0, ineq0, penalty0, *inner_stop, *config,
+                               launches);
+}
+
+// cno_al_minimize's host logic (outer loop, scratch layout) with every kernel under emulation.  Host pointers.
+extern "C" int emu_al_minimize(const cno_problem_t* objective, const cno_constraints_t* constraints, long long batch,
+                               const void* x0, const void* eq0, const void* ineq0, const void* penalty0,
+                               const cno_stop_t* inner_stop, const cno_al_stop_t* outer_stop,
+                               const cno_al_config_t* config, const cno_al_out_t* out, int* launches) {
+#define AL_CASE(FAM, DT, TY, DIM, FN)                                                                  \
+  if (objective->family == FAM && objective->dtype == DT && objective->d == DIM)                       \
+    return run_al_minimize<cno::FN<TY, DIM>>(constraints, batch, x0, eq0, ineq0, penalty0, inner_stop, outer_stop, \
+                                             config, out, launches);
+  AL_CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 2, RosenbrockFn)
+  AL_CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 8, RosenbrockFn)
+  AL_CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 37, RosenbrockFn)
+  AL_CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 128, RosenbrockFn)
+  AL_CASE(CNO_FN_ROSENBROCK, CNO_F32, float, 8, RosenbrockFn)
+  AL_CASE(CNO_FN_HALF_SQUARED_NORM, CNO_F64, double, 2, HalfSquaredNormFn)
+  AL_CASE(CNO_FN_HALF_SQUARED_NORM, CNO_F64, double, 8, HalfSquaredNormFn)
+#undef AL_CASE
+  return CNO_ERR_UNSUPPORTED;
 }
 
 extern "C" int emu_al(int op, const cno_problem_t* objective, const cno_constraints_t* constraints, long long batch,

@@ -337,3 +337,63 @@ def test_emulation_reproduces_the_logistic_kernel(emu):
     o = ob.minimize(ob.LBFGS, ob.FN_LOGISTIC, x0, data=data, n=n, param=lam)
     for key in SOLVER_KEYS:
         assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
+
+
+# ---- the host side of cno_al_minimize itself (csrc/cno_auglag_host.h) with an emulation backend ------------
+def emulated_cno_al_minimize(emu, family, x0, kinds, rows, n_eq, *, outer_stop=None, config=None, inner_stop=None,
+                             eq0=None, ineq0=None, penalty0=None):
+    """cno::al_outer_loop -- the code csrc/cno_api.cu::al_run runs with the CUDA backend -- with memcpy / memset
+    and emulated kernel launches as the backend, carving its scratch out of cno::AlLayout."""
+    x0 = np.ascontiguousarray(x0)
+    B, d = x0.shape
+    dt = x0.dtype
+    prob = _problem(family, x0)
+    k, keep = ob._constraints(kinds, rows, n_eq, dt, B, d)
+    ne, ni = k.n_eq, k.n_ineq
+    cfg = config if config is not None else ob.al_default_config()
+    ostop = outer_stop if outer_stop is not None else ob.al_default_stop()
+    istop = inner_stop if inner_stop is not None else ob.default_stop()
+    opt = lambda v, shape: None if v is None else np.ascontiguousarray(np.broadcast_to(np.asarray(v, dt), shape))  # noqa: E731
+    e0, i0, p0 = opt(eq0, (B, ne)), opt(ineq0, (B, ni)), opt(penalty0, (B,))
+    r = dict(x=np.zeros_like(x0), equality_multipliers=np.zeros((B, ne), dt), inequality_multipliers=np.zeros((B, ni), dt),
+             penalty=np.zeros(B, dt), max_violation=np.zeros(B, dt), max_lagrangian_gradient=np.zeros(B, dt),
+             num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32),
+             x_delta=np.zeros(B, dt), f_delta=np.zeros(B, dt), gradient_norm=np.zeros(B, dt))
+    out = ob.AlOut(*[_ptr(r[n]) for n, _ in ob.AlOut._fields_])
+    launches = C.c_int(0)
+    rc = emu.emu_al_minimize(C.byref(prob), C.byref(k), C.c_longlong(B), C.c_void_p(x0.ctypes.data), C.c_void_p(_ptr(e0)),
+                             C.c_void_p(_ptr(i0)), C.c_void_p(_ptr(p0)), C.byref(istop), C.byref(ostop), C.byref(cfg),
+                             C.byref(out), C.byref(launches))
+    assert rc == 0
+    del keep
+    r["launches"] = launches.value
+    return r
+
+
+@pytest.mark.parametrize("family,dtype,d,n_eq,per_instance", [
+    (ob.FN_ROSENBROCK, np.float64, 8, 1, True), (ob.FN_ROSENBROCK, np.float64, 37, 0, False),
+    (ob.FN_HALF_SQUARED_NORM, np.float64, 8, 2, True)])
+def test_host_loop_of_cno_al_minimize_under_emulation(emu, family, dtype, d, n_eq, per_instance):
+    """Initial state, auto-scale on iteration 1, warm-up inner limits, termination on the remaining-counter,
+    best-iterate epilogue, scratch layout: the shared host loop + every kernel == the oracle, bit for bit."""
+    B = 2
+    rng = np.random.default_rng(400 + d)
+    x0 = ob.fill_uniform((B, d), 0, 71 + d, -1.5, 1.5, dtype)
+    kinds = [ob.CON_AFFINE, ob.CON_SQNORM, ob.CON_AFFINE]
+    shape = (B, 3, d + 1) if per_instance else (3, d + 1)
+    rows = rng.uniform(-1, 1, shape).astype(dtype)
+    rows[..., 1, d] = 2.0 + rng.uniform(0, 1, shape[:-2])
+    stop = ob.al_default_stop()
+    stop.num_iterations = 3 if d > 8 else 5
+    r = emulated_cno_al_minimize(emu, family, x0, kinds, rows, n_eq, outer_stop=stop)
+    o = ob.al_minimize(family, x0, kinds, rows, n_eq, outer_stop=stop)
+    _assert_same(r, o)
+    # launches = 1 (auto-scale) + 2 per outer iteration of the slowest instance + 1 (finalize)
+    assert r["launches"] == 2 + 2 * int(o["num_iterations"].max())
+    if d > 8:
+        return
+    cfg = ob.al_default_config()
+    cfg.warmup_max_inner_iterations, cfg.auto_scale_initial_penalty = 0, 0
+    kw = dict(outer_stop=stop, config=cfg, eq0=0.25, ineq0=0.5, penalty0=2.0)
+    _assert_same(emulated_cno_al_minimize(emu, family, x0, kinds, rows, n_eq, **kw),
+                 ob.al_minimize(family, x0, kinds, rows, n_eq, **kw))
