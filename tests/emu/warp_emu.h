@@ -43,8 +43,29 @@ inline float4 make_float4(float x, float y, float z, float w) { return float4{x,
 
 namespace emu {
 struct Dim3 { unsigned x = 0, y = 0, z = 0; };
+// Sense-reversing spin barrier: the 32 lanes of an emulated warp meet thousands of times per solve, and a
+// futex-based std::barrier spends most of that time in the kernel; spinning (the box has >= 32 cores) is
+// several times faster.  Falls back to yielding when oversubscribed.
+struct SpinBarrier {
+  std::atomic<int> count{0};
+  std::atomic<int> sense{0};
+  int total = 32;
+  void arrive_and_wait() {
+    const int my = sense.load(std::memory_order_relaxed);
+    if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == total) {
+      count.store(0, std::memory_order_relaxed);
+      sense.store(my ^ 1, std::memory_order_release);
+    } else {
+      int spins = 0;
+      while (sense.load(std::memory_order_acquire) == my) {
+        if (++spins > 2000) { std::this_thread::yield(); spins = 0; }
+        else __builtin_ia32_pause();
+      }
+    }
+  }
+};
 struct Warp {
-  std::barrier<> bar{32};
+  SpinBarrier bar;
   uint64_t slot[32];
   double dslot[32];
   uint32_t tmem[32][512];  // Tensor Memory window of the emulated warp: [lane][column], 32-bit cells
@@ -103,7 +124,6 @@ inline void run_warp(const std::function<void(int)>& f) {
       tl_lane = l;
       tl_warp = &w;
       f(l);
-      w.bar.arrive_and_drop();
     });
   for (auto& t : ts) t.join();
 }

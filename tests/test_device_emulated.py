@@ -209,9 +209,7 @@ def test_emulated_device_loop_known_answers(emu):
 
 
 # ---- the fused inner kernel too: the whole device path of the row under emulation ----------------
-@pytest.mark.parametrize("family,dtype,d,n_eq", [(ob.FN_ROSENBROCK, np.float64, 8, 1), (ob.FN_ROSENBROCK, np.float64, 37, 2),
-                                                 (ob.FN_ROSENBROCK, np.float64, 128, 1),
-                                                 (ob.FN_ROSENBROCK, np.float32, 8, 1), (ob.FN_HALF_SQUARED_NORM, np.float64, 8, 1)])
+@pytest.mark.parametrize("family,dtype,d,n_eq", [(ob.FN_ROSENBROCK, np.float64, 128, 1), (ob.FN_ROSENBROCK, np.float32, 8, 1)])
 def test_emulated_device_loop_with_the_device_inner_kernel(emu, family, dtype, d, n_eq):
     """lbfgs_minimize_kernel<AugLagFn<Obj>> (with its active() skip of finished instances) + the outer-loop
     kernels, all device source, all under emulation == the oracle, bit for bit (d = 128: the y-history of
@@ -223,7 +221,7 @@ def test_emulated_device_loop_with_the_device_inner_kernel(emu, family, dtype, d
     rows = rng.uniform(-1, 1, (B, 3, d + 1)).astype(dtype)
     rows[:, 1, d] = 2.0 + rng.uniform(0, 1, B)
     stop = ob.al_default_stop()
-    stop.num_iterations = 3 if (d > 8 or dtype == np.float32) else 6
+    stop.num_iterations = 2 if dtype == np.float32 else 3  # (fp64 d = 8 / 37 and the half norm: the host-loop test below)
     _assert_same(emulated_al_minimize(emu, family, x0, kinds, rows, n_eq, outer_stop=stop, device_inner=True),
                  ob.al_minimize(family, x0, kinds, rows, n_eq, outer_stop=stop))
 
@@ -234,7 +232,7 @@ SOLVER_KEYS = ("num_iterations", "status", "nfev", "x", "value", "gradient", "x_
 
 @pytest.mark.parametrize("solver,hz,dtype,d,limit", [
     (ob.LBFGS, 0, np.float64, 2, 10000), (ob.LBFGS, 0, np.float64, 37, 40), (ob.LBFGS, 0, np.float32, 37, 20),
-    (ob.LBFGS, 0, np.float64, 128, 100), (ob.LBFGS, 1, np.float64, 128, 60),  # the headline shape: y-history in (emulated) Tensor Memory
+    (ob.LBFGS, 0, np.float64, 128, 50), (ob.LBFGS, 1, np.float64, 128, 25),  # the headline shape: y-history in (emulated) Tensor Memory
     (ob.LBFGS, 1, np.float64, 8, 10000), (ob.BFGS, 0, np.float64, 8, 10000), (ob.BFGS, 1, np.float64, 2, 10000),
     (ob.GRADIENT_DESCENT, 0, np.float64, 8, 40), (ob.GRADIENT_DESCENT, 1, np.float64, 8, 40),
     (ob.CONJUGATED_GRADIENT_DESCENT, 0, np.float64, 8, 8)])
