@@ -120,10 +120,13 @@ class AugmentedLagrangian:
         return ok
 
     def Minimize(self, state: AugmentedLagrangeState) -> Tuple[AugmentedLagrangeState, ConstrainedProgress]:
+        if not state.x.is_cuda:
+            raise RuntimeError("Minimize needs CUDA tensors (there is no CPU fallback)")
+        return self._minimize(state, torch.cuda.current_stream(state.x.device).cuda_stream)
+
+    def _minimize(self, state: AugmentedLagrangeState, stream: int):
         x0 = state.x
         fn = self.problem.objective
-        if not x0.is_cuda:
-            raise RuntimeError("Minimize needs CUDA tensors (there is no CPU fallback)")
         if x0.dtype != fn.ScalarType or x0.dim() != 2 or x0.shape[1] != fn.Dimension:
             raise ValueError("x0 must be [B, d] of the objective's scalar type")
         x0 = x0.contiguous()
@@ -157,7 +160,8 @@ class AugmentedLagrangian:
                          pr.x_delta.data_ptr(), pr.f_delta.data_ptr(), pr.gradient_norm.data_ptr())
         nbytes = C.c_size_t(0)
         _lib.check(L.cno_al_workspace_bytes(C.byref(prob), C.byref(k), B, C.byref(nbytes)), "cno_al_workspace_bytes")
-        ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=dev)
+        ws = torch.empty(max(nbytes.value, 256) + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (ws.data_ptr() + 255) & ~255  # the scratch layout wants 256-byte alignment
         inner = self.unconstrained_solver.stopping_progress.to_c()
         sp = self.stopping_progress
         outer = _lib.AlStop(sp.num_iterations, sp.constraint_threshold, sp.kkt_stationarity_threshold)
@@ -165,8 +169,7 @@ class AugmentedLagrangian:
         ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
         _lib.check(L.cno_al_minimize(
             C.byref(prob), C.byref(k), C.c_int64(B), C.c_void_p(x0.data_ptr()), ptr(eq0), ptr(ineq0), ptr(pen0),
-            C.byref(inner), C.byref(outer), C.byref(cfg), C.byref(out), C.c_void_p(ws.data_ptr()),
-            C.c_size_t(ws.numel()), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream),
-            C.byref(pr.launch)), "cno_al_minimize")
+            C.byref(inner), C.byref(outer), C.byref(cfg), C.byref(out), C.c_void_p(ws_ptr),
+            C.c_size_t(ws.numel() - 256), C.c_void_p(stream), C.byref(pr.launch)), "cno_al_minimize")
         del keep
         return r, pr

@@ -124,3 +124,26 @@ def test_al_entry_points_without_a_device():
     if not torch.cuda.is_available():
         assert L.cno_al_minimize(C.byref(prob), C.byref(k), C.c_int64(0), None, None, None, None, None, None, None,
                                  C.byref(out), None, C.c_size_t(0), None, None) == _lib.ERR_NO_DEVICE
+
+
+def test_python_mirror_of_the_constrained_interface_reaches_the_abi():
+    """cn.AugmentedLagrangian builds the C structs, the scratch buffer and the argument list and calls
+    cno_al_minimize; without a device that call must come back as CNO_ERR_NO_DEVICE (no CPU fallback) --
+    which also exercises every line of the Python glue before the first GPU run of the path."""
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    rows = torch.zeros(4, 2, 9, dtype=torch.float64)
+    rows[:, 1, 8] = 2.0
+    problem = cn.ConstrainedOptimizationProblem(cn.Rosenbrock(8), [_lib.CON_AFFINE, _lib.CON_SQNORM], rows, 1)
+    solver = cn.AugmentedLagrangian(problem, cn.Lbfgs(cn.ConservativeStoppingSolverProgress()),
+                                    cn.AugmentedLagrangianConfig(multiplier_max=5.0))
+    assert solver.supported()
+    solver.stopping_progress.num_iterations = 7
+    state = cn.AugmentedLagrangeState(torch.zeros(4, 8, dtype=torch.float64), equality_multipliers=0.25, penalty=2.0)
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        solver.Minimize(state)
+    with pytest.raises(_lib.CnoError) as e:
+        solver._minimize(state, 0)
+    assert e.value.code == _lib.ERR_NO_DEVICE
+    with pytest.raises(ValueError):  # rows of the wrong scalar type
+        cn.AugmentedLagrangian(cn.ConstrainedOptimizationProblem(cn.Rosenbrock(8), [0], rows[:, :1].float(), 1))._minimize(state, 0)
