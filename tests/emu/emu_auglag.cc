@@ -170,6 +170,15 @@ int run_solver(int solver, long long B, const void* x0, const cno_stop_t* stop, 
 // the LineSearch policy.  Host pointers.
 extern "C" int emu_minimize(int solver, int hager_zhang, const cno_problem_t* p, long long batch, const void* x0,
                             const cno_stop_t* stop, const cno_batch_out_t* out) {
+  // Lbfgs on a Second-mode function (diagonal preconditioner, lbfgs.h:116-139) and the Eigen-SSE2 parity policy
+  if (solver == CNO_LBFGS && !hager_zhang && p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64) {
+    if (p->mode == 2 && p->d == 37)
+      return run_solver<cno::SecondMode<cno::RosenbrockFn<double, 37>>, cno::LsMoreThuente>(solver, batch, x0, stop, out);
+    if (p->mode == 2 && p->d == 128)
+      return run_solver<cno::SecondMode<cno::RosenbrockFn<double, 128>>, cno::LsMoreThuente>(solver, batch, x0, stop, out);
+    if (p->policy == CNO_POLICY_EIGEN_SSE2 && p->d == 128)
+      return run_solver<cno::RosenbrockFn<double, 128, cno::PolicyEigenSSE2>, cno::LsMoreThuente>(solver, batch, x0, stop, out);
+  }
 #define SOLVER_CASE(DT, TY, DIM)                                                                         \
   if (p->family == CNO_FN_ROSENBROCK && p->dtype == DT && p->d == DIM)                                   \
     return hager_zhang ? run_solver<cno::RosenbrockFn<TY, DIM>, cno::LsHagerZhang>(solver, batch, x0, stop, out) \

@@ -4,7 +4,7 @@ against the oracle on edge-case inputs the GPU parity tests do not cover (NaN / 
 starts at the minimiser, degenerate constraints).  A NaN must be a NaN on both sides (its sign / payload is
 not part of the contract); everything else must agree bit for bit.
 
-    python tools/emu_sweep.py [solvers] [headline] [al] [newton]      (default: all four)
+    python tools/emu_sweep.py [solvers] [headline] [al] [newton] [modes]      (default: all)
 
 This is how the GradientDescent-HagerZhang failure-path defect was found."""
 import ctypes as C
@@ -181,9 +181,37 @@ def sweep_newton(trials=24):
     return n, bad_n
 
 
+def sweep_modes(trials=24):
+    """Lbfgs on a Second-mode function (diagonal preconditioner, lbfgs.h:116-139) and the Eigen-SSE2 parity policy."""
+    rng = np.random.default_rng(5)
+    n = bad_n = 0
+    for trial in range(trials):
+        scale = float(rng.choice([1e-3, 2.0, 30.0, 300.0, 1e6, 1e100]))
+        for d, mode, policy in ((37, 2, ob.POLICY_DMMA_TREE), (128, 2, ob.POLICY_DMMA_TREE), (128, 0, ob.POLICY_EIGEN_SSE2)):
+            x0 = rng.uniform(-scale, scale, (2, d))
+            poison(x0, trial, rng)
+            stop = ob.default_stop()
+            stop.num_iterations = 25
+            prob = ob.Problem(ob.FN_ROSENBROCK, 0, d, 0, 0.0, None, 0, policy, mode)
+            r = dict(x=np.zeros_like(x0), value=np.zeros(2), gradient=np.zeros_like(x0), num_iterations=np.zeros(2, np.uint32),
+                     status=np.zeros(2, np.int8), nfev=np.zeros(2, np.uint32), x_delta=np.zeros(2), f_delta=np.zeros(2),
+                     gradient_norm=np.zeros(2))
+            out = ob.BatchOut(*[r[k].ctypes.data for k, _ in ob.BatchOut._fields_])
+            assert emu.emu_minimize(ob.LBFGS, 0, C.byref(prob), C.c_longlong(2), C.c_void_p(x0.ctypes.data), C.byref(stop),
+                                    C.byref(out)) == 0
+            o = ob.minimize(ob.LBFGS, ob.FN_ROSENBROCK, x0, stop=stop, policy=policy, mode=mode)
+            bad = differing(r, o, T.SOLVER_KEYS)
+            n += 1
+            if bad:
+                bad_n += 1
+                print("MISMATCH d", d, "mode", mode, "policy", policy, "scale", scale, bad, flush=True)
+    return n, bad_n
+
+
 def main():
-    which = sys.argv[1:] or ["solvers", "headline", "al", "newton"]
-    for name, fn in (("solvers", sweep_solvers), ("headline", sweep_headline), ("al", sweep_al), ("newton", sweep_newton)):
+    which = sys.argv[1:] or ["solvers", "headline", "al", "newton", "modes"]
+    for name, fn in (("solvers", sweep_solvers), ("headline", sweep_headline), ("al", sweep_al), ("newton", sweep_newton),
+                     ("modes", sweep_modes)):
         if name in which:
             t0 = time.time()
             n, bad = fn()
