@@ -315,6 +315,42 @@ extern "C" int emu_al_minimize(const cno_problem_t* objective, const cno_constra
   return CNO_ERR_UNSUPPORTED;
 }
 
+// cno_minimize_steps under emulation: rounds of `every` iterations with the solver state parked in between
+// (lbfgs_minimize_kernel<Fn, M, /*kResume=*/true>), until every instance has stopped.  Host pointers.
+template <class Fn>
+int run_steps(long long B, const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out, int every, int* rounds) {
+  using T = typename Fn::Scalar;
+  using RL = cno::ResumeLayout<T, cno::Shape<Fn::Dim>::E, CNO_LBFGS_M>;
+  std::vector<unsigned char> state((size_t)B * RL::kBytes + 16);
+  unsigned char* st = state.data() + (16 - ((uintptr_t)state.data() & 15)) % 16;
+  const Fn fn{};
+  int n = 0;
+  for (int first = 1;; first = 0) {
+    unsigned long long queue = 0;
+    emu::run_warp([&](int lane) {
+      blockIdx.x = 0;
+      threadIdx.x = (unsigned)lane;
+      cno::lbfgs_minimize_kernel<Fn, CNO_LBFGS_M, true>(fn, (const T*)x0, B, cno::make_stop<T>(*stop), cno::make_out<T>(*out),
+                                                        &queue, cno::ResumeArgs{st, (long long)RL::kBytes, every, first});
+    });
+    ++n;
+    bool done = true;
+    for (long long b = 0; b < B; ++b) done = done && (out->status[b] != CNO_STATUS_CONTINUE);
+    if (done) break;
+  }
+  if (rounds) *rounds = n;
+  return 0;
+}
+
+extern "C" int emu_minimize_steps(const cno_problem_t* p, long long batch, const void* x0, const cno_stop_t* stop,
+                                  const cno_batch_out_t* out, int every, int* rounds) {
+  if (p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64 && p->d == 2)
+    return run_steps<cno::RosenbrockFn<double, 2>>(batch, x0, stop, out, every, rounds);
+  if (p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64 && p->d == 128)
+    return run_steps<cno::RosenbrockFn<double, 128>>(batch, x0, stop, out, every, rounds);
+  return CNO_ERR_UNSUPPORTED;
+}
+
 extern "C" int emu_al(int op, const cno_problem_t* objective, const cno_constraints_t* constraints, long long batch,
                       const EmuArrays* arrays_, const cno_al_config_t* config, const cno_al_stop_t* stop,
                       const void* x_in, void* value_out, void* grad_out) {

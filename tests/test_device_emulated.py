@@ -395,3 +395,31 @@ def test_host_loop_of_cno_al_minimize_under_emulation(emu, family, dtype, d, n_e
     kw = dict(outer_stop=stop, config=cfg, eq0=0.25, ineq0=0.5, penalty0=2.0)
     _assert_same(emulated_cno_al_minimize(emu, family, x0, kinds, rows, n_eq, **kw),
                  ob.al_minimize(family, x0, kinds, rows, n_eq, **kw))
+
+
+@pytest.mark.parametrize("d,every", [(2, 3), (128, 7)])
+def test_emulation_reproduces_the_stepwise_kernel(emu, d, every):
+    """cno_minimize_steps (lbfgs_minimize_kernel<Fn, M, kResume = true>): rounds of `every` iterations with the
+    solver state parked in between == the fused solve of the oracle, bit for bit, incl. a NaN start."""
+    B = 3
+    x0 = ob.fill_uniform((B, d), 0, 33 + d, -2.0, 2.0)
+    x0[2, 0] = np.nan
+    stop = ob.default_stop()
+    stop.num_iterations = 30
+    prob = _problem(ob.FN_ROSENBROCK, x0)
+    r = dict(x=np.zeros_like(x0), value=np.zeros(B), gradient=np.zeros_like(x0), num_iterations=np.zeros(B, np.uint32),
+             status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32), x_delta=np.zeros(B), f_delta=np.zeros(B),
+             gradient_norm=np.zeros(B))
+    out = ob.BatchOut(*[r[n].ctypes.data for n, _ in ob.BatchOut._fields_])
+    rounds = C.c_int(0)
+    assert emu.emu_minimize_steps(C.byref(prob), C.c_longlong(B), C.c_void_p(x0.ctypes.data), C.byref(stop), C.byref(out),
+                                  every, C.byref(rounds)) == 0
+    o = ob.minimize(ob.LBFGS, ob.FN_ROSENBROCK, x0, stop=stop)
+    for key in SOLVER_KEYS:
+        u, v = r[key], o[key]
+        if u.dtype.kind == "f":
+            nan = np.isnan(u)
+            assert np.array_equal(nan, np.isnan(v)), key
+            u, v = np.where(nan, 0, u), np.where(nan, 0, v)
+        assert np.array_equal(u.view(np.uint8), v.view(np.uint8)), key
+    assert rounds.value == -(-int(o["num_iterations"].max()) // every)
