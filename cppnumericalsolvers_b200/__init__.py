@@ -8,7 +8,7 @@ the C ABI of include/cno.h.  No CPU fallback.
 from . import _lib  # noqa: F401
 from .constrained import (AugmentedLagrangeState, AugmentedLagrangian,  # noqa: F401
                           AugmentedLagrangianConfig, ConstrainedOptimizationProblem, ConstrainedStop)
-from .function import (BatchedFunctionState, DenseQuadratic, DiagQuadratic,  # noqa: F401
+from .function import (BatchedFunctionState, DenseQuadratic, DenseQuadraticFirst, DiagQuadratic,  # noqa: F401
                        DifferentiabilityMode, Function, HalfSquaredNorm, Logistic, Rosenbrock,
                        RosenbrockFull)
 from .solver import (BatchedProgress, Bfgs, ConjugatedGradientDescent,  # noqa: F401
@@ -22,7 +22,7 @@ __all__ = [
     "ConstrainedOptimizationProblem", "ConstrainedStop",
     "BatchedFunctionState", "BatchedProgress", "Bfgs", "ConjugatedGradientDescent",
     "ConservativeStoppingSolverProgress", "GradientDescent", "HagerZhang", "MoreThuente",
-    "DefaultStoppingSolverProgress", "DenseQuadratic", "DiagQuadratic", "DifferentiabilityMode",
+    "DefaultStoppingSolverProgress", "DenseQuadratic", "DenseQuadraticFirst", "DiagQuadratic", "DifferentiabilityMode",
     "Function", "HalfSquaredNorm", "Lbfgs", "Logistic", "NewtonDescent", "PrintProgressCallback", "Progress",
     "Rosenbrock", "RosenbrockFull", "Solver", "Status", "fill_uniform",
 ]

@@ -265,6 +265,14 @@ int lbfgs_rosenbrock_second(const LaunchArgs& a) {
   if (a.stop->condition_hessian > 0) return CNO_ERR_UNSUPPORTED;  // not computed (cno_newton.cuh)
   return launch_lbfgs<Fn, CNO_LBFGS_M>(Fn{}, a);
 }
+// First-mode dense quadratic ([A | b] read from global memory per evaluation)
+template <class T, int D>
+int lbfgs_dense_quadratic(const LaunchArgs& a) {
+  const cno_problem_t* p = a.problem;
+  if (!p->data || p->data_stride < (int64_t)D * D + D) return CNO_ERR_INVALID_ARGUMENT;
+  using Fn = cno::DenseQuadraticGlobalFn<T, D>;
+  return launch_lbfgs<Fn, CNO_LBFGS_M>(Fn{static_cast<const T*>(p->data), (long long)p->data_stride}, a);
+}
 template <class T, int D>
 int lbfgs_half_sq_norm(const LaunchArgs& a) {
   return launch_lbfgs<cno::HalfSquaredNormFn<T, D>, CNO_LBFGS_M>(cno::HalfSquaredNormFn<T, D>{}, a);
@@ -327,6 +335,9 @@ const Entry kTable[] = {
     {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, lbfgs_half_sq_norm<double, 2>},
     {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 50, lbfgs_half_sq_norm<double, 50>},
     {CNO_LBFGS, CNO_FN_LOGISTIC, CNO_F32, 64, lbfgs_logistic<float, 64, 256>},
+    {CNO_LBFGS, CNO_FN_DENSE_QUADRATIC, CNO_F64, 2, lbfgs_dense_quadratic<double, 2>},
+    {CNO_LBFGS, CNO_FN_DENSE_QUADRATIC, CNO_F64, 8, lbfgs_dense_quadratic<double, 8>},
+    {CNO_LBFGS, CNO_FN_DENSE_QUADRATIC, CNO_F64, 64, lbfgs_dense_quadratic<double, 64>},
     {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 2, bfgs_rosenbrock<double, 2>},
     {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 8, bfgs_rosenbrock<double, 8>},
     {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 32, bfgs_rosenbrock<double, 32>},
@@ -520,6 +531,12 @@ template <class T, int D>
 int al_rosenbrock(const AlArgs& a) { return al_run(cno::RosenbrockFn<T, D>{}, a); }
 template <class T, int D>
 int al_half_sq_norm(const AlArgs& a) { return al_run(cno::HalfSquaredNormFn<T, D>{}, a); }
+template <class T, int D>
+int al_dense_quadratic(const AlArgs& a) {  // the batched "QP with affine / ball constraints"
+  const cno_problem_t* p = a.objective;
+  if (!p->data || p->data_stride < (int64_t)D * D + D) return CNO_ERR_INVALID_ARGUMENT;
+  return al_run(cno::DenseQuadraticGlobalFn<T, D>{static_cast<const T*>(p->data), (long long)p->data_stride}, a);
+}
 
 struct AlEntry {
   int family, dtype, d;
@@ -533,6 +550,8 @@ const AlEntry kAlTable[] = {
     {CNO_FN_ROSENBROCK, CNO_F32, 8, al_rosenbrock<float, 8>},
     {CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, al_half_sq_norm<double, 2>},
     {CNO_FN_HALF_SQUARED_NORM, CNO_F64, 8, al_half_sq_norm<double, 8>},
+    {CNO_FN_DENSE_QUADRATIC, CNO_F64, 2, al_dense_quadratic<double, 2>},
+    {CNO_FN_DENSE_QUADRATIC, CNO_F64, 8, al_dense_quadratic<double, 8>},
 };
 
 const AlEntry* al_find(const cno_problem_t* p) {

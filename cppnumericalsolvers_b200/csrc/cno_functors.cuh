@@ -122,6 +122,60 @@ struct HalfSquaredNormFn {
   }
 };
 
+// 0.5 x'Ax - b'x with per-instance [A (d x d col-major) | b] read from global memory (L2) at every
+// evaluation: the First-mode counterpart of DenseQuadraticFn (cno_newton.cuh), for the solvers that keep
+// no matrix on chip (Lbfgs, and AugmentedLagrangian's batched "QP with affine constraints" use).
+// Reference analogue: src/examples/debug.cc:43-65; src/test/augmented_lagrangian_test.cc:78-176
+// (QuadraticAt12 / QuadraticAt20).  (Ax)_i = sum_j A_ij x_j, j ascending from the first product;
+// x_j is broadcast from its owner lane.  STATUS: checked under the CPU warp emulation against the oracle
+// (tests/test_device_emulated.py); first GPU run pending with the AugmentedLagrangian path.
+template <class T, int D>
+struct DenseQuadraticGlobalFn {
+  using Scalar = T;
+  static constexpr int Dim = D;
+  static constexpr int Mode = 1;
+  static constexpr int E = Shape<D>::E;
+  const T* data;     // [B, stride]
+  long long stride;  // scalars per instance (>= D*D + D)
+
+  __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&x)[E], T (*grad)[E]) const {
+    const T* A = data + c.instance * stride;
+    T Ax[E], bb[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) Ax[e] = T(0);
+#pragma unroll 1
+    for (int jl = 0; jl * E < D; ++jl) {
+#pragma unroll
+      for (int ej = 0; ej < E; ++ej) {
+        const int j = jl * E + ej;
+        const T xj = __shfl_sync(kFullMask, x[ej], jl);  // x_j lives in lane j / E, slot j % E
+        if (j < D) {
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int i = c.lane * E + e;
+            if (i < D) {
+              const T a = __ldg(A + i + (long long)j * D);
+              Ax[e] = (j == 0) ? (a * xj) : (Ax[e] + a * xj);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = c.lane * E + e;
+      bb[e] = (i < D) ? __ldg(A + D * D + i) : T(0);
+    }
+    if (grad) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) (*grad)[e] = (c.lane * E + e < D) ? (Ax[e] - bb[e]) : T(0);
+    }
+    T p1 = lane_dot<T, E>(x, Ax), p2 = lane_dot<T, E>(bb, x);
+    warp_sum2(p1, p2);
+    return T(0.5) * p1 - p2;
+  }
+};
+
 }  // namespace cno
 
 #endif  // CNO_FUNCTORS_CUH_

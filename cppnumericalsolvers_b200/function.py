@@ -90,6 +90,12 @@ def DenseQuadratic(data: torch.Tensor, d: int) -> Function:
                     data=data)
 
 
+def DenseQuadraticFirst(data: torch.Tensor, d: int) -> Function:
+    """The same objective as a First-mode function (value and gradient only): for Lbfgs and for
+    AugmentedLagrangian's batched "quadratic objective, affine / ball constraints" problems."""
+    return Function(d, data.dtype, DifferentiabilityMode.First, _lib.FN_DENSE_QUADRATIC, data=data)
+
+
 @dataclass
 class BatchedFunctionState:
     """FunctionState with a batch axis (function_base.h:298-332)."""

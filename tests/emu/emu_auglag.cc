@@ -87,12 +87,11 @@ cno::AlParams<T> params(const cno_al_config_t* c, const cno_al_stop_t* s) {  // 
 enum Op { kComposite = 0, kAutoscale = 1, kOuterStep = 2, kFinalize = 3, kInner = 4 };
 
 template <class Obj>
-int run(int op, const cno_constraints_t* k, long long B, const EmuArrays& e, const cno_al_config_t* cfg,
+int run(const Obj& obj, int op, const cno_constraints_t* k, long long B, const EmuArrays& e, const cno_al_config_t* cfg,
         const cno_al_stop_t* stop, const void* x_in, void* value_out, void* grad_out) {
   using T = typename Obj::Scalar;
   constexpr int D = Obj::Dim;
   constexpr int E = cno::Shape<D>::E;
-  const Obj obj{};
   const cno::AlView<T> v = view<T>(k, e);
   if (op == kComposite) {  // AugLagFn::operator() at x_in under (lambda, mu, penalty)
     const cno::AugLagFn<Obj> fn{obj, v};
@@ -140,9 +139,9 @@ int run(int op, const cno_constraints_t* k, long long B, const EmuArrays& e, con
 
 // ---- the unconstrained solver kernels under emulation (one warp draining the queue) ----
 template <class Fn, class LS>
-int run_solver(int solver, long long B, const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out) {
+int run_solver(int solver, long long B, const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out,
+               const Fn fn = Fn{}) {
   using T = typename Fn::Scalar;
-  const Fn fn{};
   unsigned long long queue = 0;
   int rc = 0;
   emu::run_warp([&](int lane) {
@@ -170,6 +169,14 @@ int run_solver(int solver, long long B, const void* x0, const cno_stop_t* stop, 
 // the LineSearch policy.  Host pointers.
 extern "C" int emu_minimize(int solver, int hager_zhang, const cno_problem_t* p, long long batch, const void* x0,
                             const cno_stop_t* stop, const cno_batch_out_t* out) {
+  if (solver == CNO_LBFGS && !hager_zhang && p->family == CNO_FN_DENSE_QUADRATIC && p->dtype == CNO_F64 && p->mode != 2) {
+    const double* data = (const double*)p->data;
+    const long long stride = (long long)p->data_stride;
+    if (p->d == 8)
+      return run_solver<cno::DenseQuadraticGlobalFn<double, 8>, cno::LsMoreThuente>(solver, batch, x0, stop, out, {data, stride});
+    if (p->d == 64)
+      return run_solver<cno::DenseQuadraticGlobalFn<double, 64>, cno::LsMoreThuente>(solver, batch, x0, stop, out, {data, stride});
+  }
   // Lbfgs on a Second-mode function (diagonal preconditioner, lbfgs.h:116-139) and the Eigen-SSE2 parity policy
   if (solver == CNO_LBFGS && !hager_zhang && p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64) {
     if (p->mode == 2 && p->d == 37)
@@ -281,14 +288,14 @@ struct AlEmuBackend {
 };
 
 template <class Obj>
-int run_al_minimize(const cno_constraints_t* k, long long B, const void* x0, const void* eq0, const void* ineq0,
+int run_al_minimize(const Obj& obj, const cno_constraints_t* k, long long B, const void* x0, const void* eq0, const void* ineq0,
                     const void* penalty0, const cno_stop_t* inner_stop, const cno_al_stop_t* outer_stop,
                     const cno_al_config_t* config, const cno_al_out_t* out, int* launches) {
   using T = typename Obj::Scalar;
   const cno::AlLayout L((size_t)B, Obj::Dim, (size_t)k->n_eq, (size_t)k->n_ineq, sizeof(T));
   std::vector<unsigned char> storage(L.total + 256);
   unsigned char* ws = storage.data() + (256 - ((uintptr_t)storage.data() & 255)) % 256;
-  AlEmuBackend<Obj> be{Obj{}, B, cno::al_make_arrays<T>(*out, ws, L), {}, {}};
+  AlEmuBackend<Obj> be{obj, B, cno::al_make_arrays<T>(*out, ws, L), {}, {}};
   be.view = cno::al_make_view<T>(*k, be.a);
   be.p = cno::al_make_params<T>(*config, *outer_stop);
   return cno::al_outer_loop<T>(be, be.a, B, Obj::Dim, k->n_eq, k->n_ineq, x0, eq0, ineq0, penalty0, *inner_stop, *config,
@@ -302,8 +309,8 @@ extern "C" int emu_al_minimize(const cno_problem_t* objective, const cno_constra
                                const cno_al_config_t* config, const cno_al_out_t* out, int* launches) {
 #define AL_CASE(FAM, DT, TY, DIM, FN)                                                                  \
   if (objective->family == FAM && objective->dtype == DT && objective->d == DIM)                       \
-    return run_al_minimize<cno::FN<TY, DIM>>(constraints, batch, x0, eq0, ineq0, penalty0, inner_stop, outer_stop, \
-                                             config, out, launches);
+    return run_al_minimize(cno::FN<TY, DIM>{}, constraints, batch, x0, eq0, ineq0, penalty0, inner_stop, outer_stop, \
+                           config, out, launches);
   AL_CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 2, RosenbrockFn)
   AL_CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 8, RosenbrockFn)
   AL_CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 37, RosenbrockFn)
@@ -312,6 +319,15 @@ extern "C" int emu_al_minimize(const cno_problem_t* objective, const cno_constra
   AL_CASE(CNO_FN_HALF_SQUARED_NORM, CNO_F64, double, 2, HalfSquaredNormFn)
   AL_CASE(CNO_FN_HALF_SQUARED_NORM, CNO_F64, double, 8, HalfSquaredNormFn)
 #undef AL_CASE
+  if (objective->family == CNO_FN_DENSE_QUADRATIC && objective->dtype == CNO_F64 && (objective->d == 2 || objective->d == 8)) {
+    const double* data = (const double*)objective->data;
+    const long long stride = (long long)objective->data_stride;
+    if (objective->d == 2)
+      return run_al_minimize(cno::DenseQuadraticGlobalFn<double, 2>{data, stride}, constraints, batch, x0, eq0, ineq0,
+                             penalty0, inner_stop, outer_stop, config, out, launches);
+    return run_al_minimize(cno::DenseQuadraticGlobalFn<double, 8>{data, stride}, constraints, batch, x0, eq0, ineq0,
+                           penalty0, inner_stop, outer_stop, config, out, launches);
+  }
   return CNO_ERR_UNSUPPORTED;
 }
 
@@ -356,7 +372,7 @@ extern "C" int emu_al(int op, const cno_problem_t* objective, const cno_constrai
                       const void* x_in, void* value_out, void* grad_out) {
 #define CASE(FAM, DT, TY, DIM, FN)                                                                  \
   if (objective->family == FAM && objective->dtype == DT && objective->d == DIM)                    \
-    return run<cno::FN<TY, DIM>>(op, constraints, batch, *arrays_, config, stop, x_in, value_out, grad_out);
+    return run(cno::FN<TY, DIM>{}, op, constraints, batch, *arrays_, config, stop, x_in, value_out, grad_out);
   CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 2, RosenbrockFn)
   CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 8, RosenbrockFn)
   CASE(CNO_FN_ROSENBROCK, CNO_F64, double, 37, RosenbrockFn)
@@ -365,5 +381,8 @@ extern "C" int emu_al(int op, const cno_problem_t* objective, const cno_constrai
   CASE(CNO_FN_HALF_SQUARED_NORM, CNO_F64, double, 2, HalfSquaredNormFn)
   CASE(CNO_FN_HALF_SQUARED_NORM, CNO_F64, double, 8, HalfSquaredNormFn)
 #undef CASE
+  if (objective->family == CNO_FN_DENSE_QUADRATIC && objective->dtype == CNO_F64 && objective->d == 8)
+    return run(cno::DenseQuadraticGlobalFn<double, 8>{(const double*)objective->data, (long long)objective->data_stride}, op,
+               constraints, batch, *arrays_, config, stop, x_in, value_out, grad_out);
   return CNO_ERR_UNSUPPORTED;
 }

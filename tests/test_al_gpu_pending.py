@@ -116,3 +116,50 @@ def test_al_cpp_mirror_equality_only_quadratic():
     exe = os.path.join(os.path.dirname(__file__), "cpp", "build", "al_host_pending")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+
+
+def _quadratic(center, scale):
+    d = len(center)
+    return np.array([list((scale * np.eye(d)).T.ravel()) + [scale * c for c in center]])
+
+
+def test_lbfgs_first_mode_dense_quadratic_bitwise_equals_oracle():
+    """DenseQuadraticGlobalFn (csrc/cno_functors.cuh), added after the last GPU session: Lbfgs on per-instance
+    dense quadratics read from global memory."""
+    for d, B in ((8, 64), (64, 32)):
+        rng = np.random.default_rng(d)
+        M = rng.uniform(-1, 1, (B, d, d))
+        A = np.einsum("bij,bkj->bik", M, M) / d + np.eye(d)
+        A = (A + A.transpose(0, 2, 1)) / 2
+        data = np.concatenate([A.transpose(0, 2, 1).reshape(B, -1), rng.uniform(-1, 1, (B, d))], 1)
+        x0 = ob.fill_uniform((B, d), 0, 17 + d, -2.0, 2.0)
+        fn = cn.DenseQuadraticFirst(torch.from_numpy(data).to(DEV), d)
+        assert cn.Lbfgs().supported(fn)
+        st, pr = cn.Lbfgs().Minimize(fn, cn.BatchedFunctionState(torch.from_numpy(x0).to(DEV)))
+        o = ob.minimize(ob.LBFGS, ob.FN_DENSE_QUADRATIC, x0, data=data)
+        assert np.array_equal(st.x.cpu().numpy().view(np.uint8), o["x"].view(np.uint8))
+        assert np.array_equal(pr.num_iterations.cpu().numpy().astype(np.uint32), o["num_iterations"])
+        assert np.array_equal(pr.nfev.cpu().numpy().astype(np.uint32), o["nfev"])
+
+
+def test_al_reference_kkt_known_answers_quadratic_objectives():
+    """augmented_lagrangian_test.cc:541-625: InequalityActiveRecoversMultiplier, BothEqualityAndInequalityActive."""
+    def gpu(data, x0, kinds, rows, n_eq):
+        fn = cn.DenseQuadraticFirst(torch.from_numpy(data).to(DEV), 2)
+        problem = cn.ConstrainedOptimizationProblem(fn, kinds, torch.tensor(rows, dtype=torch.float64, device=DEV), n_eq)
+        st, pr = cn.AugmentedLagrangian(problem).Minimize(cn.AugmentedLagrangeState(torch.tensor(x0, dtype=torch.float64, device=DEV), penalty=1.0))
+        return st, pr
+    data = _quadratic([2.0, 0.0], 1.0)
+    st, pr = gpu(data, [[5.0, 5.0]], [ob.CON_AFFINE], [[-1.0, 0.0, -1.0]], 0)
+    o = ob.al_minimize(ob.FN_DENSE_QUADRATIC, np.array([[5.0, 5.0]]), [ob.CON_AFFINE], [[-1.0, 0.0, -1.0]], 0, data=data, penalty0=1.0)
+    x = st.x.cpu().numpy()
+    assert abs(x[0, 0] - 1.0) <= 1e-3 and abs(x[0, 1]) <= 1e-3
+    assert abs(st.inequality_multipliers.cpu().numpy()[0, 0] - 1.0) <= 1e-2
+    assert np.array_equal(x.view(np.uint8), o["x"].view(np.uint8))
+    data = _quadratic([1.0, 2.0], 2.0)
+    rows = [[1.0, 0.0, 0.5], [-1.0, -1.0, -2.0]]
+    st, pr = gpu(data, [[1.0, 1.0]], [ob.CON_AFFINE, ob.CON_AFFINE], rows, 1)
+    o = ob.al_minimize(ob.FN_DENSE_QUADRATIC, np.array([[1.0, 1.0]]), [ob.CON_AFFINE, ob.CON_AFFINE], rows, 1, data=data, penalty0=1.0)
+    x = st.x.cpu().numpy()
+    assert abs(x[0, 0] - 0.5) <= 1e-3 and abs(x[0, 1] - 1.5) <= 1e-3
+    assert np.array_equal(x.view(np.uint8), o["x"].view(np.uint8))

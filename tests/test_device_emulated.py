@@ -47,9 +47,9 @@ def _ptr(a):
     return a.ctypes.data if a is not None and a.size else None
 
 
-def _problem(family, x0, policy=None):
-    return ob.Problem(family, ob._np_dtype(x0), x0.shape[1], 0, 0.0, None, 0,
-                      ob.device_policy(x0.dtype) if policy is None else policy, 0)
+def _problem(family, x0, policy=None, data=None):
+    return ob.Problem(family, ob._np_dtype(x0), x0.shape[1], 0, 0.0, data.ctypes.data if data is not None else None,
+                      data.shape[1] if data is not None else 0, ob.device_policy(x0.dtype) if policy is None else policy, 0)
 
 
 def emulated_al_minimize(emu, family, x0, kinds, rows, n_eq, *, outer_stop=None, config=None, inner_stop=None,
@@ -339,13 +339,13 @@ def test_emulation_reproduces_the_logistic_kernel(emu):
 
 # ---- the host side of cno_al_minimize itself (csrc/cno_auglag_host.h) with an emulation backend ------------
 def emulated_cno_al_minimize(emu, family, x0, kinds, rows, n_eq, *, outer_stop=None, config=None, inner_stop=None,
-                             eq0=None, ineq0=None, penalty0=None):
+                             eq0=None, ineq0=None, penalty0=None, data=None):
     """cno::al_outer_loop -- the code csrc/cno_api.cu::al_run runs with the CUDA backend -- with memcpy / memset
     and emulated kernel launches as the backend, carving its scratch out of cno::AlLayout."""
     x0 = np.ascontiguousarray(x0)
     B, d = x0.shape
     dt = x0.dtype
-    prob = _problem(family, x0)
+    prob = _problem(family, x0, data=data)
     k, keep = ob._constraints(kinds, rows, n_eq, dt, B, d)
     ne, ni = k.n_eq, k.n_ineq
     cfg = config if config is not None else ob.al_default_config()
@@ -423,3 +423,51 @@ def test_emulation_reproduces_the_stepwise_kernel(emu, d, every):
             u, v = np.where(nan, 0, u), np.where(nan, 0, v)
         assert np.array_equal(u.view(np.uint8), v.view(np.uint8)), key
     assert rounds.value == -(-int(o["num_iterations"].max()) // every)
+
+
+# ---- the First-mode dense quadratic functor (csrc/cno_functors.cuh: DenseQuadraticGlobalFn) ------------------
+def _quadratic(center, scale):
+    """scale/2 |x - center|^2 up to a constant, as a DenseQuadratic data row [A col-major | b]."""
+    d = len(center)
+    return np.array([list((scale * np.eye(d)).T.ravel()) + [scale * c for c in center]])
+
+
+@pytest.mark.parametrize("d", [8, 64])
+def test_emulated_lbfgs_on_dense_quadratics_equals_oracle(emu, d):
+    B = 2
+    x0 = ob.fill_uniform((B, d), 0, 17 + d, -2.0, 2.0)
+    data = _spd_data(B, d, 21)
+    prob = _problem(ob.FN_DENSE_QUADRATIC, x0, data=data)
+    stop = ob.default_stop()
+    r = dict(x=np.zeros_like(x0), value=np.zeros(B), gradient=np.zeros_like(x0), num_iterations=np.zeros(B, np.uint32),
+             status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32), x_delta=np.zeros(B), f_delta=np.zeros(B),
+             gradient_norm=np.zeros(B))
+    out = ob.BatchOut(*[r[n].ctypes.data for n, _ in ob.BatchOut._fields_])
+    assert emu.emu_minimize(ob.LBFGS, 0, C.byref(prob), C.c_longlong(B), C.c_void_p(x0.ctypes.data), C.byref(stop),
+                            C.byref(out)) == 0
+    o = ob.minimize(ob.LBFGS, ob.FN_DENSE_QUADRATIC, x0, data=data, stop=stop)
+    for key in SOLVER_KEYS:
+        assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
+    # A x* = b
+    A = data[:, :d * d].reshape(B, d, d).transpose(0, 2, 1)
+    assert np.abs(np.einsum("bij,bj->bi", A, r["x"]) - data[:, d * d:]).max() < 1e-4
+
+
+def test_emulated_al_reference_kkt_known_answers_on_the_device_path(emu):
+    """src/test/augmented_lagrangian_test.cc:541-625 on the device source (quadratic objectives through
+    DenseQuadraticGlobalFn): InequalityActiveRecoversMultiplier and BothEqualityAndInequalityActive."""
+    kw = dict(penalty0=1.0)
+    data = _quadratic([2.0, 0.0], 1.0)  # QuadraticAt20
+    r = emulated_cno_al_minimize(emu, ob.FN_DENSE_QUADRATIC, np.array([[5.0, 5.0]]), [ob.CON_AFFINE], [[-1.0, 0.0, -1.0]], 0,
+                                 data=data, **kw)
+    x, mu = r["x"][0], r["inequality_multipliers"][0, 0]
+    assert abs(x[0] - 1.0) <= 1e-3 and abs(x[1]) <= 1e-3 and 1.0 - x[0] >= -1e-5 and abs(mu - 1.0) <= 1e-2
+    _assert_same(r, ob.al_minimize(ob.FN_DENSE_QUADRATIC, np.array([[5.0, 5.0]]), [ob.CON_AFFINE], [[-1.0, 0.0, -1.0]], 0,
+                                   data=data, **kw))
+    data = _quadratic([1.0, 2.0], 2.0)  # QuadraticAt12
+    args = (ob.FN_DENSE_QUADRATIC, np.array([[1.0, 1.0]]), [ob.CON_AFFINE, ob.CON_AFFINE], [[1.0, 0.0, 0.5], [-1.0, -1.0, -2.0]], 1)
+    r = emulated_cno_al_minimize(emu, *args, data=data, **kw)
+    x = r["x"][0]
+    assert abs(x[0] - 0.5) <= 1e-3 and abs(x[1] - 1.5) <= 1e-3 and 2.0 - (x[0] + x[1]) >= -1e-5
+    assert r["inequality_multipliers"][0, 0] >= -1e-2
+    _assert_same(r, ob.al_minimize(*args, data=data, **kw))
