@@ -139,6 +139,17 @@ def lib() -> C.CDLL:
         L.cno_done_bitmap.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.cno_device_cstep.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.cno_al_default_config.argtypes = [C.POINTER(AlConfig)]
+        L.cno_al_default_config.restype = None
+        L.cno_al_default_stop.argtypes = [C.POINTER(AlStop)]
+        L.cno_al_default_stop.restype = None
+        L.cno_al_supported.argtypes = [C.POINTER(Problem), C.POINTER(Constraints)]
+        L.cno_al_workspace_bytes.argtypes = [C.POINTER(Problem), C.POINTER(Constraints), C.c_int64,
+                                             C.POINTER(C.c_size_t)]
+        L.cno_al_minimize.argtypes = [
+            C.POINTER(Problem), C.POINTER(Constraints), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.POINTER(Stop), C.POINTER(AlStop), C.POINTER(AlConfig), C.POINTER(AlOut),
+            C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(LaunchInfo)]
         _lib = L
     return _lib
 

@@ -62,9 +62,9 @@ def build_cpp_tests(verbose: bool = False) -> list:
            "-o", os.path.join(out, "verify_host"), *link]
     subprocess.run(cmd, check=True)
     exes.append(os.path.join(out, "verify_host"))
-    # compiled here, run only with the pending AugmentedLagrangian GPU tests (tests/test_al_gpu_pending.py)
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", os.path.join(src, "al_host_pending.cc"), *inc,
-           "-o", os.path.join(out, "al_host_pending"), *link]
+    # the constrained C++ mirror (run by tests/test_al_gpu.py)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", os.path.join(src, "al_host.cc"), *inc,
+           "-o", os.path.join(out, "al_host"), *link]
     subprocess.run(cmd, check=True)
     nvcc = os.environ.get("NVCC", f"{cuda}/bin/nvcc")
     xlink = ["-Xlinker", f"-rpath={HERE}"]

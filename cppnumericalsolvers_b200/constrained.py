@@ -3,8 +3,8 @@
 AugmentedLagrangianConfig / AugmentedLagrangeState / AugmentedLagrangian) over the C ABI of
 include/cno_al.h.
 
-STATUS: the device path has not had its first GPU run yet (tests/test_al_gpu_pending.py); the
-algorithm it restates is pinned on the CPU (oracle/cno_al_oracle.h, tests/test_al_oracle.py)."""
+The algorithm is pinned on the CPU (oracle/cno_al_oracle.h, tests/test_al_oracle.py); the device path
+equals it bit for bit on a B200 (tests/test_al_gpu.py)."""
 from __future__ import annotations
 
 import ctypes as C

@@ -2,9 +2,9 @@
 // composite device functor the fused L-BFGS kernel minimises, and the kernels of the
 // outer loop (one warp per instance, sm_100a).
 //
-// STATUS: written against the pinned CPU oracle (oracle/cno_oracle_impl.inc:
-// eval_auglag, al_minimize_one -- bit-identical to the reference's own headers), NOT
-// yet run on a GPU (tests/test_al_gpu_pending.py, marker gpu_pending).  DESIGN.md 8.
+// Parity: bit-identical on a B200 to the pinned CPU oracle (oracle/cno_oracle_impl.inc:
+// eval_auglag, al_minimize_one) and to the reference-headers fixtures tests/golden/al_*.npz
+// (tests/test_al_gpu.py).  DESIGN.md 8.
 //
 // Reference path (include/cppoptlib/...):
 //   function_penalty.h:97-250              ToAugmentedLagrangian = ((f + Lag) + Pen) + Ineq (PHR)

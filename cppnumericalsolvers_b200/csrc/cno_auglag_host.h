@@ -1,8 +1,7 @@
 // cno_auglag_host.h -- the host side of AugmentedLagrangian::Minimize (solver/augmented_lagrangian.h:
 // 295-449), independent of how memory is moved and kernels are launched: the outer loop, the scratch
 // layout, the parameter narrowing.  csrc/cno_api.cu drives it with the CUDA backend; tests/emu drives
-// the SAME code with the CPU warp emulation, which is how this logic is tested while the first GPU run
-// of the path is pending.
+// the SAME code with the CPU warp emulation (the `-m "not gpu"` check of this logic).
 //
 // Backend concept (all return 0 or a cno_error_t):
 //   int copy_or_zero(void* dst, const void* src, size_t bytes)   device copy, or zero fill when src == nullptr

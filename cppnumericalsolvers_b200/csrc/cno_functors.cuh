@@ -127,8 +127,8 @@ struct HalfSquaredNormFn {
 // no matrix on chip (Lbfgs, and AugmentedLagrangian's batched "QP with affine constraints" use).
 // Reference analogue: src/examples/debug.cc:43-65; src/test/augmented_lagrangian_test.cc:78-176
 // (QuadraticAt12 / QuadraticAt20).  (Ax)_i = sum_j A_ij x_j, j ascending from the first product;
-// x_j is broadcast from its owner lane.  STATUS: checked under the CPU warp emulation against the oracle
-// (tests/test_device_emulated.py); first GPU run pending with the AugmentedLagrangian path.
+// x_j is broadcast from its owner lane.  Parity: tests/test_al_gpu.py (B200) and the CPU warp emulation
+// (tests/test_device_emulated.py), both bit for bit against the oracle.
 template <class T, int D>
 struct DenseQuadraticGlobalFn {
   using Scalar = T;

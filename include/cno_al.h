@@ -2,10 +2,9 @@
  * cno_al.h -- C ABI of the batched AugmentedLagrangian solver (SURVEY.md 8(f)
  * rank 1: the main in-tree caller of the hot path).
  *
- * STATUS: the device path behind these entry points is written against the pinned
- * CPU oracle (oracle/cno_al_oracle.h, tests/test_al_oracle.py) but has NOT had its
- * first run on a GPU yet (round 1 ran out of GPU budget): its parity tests are
- * marked `gpu_pending` (tests/test_al_gpu_pending.py), not `gpu`.  DESIGN.md 8.
+ * Parity: the device path behind these entry points equals the pinned CPU oracle
+ * (oracle/cno_al_oracle.h, tests/test_al_oracle.py) and the reference-headers
+ * fixtures bit for bit on a B200 (tests/test_al_gpu.py).  DESIGN.md 8.
  *
  * Reference interfaces replaced (include/cppoptlib/...):
  *   solver/augmented_lagrangian.h:63-239    AugmentedLagrangianConfig   cno_al_config_t

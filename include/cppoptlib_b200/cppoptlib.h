@@ -510,8 +510,7 @@ template <class F> class ConjugatedGradientDescent : public Solver<F, CNO_CONJUG
 
 
 // ---- the constrained caller of the path (solver/augmented_lagrangian.h, function_problem.h) ----
-// STATUS: like include/cno_al.h -- written against the pinned CPU oracle and checked under the CPU warp
-// emulation; its first GPU run is pending.
+// Parity: tests/cpp/al_host.cc, run on a B200 by tests/test_al_gpu.py.
 }  // namespace solver
 
 namespace function {

@@ -34,6 +34,8 @@ inline int launch_user(Kernel kernel, const Fn& fn, int64_t batch, const void* x
   if (batch == 0) return CNO_OK;
   cno_stop_t dflt;
   if (!stop) { cno_default_stop(&dflt); stop = &dflt; }
+  // the kernels' past-f ring is CNO_MAX_PAST warp-private scalars (same check as cno_minimize)
+  if (stop->past > CNO_MAX_PAST || stop->past < 0) return CNO_ERR_INVALID_ARGUMENT;
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return CNO_ERR_NO_DEVICE;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

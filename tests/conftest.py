@@ -10,8 +10,6 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu)")
-    config.addinivalue_line("markers", "gpu_pending: device paths written against a pinned oracle whose first "
-                            "GPU run is still pending; skipped unless CNO_RUN_PENDING=1")
 
 
 @pytest.fixture(scope="session", autouse=True)

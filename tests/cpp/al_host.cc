@@ -1,7 +1,6 @@
-// tests/cpp/al_host_pending.cc -- the C++ mirror of the constrained interface, written like
+// tests/cpp/al_host.cc -- the C++ mirror of the constrained interface, written like
 // src/test/augmented_lagrangian_test.cc:492-539 (AugmentedLagrangianKKT.EqualityOnlyQuadratic).
-// COMPILED by the CPU suite (tests/test_cpp_api.py); RUN only with the other pending AugmentedLagrangian
-// GPU tests (CNO_RUN_PENDING=1), because the device path behind it has not had its first GPU run yet.
+// Compiled by the CPU suite (tests/test_cpp_api.py); run on the GPU by tests/test_al_gpu.py.
 #include <cmath>
 #include <cstdio>
 #include <vector>

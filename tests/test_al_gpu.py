@@ -1,10 +1,6 @@
 """AugmentedLagrangian on the device (include/cno_al.h, csrc/cno_auglag.cuh) against the pinned CPU
-oracle -- FIRST GPU RUN PENDING.  Round 1 ran out of GPU budget before this path could be executed
-once, so these tests are NOT part of `-m gpu` yet: they are skipped unless CNO_RUN_PENDING=1.
-
-    CNO_RUN_PENDING=1 python -m pytest tests/test_al_gpu_pending.py -x -q        (on a B200)
-
-When they pass: drop the skip and mark them `gpu`."""
+oracle and the reference-headers fixtures tests/golden/al_*.npz, bit for bit (first green B200 run:
+round 2, gpurun_out/r02_al_first.log)."""
 import glob
 import os
 
@@ -15,9 +11,7 @@ import torch
 import cppnumericalsolvers_b200 as cn
 from oracle import oracle_binding as ob
 
-pytestmark = [pytest.mark.gpu_pending,
-              pytest.mark.skipif(os.environ.get("CNO_RUN_PENDING") != "1",
-                                 reason="AugmentedLagrangian device path: first GPU validation pending")]
+pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 DEV = "cuda:0"
 TDT = {np.float64: torch.float64, np.float32: torch.float32}
@@ -108,12 +102,12 @@ def test_al_reference_known_answers_and_user_state():
 
 
 def test_al_cpp_mirror_equality_only_quadratic():
-    """tests/cpp/al_host_pending.cc: the C++ mirror (cppoptlib::solver::AugmentedLagrangian) on
+    """tests/cpp/al_host.cc: the C++ mirror (cppoptlib::solver::AugmentedLagrangian) on
     augmented_lagrangian_test.cc:492-539."""
     import subprocess
     from cppnumericalsolvers_b200 import build
     build.build_cpp_tests()
-    exe = os.path.join(os.path.dirname(__file__), "cpp", "build", "al_host_pending")
+    exe = os.path.join(os.path.dirname(__file__), "cpp", "build", "al_host")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
 

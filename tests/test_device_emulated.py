@@ -10,7 +10,7 @@ device kernel itself under emulation.  Everything must equal the oracle -- which
 reference's own headers -- bit for bit; the GPU-validated kernels are run too, to show that the
 emulation reproduces what the B200 computes.
 
-This is what stands in for the pending first GPU run of this path (tests/test_al_gpu_pending.py)."""
+The same paths run on a B200 in tests/test_al_gpu.py; this is their `-m "not gpu"` counterpart."""
 import ctypes as C
 import glob
 import os
