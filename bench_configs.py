@@ -24,7 +24,7 @@ def peak():
     return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
 
 
-def run(name, solver, fn, x0, bytes_fn, reps=3):
+def run(name, solver, fn, x0, bytes_fn, reps=3, extra=None):
     ms = []
     for _ in range(reps + 1):
         st, pr = solver.Minimize(fn, cn.BatchedFunctionState(x0), timed=True)
@@ -41,7 +41,18 @@ def run(name, solver, fn, x0, bytes_fn, reps=3):
            "frac_of_hbm_roofline": alg / ms / 1e6 / peak(),
            "grid": pr.launch.grid, "warps_per_cta": pr.launch.warps_per_cta,
            "dynamic_smem": pr.launch.dynamic_smem}
-    print(json.dumps(out), flush=True)
+    out.update(extra or {})
+    bind = binding_pipes().get(name.split()[0])
+    if bind:
+        out["binding"] = bind
+    return out
+
+
+def binding_pipes():
+    """Per-config summary of the ncu capture (which pipe binds the kernel), written by hand from
+    profiles/r02_*_ncu_full.txt into profiles/r02_binding.json."""
+    p = os.path.join(ROOT, "profiles", "r02_binding.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 def lbfgs_bytes(w, d, m=10):
@@ -53,19 +64,21 @@ def lbfgs_bytes(w, d, m=10):
     return f
 
 
-def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
-    scale = int(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 0
-    which = args or ["c2", "c3", "c4", "c5"]  # "gd", "cg", "hz", "al": the SURVEY.md 8(f) rows, on request
-    gen = torch.Generator(device=DEV)
-    gen.manual_seed(0)
-    if "c2" in which:  # Rosenbrock d=128 fp64 L-BFGS, B = 2^20
+def _gen():
+    g = torch.Generator(device=DEV)
+    g.manual_seed(0)
+    return g
+
+
+def run_config(which: str, scale: int = 0, reps: int = 3) -> dict:
+    """Builds the synthetic inputs of one config, times it on the current device and returns the record."""
+    gen = _gen()
+    if which == "c2":  # Rosenbrock d=128 fp64 L-BFGS, B = 2^20
         B = (1 << 20) >> scale
         x0 = torch.empty(B, 128, dtype=torch.float64, device=DEV)
         cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
-        run("c2 lbfgs rosenbrock d128 f64", cn.Lbfgs(), cn.Rosenbrock(128), x0, lbfgs_bytes(8, 128))
-        del x0
-    if "c3" in which:  # logistic n=256 d=64 fp32 L-BFGS, B = 2^18
+        return run("c2 lbfgs rosenbrock d128 f64", cn.Lbfgs(), cn.Rosenbrock(128), x0, lbfgs_bytes(8, 128), reps)
+    if which == "c3":  # logistic n=256 d=64 fp32 L-BFGS, B = 2^18
         B, n, d, lam = (1 << 18) >> scale, 256, 64, 1e-2
         data = torch.empty(B, d * n + n, dtype=torch.float32, device=DEV)
         chunk = 1 << 14
@@ -77,19 +90,18 @@ def main():
             y[y == 0] = 1
             data[lo:hi, : d * n] = X.transpose(1, 2).reshape(hi - lo, -1)
             data[lo:hi, d * n:] = y
+            del X, ws, y
         x0 = torch.zeros(B, d, dtype=torch.float32, device=DEV)
         lb = lbfgs_bytes(4, d)
-        run("c3 lbfgs logistic n256 d64 f32", cn.Lbfgs(), cn.Logistic(data, n, d, lam), x0,
-            lambda it, nf: lb(it, nf) + (nf * 4 * (n * d + n)).sum())
-        del data, x0
-    if "c4" in which:  # BFGS Rosenbrock d=32 fp64, B = 2^19
+        return run("c3 lbfgs logistic n256 d64 f32", cn.Lbfgs(), cn.Logistic(data, n, d, lam), x0,
+                   lambda it, nf: lb(it, nf) + (nf * 4 * (n * d + n)).sum(), reps)
+    if which == "c4":  # BFGS Rosenbrock d=32 fp64, B = 2^19
         B = (1 << 19) >> scale
         x0 = torch.empty(B, 32, dtype=torch.float64, device=DEV)
         cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
-        run("c4 bfgs rosenbrock d32 f64", cn.Bfgs(), cn.Rosenbrock(32), x0,
-            lambda it, nf: (8 * (2 * 32 * 32 + 4 * 32) * it).sum())
-        del x0
-    if "c5" in which:  # NewtonDescent dense quadratic d=64 fp64, B = 2^17
+        return run("c4 bfgs rosenbrock d32 f64", cn.Bfgs(), cn.Rosenbrock(32), x0,
+                   lambda it, nf: (8 * (2 * 32 * 32 + 4 * 32) * it).sum(), reps)
+    if which == "c5":  # NewtonDescent dense quadratic d=64 fp64, B = 2^17
         B, d = (1 << 17) >> scale, 64
         data = torch.empty(B, d * d + d, dtype=torch.float64, device=DEV)
         chunk = 1 << 13
@@ -103,30 +115,30 @@ def main():
             data[lo:hi, d * d:] = torch.rand(hi - lo, d, dtype=torch.float64, device=DEV, generator=gen) * 2 - 1
         x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
         cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
-        run("c5 newton dense quadratic d64 f64", cn.NewtonDescent(), cn.DenseQuadratic(data, d), x0,
-            lambda it, nf: (8 * (d * d + 3 * d) * it).sum())
-    for tag, solver, limit in (("gd", cn.GradientDescent, 200), ("cg", cn.ConjugatedGradientDescent, 100)):
-        if tag not in which:
-            continue
-        # Rosenbrock d=128 fp64, B = 2^18, iteration limit `limit` (these solvers crawl on Rosenbrock:
-        # the limit fixes the work per instance).  Algorithmic bytes as in SURVEY.md 8(d): every
-        # evaluation the kernel makes reads x and writes g; an iteration touches x, g, d once more.
+        flops = lambda it: float(((2.0 / 3.0) * d ** 3 + 4.0 * d * d) * it.sum())  # noqa: E731  SURVEY.md 8(d)
+        rec = run("c5 newton dense quadratic d64 f64", cn.NewtonDescent(), cn.DenseQuadratic(data, d), x0,
+                  lambda it, nf: (8 * (d * d + 3 * d) * it).sum(), reps)
+        rec["algorithmic_TFLOPs"] = flops(np.full(B, rec["mean_iterations"])) / rec["kernel_ms"] / 1e9
+        return rec
+    if which in ("gd", "cg"):
+        # Rosenbrock d=128 fp64, B = 2^18, iteration limit (these solvers crawl on Rosenbrock: the limit fixes
+        # the work per instance).  Algorithmic bytes as in SURVEY.md 8(d): every evaluation the kernel makes
+        # reads x and writes g; an iteration touches x, g, d once more.
+        solver, limit = (cn.GradientDescent, 200) if which == "gd" else (cn.ConjugatedGradientDescent, 100)
         B, d = (1 << 18) >> scale, 128
         x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
         cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
         prog = cn.DefaultStoppingSolverProgress()
         prog.num_iterations = limit
-        run(f"{tag} rosenbrock d128 f64 (iteration limit {limit})", solver(prog), cn.Rosenbrock(d), x0,
-            lambda it, nf: (8 * d * (2 * (nf - 3 * it) + 6 * it)).sum())
-        del x0
-    if "hz" in which:  # Lbfgs<F, 10, HagerZhang>, same workload as c2 (not yet timed on a GPU: DESIGN.md 9)
+        return run(f"{which} rosenbrock d128 f64 (iteration limit {limit})", solver(prog), cn.Rosenbrock(d), x0,
+                   lambda it, nf: (8 * d * (2 * (nf - 3 * it) + 6 * it)).sum(), reps)
+    if which == "hz":  # Lbfgs<F, 10, HagerZhang>, same workload as c2 at B = 2^18
         B = (1 << 18) >> scale
         x0 = torch.empty(B, 128, dtype=torch.float64, device=DEV)
         cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
-        run("hz lbfgs(HagerZhang) rosenbrock d128 f64", cn.Lbfgs(linesearch=cn.HagerZhang), cn.Rosenbrock(128), x0,
-            lbfgs_bytes(8, 128))
-        del x0
-    if "al" in which:  # AugmentedLagrangian (GPU validation pending: DESIGN.md 8): Rosenbrock d=128 on a ball + halfspace
+        return run("hz lbfgs(HagerZhang) rosenbrock d128 f64", cn.Lbfgs(linesearch=cn.HagerZhang), cn.Rosenbrock(128),
+                   x0, lbfgs_bytes(8, 128), reps)
+    if which == "al":  # AugmentedLagrangian: Rosenbrock d=128 on a sphere (equality) + a halfspace
         B, d = (1 << 15) >> scale, 128
         x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
         cn.fill_uniform(x0, 0, 12345, -1.5, 1.5)
@@ -141,13 +153,25 @@ def main():
         for _ in range(3):
             st, pr = solver.Minimize(cn.AugmentedLagrangeState(x0))
             ms.append(pr.launch.total_ms)
-        print(json.dumps({"config": "al rosenbrock d128 f64 sphere+halfspace (outer limit 20)", "batch": B,
-                          "total_ms": float(np.mean(ms[1:])), "instances_per_s": B / float(np.mean(ms[1:])) * 1e3,
-                          "kernel_launches": pr.launch.kernel_launches,
-                          "mean_outer_iterations": float(pr.num_iterations.float().mean()),
-                          "mean_objective_evaluations": float(pr.nfev.float().mean()),
-                          "status_histogram": np.bincount(pr.status.cpu().numpy().astype(np.int64) + 1).tolist(),
-                          "max_violation_max": float(st.max_violation.max())}), flush=True)
+        return {"config": "al rosenbrock d128 f64 sphere+halfspace (outer limit 20)", "batch": B,
+                "total_ms": float(np.mean(ms[1:])), "instances_per_s": B / float(np.mean(ms[1:])) * 1e3,
+                "kernel_launches": pr.launch.kernel_launches,
+                "mean_outer_iterations": float(pr.num_iterations.float().mean()),
+                "mean_objective_evaluations": float(pr.nfev.float().mean()),
+                "status_histogram": np.bincount(pr.status.cpu().numpy().astype(np.int64) + 1).tolist(),
+                "max_violation_max": float(st.max_violation.max())}
+    raise ValueError(f"unknown config {which!r}")
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    scale = int(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 0
+    which = args or ["c2", "c3", "c4", "c5"]  # "gd", "cg", "hz", "al": the SURVEY.md 8(f) rows, on request
+    for w in which:
+        if w.isdigit():  # (the value of --scale)
+            continue
+        print(json.dumps(run_config(w, scale)), flush=True)
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":

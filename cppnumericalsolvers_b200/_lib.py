@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcno.so")
+# CNO_LIB selects another build of the same library (kernel-variant experiments, e.g. libcno_w20.so)
+LIB_PATH = os.path.join(HERE, os.environ.get("CNO_LIB", "libcno.so"))
 
 # enums of include/cno.h
 LBFGS, BFGS, NEWTON, GRADIENT_DESCENT, CONJUGATED_GRADIENT_DESCENT = 0, 1, 2, 3, 4
@@ -89,7 +90,7 @@ EXPORTS = (
     "cno_version", "cno_error_string", "cno_last_cuda_error", "cno_default_stop",
     "cno_conservative_stop", "cno_supported", "cno_workspace_bytes", "cno_minimize",
     "cno_state_bytes", "cno_minimize_steps",
-    "cno_minimize_host", "cno_fill_uniform", "cno_done_bitmap", "cno_device_cstep",
+    "cno_minimize_host", "cno_release_host_arena", "cno_fill_uniform", "cno_done_bitmap", "cno_device_cstep",
 )
 
 _lib = None

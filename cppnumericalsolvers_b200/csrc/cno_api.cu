@@ -55,6 +55,17 @@ struct DeviceBuffer {
   cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
 };
 
+// The device arena of cno_minimize_host, kept between calls (a 4 GiB cudaMalloc + cudaFree per call is
+// ~70 ms of the end-to-end time at the headline size).  One arena per process, owned by whichever call
+// holds the lock; a concurrent call on another thread allocates its own.  cno_release_host_arena() frees it.
+struct HostArena {
+  std::mutex m;
+  void* p = nullptr;
+  size_t bytes = 0;
+  int device = -1;
+};
+HostArena g_host_arena;
+
 int device_sm_count(int* sms) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -784,9 +795,34 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, c
   const size_t o_st = off; off += out->status ? up((size_t)batch) : 0;
   const size_t o_ws = off; off += kWorkspaceBytes;  // one 16-byte queue slot per chunk
   const size_t o_data = off; off += up(data_bytes);
-  DeviceBuffer arena_owner;
-  CNO_CUDA(arena_owner.alloc(off));
-  unsigned char* const arena = static_cast<unsigned char*>(arena_owner.p);
+  DeviceBuffer arena_owner;  // (a private arena when another thread holds the cached one)
+  std::unique_lock<std::mutex> arena_lock(g_host_arena.m, std::try_to_lock);
+  struct Drain {  // on every return path: no copy or kernel of this call still uses the arena when it is handed on
+    cudaStream_t a, b;
+    ~Drain() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); }
+  } drain{s, s2};
+  unsigned char* arena = nullptr;
+  if (arena_lock.owns_lock()) {
+    int dev = 0;
+    CNO_CUDA(cudaGetDevice(&dev));
+    if (g_host_arena.device != dev || g_host_arena.bytes < off) {
+      if (g_host_arena.p) {
+        int prev = dev;
+        if (g_host_arena.device >= 0 && g_host_arena.device != dev) { cudaSetDevice(g_host_arena.device); prev = g_host_arena.device; }
+        cudaFree(g_host_arena.p);
+        if (prev != dev) cudaSetDevice(dev);
+        g_host_arena.p = nullptr;
+        g_host_arena.bytes = 0;
+      }
+      CNO_CUDA(cudaMalloc(&g_host_arena.p, off));
+      g_host_arena.bytes = off;
+      g_host_arena.device = dev;
+    }
+    arena = static_cast<unsigned char*>(g_host_arena.p);
+  } else {
+    CNO_CUDA(arena_owner.alloc(off));
+    arena = static_cast<unsigned char*>(arena_owner.p);
+  }
 
   // Chunked pipeline on two streams: H2D of chunk c+1 and D2H of chunk c-1 overlap
   // the solve of chunk c, so only ~1/kChunks of the copy time is exposed.
@@ -860,6 +896,22 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, c
   local.kernel_ms = ms;
   if (info) *info = local;
   g_last_info = local;
+  return CNO_OK;
+}
+
+int cno_release_host_arena(void) {
+  std::lock_guard<std::mutex> lk(g_host_arena.m);
+  if (g_host_arena.p) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_host_arena.device >= 0 && g_host_arena.device != dev) cudaSetDevice(g_host_arena.device);
+    cudaError_t e = cudaFree(g_host_arena.p);
+    if (g_host_arena.device != dev) cudaSetDevice(dev);
+    g_host_arena.p = nullptr;
+    g_host_arena.bytes = 0;
+    g_host_arena.device = -1;
+    if (e != cudaSuccess) { g_last_cuda = e; return CNO_ERR_CUDA; }
+  }
   return CNO_OK;
 }
 

@@ -363,7 +363,7 @@ al_outer_step_kernel(const Obj obj, const AlView<typename Obj::Scalar> v, const 
 #pragma unroll
     for (int k = 0; k < E; ++k) sum_grad[k] = sum_grad[k] - m * gc[k];
   }
-  const T max_lagr = warp_max_nonneg(lane_maxabs<T, E>(sum_grad));
+  const T max_lagr = warp_maxabs<T, E>(sum_grad);
 
   // ---- UpdateBestIterateInPlace (:546-594); its objective(x) = the value just computed ----
   {
@@ -412,8 +412,8 @@ al_outer_step_kernel(const Obj obj, const AlView<typename Obj::Scalar> v, const 
   T dx[E];
 #pragma unroll
   for (int k = 0; k < E; ++k) dx[k] = x[k] - xp[k];
-  const T x_delta = warp_max_nonneg(lane_maxabs<T, E>(dx));
-  const T gnorm = warp_max_nonneg(lane_maxabs<T, E>(cg));
+  const T x_delta = warp_maxabs<T, E>(dx);
+  const T gnorm = warp_maxabs<T, E>(cg);
   const unsigned long long it = (unsigned long long)a.num_iterations[b] + 1ULL;
   int status;
   if ((p.num_iterations > 0) && (it > p.num_iterations)) {

@@ -151,12 +151,12 @@ bfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
       // ---- Progress::Update ----
       const T prev_value = f;
-      const T x_delta = warp_max_nonneg(lane_maxabs<T, 1>(s));
+      const T x_delta = warp_maxabs<T, 1>(s);
       x[0] = xn[0];
       g[0] = gn[0];
       f = fn_val;
-      const T gnorm_inf = warp_max_nonneg(lane_maxabs<T, 1>(g));
-      const T x_inf = warp_max_nonneg(lane_maxabs<T, 1>(x));
+      const T gnorm_inf = warp_maxabs<T, 1>(g);
+      const T x_inf = warp_maxabs<T, 1>(x);
       progress_update<T>(prog, stop, ring, lane, prev_value, f, x_delta, gnorm_inf, x_inf);
     } while (uni(prog.status == CNO_STATUS_CONTINUE));
 

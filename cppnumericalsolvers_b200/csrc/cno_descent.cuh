@@ -142,12 +142,12 @@ descent_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 #pragma unroll
       for (int e = 0; e < E; ++e) sdx[e] = xn[e] - x[e];
       const T prev_value = f;
-      const T x_delta = warp_max_nonneg(lane_maxabs<T, E>(sdx));
+      const T x_delta = warp_maxabs<T, E>(sdx);
 #pragma unroll
       for (int e = 0; e < E; ++e) { x[e] = xn[e]; g[e] = gn[e]; }
       f = fn_val;
-      const T gnorm_inf = warp_max_nonneg(lane_maxabs<T, E>(g));
-      const T x_inf = warp_max_nonneg(lane_maxabs<T, E>(x));
+      const T gnorm_inf = warp_maxabs<T, E>(g);
+      const T x_inf = warp_maxabs<T, E>(x);
       progress_update<T>(prog, stop, ring, lane, prev_value, f, x_delta, gnorm_inf, x_inf);
     } while (uni(prog.status == CNO_STATUS_CONTINUE));
 

@@ -34,8 +34,14 @@ struct RosenbrockFn {
   static constexpr int Mode = 1;
   static constexpr int E = Shape<D>::E;
 
+  static constexpr bool kHasPartial = true;
   __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&x)[E],
                                           T (*grad)[E]) const {
+    return warp_sum_p<P, T, E>(partial(c, x, grad), RedCtx<T>{static_cast<T*>(c.stage), c.lane});
+  }
+  // the lane's share of sum_i term_i (unreduced) and, if grad != nullptr, its slice of the gradient
+  __device__ __forceinline__ typename LanePartial<P, T, E>::type partial(const EvalCtx& c, const T (&x)[E],
+                                                                         T (*grad)[E]) const {
     const int lane = c.lane;
     // x_{i+1} of this lane's last element lives in lane+1, slot 0.
     const T x_next_lane = __shfl_down_sync(kFullMask, x[0], 1);
@@ -67,7 +73,7 @@ struct RosenbrockFn {
         (*grad)[j] = (i < D) ? gi : T(0);
       }
     }
-    return warp_sum_p<P, T, E>(lane_terms_p<P, T, E>(term), RedCtx<T>{static_cast<T*>(c.stage), c.lane});
+    return lane_terms_p<P, T, E>(term);
   }
 
   // Diagonal of the Hessian (Second mode; at D = 2 src/test/verify.cc:93-97 incl. the

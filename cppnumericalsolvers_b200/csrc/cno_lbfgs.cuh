@@ -30,6 +30,10 @@
 #include "cno_linesearch.cuh"
 #include "cno_kernel_params.h"
 
+#ifndef CNO_LBFGS_MAX_WARPS
+#define CNO_LBFGS_MAX_WARPS 16  // resident warps per SM of the L-BFGS kernels (register budget: 65536 / (32 * warps))
+#endif
+
 namespace cno {
 
 template <class T, int D, int M, int kStage = 0, int kScratchPerLane = 0, int kFnTmem = 0>
@@ -48,10 +52,12 @@ struct LbfgsSmem {
   static constexpr int kMaxSmem = 227 * 1024;
   static constexpr int kWarpsFit = (int)(kMaxSmem / kWarpBytes);
   // a functor that keeps data in Tensor Memory limits the warps per lane quadrant
-  static constexpr int kTmemWarpCap = kFnTmem > 0 ? 4 * (512 / kFnTmem) : 16;
-  static constexpr int kCap = kTmemWarpCap < 16 ? kTmemWarpCap : 16;
+  static constexpr int kMaxWarps = CNO_LBFGS_MAX_WARPS;
+  static constexpr int kTmemColsPerWarp = M * 8;             // a stored y vector = 8 columns of the warp's 32 lanes
+  static constexpr int kTmemYCap = kTmemY ? 4 * (512 / kTmemColsPerWarp) : kMaxWarps;  // warps per lane quadrant x 4
+  static constexpr int kTmemWarpCap = kFnTmem > 0 ? 4 * (512 / kFnTmem) : kTmemYCap;
+  static constexpr int kCap = kTmemWarpCap < kMaxWarps ? kTmemWarpCap : kMaxWarps;
   static constexpr int kWarps = kWarpsFit > kCap ? kCap : (kWarpsFit < 1 ? 1 : kWarpsFit);
-  static constexpr int kTmemColsPerWarp = 128;               // 512 columns / 4 warps per lane quadrant
 };
 
 // y-history accessors: shared memory (chunk-interleaved) or Tensor Memory.
@@ -449,12 +455,13 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       }
       const T descent_direction = -gq;
       T dginit = descent_direction;  // = g.(-q), bit for bit
-      T sdir[E];
+      // The search runs along -q (the line search negates inside its products, cno_linesearch.cuh
+      // kNeg), so no negated copy of q is ever made.
       if (uni(!cfinite(descent_direction) || descent_direction > -eps * relative_eps)) {
         // fallback: search_direction = -g, and the reference then searches
         // along -search_direction = +g: dginit = g.g >= 0.
 #pragma unroll
-        for (int j = 0; j < E; ++j) sdir[j] = g[j];
+        for (int j = 0; j < E; ++j) q[j] = -g[j];
         mem_count = 0;
         mem_pos = 0;
         valid = 0;
@@ -462,31 +469,40 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         const T gn = csqrt(gg);
         alpha_init = (gn > eps) ? T(1) / gn : T(1);
         dginit = gg;
-      } else {
-#pragma unroll
-        for (int j = 0; j < E; ++j) sdir[j] = -q[j];
       }
 
       // ---- MoreThuente::Search (:231-232) ----
       T xn[E], gn[E];
       T fn_val;
-      nfev += LS::template search<Fn, T, E>(fn, ctx, rc, x, f, g, xn, fn_val, gn, alpha_init, sdir, dginit);
+      if (uni(dginit >= T(0))) {  // the search's own early return (more_thuente.h:152-156): state untouched
+#pragma unroll
+        for (int j = 0; j < E; ++j) { xn[j] = x[j]; gn[j] = g[j]; }
+        fn_val = f;
+      } else {
+        nfev += LS::template search<Fn, T, E, true, std::is_same<LS, LsMoreThuente>::value>(
+            fn, ctx, rc, x, f, g, xn, fn_val, gn, alpha_init, q, dginit);
+      }
 
       const T prev_value = f;
       T x_delta, gnorm_inf, x_inf;
       if (uni(!cfinite(fn_val))) {
-        // :239-241 return current: x, g, f unchanged -> x_delta = 0.
-        gnorm_inf = warp_max_nonneg(lane_maxabs<T, E>(g));
-        x_inf = warp_max_nonneg(lane_maxabs<T, E>(x));
-        x_delta = T(0);
+        // :239-241 return current: x, g, f unchanged; x_delta = |x - x|_inf (progress.h:190) is 0,
+        // or NaN when x itself holds a non-finite component (rare path, computed as written).
+        gnorm_inf = warp_maxabs<T, E>(g);
+        x_inf = warp_maxabs<T, E>(x);
+        T zd[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) zd[j] = x[j] - x[j];
+        x_delta = warp_maxabs<T, E>(zd);
       } else {
         // ---- pair + gamma update (:248-298) ----
         T sd[E], yd[E];
 #pragma unroll
         for (int j = 0; j < E; ++j) { sd[j] = xn[j] - x[j]; yd[j] = gn[j] - g[j]; }
-        T sy, ss, yy;
-        warp_sum3_p<P, T, E>(lane_dot_p<P, T, E>(sd, yd), lane_dot_p<P, T, E>(sd, sd),
-                             lane_dot_p<P, T, E>(yd, yd), rc, sy, ss, yy);
+        // s.y, s.s, y.y (:265-266) and the next step's ||x||^2 (:95), reduced together
+        T sy, ss, yy, xx_next;
+        warp_sum4_p<P, T, E>(lane_dot_p<P, T, E>(sd, yd), lane_dot_p<P, T, E>(sd, sd),
+                             lane_dot_p<P, T, E>(yd, yd), lane_dot_p<P, T, E>(xn, xn), rc, sy, ss, yy, xx_next);
         const T sy_threshold = eps * csqrt(ss) * csqrt(yy);
         if (uni(sy > sy_threshold)) {
           int slot;
@@ -510,13 +526,13 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
           if (cfinite(temp_scaling) && cabs(temp_scaling) <= T(1e7)) gamma = smax(temp_scaling, eps);
         }
         // next state + the norms Progress::Update and the next step need
-        x_delta = warp_max_nonneg(lane_maxabs<T, E>(sd));
+        x_delta = warp_maxabs<T, E>(sd);
 #pragma unroll
         for (int j = 0; j < E; ++j) { x[j] = xn[j]; g[j] = gn[j]; }
         f = fn_val;
-        gnorm_inf = warp_max_nonneg(lane_maxabs<T, E>(g));
-        x_inf = warp_max_nonneg(lane_maxabs<T, E>(x));
-        xx = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(x, x), rc);
+        gnorm_inf = warp_maxabs<T, E>(g);
+        x_inf = warp_maxabs<T, E>(x);
+        xx = xx_next;
         __syncwarp();
       }
 

@@ -134,11 +134,36 @@ __device__ __forceinline__ int cstep(T& stx, T& fx, T& dx, T& sty, T& fy, T& dy,
 // with rounding).  On exit x/g/f hold the last evaluated point exactly as in the
 // reference; when dginit >= 0 the search returns at once (:152-156) and
 // x/g/f = x0/g0/f0.  Returns the number of objective evaluations.
-template <class Fn, class T, int E>
+// kNeg: the search direction is -s (the caller passes q of an L-BFGS step instead of a materialised
+// -q): x = x0 - stp*s and g.(-s) with the negation folded into the products -- the same bits as a
+// search along a stored -s, without the negation pass and its registers.  kChecked: the caller has
+// already taken the dginit >= 0 early return (so the start state is not copied speculatively).
+template <class P, bool kNeg, class T, int E>
+__device__ __forceinline__ typename LanePartial<P, T, E>::type ls_dir_dot(const T (&g)[E], const T (&s)[E]) {
+  if constexpr (kNeg) return lane_dot_neg_p<P, T, E>(g, s);
+  else return lane_dot_p<P, T, E>(g, s);
+}
+// f(x0 +- stp*s) and g.(+-s): the trial point of every line search (more_thuente.h:198-201,
+// hager_zhang.h:152-159), f and the slope reduced together when the functor exposes its partial.
+template <bool kNeg, class Fn, class T, int E>
+__device__ __forceinline__ void ls_eval(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc, const T (&x0)[E],
+                                        const T stp, const T (&s)[E], T (&x)[E], T& f, T (&g)[E], T& dg) {
+  using P = typename PolicyOf<Fn>::type;
+#pragma unroll
+  for (int j = 0; j < E; ++j) x[j] = kNeg ? (x0[j] - stp * s[j]) : (x0[j] + stp * s[j]);
+  if constexpr (FnHasPartial<Fn>::value) {
+    const auto pf = fn.partial(ctx, x, &g);
+    warp_sum2_p<P, T, E>(pf, ls_dir_dot<P, kNeg, T, E>(g, s), rc, f, dg);
+  } else {
+    f = fn(ctx, x, &g);
+    dg = warp_sum_p<P, T, E>(ls_dir_dot<P, kNeg, T, E>(g, s), rc);
+  }
+}
+
+template <class Fn, class T, int E, bool kNeg = false, bool kChecked = false>
 __device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc, const T (&x0)[E],
                                       const T f0, const T (&g0)[E], T (&x)[E], T& f,
                                       T (&g)[E], T stp, const T (&s)[E], const T dginit) {
-  using P = typename PolicyOf<Fn>::type;
   int info = 0;
   int infoc = 1;
   const T xtol = T(1e-15);
@@ -150,11 +175,13 @@ __device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx, const Re
   const int maxfev = 20;
   int nfev = 0;
 
-  if (uni(dginit >= T(0))) {  // :152-156 (state untouched)
+  if constexpr (!kChecked) {
+    if (uni(dginit >= T(0))) {  // :152-156 (state untouched)
 #pragma unroll
-    for (int j = 0; j < E; ++j) { x[j] = x0[j]; g[j] = g0[j]; }
-    f = f0;
-    return 0;
+      for (int j = 0; j < E; ++j) { x[j] = x0[j]; g[j] = g0[j]; }
+      f = f0;
+      return 0;
+    }
   }
 
   bool brackt = false;
@@ -183,11 +210,9 @@ __device__ __forceinline__ int cvsrch(const Fn& fn, const EvalCtx& ctx, const Re
       stp = stx;
     }
 
-#pragma unroll
-    for (int j = 0; j < E; ++j) x[j] = x0[j] + stp * s[j];  // :198
-    f = fn(ctx, x, &g);                                      // :199 (already reduced)
+    T dg;
+    ls_eval<kNeg, Fn, T, E>(fn, ctx, rc, x0, stp, s, x, f, g, dg);  // :198-201
     nfev++;
-    const T dg = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(g, s), rc);  // :201
     const T ftest1 = finit + stp * dgtest;
 
     if ((brackt & ((stp <= stmin) | (stp >= stmax))) | (infoc == 0)) info = 6;
@@ -242,7 +267,7 @@ struct HzSample {
   int id;
 };
 
-template <class Fn, class T, int E>
+template <class Fn, class T, int E, bool kNeg = false>
 struct HzSearch {
   using P = typename PolicyOf<Fn>::type;
   const Fn& fn;
@@ -259,11 +284,8 @@ struct HzSearch {
   // PhiDphi (:152-159) + history.push_back
   __device__ __forceinline__ HzSample<T> eval(T alpha) {
     HzSample<T> r;
-#pragma unroll
-    for (int j = 0; j < E; ++j) xa[j] = x0[j] + alpha * s[j];
     r.alpha = alpha;
-    r.phi = fn(ctx, xa, &gx);
-    r.dphi = warp_sum_p<P, T, E>(lane_dot_p<P, T, E>(gx, s), rc);
+    ls_eval<kNeg, Fn, T, E>(fn, ctx, rc, x0, alpha, s, xa, r.phi, gx, r.dphi);
     r.id = -1;
     nfev++;
     return r;
@@ -332,7 +354,7 @@ struct HzSearch {
 // stp_out / ok = the reference's `*stp` on return and `return value == 0`: GradientDescent rebuilds
 // its next point from the step width alone (gradient_descent.h:72), which differs from the
 // returned state exactly when the search failed.
-template <class Fn, class T, int E>
+template <class Fn, class T, int E, bool kNeg = false>
 __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc, const T (&x0)[E],
                                  const T f0, const T (&g0)[E], T (&x)[E], T& f, T (&g)[E], T stp,
                                  const T (&s)[E], const T dginit, T& stp_out, bool& ok) {
@@ -347,7 +369,7 @@ __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedC
   ok = false;
   if (uni(dginit >= T(0))) return 0;  // :316 (the step is left at its initial value)
 
-  HzSearch<Fn, T, E> z{fn, ctx, rc, x0, s, x, g, f0, dginit, T(0), T(1) / T(10), T(9) / T(10), 1, 0};
+  HzSearch<Fn, T, E, kNeg> z{fn, ctx, rc, x0, s, x, g, f0, dginit, T(0), T(1) / T(10), T(9) / T(10), 1, 0};
   z.phi_lim = f0 + epsilon_k * cabs(f0);
   const HzSample<T> origin{T(0), f0, dginit, 0};
   T best_alpha = T(0), best_phi = f0;
@@ -471,23 +493,23 @@ __device__ __forceinline__ int hzls(const Fn& fn, const EvalCtx& ctx, const RedC
 struct LsMoreThuente {
   // cvsrch always evaluates at the step it returns: the returned state IS x0 + stp * s
   static constexpr bool kStateMayDifferFromStep = false;
-  template <class Fn, class T, int E>
+  template <class Fn, class T, int E, bool kNeg = false, bool kChecked = false>
   __device__ __forceinline__ static int search(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc,
                                                const T (&x0)[E], const T f0, const T (&g0)[E], T (&x)[E],
                                                T& f, T (&g)[E], T stp, const T (&s)[E], const T dginit) {
-    return cvsrch<Fn, T, E>(fn, ctx, rc, x0, f0, g0, x, f, g, stp, s, dginit);
+    return cvsrch<Fn, T, E, kNeg, kChecked>(fn, ctx, rc, x0, f0, g0, x, f, g, stp, s, dginit);
   }
 };
 struct LsHagerZhang {
   // a failed hzls leaves the state at the start point and the step at 0 (or at its initial value)
   static constexpr bool kStateMayDifferFromStep = true;
-  template <class Fn, class T, int E>
+  template <class Fn, class T, int E, bool kNeg = false, bool kChecked = false>
   __device__ __forceinline__ static int search(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc,
                                                const T (&x0)[E], const T f0, const T (&g0)[E], T (&x)[E],
                                                T& f, T (&g)[E], T stp, const T (&s)[E], const T dginit) {
     T stp_out;
     bool ok;
-    return hzls<Fn, T, E>(fn, ctx, rc, x0, f0, g0, x, f, g, stp, s, dginit, stp_out, ok);
+    return hzls<Fn, T, E, kNeg>(fn, ctx, rc, x0, f0, g0, x, f, g, stp, s, dginit, stp_out, ok);
   }
   template <class Fn, class T, int E>
   __device__ __forceinline__ static int search_with_step(const Fn& fn, const EvalCtx& ctx, const RedCtx<T>& rc,

@@ -788,12 +788,12 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 #pragma unroll
       for (int e = 0; e < E; ++e) sdx[e] = xt[e] - x[e];
       const T prev_value = f;
-      const T x_delta = warp_max_nonneg(lane_maxabs<T, E>(sdx));
+      const T x_delta = warp_maxabs<T, E>(sdx);
 #pragma unroll
       for (int e = 0; e < E; ++e) { x[e] = xt[e]; g[e] = gt[e]; }
       f = ft;
-      const T gnorm_inf = warp_max_nonneg(lane_maxabs<T, E>(g));
-      const T x_inf = warp_max_nonneg(lane_maxabs<T, E>(x));
+      const T gnorm_inf = warp_maxabs<T, E>(g);
+      const T x_inf = warp_maxabs<T, E>(x);
       nfev++;  // Progress::Update's Hessian evaluation (progress.h:206-207)
       staged = Fn::kHessianConstant;
       progress_update<T>(prog, stop, ring, lane, prev_value, f, x_delta, gnorm_inf, x_inf);

@@ -225,6 +225,10 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch,
                       const void* x0, const cno_stop_t* stop,
                       const cno_batch_out_t* out, cno_launch_info_t* info);
 
+/* cno_minimize_host keeps its device staging arena between calls (grown on demand, one per process);
+ * this frees it.  Returns 0 or CNO_ERR_CUDA. */
+int cno_release_host_arena(void);
+
 /* Counter-based start generator: element with global counter
  * n = first + k gets lo + (hi - lo) * u, u = (mix64(seed + (n+1)*GOLDEN) >> 11)
  * * 2^-53 (f64) or (>> 40) * 2^-24 (f32).  dst is a device pointer. */
