@@ -90,7 +90,7 @@ EXPORTS = (
     "cno_version", "cno_error_string", "cno_last_cuda_error", "cno_default_stop",
     "cno_conservative_stop", "cno_supported", "cno_workspace_bytes", "cno_minimize",
     "cno_state_bytes", "cno_minimize_steps",
-    "cno_minimize_host", "cno_release_host_arena", "cno_fill_uniform", "cno_done_bitmap", "cno_device_cstep",
+    "cno_minimize_host", "cno_release_host_arena", "cno_evaluate", "cno_fill_uniform", "cno_done_bitmap", "cno_device_cstep",
 )
 
 _lib = None
@@ -135,6 +135,7 @@ def lib() -> C.CDLL:
         L.cno_minimize_host.argtypes = [
             C.c_int, C.POINTER(Problem), C.c_int64, C.c_void_p, C.POINTER(Stop),
             C.POINTER(BatchOut), C.POINTER(LaunchInfo)]
+        L.cno_evaluate.argtypes = [C.POINTER(Problem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cno_fill_uniform.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64,
                                        C.c_double, C.c_double, C.c_void_p]
         L.cno_done_bitmap.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]

@@ -68,10 +68,22 @@ def build_cpp_tests(verbose: bool = False) -> list:
     subprocess.run(cmd, check=True)
     nvcc = os.environ.get("NVCC", f"{cuda}/bin/nvcc")
     xlink = ["-Xlinker", f"-rpath={HERE}"]
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-fmad=false", os.path.join(src, "user_functor.cu"), *inc, "-o",
-           os.path.join(out, "user_functor"), f"-L{HERE}", "-lcno", *xlink]
-    subprocess.run(cmd, check=True)
+    dev_flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                 "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
+    jobs = [(os.path.join(src, "user_functor.cu"), os.path.join(out, "user_functor"), []),
+            # user functors + composites as a shared library for the Python parity tests (tests/usertest_binding.py)
+            (os.path.join(src, "user_functions.cu"), os.path.join(out, "libcno_usertest.so"),
+             ["-shared", "-Xcompiler", "-fPIC"])]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + \
+           [os.path.join(root, "include", "cppoptlib_b200", f) for f in os.listdir(os.path.join(root, "include", "cppoptlib_b200"))]
+    procs = []
+    for source, target, extra in jobs:
+        if os.path.exists(target) and all(os.path.getmtime(d) <= os.path.getmtime(target) for d in deps + [source]):
+            continue
+        procs.append(subprocess.Popen([nvcc, *dev_flags, *extra, source, *inc, "-o", target, f"-L{HERE}", "-lcno", *xlink]))
+    for p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, p.args)
     exes.append(os.path.join(out, "user_functor"))
     return exes
 

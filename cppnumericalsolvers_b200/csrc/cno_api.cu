@@ -17,6 +17,7 @@
 #include "cno_lbfgs.cuh"
 #include "cno_bfgs.cuh"
 #include "cno_descent.cuh"
+#include "cno_evaluate.cuh"
 #include "cno_newton.cuh"
 #include "cno_logistic.cuh"
 #include "cno_auglag.cuh"
@@ -379,6 +380,43 @@ const Entry kTable[] = {
     {CNO_BFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 32, bfgs_rosenbrock_hz<double, 32>},
     {CNO_GRADIENT_DESCENT_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 8, gd_rosenbrock_hz<double, 8>},
     {CNO_GRADIENT_DESCENT_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 37, gd_rosenbrock_hz<double, 37>},
+};
+
+// ---- cno_evaluate: F::operator()(x, &gradient) of the built-in families ----
+typedef int (*evaluator_t)(const cno_problem_t*, int64_t, const void*, void*, void*, void*);
+template <class T, int D>
+int eval_rosenbrock(const cno_problem_t*, int64_t b, const void* x, void* f, void* g, void* s) {
+  return cno::launch_evaluate(cno::RosenbrockFn<T, D>{}, b, x, f, g, s);
+}
+template <class T>
+int eval_diag_quadratic(const cno_problem_t*, int64_t b, const void* x, void* f, void* g, void* s) {
+  return cno::launch_evaluate(cno::DiagQuadraticFn<T>{}, b, x, f, g, s);
+}
+template <class T, int D>
+int eval_half_sq_norm(const cno_problem_t*, int64_t b, const void* x, void* f, void* g, void* s) {
+  return cno::launch_evaluate(cno::HalfSquaredNormFn<T, D>{}, b, x, f, g, s);
+}
+template <class T, int D>
+int eval_dense_quadratic(const cno_problem_t* p, int64_t b, const void* x, void* f, void* g, void* s) {
+  if (!p->data || p->data_stride < (int64_t)D * D + D) return CNO_ERR_INVALID_ARGUMENT;
+  return cno::launch_evaluate(cno::DenseQuadraticGlobalFn<T, D>{static_cast<const T*>(p->data), (long long)p->data_stride},
+                              b, x, f, g, s);
+}
+struct EvalEntry { int family, dtype, d; evaluator_t fn; };
+const EvalEntry kEvalTable[] = {
+    {CNO_FN_ROSENBROCK, CNO_F64, 2, eval_rosenbrock<double, 2>},   {CNO_FN_ROSENBROCK, CNO_F64, 3, eval_rosenbrock<double, 3>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 8, eval_rosenbrock<double, 8>},   {CNO_FN_ROSENBROCK, CNO_F64, 32, eval_rosenbrock<double, 32>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 37, eval_rosenbrock<double, 37>}, {CNO_FN_ROSENBROCK, CNO_F64, 64, eval_rosenbrock<double, 64>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 128, eval_rosenbrock<double, 128>},
+    {CNO_FN_ROSENBROCK, CNO_F32, 2, eval_rosenbrock<float, 2>},    {CNO_FN_ROSENBROCK, CNO_F32, 32, eval_rosenbrock<float, 32>},
+    {CNO_FN_ROSENBROCK, CNO_F32, 37, eval_rosenbrock<float, 37>},  {CNO_FN_ROSENBROCK, CNO_F32, 128, eval_rosenbrock<float, 128>},
+    {CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, eval_diag_quadratic<double>},
+    {CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, eval_half_sq_norm<double, 2>},
+    {CNO_FN_HALF_SQUARED_NORM, CNO_F64, 8, eval_half_sq_norm<double, 8>},
+    {CNO_FN_HALF_SQUARED_NORM, CNO_F64, 50, eval_half_sq_norm<double, 50>},
+    {CNO_FN_DENSE_QUADRATIC, CNO_F64, 2, eval_dense_quadratic<double, 2>},
+    {CNO_FN_DENSE_QUADRATIC, CNO_F64, 8, eval_dense_quadratic<double, 8>},
+    {CNO_FN_DENSE_QUADRATIC, CNO_F64, 64, eval_dense_quadratic<double, 64>},
 };
 
 const Entry* find_entry(int solver, const cno_problem_t* p) {
@@ -897,6 +935,20 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, c
   if (info) *info = local;
   g_last_info = local;
   return CNO_OK;
+}
+
+int cno_evaluate(const cno_problem_t* problem, int64_t batch, const void* x, void* value, void* gradient,
+                 void* stream) {
+  if (!problem || batch < 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (problem->dtype != CNO_F64 && problem->dtype != CNO_F32) return CNO_ERR_INVALID_ARGUMENT;
+  const int dflt = (problem->dtype == CNO_F64) ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE;
+  if (problem->policy != dflt) return CNO_ERR_UNSUPPORTED;
+  for (const EvalEntry& e : kEvalTable)
+    if (e.family == problem->family && e.dtype == problem->dtype && e.d == problem->d) {
+      if (!have_device()) return CNO_ERR_NO_DEVICE;
+      return e.fn(problem, batch, x, value, gradient, stream);
+    }
+  return CNO_ERR_UNSUPPORTED;
 }
 
 int cno_release_host_arena(void) {

@@ -93,6 +93,28 @@ struct RosenbrockFn {
       h[j] = (i < D) ? v : T(1);
     }
   }
+
+  // Column j of the (symmetric, tridiagonal) Hessian, this lane's rows: H_jj as in hess_diag,
+  // H_{j+1,j} = H_{j,j+1} = -400 x_j (src/test/verify.cc:93-97 at D = 2).
+  __device__ __forceinline__ void hess_col(const EvalCtx& c, const T (&x)[E], int j, bool, T (&col)[E]) const {
+    const T xj = lane_bcast<T, E>(x, j);
+    const T xjn = lane_bcast<T, E>(x, (j + 1 < D) ? j + 1 : j);
+    const T hii = 1200 * xj * xj - 400 * xjn + 1;
+    T djj;
+    if (j == 0) djj = hii;
+    else if (j == D - 1) djj = T(200);
+    else djj = T(200) + hii;
+    if (D == 1) djj = T(0);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int r = c.lane * E + e;
+      T v = T(0);
+      if (r == j) v = djj;
+      else if (r == j + 1) v = -400 * xj;       // below the diagonal
+      else if (r + 1 == j) v = -400 * x[e];     // above it: -400 x_{j-1} = -400 x_r
+      col[e] = (r < D) ? v : T(0);
+    }
+  }
 };
 
 // Dockerfile.test:21-29: 5 x0^2 + 100 x1^2 + 5 (D = 2).
@@ -108,6 +130,12 @@ struct DiagQuadraticFn {
     const T x1 = __shfl_sync(kFullMask, x[0], 1);
     if (grad) (*grad)[0] = (c.lane == 0) ? (10 * x0) : ((c.lane == 1) ? (200 * x1) : T(0));
     return 5 * x0 * x0 + 100 * x1 * x1 + 5;
+  }
+  __device__ __forceinline__ void hess_diag(const EvalCtx& c, const T (&)[1], T (&h)[1]) const {
+    h[0] = (c.lane == 0) ? T(10) : ((c.lane == 1) ? T(200) : T(0));
+  }
+  __device__ __forceinline__ void hess_col(const EvalCtx& c, const T (&)[1], int j, bool, T (&col)[1]) const {
+    col[0] = (c.lane == j) ? ((j == 0) ? T(10) : T(200)) : T(0);
   }
 };
 
@@ -125,6 +153,14 @@ struct HalfSquaredNormFn {
       for (int j = 0; j < E; ++j) (*grad)[j] = x[j];
     }
     return T(0.5) * warp_dot<T, E>(x, x);
+  }
+  __device__ __forceinline__ void hess_diag(const EvalCtx& c, const T (&)[E], T (&h)[E]) const {
+#pragma unroll
+    for (int e = 0; e < E; ++e) h[e] = (c.lane * E + e < D) ? T(1) : T(0);
+  }
+  __device__ __forceinline__ void hess_col(const EvalCtx& c, const T (&)[E], int j, bool, T (&col)[E]) const {
+#pragma unroll
+    for (int e = 0; e < E; ++e) col[e] = (c.lane * E + e == j) ? T(1) : T(0);
   }
 };
 

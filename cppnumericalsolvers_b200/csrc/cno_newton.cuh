@@ -307,9 +307,35 @@ __device__ __forceinline__ void aug_gemv(const AugStore<T, D>& A, const T* vec, 
   }
 }
 
+// out_i = sum_j H_ij v_j with H (d x d col-major) streamed from GLOBAL memory (L2: the block was read a moment
+// ago), j ascending from the first product; v is read from the warp-private shared vector `vec`.  kU columns are
+// in flight per lane so the L2 latency is paid once per group, not once per column.
+template <class T, int D>
+__device__ __forceinline__ void gemv_global(const T* __restrict__ H, const T* vec, int lane, T (&out)[Shape<D>::E]) {
+  constexpr int E = Shape<D>::E;
+  constexpr int kU = (E <= 2) ? 16 : 8;
+#pragma unroll 1
+  for (int j0 = 0; j0 < D; j0 += kU) {
+    T c[kU][E];
+#pragma unroll
+    for (int t = 0; t < kU; ++t)
+      if (j0 + t < D) load_row<T, D>(H + (size_t)(j0 + t) * D, lane, c[t]);
+#pragma unroll
+    for (int t = 0; t < kU; ++t) {
+      if (j0 + t < D) {
+        const T vj = vec[j0 + t];
+#pragma unroll
+        for (int e = 0; e < E; ++e) out[e] = (j0 + t == 0) ? (c[t][e] * vj) : (out[e] + c[t][e] * vj);
+      }
+    }
+  }
+}
+
 // 0.5 x'Ax - b'x with per-instance [A (d x d col-major, bitwise symmetric) | b].
 // Reference analogue: src/examples/debug.cc:43-65.  (Ax)_i = sum_j A_ij x_j,
-// j ascending from the first product.
+// j ascending from the first product.  The Hessian is CONSTANT, so the solver factors H + 1e-5 I once per
+// instance and keeps the factors in the warp's store; evaluations and the Armijo slope stream A from global
+// memory (gemv_global) instead of restaging it over the factors.
 template <class T, int D>
 struct DenseQuadraticFn {
   using Scalar = T;
@@ -349,17 +375,27 @@ struct DenseQuadraticFn {
     parity ^= 1u;
   }
 
-  // value/gradient from the staged (unshifted) A; b = the rhs column.
+  // H v (= v'H: A is bitwise symmetric) for the Armijo slope, A streamed from global memory
+  __device__ __forceinline__ void hess_times(const EvalCtx& c, const T (&v)[E], T (&out)[E], T* vec) const {
+    using SV = SmemRowVec<T, D>;
+    __syncwarp();
+    SV::store(vec, c.lane, v);
+    __syncwarp();
+    gemv_global<T, D>(data + c.instance * stride, vec, c.lane, out);
+  }
+
+  // value/gradient with A and b read from global memory (the store holds the LU factors).
   // vec = D scalars of warp-private scratch for the broadcast operand.
   __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&x)[E], T (*grad)[E],
-                                          const AS& A, T* vec) const {
+                                          const AS&, T* vec) const {
     using SV = SmemRowVec<T, D>;
+    const T* src = data + c.instance * stride;
     __syncwarp();
     SV::store(vec, c.lane, x);
     __syncwarp();
     T Ax[E], bb[E];
-    aug_gemv<T, D>(A, vec, Ax);
-    SV::load(A.rhs(), c.lane, bb);
+    gemv_global<T, D>(src, vec, c.lane, Ax);
+    load_row<T, D>(src + D * D, c.lane, bb);
     if (grad) {
 #pragma unroll
       for (int e = 0; e < E; ++e) (*grad)[e] = (c.lane * E + e < D) ? (Ax[e] - bb[e]) : T(0);
@@ -547,15 +583,125 @@ __device__ __forceinline__ void aug_store_col(const AugStore<T, D>& A, int k, co
   AS::RV::store(A.smcol(k), A.lane, col);
 }
 
+// Any Second-mode functor (value/gradient through operator()(ctx, x, grad*), Hessian column by column
+// through hess_col: cno_device.cuh) as a NewtonDescent objective -- user functors and the expression
+// templates of include/cppoptlib_b200/expressions.h.  H(x) is written into the warp's store one column
+// at a time; for the Armijo slope, whose d'H the kernel evaluates as a column sweep, the TRANSPOSE is
+// staged, so a Hessian that is not bitwise symmetric (a product of functions) still gives the
+// reference's sum_i d_i H_ij, i ascending.
+template <class F>
+struct SecondOrderAdapter {
+  using Scalar = typename F::Scalar;
+  using T = Scalar;
+  static constexpr int Dim = F::Dim;
+  static constexpr int Mode = 2;
+  static constexpr int E = Shape<Dim>::E;
+  using AS = AugStore<T, Dim>;
+  static constexpr bool kHessianConstant = false;
+  static constexpr bool kStageTakesTranspose = true;
+  F f;
+  __device__ __forceinline__ void stage(const EvalCtx& c, const T (&x)[E], const AS& A, uint64_t*, uint32_t&,
+                                        bool transposed = false) const {
+    __syncwarp();
+    const auto st = hess_prepare(f, c, x);
+#pragma unroll 1
+    for (int j = 0; j < Dim; ++j) {
+      T col[E];
+      hess_col(f, c, x, st, j, transposed, col);
+      aug_store_col<T, Dim>(A, j, col);
+    }
+    __syncwarp();
+  }
+  __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&x)[E], T (*grad)[E], const AS&, T*) const {
+    return f(c, x, grad);
+  }
+};
+template <class Fn, class = void>
+struct StageTakesTranspose : std::false_type {};
+template <class Fn>
+struct StageTakesTranspose<Fn, std::void_t<decltype(Fn::kStageTakesTranspose)>> : std::true_type {};
+
 // delta = (H + shift I)^{-1} rhs by unblocked partial-pivot LU with implicit row
 // exchanges.  A = [H | rhs] col-major, lane owns rows lane*E .. lane*E+E-1.  On
 // return delta holds this lane's slice of the solution.
+// Back substitution U x = y (pivot order), column oriented, on the factored store; vpos = the rows' final
+// virtual positions.  On return delta holds this lane's slice of the solution.
 template <class T, int D>
-__device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&delta)[Shape<D>::E]) {
+__device__ __forceinline__ void lu_back_substitute(const AugStore<T, D>& A, const int (&vpos)[Shape<D>::E],
+                                                   T (&delta)[Shape<D>::E]) {
+  constexpr int E = Shape<D>::E;
+  const int lane = A.lane;
+  T* const rhs = A.rhs();
+#pragma unroll 1
+  for (int k = D - 1; k >= 0; --k) {
+    T col[E];
+    aug_load_col<T, D>(A, k, col);
+    T xk_local = T(0);
+    bool mine = false;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if ((lane * E + e < D) && vpos[e] == k) {
+        xk_local = rhs[lane * E + e] / col[e];
+        mine = true;
+      }
+    }
+    const unsigned owner = __ballot_sync(kFullMask, mine);
+    const T xk = __shfl_sync(kFullMask, xk_local, __ffs(owner) - 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int row = lane * E + e;
+      if ((row < D) && vpos[e] < k) rhs[row] = rhs[row] - col[e] * xk;
+      if (row == k) delta[e] = xk;  // unknown k belongs to element k
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e)
+    if (lane * E + e >= D) delta[e] = T(0);
+}
+
+// Solve with the factors a previous lu_solve_inplace left in the store (a functor with a constant Hessian is
+// factored once per instance): the right-hand side receives, in pivot order, exactly the updates it received while
+// it rode along the elimination -- rhs_i -= l_ik * rhs_{pivot row k} for the rows not yet used as a pivot, l_ik
+// being the multiplier stored in column k -- then the same back substitution.  Bit-identical to factoring again.
+template <class T, int D>
+__device__ __forceinline__ void lu_resolve(const AugStore<T, D>& A, const int (&vpos)[Shape<D>::E],
+                                           T (&delta)[Shape<D>::E]) {
+  constexpr int E = Shape<D>::E;
+  const int lane = A.lane;
+  T* const rhs = A.rhs();
+#pragma unroll 1
+  for (int k = 0; k < D; ++k) {
+    T col[E];
+    aug_load_col<T, D>(A, k, col);
+    T u_local = T(0);
+    bool mine = false;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if ((lane * E + e < D) && vpos[e] == k) {
+        u_local = rhs[lane * E + e];
+        mine = true;
+      }
+    }
+    const unsigned owner = __ballot_sync(kFullMask, mine);
+    const T u = __shfl_sync(kFullMask, u_local, __ffs(owner) - 1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int row = lane * E + e;
+      if ((row < D) && vpos[e] > k) rhs[row] = rhs[row] - col[e] * u;
+    }
+    __syncwarp();
+  }
+  lu_back_substitute<T, D>(A, vpos, delta);
+}
+
+template <class T, int D>
+__device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&delta)[Shape<D>::E],
+                                                 int (&vpos)[Shape<D>::E]) {
   constexpr int E = Shape<D>::E;
   using AS = AugStore<T, D>;
   const int lane = A.lane;
-  int vpos[E];  // virtual row position (what the reference's explicit swaps would give)
+  // vpos = virtual row position (what the reference's explicit swaps would give)
 #pragma unroll
   for (int e = 0; e < E; ++e) vpos[e] = lane * E + e;
 
@@ -621,34 +767,7 @@ __device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&de
     }
     __syncwarp();
   }
-  // ---- back substitution U x = y (pivot order), column oriented ----
-  T* const rhs = A.rhs();
-#pragma unroll 1
-  for (int k = D - 1; k >= 0; --k) {
-    T col[E];
-    aug_load_col<T, D>(A, k, col);
-    T xk_local = T(0);
-    bool mine = false;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      if ((lane * E + e < D) && vpos[e] == k) {
-        xk_local = rhs[lane * E + e] / col[e];
-        mine = true;
-      }
-    }
-    const unsigned owner = __ballot_sync(kFullMask, mine);
-    const T xk = __shfl_sync(kFullMask, xk_local, __ffs(owner) - 1);
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int row = lane * E + e;
-      if ((row < D) && vpos[e] < k) rhs[row] = rhs[row] - col[e] * xk;
-      if (row == k) delta[e] = xk;  // unknown k belongs to element k
-    }
-    __syncwarp();
-  }
-#pragma unroll
-  for (int e = 0; e < E; ++e)
-    if (lane * E + e >= D) delta[e] = T(0);
+  lu_back_substitute<T, D>(A, vpos, delta);
 }
 
 template <class Fn>
@@ -706,9 +825,16 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
     T x[E], g[E];
     load_row<T, D>(x0 + b * D, lane, x);
+    // A functor with a CONSTANT Hessian (kHessianConstant: the dense quadratic) is factored ONCE per instance:
+    // the store keeps the LU factors of H + 1e-5 I, later iterations re-solve with them (lu_resolve: the same
+    // arithmetic as factoring again), and evaluations / the Armijo slope read the matrix from global memory.
     fn.stage(ctx, x, A, bar, parity);
     T f = fn(ctx, x, &g, A, vec);  // solver.h:189-192
     uint32_t nfev = 1;
+    bool factored = false;
+    int vpos[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) vpos[e] = lane * E + e;
 
     ProgressState<T> prog;
     prog.num_iterations = 0;
@@ -722,8 +848,17 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
     do {  // solver.h:196-220
       // ---- newton_descent.h:73-76 ----
-      if (!staged) fn.stage(ctx, x, A, bar, parity);
       nfev++;  // function(current.x, &gradient, &hessian)
+      T delta[E];
+      if (uni(Fn::kHessianConstant && factored)) {
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if (lane * E + e < D) A.rhs()[lane * E + e] = -g[e];
+        __syncwarp();
+        lu_resolve<T, D>(A, vpos, delta);
+      } else {
+      if (!staged) fn.stage(ctx, x, A, bar, parity);
       // hessian += safe_guard * I ; rhs = -gradient
 #pragma unroll
       for (int e = 0; e < E; ++e) {
@@ -751,21 +886,28 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         tmem_wait_st();
       }
       __syncwarp();
-      T delta[E];
-      lu_solve_inplace<T, D>(A, delta);
+      lu_solve_inplace<T, D>(A, delta, vpos);
+      factored = true;
+      }
 
       // ---- Armijo<F,2>::Search (armijo.h:82-101) ----
-      fn.stage(ctx, x, A, bar, parity);  // unshifted H(x) again
       nfev++;                            // f_in = function(x, &gradient, &hessian)
       const T cc = T(0.2), rho = T(0.9);
       T sd[E], r[E];
       const T half_cc = T(0.5) * cc * cc;
 #pragma unroll
       for (int e = 0; e < E; ++e) sd[e] = half_cc * delta[e];
-      __syncwarp();
-      SV::store(vec, lane, sd);
-      __syncwarp();
-      aug_gemv<T, D>(A, vec, r);  // ((0.5 c^2) d') H, H bitwise symmetric
+      if constexpr (Fn::kHessianConstant) {
+        fn.hess_times(ctx, sd, r, vec);  // ((0.5 c^2) d') H from global memory; the store keeps the factors
+      } else {
+        // unshifted H(x) again (its transpose where the functor tells them apart: the slope below is d'H)
+        if constexpr (StageTakesTranspose<Fn>::value) fn.stage(ctx, x, A, bar, parity, true);
+        else fn.stage(ctx, x, A, bar, parity);
+        __syncwarp();
+        SV::store(vec, lane, sd);
+        __syncwarp();
+        aug_gemv<T, D>(A, vec, r);  // ((0.5 c^2) d') H, H bitwise symmetric (or its staged transpose)
+      }
       T p1 = lane_dot<T, E>(g, delta), p2 = lane_dot<T, E>(r, delta);
       warp_sum2(p1, p2);
       const T cache = cc * p1 + p2;
@@ -795,7 +937,7 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       const T gnorm_inf = warp_maxabs<T, E>(g);
       const T x_inf = warp_maxabs<T, E>(x);
       nfev++;  // Progress::Update's Hessian evaluation (progress.h:206-207)
-      staged = Fn::kHessianConstant;
+      staged = false;  // (a non-constant Hessian is staged again at the new x; a constant one stays factored)
       progress_update<T>(prog, stop, ring, lane, prev_value, f, x_delta, gnorm_inf, x_inf);
     } while (uni(prog.status == CNO_STATUS_CONTINUE));
 

@@ -225,6 +225,13 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch,
                       const void* x0, const cno_stop_t* stop,
                       const cno_batch_out_t* out, cno_launch_info_t* info);
 
+/* Batched F::operator()(x, &gradient) (function_base.h:103-120; the evaluating FunctionState constructor,
+ * :315-326): value [B] and/or gradient [B, d] of the built-in family at x [B, d].  DEVICE pointers; either
+ * output may be NULL.  Families that stage per-instance data on chip (CNO_FN_LOGISTIC) are not evaluated
+ * stand-alone: CNO_ERR_UNSUPPORTED. */
+int cno_evaluate(const cno_problem_t* problem, int64_t batch, const void* x, void* value, void* gradient,
+                 void* stream);
+
 /* cno_minimize_host keeps its device staging arena between calls (grown on demand, one per process);
  * this frees it.  Returns 0 or CNO_ERR_CUDA. */
 int cno_release_host_arena(void);

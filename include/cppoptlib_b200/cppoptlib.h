@@ -44,6 +44,7 @@
 
 #include "../cno.h"
 #include "../cno_al.h"
+#include "modes.h"
 
 namespace cppoptlib {
 
@@ -107,7 +108,6 @@ template <> struct DType<float> { static constexpr int value = CNO_F32; };
 
 namespace function {
 
-enum class DifferentiabilityMode { None = 0, First = 1, Second = 2 };  // function_base.h:42-46
 
 // function_base.h:96-126.  A user objective derives from FunctionCRTP exactly as
 // with the reference; its operator() is the warp-cooperative __device__ form
@@ -125,11 +125,20 @@ struct FunctionCRTP {
 };
 
 // What a solver needs to know about an objective: which kernels to launch.
-// Built-in families go through cno_minimize's table; user functors through the
-// extern "C" symbols generated by CNO_INSTANTIATE_FUNCTION(tag, F).
-typedef int (*RawMinimizeFn)(int solver, const void* functor_bytes, int64_t batch, const void* x0,
+// Built-in families go through cno_minimize's table; user functors (and composites of functors,
+// expressions.h) through the extern "C" symbols generated by CNO_INSTANTIATE_FUNCTION(tag, F).
+// `mode` = the DifferentiabilityMode the function is USED with (a Second-mode functor bound through a
+// First-mode FunctionExpr is minimised as a First-mode function: function_base.h:210-230).
+typedef int (*RawMinimizeFn)(int solver, int mode, const void* functor_bytes, int64_t batch, const void* x0,
                              const cno_stop_t* stop, const cno_batch_out_t* out, void* workspace,
                              size_t workspace_bytes, void* stream, cno_launch_info_t* info);
+typedef int (*RawStateBytesFn)(int solver, int64_t batch, size_t* bytes);
+typedef int (*RawMinimizeStepsFn)(int solver, int mode, const void* functor_bytes, int64_t batch, const void* x0,
+                                  const cno_stop_t* stop, const cno_batch_out_t* out, void* state,
+                                  size_t state_bytes, int32_t max_iterations, int32_t first_call, void* workspace,
+                                  size_t workspace_bytes, void* stream, cno_launch_info_t* info);
+typedef int (*RawEvaluateFn)(const void* functor_bytes, int64_t batch, const void* x, void* value, void* gradient,
+                             void* stream);
 
 template <class F, class = void>
 struct LauncherTraits;  // specialised by CNO_DECLARE_FUNCTION / the built-ins below
@@ -144,17 +153,52 @@ struct FunctionExpr {
   static constexpr DifferentiabilityMode Differentiability = TMode;
 
   cno_problem_t problem{};          // built-in family (raw == nullptr)
-  RawMinimizeFn raw = nullptr;      // user functor launcher
+  RawMinimizeFn raw = nullptr;      // user functor launchers (CNO_DECLARE_FUNCTION)
+  RawStateBytesFn raw_state_bytes = nullptr;
+  RawMinimizeStepsFn raw_steps = nullptr;
+  RawEvaluateFn raw_evaluate = nullptr;
   std::vector<unsigned char> pod;   // the user functor's bytes
+  int dimension = TDimension;       // (TDimension == -1: taken from the bound function)
 
   FunctionExpr() = default;
+  // function_base.h:210-230: accepts any source at least as differentiable as TMode.  A stronger source
+  // is used AS a TMode function (the reference wraps it in ModeDowngradeAdapter, :151-189; here the
+  // launcher is told the mode, so e.g. Lbfgs does not take its Second-mode preconditioner branch).
   template <class F, class = std::enable_if_t<!std::is_same_v<std::decay_t<F>, FunctionExpr>>>
   FunctionExpr(const F& f) {  // NOLINT (converting, like function_base.h:210)
     static_assert(static_cast<int>(F::Differentiability) >= static_cast<int>(TMode),
-                  "Differentiability mode mismatch (downgrades are accepted, upgrades are not)");
-    static_assert(std::is_same_v<typename F::ScalarType, TScalar>, "scalar-type mismatch");
+                  "Differentiability mode mismatch: source must supply at least as much derivative information "
+                  "as the target mode requires (downgrades are accepted, upgrades are not).");
+    static_assert(std::is_same_v<typename F::ScalarType, TScalar>, "Compile-time scalar-type mismatch");
     static_assert(TDimension == -1 || F::Dimension == TDimension, "Dimension mismatch");
     LauncherTraits<F>::Bind(f, *this);
+    dimension = F::Dimension;
+    problem.mode = static_cast<int>(TMode);
+  }
+  int mode() const { return static_cast<int>(TMode); }
+
+  // function_base.h:247-250 with a batch axis: value [B] (and gradient [B, d]) of the bound function at
+  // x [B, d]; all three are device arrays.
+  void operator()(int64_t batch, const TScalar* x, TScalar* value, TScalar* gradient = nullptr,
+                  cudaStream_t stream = nullptr) const {
+    const int rc = raw_evaluate ? raw_evaluate(pod.data(), batch, x, value, gradient, stream)
+                                : cno_evaluate(&problem, batch, x, value, gradient, stream);
+    detail::check_cno(rc, "FunctionExpr::operator()");
+  }
+};
+
+// function_base.h:298-332 as in the reference: one instance, host vectors (the B = 1 signature of
+// Solver::Minimize takes and returns it).
+template <class TScalar, int TDimension>
+struct FunctionState {
+  using ScalarType = TScalar;
+  static constexpr bool IsConstrained = false;
+  std::vector<TScalar> x;
+  TScalar value = TScalar(0);
+  std::vector<TScalar> gradient;
+  FunctionState() = default;
+  explicit FunctionState(const std::vector<TScalar>& x_) : x(x_) {  // "legacy x-only constructor" (:315)
+    if (static_cast<int>(x.size()) != TDimension) throw std::runtime_error("x must have Dimension entries");
   }
 };
 
@@ -179,14 +223,55 @@ struct BatchedFunctionState {
 };
 
 // ---- objective families compiled into libcno.so --------------------------------
+// In nvcc translation units (device.cuh) the tags are also DEVICE functors (they forward to the
+// functors of csrc/cno_functors.cuh), so they can be operands of the expression templates
+// (expressions.h): decltype(Rosenbrock<double, 8>{} + 0.5 * HalfSquaredNorm<double, 8>{}).
+#ifdef CPPOPTLIB_B200_WITH_DEVICE
+#define CNO_BUILTIN_DEVICE_MEMBERS(...)                                                                           \
+  using DeviceFn = __VA_ARGS__;                                                                                   \
+  static constexpr int E = cno::Shape<DeviceFn::Dim>::E;                                                          \
+  __device__ __forceinline__ typename DeviceFn::Scalar operator()(const cno::EvalCtx& c,                          \
+                                                                  const typename DeviceFn::Scalar (&x)[E],        \
+                                                                  typename DeviceFn::Scalar (*grad)[E]) const {   \
+    return DeviceFn{}(c, x, grad);                                                                                \
+  }                                                                                                               \
+  __device__ __forceinline__ void hess_diag(const cno::EvalCtx& c, const typename DeviceFn::Scalar (&x)[E],       \
+                                            typename DeviceFn::Scalar (&h)[E]) const {                            \
+    DeviceFn{}.hess_diag(c, x, h);                                                                                \
+  }                                                                                                               \
+  __device__ __forceinline__ void hess_col(const cno::EvalCtx& c, const typename DeviceFn::Scalar (&x)[E], int j, \
+                                           bool transposed, typename DeviceFn::Scalar (&col)[E]) const {          \
+    DeviceFn{}.hess_col(c, x, j, transposed, col);                                                                \
+  }
+#else
+#define CNO_BUILTIN_DEVICE_MEMBERS(...)
+#endif
 template <class T, int D>
-struct Rosenbrock : FunctionCRTP<Rosenbrock<T, D>, T, DifferentiabilityMode::First, D> {};
+struct Rosenbrock : FunctionCRTP<Rosenbrock<T, D>, T, DifferentiabilityMode::First, D> {
+  CNO_BUILTIN_DEVICE_MEMBERS(cno::RosenbrockFn<T, D>)
+};
 template <class T, int D>
-struct RosenbrockFull : FunctionCRTP<RosenbrockFull<T, D>, T, DifferentiabilityMode::Second, D> {};
+struct RosenbrockFull : FunctionCRTP<RosenbrockFull<T, D>, T, DifferentiabilityMode::Second, D> {
+  CNO_BUILTIN_DEVICE_MEMBERS(cno::RosenbrockFn<T, D>)
+};
 template <class T>
-struct DiagQuadratic : FunctionCRTP<DiagQuadratic<T>, T, DifferentiabilityMode::First, 2> {};
+struct DiagQuadratic : FunctionCRTP<DiagQuadratic<T>, T, DifferentiabilityMode::First, 2> {
+  CNO_BUILTIN_DEVICE_MEMBERS(cno::DiagQuadraticFn<T>)
+};
 template <class T, int D>
-struct HalfSquaredNorm : FunctionCRTP<HalfSquaredNorm<T, D>, T, DifferentiabilityMode::First, D> {};
+struct HalfSquaredNorm : FunctionCRTP<HalfSquaredNorm<T, D>, T, DifferentiabilityMode::First, D> {
+  CNO_BUILTIN_DEVICE_MEMBERS(cno::HalfSquaredNormFn<T, D>)
+};
+// The Second-mode twins of the two families above (function_base.h:96-126 with Mode = Second), for
+// composites that need Hessians (NewtonDescent, Lbfgs's preconditioner branch).
+template <class T>
+struct DiagQuadraticSecond : FunctionCRTP<DiagQuadraticSecond<T>, T, DifferentiabilityMode::Second, 2> {
+  CNO_BUILTIN_DEVICE_MEMBERS(cno::DiagQuadraticFn<T>)
+};
+template <class T, int D>
+struct HalfSquaredNormSecond : FunctionCRTP<HalfSquaredNormSecond<T, D>, T, DifferentiabilityMode::Second, D> {
+  CNO_BUILTIN_DEVICE_MEMBERS(cno::HalfSquaredNormFn<T, D>)
+};
 // 0.5 x'Ax - b'x; data[b] = [A (d x d col-major, symmetric) | b] on the device.
 template <class T, int D>
 struct DenseQuadratic : FunctionCRTP<DenseQuadratic<T, D>, T, DifferentiabilityMode::Second, D> {
@@ -377,15 +462,25 @@ class Solver {
     detail::DeviceArray<unsigned char> workspace(256);
     const cno_stop_t stop = stopping_progress.to_c();
     int rc;
-    if (step_callback_ && !expr.raw) {
+    if (step_callback_) {
+      // solver.h:197 per-iteration callback: rounds of `callback_every_` iterations, the solver's members
+      // parked on the device in between.  A (solver, function) pair without a stepwise kernel THROWS
+      // (CNO_ERR_UNSUPPORTED) -- the callback is never silently dropped.
+      if (expr.raw && (!expr.raw_steps || !expr.raw_state_bytes))
+        throw std::runtime_error("SetCallback: this function has no stepwise launcher (CNO_DECLARE_FUNCTION)");
       size_t nbytes = 0;
-      detail::check_cno(cno_state_bytes(SolverId, &expr.problem, B, &nbytes), "cno_state_bytes");
+      detail::check_cno(expr.raw ? expr.raw_state_bytes(SolverId, B, &nbytes)
+                                 : cno_state_bytes(SolverId, &expr.problem, B, &nbytes),
+                        "SetCallback (stepwise solves: cno_state_bytes)");
       detail::DeviceArray<unsigned char> state(nbytes < 16 ? 16 : nbytes);
       for (int first = 1;; first = 0) {
-        detail::check_cno(cno_minimize_steps(SolverId, &expr.problem, B, function_state.x.data(), &stop,
-                                             &out, state.data(), state.size(), callback_every_, first,
-                                             workspace.data(), workspace.size(), stream, nullptr),
-                          "cno_minimize_steps");
+        rc = expr.raw ? expr.raw_steps(SolverId, expr.mode(), expr.pod.data(), B, function_state.x.data(), &stop, &out,
+                                       state.data(), state.size(), callback_every_, first, workspace.data(),
+                                       workspace.size(), stream, nullptr)
+                      : cno_minimize_steps(SolverId, &expr.problem, B, function_state.x.data(), &stop, &out,
+                                           state.data(), state.size(), callback_every_, first, workspace.data(),
+                                           workspace.size(), stream, nullptr);
+        detail::check_cno(rc, "cno_minimize_steps");
         detail::check_cuda(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
         step_callback_(function, result, prog);
         bool done = true;
@@ -395,7 +490,7 @@ class Solver {
       return {std::move(result), std::move(prog)};
     }
     if (expr.raw) {
-      rc = expr.raw(SolverId, expr.pod.data(), B, function_state.x.data(), &stop, &out,
+      rc = expr.raw(SolverId, expr.mode(), expr.pod.data(), B, function_state.x.data(), &stop, &out,
                     workspace.data(), workspace.size(), stream, &prog.launch);
     } else {
       rc = cno_minimize(SolverId, &expr.problem, B, function_state.x.data(), &stop, &out,
@@ -403,6 +498,24 @@ class Solver {
     }
     detail::check_cno(rc, "Minimize");
     return {std::move(result), std::move(prog)};
+  }
+
+  // The reference's own signature (solver.h:181-182): ONE problem instance, host vectors in and out.
+  // A batch of one through the same kernels (C1 plumbing: `Lbfgs<F> s; auto [sol, prog] = s.Minimize(f, FunctionState(x0));`).
+  std::tuple<function::FunctionState<ScalarType, FunctionType::Dimension>, ProgressType> Minimize(
+      const FunctionType& function, const function::FunctionState<ScalarType, FunctionType::Dimension>& initial) {
+    auto [state, prog] = Minimize(function, StateType::FromHost(initial.x, 1), nullptr);
+    function::FunctionState<ScalarType, FunctionType::Dimension> sol;
+    sol.x = state.x.ToHost();
+    sol.gradient = state.gradient.ToHost();
+    sol.value = state.value.ToHost()[0];
+    ProgressType p = stopping_progress;  // thresholds stay; the counters are the run's
+    p.num_iterations = prog.num_iterations.ToHost()[0];
+    p.x_delta = prog.x_delta.ToHost()[0];
+    p.f_delta = prog.f_delta.ToHost()[0];
+    p.gradient_norm = prog.gradient_norm.ToHost()[0];
+    p.status = static_cast<Status>(prog.status.ToHost()[0]);
+    return {std::move(sol), p};
   }
 
  protected:
@@ -669,26 +782,38 @@ class AugmentedLagrangian {
 }  // namespace solver
 }  // namespace cppoptlib
 
-// Declares (for a host translation unit) the extern "C" launcher that
+// Declares (for a host translation unit) the extern "C" launchers that
 // CNO_INSTANTIATE_FUNCTION(tag, F) defines in an nvcc translation unit, and
-// binds F to it.
-#define CNO_DECLARE_FUNCTION(tag, F)                                                              \
-  extern "C" int cno_##tag##_minimize(int solver, const void* functor_bytes, int64_t batch,       \
-                                      const void* x0, const cno_stop_t* stop,                      \
-                                      const cno_batch_out_t* out, void* workspace,                 \
-                                      size_t workspace_bytes, void* stream,                        \
-                                      cno_launch_info_t* info);                                    \
-  namespace cppoptlib::function {                                                                  \
-  template <>                                                                                      \
-  struct LauncherTraits<F> {                                                                       \
-    template <class E>                                                                             \
-    static void Bind(const F& f, E& e) {                                                           \
-      static_assert(std::is_trivially_copyable_v<F>, "device functors are passed by value");      \
-      e.raw = &cno_##tag##_minimize;                                                               \
-      e.pod.assign(reinterpret_cast<const unsigned char*>(&f),                                    \
-                   reinterpret_cast<const unsigned char*>(&f) + sizeof(F));                       \
-    }                                                                                              \
-  };                                                                                               \
+// binds F to them.
+#define CNO_DECLARE_FUNCTION(tag, F)                                                                             \
+  extern "C" int cno_##tag##_minimize(int solver, int mode, const void* functor_bytes, int64_t batch,            \
+                                      const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out,         \
+                                      void* workspace, size_t workspace_bytes, void* stream,                      \
+                                      cno_launch_info_t* info);                                                   \
+  extern "C" int cno_##tag##_state_bytes(int solver, int64_t batch, size_t* bytes);                               \
+  extern "C" int cno_##tag##_minimize_steps(int solver, int mode, const void* functor_bytes, int64_t batch,       \
+                                            const void* x0, const cno_stop_t* stop,                               \
+                                            const cno_batch_out_t* out, void* state, size_t state_bytes,          \
+                                            int32_t max_iterations, int32_t first_call, void* workspace,          \
+                                            size_t workspace_bytes, void* stream, cno_launch_info_t* info);       \
+  extern "C" int cno_##tag##_evaluate(const void* functor_bytes, int64_t batch, const void* x, void* value,       \
+                                      void* gradient, void* stream);                                              \
+  namespace cppoptlib::function {                                                                                 \
+  template <>                                                                                                     \
+  struct LauncherTraits<F> {                                                                                      \
+    template <class E>                                                                                            \
+    static void Bind(const F& f, E& e) {                                                                          \
+      static_assert(std::is_trivially_copyable_v<F>, "device functors are passed by value");                     \
+      e.raw = &cno_##tag##_minimize;                                                                              \
+      e.raw_state_bytes = &cno_##tag##_state_bytes;                                                               \
+      e.raw_steps = &cno_##tag##_minimize_steps;                                                                  \
+      e.raw_evaluate = &cno_##tag##_evaluate;                                                                     \
+      e.pod.assign(reinterpret_cast<const unsigned char*>(&f),                                                   \
+                   reinterpret_cast<const unsigned char*>(&f) + sizeof(F));                                      \
+    }                                                                                                             \
+  };                                                                                                              \
   }
+
+#include "expressions.h"
 
 #endif  // CPPOPTLIB_B200_CPPOPTLIB_H_

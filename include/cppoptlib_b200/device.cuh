@@ -1,27 +1,45 @@
-// cppoptlib_b200/device.cuh -- compile a USER objective for the device.
+// cppoptlib_b200/device.cuh -- compile a USER objective (or a composite of objectives) for the device.
 //
-// In an nvcc translation unit (-gencode arch=compute_100a,code=sm_100a
-// -fmad=false, include path = cppnumericalsolvers_b200/csrc):
+// In an nvcc translation unit (-gencode arch=compute_100a,code=sm_100a -fmad=false, include path =
+// cppnumericalsolvers_b200/csrc; include THIS header before any other cppoptlib_b200 header):
 //
 //   struct MyF : cppoptlib::function::FunctionCRTP<MyF, double, First, 64> {
 //     double shift;   // POD parameters, passed to the kernel by value
 //     __device__ double operator()(const cno::EvalCtx& ctx, const double (&x)[2],
 //                                  double (*grad)[2]) const { ... }
+//     // Second mode only (function_base.h:103-120, the 3-argument operator()):
+//     __device__ void hess_diag(const cno::EvalCtx&, const double (&x)[2], double (&h)[2]) const;
+//     __device__ void hess_col(const cno::EvalCtx&, const double (&x)[2], int j, bool transposed,
+//                              double (&col)[2]) const;
 //   };
+//   using H = decltype(MyF{} + 0.5 * cppoptlib::function::HalfSquaredNorm<double, 64>{});   // expressions.h
 //   CNO_DECLARE_FUNCTION(myf, MyF)        // host side: binds MyF to the symbols
 //   CNO_INSTANTIATE_FUNCTION(myf, MyF)    // device side: defines the symbols
 //
-// This is the "thin extern-C layer": one symbol per instantiated functor
-// (SURVEY.md 8(b)), behind which Lbfgs/Bfgs/GradientDescent/ConjugatedGradientDescent<MyF>::Minimize launch the same
-// persistent kernels as the built-in families.
+// This is the "thin extern-C layer": one symbol set per instantiated functor, behind
+// which Lbfgs / Bfgs / NewtonDescent / GradientDescent / ConjugatedGradientDescent<MyF>::Minimize,
+// SetCallback (stepwise solves) and FunctionExpr::operator() launch the same persistent kernels as the
+// built-in families:
+//   cno_<tag>_minimize        Solver::Minimize                    (solver.h:181-224)
+//   cno_<tag>_state_bytes /
+//   cno_<tag>_minimize_steps  OptimizationStep rounds + callback  (solver.h:163-176, 226-228; Lbfgs)
+//   cno_<tag>_evaluate        F::operator()(x, &grad) per instance (function_base.h:103-120)
 #ifndef CPPOPTLIB_B200_DEVICE_CUH_
 #define CPPOPTLIB_B200_DEVICE_CUH_
 
+#ifdef CPPOPTLIB_B200_CPPOPTLIB_H_
+#error "include cppoptlib_b200/device.cuh BEFORE cppoptlib_b200/cppoptlib.h in nvcc translation units"
+#endif
+#include "cno_device.cuh"
+#include "cno_functors.cuh"
+#define CPPOPTLIB_B200_WITH_DEVICE 1
 #include "cppoptlib.h"
+#include "expressions.h"
 #include "cno_bfgs.cuh"
 #include "cno_descent.cuh"
-#include "cno_device.cuh"
+#include "cno_evaluate.cuh"
 #include "cno_lbfgs.cuh"
+#include "cno_newton.cuh"
 
 namespace cno {
 template <class Fn, class Smem, class Kernel, class... Extra>
@@ -76,60 +94,150 @@ template <class F>
 using UserLbfgsSmem = LbfgsSmem<typename F::Scalar, F::Dim, CNO_LBFGS_M, StageElems<F>::value,
                                 PolicyScratch<typename PolicyOf<F>::type>::kElemsPerLane, FnTmemCols<F>::value>;
 
-// BFGS keeps a row of the inverse Hessian in registers: D <= 32 only.
-template <class F, class LS = LsMoreThuente, bool Small = (F::Dim <= 32)>
-struct BfgsDispatch {
-  static int run(const F&, int64_t, const void*, const cno_stop_t*, const cno_batch_out_t*, void*,
-                 size_t, void*, cno_launch_info_t*) {
+// ---- which optional members a functor has ----
+template <class F, class = void>
+struct HasHessDiag : std::false_type {};
+template <class F>
+struct HasHessDiag<F, std::void_t<decltype(&F::hess_diag)>> : std::true_type {};
+template <class F, class = void>
+struct HasHessCol : std::false_type {};
+template <class F>
+struct HasHessCol<F, std::void_t<decltype(&F::hess_col)>> : std::true_type {};
+
+template <class F, class LS>
+inline int user_lbfgs(const F& fn, int mode, int64_t batch, const void* x0, const cno_stop_t* stop,
+                      const cno_batch_out_t* out, void* workspace, size_t workspace_bytes, void* stream,
+                      cno_launch_info_t* info) {
+  // Lbfgs on a Second-mode function takes the diagonal-preconditioner branch (lbfgs.h:116-139), unless
+  // the function was bound through a First-mode FunctionExpr (function_base.h:210-230: downgrade)
+  if constexpr (F::Mode == 2 && HasHessDiag<F>::value) {
+    if (mode == 2) {
+      using F2 = SecondMode<F>;
+      if (stop && stop->condition_hessian > 0) return CNO_ERR_UNSUPPORTED;
+      const F2 f2(fn);
+      return launch_user<F2, UserLbfgsSmem<F2>>(lbfgs_minimize_kernel<F2, CNO_LBFGS_M, false, LS>, f2, batch, x0, stop,
+                                                out, workspace, workspace_bytes, stream, info,
+                                                ResumeArgs{nullptr, 0, 0, 0});
+    }
+  }
+  return launch_user<F, UserLbfgsSmem<F>>(lbfgs_minimize_kernel<F, CNO_LBFGS_M, false, LS>, fn, batch, x0, stop, out,
+                                          workspace, workspace_bytes, stream, info, ResumeArgs{nullptr, 0, 0, 0});
+}
+
+template <class F, class LS>
+inline int user_bfgs(const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out,
+                     void* workspace, size_t workspace_bytes, void* stream, cno_launch_info_t* info) {
+  if constexpr (F::Dim <= 32) {  // the register-resident inverse Hessian (cno_bfgs.cuh)
+    return launch_user<F, BfgsSmem<typename F::Scalar, F::Dim>>(bfgs_minimize_kernel<F, LS>, fn, batch, x0, stop, out,
+                                                                 workspace, workspace_bytes, stream, info);
+  } else {
     return CNO_ERR_UNSUPPORTED;
   }
-};
-template <class F, class LS>
-struct BfgsDispatch<F, LS, true> {
-  static int run(const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop,
-                 const cno_batch_out_t* out, void* workspace, size_t workspace_bytes, void* stream,
-                 cno_launch_info_t* info) {
-    return launch_user<F, BfgsSmem<typename F::Scalar, F::Dim>>(
-        bfgs_minimize_kernel<F, LS>, fn, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
+}
+
+template <class F>
+inline int user_newton(const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out,
+                       void* workspace, size_t workspace_bytes, void* stream, cno_launch_info_t* info) {
+  if constexpr (F::Mode == 2 && HasHessCol<F>::value) {
+    using A = SecondOrderAdapter<F>;
+    if (stop && stop->condition_hessian > 0) return CNO_ERR_UNSUPPORTED;
+    return launch_user<A, NewtonSmem<typename F::Scalar, F::Dim>>(newton_minimize_kernel<A>, A{fn}, batch, x0, stop, out,
+                                                                   workspace, workspace_bytes, stream, info);
+  } else {
+    return CNO_ERR_UNSUPPORTED;  // NewtonDescent only supports second-order differentiable functions
   }
-};
+}
+
+template <class F>
+inline int user_minimize(int solver, int mode, const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop,
+                         const cno_batch_out_t* out, void* workspace, size_t workspace_bytes, void* stream,
+                         cno_launch_info_t* info) {
+  using T = typename F::Scalar;
+  switch (solver) {
+    case CNO_LBFGS:
+      return user_lbfgs<F, LsMoreThuente>(fn, mode, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
+    case CNO_LBFGS_HAGER_ZHANG:
+      return user_lbfgs<F, LsHagerZhang>(fn, mode, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
+    case CNO_BFGS:
+      return user_bfgs<F, LsMoreThuente>(fn, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
+    case CNO_BFGS_HAGER_ZHANG:
+      return user_bfgs<F, LsHagerZhang>(fn, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
+    case CNO_NEWTON:
+      return user_newton<F>(fn, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
+    case CNO_GRADIENT_DESCENT:
+      return launch_user<F, DescentSmem<T>>(descent_minimize_kernel<F, false>, fn, batch, x0, stop, out, workspace,
+                                            workspace_bytes, stream, info);
+    case CNO_GRADIENT_DESCENT_HAGER_ZHANG:
+      return launch_user<F, DescentSmem<T>>(descent_minimize_kernel<F, false, LsHagerZhang>, fn, batch, x0, stop, out,
+                                            workspace, workspace_bytes, stream, info);
+    case CNO_CONJUGATED_GRADIENT_DESCENT:
+      if constexpr (sizeof(T) == 8)  // fp64 only: the reference computes beta in double
+        return launch_user<F, DescentSmem<T>>(descent_minimize_kernel<F, true>, fn, batch, x0, stop, out, workspace,
+                                              workspace_bytes, stream, info);
+      else
+        return CNO_ERR_UNSUPPORTED;
+  }
+  return CNO_ERR_UNSUPPORTED;
+}
+
+// stepwise Lbfgs (MoreThuente) for a user functor: the kResume build of the same kernel
+template <class F>
+inline int user_minimize_steps(int solver, int mode, const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop,
+                               const cno_batch_out_t* out, void* state, size_t state_bytes, int32_t max_iterations,
+                               int32_t first_call, void* workspace, size_t workspace_bytes, void* stream,
+                               cno_launch_info_t* info) {
+  using T = typename F::Scalar;
+  using RL = ResumeLayout<T, Shape<F::Dim>::E, CNO_LBFGS_M>;
+  if (solver != CNO_LBFGS || (mode == 2 && F::Mode == 2)) return CNO_ERR_UNSUPPORTED;
+  if (batch < 0 || !out || max_iterations <= 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (!out->x || !out->value || !out->gradient || !out->status || !out->num_iterations) return CNO_ERR_INVALID_ARGUMENT;
+  if (batch > 0 && (!state || state_bytes < (size_t)batch * RL::kBytes || ((uintptr_t)state & 15))) return CNO_ERR_WORKSPACE;
+  if (!x0 && first_call) return CNO_ERR_INVALID_ARGUMENT;
+  return launch_user<F, UserLbfgsSmem<F>>(lbfgs_minimize_kernel<F, CNO_LBFGS_M, true, LsMoreThuente>, fn, batch, x0, stop,
+                                          out, workspace, workspace_bytes, stream, info,
+                                          ResumeArgs{static_cast<unsigned char*>(state), (long long)RL::kBytes,
+                                                     max_iterations, first_call ? 1 : 0});
+}
+template <class F>
+inline int user_state_bytes(int solver, int64_t batch, size_t* bytes) {
+  using RL = ResumeLayout<typename F::Scalar, Shape<F::Dim>::E, CNO_LBFGS_M>;
+  if (solver != CNO_LBFGS) return CNO_ERR_UNSUPPORTED;
+  if (!bytes || batch < 0) return CNO_ERR_INVALID_ARGUMENT;
+  *bytes = (size_t)batch * RL::kBytes;
+  return CNO_OK;
+}
 }  // namespace cno
 
-#define CNO_INSTANTIATE_FUNCTION(tag, F)                                                           \
-  extern "C" int cno_##tag##_minimize(int solver, const void* functor_bytes, int64_t batch,        \
-                                      const void* x0, const cno_stop_t* stop,                       \
-                                      const cno_batch_out_t* out, void* workspace,                  \
-                                      size_t workspace_bytes, void* stream,                         \
-                                      cno_launch_info_t* info) {                                    \
-    F fn;                                                                                           \
-    memcpy(&fn, functor_bytes, sizeof(F));                                                          \
-    if (solver == CNO_LBFGS)                                                                        \
-      return cno::launch_user<F, cno::UserLbfgsSmem<F>>(                                            \
-          cno::lbfgs_minimize_kernel<F, CNO_LBFGS_M>, fn, batch, x0, stop, out, workspace,          \
-          workspace_bytes, stream, info, cno::ResumeArgs{nullptr, 0, 0, 0});                        \
-    if (solver == CNO_BFGS)                                                                         \
-      return cno::BfgsDispatch<F>::run(fn, batch, x0, stop, out, workspace, workspace_bytes,        \
-                                       stream, info);                                               \
-    if (solver == CNO_LBFGS_HAGER_ZHANG)                                                            \
-      return cno::launch_user<F, cno::UserLbfgsSmem<F>>(                                            \
-          cno::lbfgs_minimize_kernel<F, CNO_LBFGS_M, false, cno::LsHagerZhang>, fn, batch, x0,      \
-          stop, out, workspace, workspace_bytes, stream, info, cno::ResumeArgs{nullptr, 0, 0, 0});  \
-    if (solver == CNO_BFGS_HAGER_ZHANG)                                                             \
-      return cno::BfgsDispatch<F, cno::LsHagerZhang>::run(fn, batch, x0, stop, out, workspace,      \
-                                                          workspace_bytes, stream, info);           \
-    if (solver == CNO_GRADIENT_DESCENT_HAGER_ZHANG)                                                 \
-      return cno::launch_user<F, cno::DescentSmem<typename F::Scalar>>(                             \
-          cno::descent_minimize_kernel<F, false, cno::LsHagerZhang>, fn, batch, x0, stop, out,      \
-          workspace, workspace_bytes, stream, info);                                                \
-    if (solver == CNO_GRADIENT_DESCENT)                                                             \
-      return cno::launch_user<F, cno::DescentSmem<typename F::Scalar>>(                             \
-          cno::descent_minimize_kernel<F, false>, fn, batch, x0, stop, out, workspace,              \
-          workspace_bytes, stream, info);                                                           \
-    if (solver == CNO_CONJUGATED_GRADIENT_DESCENT)                                                  \
-      return cno::launch_user<F, cno::DescentSmem<typename F::Scalar>>(                             \
-          cno::descent_minimize_kernel<F, true>, fn, batch, x0, stop, out, workspace,               \
-          workspace_bytes, stream, info);                                                           \
-    return CNO_ERR_UNSUPPORTED;                                                                     \
+#define CNO_INSTANTIATE_FUNCTION(tag, F)                                                                      \
+  static_assert(std::is_trivially_copyable<F>::value, "device functors are passed to the kernel by value");   \
+  extern "C" int cno_##tag##_minimize(int solver, int mode, const void* functor_bytes, int64_t batch,         \
+                                      const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out,      \
+                                      void* workspace, size_t workspace_bytes, void* stream,                   \
+                                      cno_launch_info_t* info) {                                               \
+    alignas(F) unsigned char raw__[sizeof(F)];                                                                 \
+    memcpy(raw__, functor_bytes, sizeof(F));                                                                   \
+    return cno::user_minimize<F>(solver, mode, *reinterpret_cast<const F*>(raw__), batch, x0, stop, out,       \
+                                 workspace, workspace_bytes, stream, info);                                    \
+  }                                                                                                            \
+  extern "C" int cno_##tag##_state_bytes(int solver, int64_t batch, size_t* bytes) {                           \
+    return cno::user_state_bytes<F>(solver, batch, bytes);                                                     \
+  }                                                                                                            \
+  extern "C" int cno_##tag##_minimize_steps(int solver, int mode, const void* functor_bytes, int64_t batch,    \
+                                            const void* x0, const cno_stop_t* stop,                            \
+                                            const cno_batch_out_t* out, void* state, size_t state_bytes,       \
+                                            int32_t max_iterations, int32_t first_call, void* workspace,       \
+                                            size_t workspace_bytes, void* stream, cno_launch_info_t* info) {   \
+    alignas(F) unsigned char raw__[sizeof(F)];                                                                 \
+    memcpy(raw__, functor_bytes, sizeof(F));                                                                   \
+    return cno::user_minimize_steps<F>(solver, mode, *reinterpret_cast<const F*>(raw__), batch, x0, stop, out, \
+                                       state, state_bytes, max_iterations, first_call, workspace,              \
+                                       workspace_bytes, stream, info);                                         \
+  }                                                                                                            \
+  extern "C" int cno_##tag##_evaluate(const void* functor_bytes, int64_t batch, const void* x, void* value,    \
+                                      void* gradient, void* stream) {                                          \
+    alignas(F) unsigned char raw__[sizeof(F)];                                                                 \
+    memcpy(raw__, functor_bytes, sizeof(F));                                                                   \
+    return cno::launch_evaluate<F>(*reinterpret_cast<const F*>(raw__), batch, x, value, gradient, stream);     \
   }
 
 #endif  // CPPOPTLIB_B200_DEVICE_CUH_

@@ -312,3 +312,44 @@ def hz_search_poly(coef, x0: float, alpha_init: float, impl: str = "oracle"):
     fn = oracle_lib().cno_oracle_hz_search_poly if impl == "oracle" else ref_lib().cno_ref_hz_search_poly
     fn(k, C.c_double(x0), C.c_double(alpha_init), C.byref(a), C.byref(f), C.byref(x), C.byref(n))
     return a.value, f.value, x.value, n.value
+
+
+# ---- function composition: the reference's own operators over the ref functors (ref_driver.cc EXPR_*) ----
+(EXPR_BOWL, EXPR_ROSEN_PLUS_HALF, EXPR_PROD, EXPR_SUB, EXPR_PENALTY, EXPR_ZERO_MUL, EXPR_SECOND_SUM,
+ EXPR_SECOND_PROD, EXPR_DOWNGRADE) = range(9)
+
+
+def ref_minimize_expr(expr: int, solver: int, x0: np.ndarray, *, param: float = 0.0, stop: Stop | None = None,
+                      linesearch: int = LS_MORE_THUENTE, policy: int | None = None, threads: int = 0) -> dict:
+    """Solver<decltype(composite)>::Minimize per instance, the composite built with the reference's own
+    operator+ - * / MinZero / MaxZero (function_expressions.h) -- oracle/_ref only."""
+    x0 = np.ascontiguousarray(x0)
+    B, d = x0.shape
+    dt = x0.dtype
+    if policy is None:
+        policy = device_policy(dt)
+    r = dict(x=np.zeros_like(x0), value=np.zeros(B, dt), gradient=np.zeros_like(x0),
+             num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8),
+             nfev=np.zeros(B, np.uint32), x_delta=np.zeros(B, dt), f_delta=np.zeros(B, dt),
+             gradient_norm=np.zeros(B, dt))
+    o = BatchOut(*[r[k].ctypes.data for k in (
+        "x", "value", "gradient", "num_iterations", "status", "nfev", "x_delta", "f_delta", "gradient_norm")])
+    rc = ref_lib().cno_ref_minimize_expr(expr, C.c_double(param), solver, linesearch, _np_dtype(x0), d, policy,
+                                         C.c_int64(B), C.c_void_p(x0.ctypes.data),
+                                         C.byref(stop) if stop is not None else None, C.byref(o), threads)
+    if rc != 0:
+        raise RuntimeError(f"ref minimize_expr failed: {rc}")
+    return r
+
+
+def ref_evaluate_expr(expr: int, x: np.ndarray, *, param: float = 0.0, policy: int | None = None):
+    x = np.ascontiguousarray(x)
+    B, d = x.shape
+    if policy is None:
+        policy = device_policy(x.dtype)
+    f, g = np.zeros(B, x.dtype), np.zeros_like(x)
+    rc = ref_lib().cno_ref_evaluate_expr(expr, C.c_double(param), _np_dtype(x), d, policy, C.c_int64(B),
+                                         C.c_void_p(x.ctypes.data), C.c_void_p(f.ctypes.data), C.c_void_p(g.ctypes.data))
+    if rc != 0:
+        raise RuntimeError(f"ref evaluate_expr failed: {rc}")
+    return f, g

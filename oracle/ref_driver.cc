@@ -19,6 +19,7 @@
 #include "cno_al_oracle.h"
 #include "cno_oracle.h"
 #include "cppoptlib/function.h"
+#include "cppoptlib/function_expressions.h"
 #include "cppoptlib/linesearch/hager_zhang.h"
 #include "cppoptlib/solver/augmented_lagrangian.h"
 #include "cppoptlib/solver/bfgs.h"
@@ -376,6 +377,222 @@ int al_dispatch_family(const cno_problem_t* prob, const cno_constraints_t* cons,
   }
 }
 
+// ---- function composition: the reference's OWN operators (function_expressions.h:403-518)
+// over the functors above.  The device twins are the composites of tests/cpp/user_functions.cu, built from
+// include/cppoptlib_b200/expressions.h; ids = cno_test_expr_t there. ----------------------------------------
+// f(x) = sum_i a_i (x_i - c)^2, a_i = 1 + i/8 (tests/cpp/user_functions.cu: Bowl<D>)
+template <class T, DifferentiabilityMode Mode>
+struct Bowl : FunctionCRTP<Bowl<T, Mode>, T, Mode>, Payload<T> {
+  using Base = FunctionCRTP<Bowl<T, Mode>, T, Mode>;
+  using typename Base::MatrixType;
+  using typename Base::VectorType;
+  T c = T(0);
+  T operator()(const VectorType& x, VectorType* grad = nullptr, MatrixType* hess = nullptr) const {
+    this->count();
+    const int d = static_cast<int>(x.size());
+    VectorType t(d);
+    if (grad) *grad = VectorType::Zero(d);
+    if (hess) *hess = MatrixType::Zero(d, d);
+    for (int i = 0; i < d; ++i) {
+      const T a = T(1.0) + T(0.125) * i;
+      const T r = x[i] - c;
+      t[i] = a * r * r;
+      if (grad) (*grad)[i] = T(2.0) * a * r;
+      if (hess) (*hess)(i, i) = T(2.0) * a;
+    }
+    return t.sum();
+  }
+};
+// src/test/augmented_lagrangian_test.cc: DiagonalQuadratic2dSecond, f = 2 x0^2 + x1^2
+template <class T, DifferentiabilityMode Mode>
+struct DiagonalQuadratic2d : FunctionCRTP<DiagonalQuadratic2d<T, Mode>, T, Mode>, Payload<T> {
+  using Base = FunctionCRTP<DiagonalQuadratic2d<T, Mode>, T, Mode>;
+  using typename Base::MatrixType;
+  using typename Base::VectorType;
+  T operator()(const VectorType& x, VectorType* grad = nullptr, MatrixType* hess = nullptr) const {
+    this->count();
+    if (grad) {
+      *grad = VectorType::Zero(2);
+      (*grad)[0] = 4 * x[0];
+      (*grad)[1] = 2 * x[1];
+    }
+    if (hess) {
+      *hess = MatrixType::Zero(2, 2);
+      (*hess)(0, 0) = 4;
+      (*hess)(1, 1) = 2;
+    }
+    return 2 * x[0] * x[0] + x[1] * x[1];
+  }
+};
+
+enum {  // keep in step with tests/cpp/user_functions.cu and tests/expr_ids.py
+  EXPR_BOWL = 0,            // Bowl(c = param)
+  EXPR_ROSEN_PLUS_HALF = 1, // Rosenbrock + 0.5 * HalfSquaredNorm
+  EXPR_PROD = 2,            // (HalfSquaredNorm + 1) * (Rosenbrock + 1)
+  EXPR_SUB = 3,             // (2 * Rosenbrock - (-HalfSquaredNorm)) - 3
+  EXPR_PENALTY = 4,         // Rosenbrock + 5 (MaxZero(h - 2))^2 + 5 (MinZero(h - 1/8))^2,  h = HalfSquaredNorm
+  EXPR_ZERO_MUL = 5,        // 0 * Rosenbrock + HalfSquaredNorm
+  EXPR_SECOND_SUM = 6,      // RosenbrockFull + 0.5 * HalfSquaredNorm(Second)
+  EXPR_SECOND_PROD = 7,     // (DiagQuadratic(Second) + 1) * (HalfSquaredNorm(Second) + 1), d = 2
+  EXPR_DOWNGRADE = 8        // DiagonalQuadratic2d(Second) used through FunctionExpr<First> (function_base.h:210-230)
+};
+
+template <class T, class Solver, class Fn>
+void run_expr_solver(const Fn& f, uint32_t* counter, int d, int64_t b, const T* x0, const cno_stop_t* stop,
+                     const cno_batch_out_t* out) {
+  using State = FunctionState<T, Eigen::Dynamic>;
+  typename Fn::VectorType x(d);
+  for (int i = 0; i < d; ++i) x[i] = x0[i];
+  auto progress = cppoptlib::solver::DefaultStoppingSolverProgress<Fn, State>();
+  if (stop) {
+    progress.num_iterations = stop->num_iterations;
+    progress.x_delta = static_cast<T>(stop->x_delta);
+    progress.x_delta_violations = stop->x_delta_violations;
+    progress.f_delta = static_cast<T>(stop->f_delta);
+    progress.f_delta_violations = stop->f_delta_violations;
+    progress.f_delta_relative = stop->f_delta_relative != 0;
+    progress.gradient_norm = static_cast<T>(stop->gradient_norm);
+    progress.gradient_norm_relative = stop->gradient_norm_relative != 0;
+    progress.condition_hessian = static_cast<T>(stop->condition_hessian);
+    progress.past = stop->past;
+    progress.past_delta = static_cast<T>(stop->past_delta);
+  }
+  Solver solver(progress);
+  auto [solution, state] = solver.Minimize(f, State(x));
+  if (out->x) for (int i = 0; i < d; ++i) static_cast<T*>(out->x)[b * d + i] = solution.x[i];
+  if (out->gradient) for (int i = 0; i < d; ++i) static_cast<T*>(out->gradient)[b * d + i] = solution.gradient[i];
+  if (out->value) static_cast<T*>(out->value)[b] = solution.value;
+  if (out->num_iterations) out->num_iterations[b] = static_cast<uint32_t>(state.num_iterations);
+  if (out->status) out->status[b] = static_cast<int8_t>(state.status);
+  if (out->nfev) out->nfev[b] = *counter;
+  if (out->x_delta) static_cast<T*>(out->x_delta)[b] = state.x_delta;
+  if (out->f_delta) static_cast<T*>(out->f_delta)[b] = state.f_delta;
+  if (out->gradient_norm) static_cast<T*>(out->gradient_norm)[b] = state.gradient_norm;
+}
+
+// what to do with a composite once it is built: minimise it or evaluate it
+template <class T>
+struct ExprJob {
+  int solver;      // < 0: evaluate
+  int linesearch;
+  int d;
+  int64_t b;
+  const T* x;
+  const cno_stop_t* stop;
+  const cno_batch_out_t* out;  // minimise
+  T* value;                    // evaluate
+  T* gradient;
+  uint32_t* counter;
+};
+
+template <class T, class Fn>
+int expr_first_mode(const Fn& f, const ExprJob<T>& j) {
+  namespace ls = cppoptlib::solver::linesearch;
+  if (j.solver < 0) {
+    typename Fn::VectorType x(j.d), g(j.d);
+    for (int i = 0; i < j.d; ++i) x[i] = j.x[i];
+    const T v = f(x, &g);
+    if (j.value) j.value[j.b] = v;
+    if (j.gradient) for (int i = 0; i < j.d; ++i) j.gradient[j.b * j.d + i] = g[i];
+    return 0;
+  }
+  if (j.linesearch == CNO_LS_HAGER_ZHANG) {
+    if (j.solver == CNO_LBFGS) run_expr_solver<T, cppoptlib::solver::Lbfgs<Fn, 10, ls::HagerZhang>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out);
+    else if (j.solver == CNO_BFGS) run_expr_solver<T, cppoptlib::solver::Bfgs<Fn, ls::HagerZhang>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out);
+    else return CNO_ERR_UNSUPPORTED;
+    return 0;
+  }
+  switch (j.solver) {
+    case CNO_LBFGS: run_expr_solver<T, cppoptlib::solver::Lbfgs<Fn>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out); return 0;
+    case CNO_BFGS: run_expr_solver<T, cppoptlib::solver::Bfgs<Fn>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out); return 0;
+    case CNO_GRADIENT_DESCENT: run_expr_solver<T, cppoptlib::solver::GradientDescent<Fn>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out); return 0;
+    case CNO_CONJUGATED_GRADIENT_DESCENT:
+      if constexpr (std::is_same_v<T, double>) {
+        run_expr_solver<T, cppoptlib::solver::ConjugatedGradientDescent<Fn>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out);
+        return 0;
+      }
+      return CNO_ERR_UNSUPPORTED;
+  }
+  return CNO_ERR_UNSUPPORTED;
+}
+template <class T, class Fn>
+int expr_second_mode(const Fn& f, const ExprJob<T>& j) {
+  if (j.solver == CNO_NEWTON) { run_expr_solver<T, cppoptlib::solver::NewtonDescent<Fn>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out); return 0; }
+  if (j.solver == CNO_LBFGS && j.linesearch == CNO_LS_MORE_THUENTE) {  // Lbfgs on a Second-mode function: preconditioner branch
+    run_expr_solver<T, cppoptlib::solver::Lbfgs<Fn>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out);
+    return 0;
+  }
+  return expr_first_mode<T, Fn>(f, j);
+}
+
+template <class T>
+int expr_dispatch(int expr, double param, const ExprJob<T>& j) {
+  using namespace cppoptlib::function;
+  constexpr auto First = DifferentiabilityMode::First;
+  constexpr auto Second = DifferentiabilityMode::Second;
+  auto tag = [&](auto& f) { f.shared_nfev = j.counter; };
+  switch (expr) {
+    case EXPR_BOWL: {
+      Bowl<T, First> f; tag(f); f.c = static_cast<T>(param);
+      return expr_first_mode<T>(f, j);
+    }
+    case EXPR_ROSEN_PLUS_HALF: {
+      Rosenbrock<T, First> r; tag(r);
+      HalfSquaredNorm<T, First> h; tag(h);
+      const auto f = r + T(0.5) * h;
+      return expr_first_mode<T>(f, j);
+    }
+    case EXPR_PROD: {
+      Rosenbrock<T, First> r; tag(r);
+      HalfSquaredNorm<T, First> h; tag(h);
+      const auto f = (h + T(1)) * (r + T(1));
+      return expr_first_mode<T>(f, j);
+    }
+    case EXPR_SUB: {
+      Rosenbrock<T, First> r; tag(r);
+      HalfSquaredNorm<T, First> h; tag(h);
+      const auto f = (T(2) * r - (-h)) - T(3);
+      return expr_first_mode<T>(f, j);
+    }
+    case EXPR_PENALTY: {
+      Rosenbrock<T, First> r; tag(r);
+      HalfSquaredNorm<T, First> h; tag(h);
+      const auto g1 = h - T(2);
+      const auto g2 = h - T(0.125);
+      using G1 = std::decay_t<decltype(g1)>;
+      using G2 = std::decay_t<decltype(g2)>;
+      const MaxZeroExpression<G1> p1(g1);
+      const MinZeroExpression<G2> p2(g2);
+      const auto f = (r + T(5) * (p1 * p1)) + T(5) * (p2 * p2);
+      return expr_first_mode<T>(f, j);
+    }
+    case EXPR_ZERO_MUL: {
+      Rosenbrock<T, First> r; tag(r);
+      HalfSquaredNorm<T, First> h; tag(h);
+      const auto f = T(0) * r + h;
+      return expr_first_mode<T>(f, j);
+    }
+    case EXPR_SECOND_SUM: {
+      Rosenbrock<T, Second> r; tag(r);
+      HalfSquaredNorm<T, Second> h; tag(h);
+      const auto f = r + T(0.5) * h;
+      return expr_second_mode<T>(f, j);
+    }
+    case EXPR_SECOND_PROD: {
+      DiagQuadratic<T, Second> q; tag(q);
+      HalfSquaredNorm<T, Second> h; tag(h);
+      const auto f = (q + T(1)) * (h + T(1));
+      return expr_second_mode<T>(f, j);
+    }
+    case EXPR_DOWNGRADE: {
+      DiagonalQuadratic2d<T, Second> q; tag(q);
+      const FunctionExpr<T, First, Eigen::Dynamic> wrapped = q;  // function_base.h:210-230
+      return expr_first_mode<T>(wrapped, j);
+    }
+  }
+  return CNO_ERR_INVALID_ARGUMENT;
+}
+
 // The 1-D quartic of src/test/hager_zhang_test.cc:40-85, Horner form (cno_oracle_hz_search_poly).
 struct Poly1D : FunctionCRTP<Poly1D, double, DifferentiabilityMode::First, 1> {
   double c4 = 0, c3 = 0, c2 = 0, c1 = 0, c0 = 0;
@@ -492,6 +709,54 @@ int cno_ref_al_minimize(const cno_problem_t* objective, const cno_constraints_t*
       r = al_dispatch_family<float>(objective, constraints, b, static_cast<const float*>(x0) + b * d, e, q,
                                     penalty0 ? static_cast<const float*>(penalty0)[b] : 0.0f, inner_stop,
                                     outer_stop, config, out);
+    }
+    if (r) rc = r;
+  }
+  return rc;
+}
+
+// Minimise / evaluate one of the composites above per instance (expr = EXPR_*; param = Bowl's c).
+int cno_ref_minimize_expr(int expr, double param, int solver, int linesearch, int dtype, int d, int policy, int64_t batch,
+                          const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out, int threads) {
+  if (!x0 || !out || d <= 0) return CNO_ERR_INVALID_ARGUMENT;
+  Eigen::cno_policy_ref() = policy;
+  int rc = 0;
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#else
+  threads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (int64_t b = 0; b < batch; ++b) {
+    uint32_t counter = 0;
+    int r;
+    if (dtype == CNO_F64) {
+      const ExprJob<double> j{solver, linesearch, d, b, static_cast<const double*>(x0) + b * d, stop, out, nullptr, nullptr, &counter};
+      r = expr_dispatch<double>(expr, param, j);
+    } else {
+      const ExprJob<float> j{solver, linesearch, d, b, static_cast<const float*>(x0) + b * d, stop, out, nullptr, nullptr, &counter};
+      r = expr_dispatch<float>(expr, param, j);
+    }
+    if (r) rc = r;
+  }
+  return rc;
+}
+int cno_ref_evaluate_expr(int expr, double param, int dtype, int d, int policy, int64_t batch, const void* x, void* value,
+                          void* gradient) {
+  if (!x || d <= 0) return CNO_ERR_INVALID_ARGUMENT;
+  Eigen::cno_policy_ref() = policy;
+  int rc = 0;
+  for (int64_t b = 0; b < batch; ++b) {
+    uint32_t counter = 0;
+    int r;
+    if (dtype == CNO_F64) {
+      const ExprJob<double> j{-1, 0, d, b, static_cast<const double*>(x) + b * d, nullptr, nullptr,
+                              static_cast<double*>(value), static_cast<double*>(gradient), &counter};
+      r = expr_dispatch<double>(expr, param, j);
+    } else {
+      const ExprJob<float> j{-1, 0, d, b, static_cast<const float*>(x) + b * d, nullptr, nullptr,
+                             static_cast<float*>(value), static_cast<float*>(gradient), &counter};
+      r = expr_dispatch<float>(expr, param, j);
     }
     if (r) rc = r;
   }

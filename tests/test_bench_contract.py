@@ -39,3 +39,16 @@ def test_algorithmic_bytes_model():
     for K in (10, 11, 640):
         assert bench.algorithmic_bytes(np.array([K])) == 1024 * (26 * K - 110)
     assert bench.algorithmic_bytes(np.array([3])) == 8 * 128 * (6 * 3 + 2 * (0 + 1 + 2))
+
+
+def test_reference_arm_ignores_torchrun_omp_num_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arms set their thread count explicitly."""
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1",
+                        "--steps", "1", "--warmup", "0", "--ref-seconds", "0.5"],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    cores = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == cores and d["cpu_port_same_cores"]["cores"] == cores
+    assert d["config"]["host_threads"] == cores and d["config"]["omp_num_threads_env"] == "1"
