@@ -36,7 +36,7 @@ class Problem(C.Structure):  # cno_problem_t
     _fields_ = [
         ("family", C.c_int32), ("dtype", C.c_int32), ("d", C.c_int32), ("n", C.c_int32),
         ("param", C.c_double), ("data", C.c_void_p), ("data_stride", C.c_int64),
-        ("policy", C.c_int32), ("mode", C.c_int32),
+        ("policy", C.c_int32), ("mode", C.c_int32), ("lbfgs_m", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -91,6 +91,7 @@ EXPORTS = (
     "cno_conservative_stop", "cno_supported", "cno_workspace_bytes", "cno_minimize",
     "cno_state_bytes", "cno_minimize_steps",
     "cno_minimize_host", "cno_release_host_arena", "cno_evaluate", "cno_fill_uniform", "cno_done_bitmap", "cno_device_cstep",
+    "cno_allgather_done", "cno_count_done",
 )
 
 _lib = None

@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *sources()]
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *sources(), "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
@@ -66,6 +66,11 @@ def build_cpp_tests(verbose: bool = False) -> list:
     cmd = ["g++", "-std=c++17", "-O2", "-Wall", os.path.join(src, "al_host.cc"), *inc,
            "-o", os.path.join(out, "al_host"), *link]
     subprocess.run(cmd, check=True)
+    # the multi-GPU path below Python: MinimizeSharded + cno_allgather_done (NCCL resolved with dlopen)
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-pthread", os.path.join(src, "sharded_nccl.cc"), *inc,
+           "-o", os.path.join(out, "sharded_nccl"), *link, "-ldl"]
+    subprocess.run(cmd, check=True)
+    exes.append(os.path.join(out, "sharded_nccl"))
     nvcc = os.environ.get("NVCC", f"{cuda}/bin/nvcc")
     xlink = ["-Xlinker", f"-rpath={HERE}"]
     dev_flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -7,6 +7,8 @@
 // canonical build forms no FMAs (generator.bzl:13, Dockerfile.test:111).
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
+
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -92,9 +94,7 @@ struct LaunchArgs {
 template <class Fn, int M, bool kResume = false, class LS = cno::LsMoreThuente>
 int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
   using T = typename Fn::Scalar;
-  using SM = cno::LbfgsSmem<T, Fn::Dim, M, cno::StageElems<Fn>::value,
-                            cno::PolicyScratch<typename cno::PolicyOf<Fn>::type>::kElemsPerLane,
-                            cno::FnTmemCols<Fn>::value>;
+  using SM = typename cno::LbfgsPlan<Fn, M, kResume, LS>::SM;
   auto kernel = cno::lbfgs_minimize_kernel<Fn, M, kResume, LS>;
   const size_t smem = SM::kWarpBytes * SM::kWarps;
   CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -121,13 +121,25 @@ int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
   return CNO_OK;
 }
 
-// One persistent launch of bfgs_minimize_kernel<Fn>.
+// One persistent launch of bfgs_minimize_kernel<Fn> (D <= 32: inverse Hessian in registers) or
+// bfgs_smem_minimize_kernel<Fn> (D > 32: in shared memory).
+template <class Fn, class LS, bool kBig = (Fn::Dim > 32)>
+struct BfgsKernelOf {
+  using SM = cno::BfgsSmem<typename Fn::Scalar, Fn::Dim>;
+  static auto kernel() { return cno::bfgs_minimize_kernel<Fn, LS>; }
+};
+template <class Fn, class LS>
+struct BfgsKernelOf<Fn, LS, true> {
+  using SM = cno::BfgsBigSmem<typename Fn::Scalar, Fn::Dim>;
+  static auto kernel() { return cno::bfgs_smem_minimize_kernel<Fn, LS>; }
+};
 template <class Fn, class LS = cno::LsMoreThuente>
 int launch_bfgs(const Fn& fn, const LaunchArgs& a) {
   using T = typename Fn::Scalar;
-  using SM = cno::BfgsSmem<T, Fn::Dim>;
-  auto kernel = cno::bfgs_minimize_kernel<Fn, LS>;
+  using SM = typename BfgsKernelOf<Fn, LS>::SM;
+  auto kernel = BfgsKernelOf<Fn, LS>::kernel();
   const size_t smem = SM::kWarpBytes * SM::kWarps;
+  CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = 0;
   int rc = device_sm_count(&sms);
   if (rc) return rc;
@@ -265,6 +277,11 @@ template <class T, int D>
 int lbfgs_rosenbrock(const LaunchArgs& a) {
   return launch_lbfgs<cno::RosenbrockFn<T, D>, CNO_LBFGS_M>(cno::RosenbrockFn<T, D>{}, a);
 }
+// Lbfgs<F, m> for m other than the default (lbfgs.h:40-41)
+template <class T, int D, int M>
+int lbfgs_rosenbrock_m(const LaunchArgs& a) {
+  return launch_lbfgs<cno::RosenbrockFn<T, D>, M>(cno::RosenbrockFn<T, D>{}, a);
+}
 // "parity mode": Eigen-SSE2-model reduction order (CNO_POLICY_EIGEN_SSE2), d = 128 fp64
 int lbfgs_rosenbrock_d128_eigen(const LaunchArgs& a) {
   using Fn = cno::RosenbrockFn<double, 128, cno::PolicyEigenSSE2>;
@@ -299,6 +316,10 @@ template <class T, int D>
 int lbfgs_rosenbrock_steps(const LaunchArgs& a) {
   return launch_lbfgs<cno::RosenbrockFn<T, D>, CNO_LBFGS_M, true>(cno::RosenbrockFn<T, D>{}, a);
 }
+template <class Fn>
+int lbfgs_steps_stateless(const LaunchArgs& a) {  // functors without parameters
+  return launch_lbfgs<Fn, CNO_LBFGS_M, true>(Fn{}, a);
+}
 template <class T, int D>
 size_t lbfgs_state_stride() {
   return cno::ResumeLayout<T, cno::Shape<D>::E, CNO_LBFGS_M>::kBytes;
@@ -323,29 +344,48 @@ struct Entry {
   int mode = 0;     // 2 = Lbfgs on a Second-mode function (cno_problem_t::mode)
   launcher_t steps_fn = nullptr;          // stepwise variant (cno_minimize_steps), if instantiated
   size_t (*state_stride)() = nullptr;     // bytes of one parked instance
+  int m = CNO_LBFGS_M;                    // Lbfgs<F, m>: pairs kept (cno_problem_t::lbfgs_m)
 };
 
 // Every (solver, functor, T, D) compiled into this library.
 const Entry kTable[] = {
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 2, lbfgs_rosenbrock<double, 2>, -1, 0,
      lbfgs_rosenbrock_steps<double, 2>, lbfgs_state_stride<double, 2>},
-    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 3, lbfgs_rosenbrock<double, 3>},
-    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 8, lbfgs_rosenbrock<double, 8>},
-    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 32, lbfgs_rosenbrock<double, 32>},
-    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock<double, 37>},
-    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 64, lbfgs_rosenbrock<double, 64>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 3, lbfgs_rosenbrock<double, 3>, -1, 0,
+     lbfgs_rosenbrock_steps<double, 3>, lbfgs_state_stride<double, 3>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 8, lbfgs_rosenbrock<double, 8>, -1, 0,
+     lbfgs_rosenbrock_steps<double, 8>, lbfgs_state_stride<double, 8>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 32, lbfgs_rosenbrock<double, 32>, -1, 0,
+     lbfgs_rosenbrock_steps<double, 32>, lbfgs_state_stride<double, 32>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock<double, 37>, -1, 0,
+     lbfgs_rosenbrock_steps<double, 37>, lbfgs_state_stride<double, 37>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 64, lbfgs_rosenbrock<double, 64>, -1, 0,
+     lbfgs_rosenbrock_steps<double, 64>, lbfgs_state_stride<double, 64>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock<double, 128>, -1, 0,
      lbfgs_rosenbrock_steps<double, 128>, lbfgs_state_stride<double, 128>},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock_d128_eigen, CNO_POLICY_EIGEN_SSE2},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 2, lbfgs_rosenbrock_second<double, 2>, -1, 2},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock_second<double, 37>, -1, 2},
     {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock_second<double, 128>, -1, 2},
-    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 2, lbfgs_rosenbrock<float, 2>},
-    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 37, lbfgs_rosenbrock<float, 37>},
-    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 128, lbfgs_rosenbrock<float, 128>},
-    {CNO_LBFGS, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, lbfgs_diag_quadratic<double>},
-    {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, lbfgs_half_sq_norm<double, 2>},
-    {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 50, lbfgs_half_sq_norm<double, 50>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 8, lbfgs_rosenbrock_m<double, 8, 5>, -1, 0, nullptr, nullptr, 5},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock_m<double, 37, 5>, -1, 0, nullptr, nullptr, 5},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock_m<double, 128, 5>, -1, 0, nullptr, nullptr, 5},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 8, lbfgs_rosenbrock_m<double, 8, 20>, -1, 0, nullptr, nullptr, 20},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgs_rosenbrock_m<double, 37, 20>, -1, 0, nullptr, nullptr, 20},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgs_rosenbrock_m<double, 128, 20>, -1, 0, nullptr, nullptr, 20},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 37, lbfgs_rosenbrock_m<float, 37, 5>, -1, 0, nullptr, nullptr, 5},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 2, lbfgs_rosenbrock<float, 2>, -1, 0,
+     lbfgs_rosenbrock_steps<float, 2>, lbfgs_state_stride<float, 2>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 37, lbfgs_rosenbrock<float, 37>, -1, 0,
+     lbfgs_rosenbrock_steps<float, 37>, lbfgs_state_stride<float, 37>},
+    {CNO_LBFGS, CNO_FN_ROSENBROCK, CNO_F32, 128, lbfgs_rosenbrock<float, 128>, -1, 0,
+     lbfgs_rosenbrock_steps<float, 128>, lbfgs_state_stride<float, 128>},
+    {CNO_LBFGS, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, lbfgs_diag_quadratic<double>, -1, 0,
+     lbfgs_steps_stateless<cno::DiagQuadraticFn<double>>, lbfgs_state_stride<double, 2>},
+    {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, lbfgs_half_sq_norm<double, 2>, -1, 0,
+     lbfgs_steps_stateless<cno::HalfSquaredNormFn<double, 2>>, lbfgs_state_stride<double, 2>},
+    {CNO_LBFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 50, lbfgs_half_sq_norm<double, 50>, -1, 0,
+     lbfgs_steps_stateless<cno::HalfSquaredNormFn<double, 50>>, lbfgs_state_stride<double, 50>},
     {CNO_LBFGS, CNO_FN_LOGISTIC, CNO_F32, 64, lbfgs_logistic<float, 64, 256>},
     {CNO_LBFGS, CNO_FN_DENSE_QUADRATIC, CNO_F64, 2, lbfgs_dense_quadratic<double, 2>},
     {CNO_LBFGS, CNO_FN_DENSE_QUADRATIC, CNO_F64, 8, lbfgs_dense_quadratic<double, 8>},
@@ -354,6 +394,10 @@ const Entry kTable[] = {
     {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 8, bfgs_rosenbrock<double, 8>},
     {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 32, bfgs_rosenbrock<double, 32>},
     {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F32, 32, bfgs_rosenbrock<float, 32>},
+    {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 37, bfgs_rosenbrock<double, 37>},    // D > 32: H in shared memory
+    {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 64, bfgs_rosenbrock<double, 64>},
+    {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F64, 128, bfgs_rosenbrock<double, 128>},
+    {CNO_BFGS, CNO_FN_ROSENBROCK, CNO_F32, 128, bfgs_rosenbrock<float, 128>},
     {CNO_BFGS, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, bfgs_diag_quadratic<double>},
     {CNO_BFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, bfgs_half_sq_norm<double, 2>},
     {CNO_NEWTON, CNO_FN_DENSE_QUADRATIC, CNO_F64, 64, newton_dense_quadratic<double, 64>},
@@ -378,6 +422,7 @@ const Entry kTable[] = {
     {CNO_LBFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F32, 37, lbfgs_rosenbrock_hz<float, 37>},
     {CNO_BFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 8, bfgs_rosenbrock_hz<double, 8>},
     {CNO_BFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 32, bfgs_rosenbrock_hz<double, 32>},
+    {CNO_BFGS_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 64, bfgs_rosenbrock_hz<double, 64>},
     {CNO_GRADIENT_DESCENT_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 8, gd_rosenbrock_hz<double, 8>},
     {CNO_GRADIENT_DESCENT_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 37, gd_rosenbrock_hz<double, 37>},
 };
@@ -421,8 +466,10 @@ const EvalEntry kEvalTable[] = {
 
 const Entry* find_entry(int solver, const cno_problem_t* p) {
   const int dflt = (p->dtype == CNO_F64) ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE;
+  const bool is_lbfgs = (solver == CNO_LBFGS || solver == CNO_LBFGS_HAGER_ZHANG);
+  const int m = (is_lbfgs && p->lbfgs_m > 0) ? p->lbfgs_m : CNO_LBFGS_M;
   for (const Entry& e : kTable)
-    if (e.solver == solver && e.family == p->family && e.dtype == p->dtype && e.d == p->d &&
+    if (e.solver == solver && e.family == p->family && e.dtype == p->dtype && e.d == p->d && e.m == m &&
         ((e.policy < 0) ? dflt : e.policy) == p->policy &&
         ((solver == CNO_BFGS || solver == CNO_NEWTON) || (e.mode == 2) == (p->mode == 2)))
       return &e;
@@ -475,6 +522,21 @@ __global__ void done_bitmap_kernel(const int8_t* status, long long batch, uint32
                     (status[i] != CNO_STATUS_NOT_STARTED);
   const unsigned m = __ballot_sync(0xffffffffu, done);
   if ((threadIdx.x & 31) == 0 && i < batch) words[i >> 5] = m;
+}
+
+// set bits among the first `bits` bits of a bitmap
+__global__ void count_bits_kernel(const uint32_t* words, long long bits, unsigned long long* total) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nw = (bits + 31) / 32;
+  unsigned c = 0;
+  if (w < nw) {
+    uint32_t v = words[w];
+    const long long rem = bits - w * 32;
+    if (rem < 32) v &= (rem <= 0) ? 0u : ((1u << rem) - 1u);
+    c = __popc(v);
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, (unsigned long long)c);
 }
 
 __global__ void cstep_kernel(double* io, int* flags) {
@@ -992,6 +1054,57 @@ int cno_done_bitmap(const int8_t* status, int64_t batch, uint32_t* words, void* 
   const long long blocks = (batch + block - 1) / block;
   done_bitmap_kernel<<<(unsigned)blocks, block, 0, static_cast<cudaStream_t>(stream)>>>(status, batch, words);
   CNO_CUDA(cudaGetLastError());
+  return CNO_OK;
+}
+
+// ncclAllGather(sendbuff, recvbuff, sendcount, datatype, comm, stream), resolved at first use so that libcno.so
+// has no link-time dependency on NCCL (ncclUint32 = 3 in every NCCL 2.x nccl.h).
+typedef int (*nccl_allgather_t)(const void*, void*, size_t, int, void*, cudaStream_t);
+static nccl_allgather_t resolve_nccl_allgather() {
+  static std::once_flag once;
+  static nccl_allgather_t fn = nullptr;
+  std::call_once(once, [] {
+    void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");  // already in the process (e.g. loaded by PyTorch)
+    if (!sym) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (h) sym = dlsym(h, "ncclAllGather");
+    }
+    fn = reinterpret_cast<nccl_allgather_t>(sym);
+  });
+  return fn;
+}
+
+int cno_allgather_done(void* comm, const uint32_t* local_words, uint32_t* all_words, size_t words, void* stream) {
+  if (!comm || !local_words || !all_words) return CNO_ERR_INVALID_ARGUMENT;
+  if (words == 0) return CNO_OK;
+  const nccl_allgather_t allgather = resolve_nccl_allgather();
+  if (!allgather) return CNO_ERR_UNSUPPORTED;
+  const int rc = allgather(local_words, all_words, words, /*ncclUint32*/ 3, comm, static_cast<cudaStream_t>(stream));
+  if (rc != 0) { g_last_cuda = cudaErrorUnknown; return CNO_ERR_CUDA; }
+  return CNO_OK;
+}
+
+int cno_count_done(const uint32_t* all_words, int32_t ranks, size_t words_per_rank, const int64_t* bits_per_rank,
+                   int64_t* total_done, void* stream) {
+  if (!all_words || ranks <= 0 || !bits_per_rank || !total_done) return CNO_ERR_INVALID_ARGUMENT;
+  if (!have_device()) return CNO_ERR_NO_DEVICE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DeviceBuffer dcount;
+  CNO_CUDA(dcount.alloc(sizeof(unsigned long long)));
+  CNO_CUDA(cudaMemsetAsync(dcount.p, 0, sizeof(unsigned long long), s));
+  for (int r = 0; r < ranks; ++r) {
+    const long long bits = (long long)bits_per_rank[r];
+    if (bits < 0 || (size_t)((bits + 31) / 32) > words_per_rank) return CNO_ERR_INVALID_ARGUMENT;
+    if (bits == 0) continue;
+    const long long nw = (bits + 31) / 32;
+    count_bits_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, s>>>(all_words + (size_t)r * words_per_rank, bits,
+                                                                   static_cast<unsigned long long*>(dcount.p));
+    CNO_CUDA(cudaGetLastError());
+  }
+  unsigned long long h = 0;
+  CNO_CUDA(cudaMemcpyAsync(&h, dcount.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  CNO_CUDA(cudaStreamSynchronize(s));
+  *total_done = (int64_t)h;
   return CNO_OK;
 }
 

@@ -35,6 +35,8 @@ struct RosenbrockFn {
   static constexpr int E = Shape<D>::E;
 
   static constexpr bool kHasPartial = true;
+  // fp64, 4 elements per lane, default policy: light enough for 20 resident warps (cno_device.cuh: FnPreferredWarps)
+  static constexpr int kPreferredWarps = (sizeof(T) == 8 && E == 4 && std::is_same<P, PolicyFast>::value) ? 20 : 16;
   __device__ __forceinline__ T operator()(const EvalCtx& c, const T (&x)[E],
                                           T (*grad)[E]) const {
     return warp_sum_p<P, T, E>(partial(c, x, grad), RedCtx<T>{static_cast<T*>(c.stage), c.lane});

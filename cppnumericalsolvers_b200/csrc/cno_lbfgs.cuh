@@ -30,13 +30,9 @@
 #include "cno_linesearch.cuh"
 #include "cno_kernel_params.h"
 
-#ifndef CNO_LBFGS_MAX_WARPS
-#define CNO_LBFGS_MAX_WARPS 16  // resident warps per SM of the L-BFGS kernels (register budget: 65536 / (32 * warps))
-#endif
-
 namespace cno {
 
-template <class T, int D, int M, int kStage = 0, int kScratchPerLane = 0, int kFnTmem = 0>
+template <class T, int D, int M, int kStage = 0, int kScratchPerLane = 0, int kFnTmem = 0, int kMaxW = 16>
 struct LbfgsSmem {
   static constexpr int E = Shape<D>::E;
   static constexpr int kVec = 32 * E;                        // elements per stored vector
@@ -52,7 +48,7 @@ struct LbfgsSmem {
   static constexpr int kMaxSmem = 227 * 1024;
   static constexpr int kWarpsFit = (int)(kMaxSmem / kWarpBytes);
   // a functor that keeps data in Tensor Memory limits the warps per lane quadrant
-  static constexpr int kMaxWarps = CNO_LBFGS_MAX_WARPS;
+  static constexpr int kMaxWarps = kMaxW;  // register budget: 65536 / (32 * warps) per thread (FnPreferredWarps)
   static constexpr int kTmemColsPerWarp = M * 8;             // a stored y vector = 8 columns of the warp's 32 lanes
   static constexpr int kTmemYCap = kTmemY ? 4 * (512 / kTmemColsPerWarp) : kMaxWarps;  // warps per lane quadrant x 4
   static constexpr int kTmemWarpCap = kFnTmem > 0 ? 4 * (512 / kFnTmem) : kTmemYCap;
@@ -173,10 +169,19 @@ struct ResumeLayout {
   static constexpr size_t kBytes = ((kInts + kNumInts * sizeof(int) + 15) / 16) * 16;
 };
 
+// The shared-memory / warp plan of lbfgs_minimize_kernel<Fn, M, kResume, LS>.  The functor's preferred warp
+// count applies to the plain kernel only (MoreThuente, First mode, fused): the other variants carry more live
+// state per thread and keep the 128-register budget.
 template <class Fn, int M, bool kResume = false, class LS = LsMoreThuente>
-__global__ void __launch_bounds__(LbfgsSmem<typename Fn::Scalar, Fn::Dim, M, StageElems<Fn>::value,
-                                            PolicyScratch<typename PolicyOf<Fn>::type>::kElemsPerLane,
-                                            FnTmemCols<Fn>::value>::kWarps * 32, 1)
+struct LbfgsPlan {
+  static constexpr bool kPlain = std::is_same<LS, LsMoreThuente>::value && !IsSecondMode<Fn>::value && !kResume;
+  using SM = LbfgsSmem<typename Fn::Scalar, Fn::Dim, M, StageElems<Fn>::value,
+                       PolicyScratch<typename PolicyOf<Fn>::type>::kElemsPerLane, FnTmemCols<Fn>::value,
+                       kPlain ? FnPreferredWarps<Fn>::value : 16>;
+};
+
+template <class Fn, int M, bool kResume = false, class LS = LsMoreThuente>
+__global__ void __launch_bounds__(LbfgsPlan<Fn, M, kResume, LS>::SM::kWarps * 32, 1)
 lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
                       const long long batch, const StopParams<typename Fn::Scalar> stop,
                       const BatchOut<typename Fn::Scalar> out,
@@ -188,7 +193,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   using P = typename PolicyOf<Fn>::type;
   constexpr bool kSecond = IsSecondMode<Fn>::value;  // lbfgs.h:116-118 has_diagonal_preconditioner
   constexpr int kFnTmem = FnTmemCols<Fn>::value;
-  using SM = LbfgsSmem<T, D, M, kStage, PolicyScratch<P>::kElemsPerLane, kFnTmem>;
+  using SM = typename LbfgsPlan<Fn, M, kResume, LS>::SM;
   using SV = SmemVec<T, E>;
   constexpr T eps = Num<T>::eps;
 

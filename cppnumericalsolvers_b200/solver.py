@@ -125,13 +125,17 @@ class Solver:
         self._callback = callback
         self._callback_every = max(1, int(every))
 
+    def _problem(self, function: Function):
+        """cno_problem_t of `function` as this solver uses it (Lbfgs adds its template parameter m)."""
+        return function.problem()
+
     def supports_steps(self, function: Function) -> bool:
-        p = function.problem()
+        p = self._problem(function)
         n = C.c_size_t(0)
         return _lib.lib().cno_state_bytes(self._solver_id, C.byref(p), 1, C.byref(n)) == _lib.OK
 
     def supported(self, function: Function) -> bool:
-        p = function.problem()
+        p = self._problem(function)
         return _lib.lib().cno_supported(self._solver_id, C.byref(p)) == _lib.OK
 
     def Minimize(self, function: Function, state: BatchedFunctionState,
@@ -145,7 +149,7 @@ class Solver:
         x0 = x0.contiguous()
         dev, dt, B, d = x0.device, x0.dtype, x0.shape[0], x0.shape[1]
         L = _lib.lib()
-        prob = function.problem()
+        prob = self._problem(function)
         with torch.cuda.device(dev):
             x = torch.empty_like(x0)
             g = torch.empty_like(x0)
@@ -218,7 +222,7 @@ class Solver:
         self._callback_every = max(1, int(every))
         x0 = state.x.contiguous()
         dev, dt, B = x0.device, x0.dtype, x0.shape[0]
-        prob = function.problem()
+        prob = self._problem(function)
         with torch.cuda.device(dev):
             x, g = torch.empty_like(x0), torch.empty_like(x0)
             f, xd, fd, gn = (torch.empty(B, dtype=dt, device=dev) for _ in range(4))
@@ -259,7 +263,7 @@ class Solver:
         out = _lib.BatchOut(x.data_ptr(), f.data_ptr(), g.data_ptr(), it.data_ptr(),
                             st.data_ptr(), nf.data_ptr(), xd.data_ptr(), fd.data_ptr(),
                             gn.data_ptr())
-        prob = function.problem()
+        prob = self._problem(function)
         stop = self.stopping_progress.to_c()
         info = _lib.LaunchInfo()
         _lib.check(_lib.lib().cno_minimize_host(
@@ -290,9 +294,18 @@ class _LineSearchSolver(Solver):
 
 
 class Lbfgs(_LineSearchSolver):
-    """solver/lbfgs.h:40-324 (m = 10; LineSearch = MoreThuente unless given)."""
+    """solver/lbfgs.h:40-324: Lbfgs<F, m = 10, LineSearch = MoreThuente>; `m` = pairs kept (compiled: 5, 10, 20)."""
     _solver_id = _lib.LBFGS
     _solver_ids = {MoreThuente: _lib.LBFGS, HagerZhang: _lib.LBFGS_HAGER_ZHANG}
+
+    def __init__(self, progress: Optional[Progress] = None, linesearch=MoreThuente, m: int = 10):
+        super().__init__(progress, linesearch)
+        self.m = int(m)
+
+    def _problem(self, function: Function):
+        p = function.problem()
+        p.lbfgs_m = self.m
+        return p
 
 
 class Bfgs(_LineSearchSolver):

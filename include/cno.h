@@ -51,7 +51,7 @@ extern "C" {
 #endif
 
 #define CNO_VERSION_MAJOR 0
-#define CNO_VERSION_MINOR 1
+#define CNO_VERSION_MINOR 2
 
 /* solver/progress.h:37-47 (same numeric values as the reference enum). */
 typedef enum cno_status {
@@ -147,6 +147,9 @@ typedef struct cno_problem {
   int32_t mode;        /* 0/1 = use the functor as a First-mode function; 2 = Second mode:
                           Lbfgs then takes its diagonal-preconditioner branch
                           (solver/lbfgs.h:116-139,177-179).  NewtonDescent is always Second. */
+  int32_t lbfgs_m;     /* the `m` of Lbfgs<F, m, LineSearch> (solver/lbfgs.h:40-41): pairs kept; 0 = the
+                          reference's default 10.  Compiled: 5, 10, 20 (cno_supported tells). */
+  int32_t reserved_;
 } cno_problem_t;
 
 /* Per-instance outputs.  Any pointer may be NULL (not written).  x, value,
@@ -247,6 +250,16 @@ int cno_fill_uniform(int dtype, void* dst, int64_t first, int64_t count,
  * all-gather for the global stop test. */
 int cno_done_bitmap(const int8_t* status, int64_t batch, uint32_t* words,
                     void* stream);
+
+/* The ONE collective of the path: all-gathers the per-GPU convergence bitmaps for the global
+ * stop test.  comm = an ncclComm_t of the caller (one rank per GPU), local_words / all_words device pointers
+ * ([words] and [nranks * words] uint32), stream a cudaStream_t.  NCCL is resolved at first use (dlopen of
+ * libnccl.so.2 -- the copy already loaded by the process, e.g. PyTorch's, or the system one); without it the
+ * call returns CNO_ERR_UNSUPPORTED.  cno_count_done then counts the set bits of the first `bits` bits of each
+ * of the `ranks` bitmaps on the device and returns the total through a host pointer (synchronises the stream). */
+int cno_allgather_done(void* comm, const uint32_t* local_words, uint32_t* all_words, size_t words, void* stream);
+int cno_count_done(const uint32_t* all_words, int32_t ranks, size_t words_per_rank, const int64_t* bits_per_rank,
+                   int64_t* total_done, void* stream);
 
 /* Device-side known-answer hook for MoreThuente::cstep
  * (linesearch/more_thuente.h:261-407): runs the device cstep on one thread.

@@ -129,11 +129,11 @@ struct FunctionCRTP {
 // expressions.h) through the extern "C" symbols generated by CNO_INSTANTIATE_FUNCTION(tag, F).
 // `mode` = the DifferentiabilityMode the function is USED with (a Second-mode functor bound through a
 // First-mode FunctionExpr is minimised as a First-mode function: function_base.h:210-230).
-typedef int (*RawMinimizeFn)(int solver, int mode, const void* functor_bytes, int64_t batch, const void* x0,
+typedef int (*RawMinimizeFn)(int solver, int mode, int lbfgs_m, const void* functor_bytes, int64_t batch, const void* x0,
                              const cno_stop_t* stop, const cno_batch_out_t* out, void* workspace,
                              size_t workspace_bytes, void* stream, cno_launch_info_t* info);
 typedef int (*RawStateBytesFn)(int solver, int64_t batch, size_t* bytes);
-typedef int (*RawMinimizeStepsFn)(int solver, int mode, const void* functor_bytes, int64_t batch, const void* x0,
+typedef int (*RawMinimizeStepsFn)(int solver, int mode, int lbfgs_m, const void* functor_bytes, int64_t batch, const void* x0,
                                   const cno_stop_t* stop, const cno_batch_out_t* out, void* state,
                                   size_t state_bytes, int32_t max_iterations, int32_t first_call, void* workspace,
                                   size_t workspace_bytes, void* stream, cno_launch_info_t* info);
@@ -433,6 +433,7 @@ class Solver {
     constexpr int D = FunctionType::Dimension;
     const int64_t B = function_state.batch;
     function::FunctionExpr<T, FunctionType::Differentiability, D> expr(function);
+    expr.problem.lbfgs_m = lbfgs_m();
 
     StateType result;
     result.batch = B;
@@ -474,7 +475,7 @@ class Solver {
                         "SetCallback (stepwise solves: cno_state_bytes)");
       detail::DeviceArray<unsigned char> state(nbytes < 16 ? 16 : nbytes);
       for (int first = 1;; first = 0) {
-        rc = expr.raw ? expr.raw_steps(SolverId, expr.mode(), expr.pod.data(), B, function_state.x.data(), &stop, &out,
+        rc = expr.raw ? expr.raw_steps(SolverId, expr.mode(), lbfgs_m(), expr.pod.data(), B, function_state.x.data(), &stop, &out,
                                        state.data(), state.size(), callback_every_, first, workspace.data(),
                                        workspace.size(), stream, nullptr)
                       : cno_minimize_steps(SolverId, &expr.problem, B, function_state.x.data(), &stop, &out,
@@ -490,13 +491,90 @@ class Solver {
       return {std::move(result), std::move(prog)};
     }
     if (expr.raw) {
-      rc = expr.raw(SolverId, expr.mode(), expr.pod.data(), B, function_state.x.data(), &stop, &out,
+      rc = expr.raw(SolverId, expr.mode(), lbfgs_m(), expr.pod.data(), B, function_state.x.data(), &stop, &out,
                     workspace.data(), workspace.size(), stream, &prog.launch);
     } else {
       rc = cno_minimize(SolverId, &expr.problem, B, function_state.x.data(), &stop, &out,
                         workspace.data(), workspace.size(), stream, &prog.launch);
     }
     detail::check_cno(rc, "Minimize");
+    return {std::move(result), std::move(prog)};
+  }
+
+  // Multi-GPU Minimize: one process (or thread) per GPU, the batch sharded contiguously.  This
+  // rank's shard advances `every` iterations per round (cno_minimize_steps); after each round the ranks'
+  // convergence bitmaps are all-gathered -- the ONE NCCL collective of the path (cno_allgather_done) -- and all
+  // ranks leave the loop together once every instance of every shard has terminated.  `nccl_comm` is the caller's
+  // ncclComm_t (one rank per GPU); shard_sizes[r] = instances of rank r.  Results per instance are bit-identical to
+  // an unsharded Minimize.
+  std::tuple<StateType, BatchedProgress<ScalarType>> MinimizeSharded(const FunctionType& function,
+                                                                     const StateType& shard_state, void* nccl_comm,
+                                                                     int rank, const std::vector<int64_t>& shard_sizes,
+                                                                     int every = 64, cudaStream_t stream = nullptr) {
+    using T = ScalarType;
+    constexpr int D = FunctionType::Dimension;
+    const int world = static_cast<int>(shard_sizes.size());
+    if (rank < 0 || rank >= world || shard_sizes[rank] != shard_state.batch)
+      throw std::invalid_argument("MinimizeSharded: shard_sizes[rank] must equal the shard's batch");
+    const int64_t B = shard_state.batch;
+    int64_t max_shard = 0, global = 0;
+    for (int64_t n : shard_sizes) { max_shard = n > max_shard ? n : max_shard; global += n; }
+    const size_t words = static_cast<size_t>((max_shard + 31) / 32);
+    function::FunctionExpr<T, FunctionType::Differentiability, D> expr(function);
+    expr.problem.lbfgs_m = lbfgs_m();
+    if (expr.raw && (!expr.raw_steps || !expr.raw_state_bytes))
+      throw std::runtime_error("MinimizeSharded: this function has no stepwise launcher");
+
+    StateType result;
+    result.batch = B;
+    result.x = detail::DeviceArray<T>(B * D);
+    result.gradient = detail::DeviceArray<T>(B * D);
+    result.value = detail::DeviceArray<T>(B);
+    BatchedProgress<T> prog;
+    prog.batch = B;
+    prog.num_iterations = detail::DeviceArray<uint32_t>(B);
+    prog.nfev = detail::DeviceArray<uint32_t>(B);
+    prog.status = detail::DeviceArray<int8_t>(B);
+    prog.x_delta = detail::DeviceArray<T>(B);
+    prog.f_delta = detail::DeviceArray<T>(B);
+    prog.gradient_norm = detail::DeviceArray<T>(B);
+    cno_batch_out_t out{};
+    out.x = result.x.data();
+    out.value = result.value.data();
+    out.gradient = result.gradient.data();
+    out.num_iterations = prog.num_iterations.data();
+    out.status = prog.status.data();
+    out.nfev = prog.nfev.data();
+    out.x_delta = prog.x_delta.data();
+    out.f_delta = prog.f_delta.data();
+    out.gradient_norm = prog.gradient_norm.data();
+
+    detail::DeviceArray<unsigned char> workspace(256);
+    auto local = detail::DeviceArray<uint32_t>::FromHost(std::vector<uint32_t>(words, 0u));
+    detail::DeviceArray<uint32_t> all(words * static_cast<size_t>(world));
+    const cno_stop_t stop = stopping_progress.to_c();
+    size_t nbytes = 0;
+    detail::check_cno(expr.raw ? expr.raw_state_bytes(SolverId, B, &nbytes)
+                               : cno_state_bytes(SolverId, &expr.problem, B, &nbytes),
+                      "MinimizeSharded (stepwise solves: cno_state_bytes)");
+    detail::DeviceArray<unsigned char> state(nbytes < 16 ? 16 : nbytes);
+    int rounds = 0;
+    for (int first = 1;; first = 0) {
+      const int rc =
+          expr.raw ? expr.raw_steps(SolverId, expr.mode(), lbfgs_m(), expr.pod.data(), B, shard_state.x.data(), &stop, &out,
+                                    state.data(), state.size(), every, first, workspace.data(), workspace.size(), stream,
+                                    nullptr)
+                   : cno_minimize_steps(SolverId, &expr.problem, B, shard_state.x.data(), &stop, &out, state.data(),
+                                        state.size(), every, first, workspace.data(), workspace.size(), stream, nullptr);
+      detail::check_cno(rc, "cno_minimize_steps");
+      ++rounds;
+      detail::check_cno(cno_done_bitmap(prog.status.data(), B, local.data(), stream), "cno_done_bitmap");
+      detail::check_cno(cno_allgather_done(nccl_comm, local.data(), all.data(), words, stream), "cno_allgather_done");
+      int64_t done = 0;
+      detail::check_cno(cno_count_done(all.data(), world, words, shard_sizes.data(), &done, stream), "cno_count_done");
+      if (done == global) break;  // the same count on every rank: all leave together
+    }
+    prog.launch.kernel_launches = rounds;
     return {std::move(result), std::move(prog)};
   }
 
@@ -519,6 +597,7 @@ class Solver {
   }
 
  protected:
+  virtual int lbfgs_m() const { return 0; }  // Lbfgs<F, m>: pairs kept (0 = not an L-BFGS solver / the default)
   CallbackType step_callback_;
   int callback_every_ = 1;
 };
@@ -594,10 +673,15 @@ struct HagerZhang {
 }  // namespace linesearch
 
 // solver/lbfgs.h:40-42: Lbfgs<F, m = 10, LineSearch = MoreThuente>
+// (built-in families: m = 5, 10, 20 are compiled into libcno.so; user functors: the m given to
+// CNO_INSTANTIATE_FUNCTION_M -- any other combination throws CNO_ERR_UNSUPPORTED)
 template <class F, int m = CNO_LBFGS_M, class LineSearch = linesearch::MoreThuente>
 class Lbfgs : public Solver<F, LineSearch::solver_id(CNO_LBFGS)> {
-  static_assert(m == CNO_LBFGS_M, "the kernels are compiled for m = 10 (the reference's default)");
+  static_assert(m >= 1 && m <= 24, "Lbfgs<F, m>: 1 <= m <= 24");
+ public:
   using Solver<F, LineSearch::solver_id(CNO_LBFGS)>::Solver;
+ protected:
+  int lbfgs_m() const override { return m; }
 };
 // solver/bfgs.h:39-41: Bfgs<F, LineSearch = MoreThuente>
 template <class F, class LineSearch = linesearch::MoreThuente>
@@ -786,12 +870,12 @@ class AugmentedLagrangian {
 // CNO_INSTANTIATE_FUNCTION(tag, F) defines in an nvcc translation unit, and
 // binds F to them.
 #define CNO_DECLARE_FUNCTION(tag, F)                                                                             \
-  extern "C" int cno_##tag##_minimize(int solver, int mode, const void* functor_bytes, int64_t batch,            \
+  extern "C" int cno_##tag##_minimize(int solver, int mode, int lbfgs_m, const void* functor_bytes, int64_t batch, \
                                       const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out,         \
                                       void* workspace, size_t workspace_bytes, void* stream,                      \
                                       cno_launch_info_t* info);                                                   \
   extern "C" int cno_##tag##_state_bytes(int solver, int64_t batch, size_t* bytes);                               \
-  extern "C" int cno_##tag##_minimize_steps(int solver, int mode, const void* functor_bytes, int64_t batch,       \
+  extern "C" int cno_##tag##_minimize_steps(int solver, int mode, int lbfgs_m, const void* functor_bytes, int64_t batch, \
                                             const void* x0, const cno_stop_t* stop,                               \
                                             const cno_batch_out_t* out, void* state, size_t state_bytes,          \
                                             int32_t max_iterations, int32_t first_call, void* workspace,          \

@@ -89,11 +89,6 @@ inline int launch_user(Kernel kernel, const Fn& fn, int64_t batch, const void* x
   }
   return CNO_OK;
 }
-// shared-memory plan of lbfgs_minimize_kernel<F, CNO_LBFGS_M> for a user functor
-template <class F>
-using UserLbfgsSmem = LbfgsSmem<typename F::Scalar, F::Dim, CNO_LBFGS_M, StageElems<F>::value,
-                                PolicyScratch<typename PolicyOf<F>::type>::kElemsPerLane, FnTmemCols<F>::value>;
-
 // ---- which optional members a functor has ----
 template <class F, class = void>
 struct HasHessDiag : std::false_type {};
@@ -104,10 +99,11 @@ struct HasHessCol : std::false_type {};
 template <class F>
 struct HasHessCol<F, std::void_t<decltype(&F::hess_col)>> : std::true_type {};
 
-template <class F, class LS>
-inline int user_lbfgs(const F& fn, int mode, int64_t batch, const void* x0, const cno_stop_t* stop,
+template <class F, class LS, int M>
+inline int user_lbfgs(const F& fn, int mode, int lbfgs_m, int64_t batch, const void* x0, const cno_stop_t* stop,
                       const cno_batch_out_t* out, void* workspace, size_t workspace_bytes, void* stream,
                       cno_launch_info_t* info) {
+  if (lbfgs_m != 0 && lbfgs_m != M) return CNO_ERR_UNSUPPORTED;  // this tag was compiled for Lbfgs<F, M>
   // Lbfgs on a Second-mode function takes the diagonal-preconditioner branch (lbfgs.h:116-139), unless
   // the function was bound through a First-mode FunctionExpr (function_base.h:210-230: downgrade)
   if constexpr (F::Mode == 2 && HasHessDiag<F>::value) {
@@ -115,12 +111,12 @@ inline int user_lbfgs(const F& fn, int mode, int64_t batch, const void* x0, cons
       using F2 = SecondMode<F>;
       if (stop && stop->condition_hessian > 0) return CNO_ERR_UNSUPPORTED;
       const F2 f2(fn);
-      return launch_user<F2, UserLbfgsSmem<F2>>(lbfgs_minimize_kernel<F2, CNO_LBFGS_M, false, LS>, f2, batch, x0, stop,
+      return launch_user<F2, typename LbfgsPlan<F2, M, false, LS>::SM>(lbfgs_minimize_kernel<F2, M, false, LS>, f2, batch, x0, stop,
                                                 out, workspace, workspace_bytes, stream, info,
                                                 ResumeArgs{nullptr, 0, 0, 0});
     }
   }
-  return launch_user<F, UserLbfgsSmem<F>>(lbfgs_minimize_kernel<F, CNO_LBFGS_M, false, LS>, fn, batch, x0, stop, out,
+  return launch_user<F, typename LbfgsPlan<F, M, false, LS>::SM>(lbfgs_minimize_kernel<F, M, false, LS>, fn, batch, x0, stop, out,
                                           workspace, workspace_bytes, stream, info, ResumeArgs{nullptr, 0, 0, 0});
 }
 
@@ -130,8 +126,9 @@ inline int user_bfgs(const F& fn, int64_t batch, const void* x0, const cno_stop_
   if constexpr (F::Dim <= 32) {  // the register-resident inverse Hessian (cno_bfgs.cuh)
     return launch_user<F, BfgsSmem<typename F::Scalar, F::Dim>>(bfgs_minimize_kernel<F, LS>, fn, batch, x0, stop, out,
                                                                  workspace, workspace_bytes, stream, info);
-  } else {
-    return CNO_ERR_UNSUPPORTED;
+  } else {  // the inverse Hessian in shared memory
+    return launch_user<F, BfgsBigSmem<typename F::Scalar, F::Dim>>(bfgs_smem_minimize_kernel<F, LS>, fn, batch, x0, stop,
+                                                                    out, workspace, workspace_bytes, stream, info);
   }
 }
 
@@ -148,16 +145,16 @@ inline int user_newton(const F& fn, int64_t batch, const void* x0, const cno_sto
   }
 }
 
-template <class F>
-inline int user_minimize(int solver, int mode, const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop,
+template <class F, int M>
+inline int user_minimize(int solver, int mode, int lbfgs_m, const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop,
                          const cno_batch_out_t* out, void* workspace, size_t workspace_bytes, void* stream,
                          cno_launch_info_t* info) {
   using T = typename F::Scalar;
   switch (solver) {
     case CNO_LBFGS:
-      return user_lbfgs<F, LsMoreThuente>(fn, mode, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
+      return user_lbfgs<F, LsMoreThuente, M>(fn, mode, lbfgs_m, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
     case CNO_LBFGS_HAGER_ZHANG:
-      return user_lbfgs<F, LsHagerZhang>(fn, mode, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
+      return user_lbfgs<F, LsHagerZhang, M>(fn, mode, lbfgs_m, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
     case CNO_BFGS:
       return user_bfgs<F, LsMoreThuente>(fn, batch, x0, stop, out, workspace, workspace_bytes, stream, info);
     case CNO_BFGS_HAGER_ZHANG:
@@ -181,26 +178,26 @@ inline int user_minimize(int solver, int mode, const F& fn, int64_t batch, const
 }
 
 // stepwise Lbfgs (MoreThuente) for a user functor: the kResume build of the same kernel
-template <class F>
-inline int user_minimize_steps(int solver, int mode, const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop,
+template <class F, int M>
+inline int user_minimize_steps(int solver, int mode, int lbfgs_m, const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop,
                                const cno_batch_out_t* out, void* state, size_t state_bytes, int32_t max_iterations,
                                int32_t first_call, void* workspace, size_t workspace_bytes, void* stream,
                                cno_launch_info_t* info) {
   using T = typename F::Scalar;
-  using RL = ResumeLayout<T, Shape<F::Dim>::E, CNO_LBFGS_M>;
-  if (solver != CNO_LBFGS || (mode == 2 && F::Mode == 2)) return CNO_ERR_UNSUPPORTED;
+  using RL = ResumeLayout<T, Shape<F::Dim>::E, M>;
+  if (solver != CNO_LBFGS || (mode == 2 && F::Mode == 2) || (lbfgs_m != 0 && lbfgs_m != M)) return CNO_ERR_UNSUPPORTED;
   if (batch < 0 || !out || max_iterations <= 0) return CNO_ERR_INVALID_ARGUMENT;
   if (!out->x || !out->value || !out->gradient || !out->status || !out->num_iterations) return CNO_ERR_INVALID_ARGUMENT;
   if (batch > 0 && (!state || state_bytes < (size_t)batch * RL::kBytes || ((uintptr_t)state & 15))) return CNO_ERR_WORKSPACE;
   if (!x0 && first_call) return CNO_ERR_INVALID_ARGUMENT;
-  return launch_user<F, UserLbfgsSmem<F>>(lbfgs_minimize_kernel<F, CNO_LBFGS_M, true, LsMoreThuente>, fn, batch, x0, stop,
+  return launch_user<F, typename LbfgsPlan<F, M, true, LsMoreThuente>::SM>(lbfgs_minimize_kernel<F, M, true, LsMoreThuente>, fn, batch, x0, stop,
                                           out, workspace, workspace_bytes, stream, info,
                                           ResumeArgs{static_cast<unsigned char*>(state), (long long)RL::kBytes,
                                                      max_iterations, first_call ? 1 : 0});
 }
-template <class F>
+template <class F, int M>
 inline int user_state_bytes(int solver, int64_t batch, size_t* bytes) {
-  using RL = ResumeLayout<typename F::Scalar, Shape<F::Dim>::E, CNO_LBFGS_M>;
+  using RL = ResumeLayout<typename F::Scalar, Shape<F::Dim>::E, M>;
   if (solver != CNO_LBFGS) return CNO_ERR_UNSUPPORTED;
   if (!bytes || batch < 0) return CNO_ERR_INVALID_ARGUMENT;
   *bytes = (size_t)batch * RL::kBytes;
@@ -208,30 +205,32 @@ inline int user_state_bytes(int solver, int64_t batch, size_t* bytes) {
 }
 }  // namespace cno
 
-#define CNO_INSTANTIATE_FUNCTION(tag, F)                                                                      \
+// CNO_INSTANTIATE_FUNCTION_M(tag, F, M): the same with the L-BFGS kernels compiled for Lbfgs<F, M> (lbfgs.h:40-41).
+#define CNO_INSTANTIATE_FUNCTION(tag, F) CNO_INSTANTIATE_FUNCTION_M(tag, F, CNO_LBFGS_M)
+#define CNO_INSTANTIATE_FUNCTION_M(tag, F, M)                                                                 \
   static_assert(std::is_trivially_copyable<F>::value, "device functors are passed to the kernel by value");   \
-  extern "C" int cno_##tag##_minimize(int solver, int mode, const void* functor_bytes, int64_t batch,         \
+  extern "C" int cno_##tag##_minimize(int solver, int mode, int lbfgs_m, const void* functor_bytes, int64_t batch, \
                                       const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out,      \
                                       void* workspace, size_t workspace_bytes, void* stream,                   \
                                       cno_launch_info_t* info) {                                               \
     alignas(F) unsigned char raw__[sizeof(F)];                                                                 \
     memcpy(raw__, functor_bytes, sizeof(F));                                                                   \
-    return cno::user_minimize<F>(solver, mode, *reinterpret_cast<const F*>(raw__), batch, x0, stop, out,       \
-                                 workspace, workspace_bytes, stream, info);                                    \
+    return cno::user_minimize<F, M>(solver, mode, lbfgs_m, *reinterpret_cast<const F*>(raw__), batch, x0, stop, out, \
+                                    workspace, workspace_bytes, stream, info);                                 \
   }                                                                                                            \
   extern "C" int cno_##tag##_state_bytes(int solver, int64_t batch, size_t* bytes) {                           \
-    return cno::user_state_bytes<F>(solver, batch, bytes);                                                     \
+    return cno::user_state_bytes<F, M>(solver, batch, bytes);                                                  \
   }                                                                                                            \
-  extern "C" int cno_##tag##_minimize_steps(int solver, int mode, const void* functor_bytes, int64_t batch,    \
+  extern "C" int cno_##tag##_minimize_steps(int solver, int mode, int lbfgs_m, const void* functor_bytes, int64_t batch, \
                                             const void* x0, const cno_stop_t* stop,                            \
                                             const cno_batch_out_t* out, void* state, size_t state_bytes,       \
                                             int32_t max_iterations, int32_t first_call, void* workspace,       \
                                             size_t workspace_bytes, void* stream, cno_launch_info_t* info) {   \
     alignas(F) unsigned char raw__[sizeof(F)];                                                                 \
     memcpy(raw__, functor_bytes, sizeof(F));                                                                   \
-    return cno::user_minimize_steps<F>(solver, mode, *reinterpret_cast<const F*>(raw__), batch, x0, stop, out, \
-                                       state, state_bytes, max_iterations, first_call, workspace,              \
-                                       workspace_bytes, stream, info);                                         \
+    return cno::user_minimize_steps<F, M>(solver, mode, lbfgs_m, *reinterpret_cast<const F*>(raw__), batch, x0, stop, \
+                                          out, state, state_bytes, max_iterations, first_call, workspace,      \
+                                          workspace_bytes, stream, info);                                      \
   }                                                                                                            \
   extern "C" int cno_##tag##_evaluate(const void* functor_bytes, int64_t batch, const void* x, void* value,    \
                                       void* gradient, void* stream) {                                          \

@@ -18,6 +18,11 @@
 #include "cno_al_oracle.h"
 #include "cno_oracle.h"
 
+#define CNO_ORACLE_MAX_M 32
+static inline int problem_lbfgs_m(const cno_problem_t* p) {
+  return (p->lbfgs_m > 0 && p->lbfgs_m <= CNO_ORACLE_MAX_M) ? p->lbfgs_m : CNO_LBFGS_M;
+}
+
 /* ---- double ---- */
 #define REAL double
 #define FN(name) name##_f64

@@ -53,7 +53,7 @@ class Problem(C.Structure):
     _fields_ = [
         ("family", C.c_int32), ("dtype", C.c_int32), ("d", C.c_int32), ("n", C.c_int32),
         ("param", C.c_double), ("data", C.c_void_p), ("data_stride", C.c_int64),
-        ("policy", C.c_int32), ("mode", C.c_int32),
+        ("policy", C.c_int32), ("mode", C.c_int32), ("lbfgs_m", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -104,7 +104,7 @@ LS_MORE_THUENTE, LS_HAGER_ZHANG = 0, 1
 
 def minimize(solver: int, family: int, x0: np.ndarray, *, policy: int | None = None, stop: Stop | None = None,
              data: np.ndarray | None = None, n: int = 0, param: float = 0.0, threads: int = 0,
-             impl: str = "oracle", mode: int = 0, linesearch: int = LS_MORE_THUENTE) -> dict:
+             impl: str = "oracle", mode: int = 0, linesearch: int = LS_MORE_THUENTE, lbfgs_m: int = 0) -> dict:
     """Runs the CPU oracle ("oracle") or the reference-headers build ("ref").  linesearch = the
     LineSearch template parameter of Lbfgs / Bfgs / GradientDescent (HagerZhang: oracle only)."""
     x0 = np.ascontiguousarray(x0)
@@ -117,7 +117,7 @@ def minimize(solver: int, family: int, x0: np.ndarray, *, policy: int | None = N
         data = np.ascontiguousarray(data, dtype=dt)
     p = Problem(family, _np_dtype(x0), d, n, param,
                 data.ctypes.data if data is not None else None,
-                data.shape[1] if data is not None else 0, policy, mode)
+                data.shape[1] if data is not None else 0, policy, mode, lbfgs_m)
     r = dict(x=np.zeros_like(x0), value=np.zeros(B, dt), gradient=np.zeros_like(x0),
              num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8),
              nfev=np.zeros(B, np.uint32), x_delta=np.zeros(B, dt), f_delta=np.zeros(B, dt),
@@ -320,7 +320,8 @@ def hz_search_poly(coef, x0: float, alpha_init: float, impl: str = "oracle"):
 
 
 def ref_minimize_expr(expr: int, solver: int, x0: np.ndarray, *, param: float = 0.0, stop: Stop | None = None,
-                      linesearch: int = LS_MORE_THUENTE, policy: int | None = None, threads: int = 0) -> dict:
+                      linesearch: int = LS_MORE_THUENTE, policy: int | None = None, threads: int = 0,
+                      lbfgs_m: int = 0) -> dict:
     """Solver<decltype(composite)>::Minimize per instance, the composite built with the reference's own
     operator+ - * / MinZero / MaxZero (function_expressions.h) -- oracle/_ref only."""
     x0 = np.ascontiguousarray(x0)
@@ -336,7 +337,7 @@ def ref_minimize_expr(expr: int, solver: int, x0: np.ndarray, *, param: float = 
         "x", "value", "gradient", "num_iterations", "status", "nfev", "x_delta", "f_delta", "gradient_norm")])
     rc = ref_lib().cno_ref_minimize_expr(expr, C.c_double(param), solver, linesearch, _np_dtype(x0), d, policy,
                                          C.c_int64(B), C.c_void_p(x0.ctypes.data),
-                                         C.byref(stop) if stop is not None else None, C.byref(o), threads)
+                                         C.byref(stop) if stop is not None else None, C.byref(o), threads, lbfgs_m)
     if rc != 0:
         raise RuntimeError(f"ref minimize_expr failed: {rc}")
     return r

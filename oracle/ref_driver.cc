@@ -210,6 +210,14 @@ void dispatch_solver(int solver, const cno_problem_t* prob, int64_t b,
     using Fn = Family<T, DifferentiabilityMode::Second>;
     Fn f;
     run_one<T, cppoptlib::solver::Lbfgs<Fn>>(f, prob, b, x0, stop, out);
+  } else if (solver == CNO_LBFGS && prob->lbfgs_m == 5) {  // Lbfgs<F, m> (lbfgs.h:40-41)
+    using Fn = Family<T, DifferentiabilityMode::First>;
+    Fn f;
+    run_one<T, cppoptlib::solver::Lbfgs<Fn, 5>>(f, prob, b, x0, stop, out);
+  } else if (solver == CNO_LBFGS && prob->lbfgs_m == 20) {
+    using Fn = Family<T, DifferentiabilityMode::First>;
+    Fn f;
+    run_one<T, cppoptlib::solver::Lbfgs<Fn, 20>>(f, prob, b, x0, stop, out);
   } else if (solver == CNO_LBFGS) {
     using Fn = Family<T, DifferentiabilityMode::First>;
     Fn f;
@@ -474,6 +482,7 @@ void run_expr_solver(const Fn& f, uint32_t* counter, int d, int64_t b, const T* 
 template <class T>
 struct ExprJob {
   int solver;      // < 0: evaluate
+  int lbfgs_m;     // Lbfgs<Fn, m>: 0 / 10 = the default, 5
   int linesearch;
   int d;
   int64_t b;
@@ -500,6 +509,10 @@ int expr_first_mode(const Fn& f, const ExprJob<T>& j) {
     if (j.solver == CNO_LBFGS) run_expr_solver<T, cppoptlib::solver::Lbfgs<Fn, 10, ls::HagerZhang>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out);
     else if (j.solver == CNO_BFGS) run_expr_solver<T, cppoptlib::solver::Bfgs<Fn, ls::HagerZhang>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out);
     else return CNO_ERR_UNSUPPORTED;
+    return 0;
+  }
+  if (j.solver == CNO_LBFGS && j.lbfgs_m == 5) {
+    run_expr_solver<T, cppoptlib::solver::Lbfgs<Fn, 5>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out);
     return 0;
   }
   switch (j.solver) {
@@ -717,7 +730,7 @@ int cno_ref_al_minimize(const cno_problem_t* objective, const cno_constraints_t*
 
 // Minimise / evaluate one of the composites above per instance (expr = EXPR_*; param = Bowl's c).
 int cno_ref_minimize_expr(int expr, double param, int solver, int linesearch, int dtype, int d, int policy, int64_t batch,
-                          const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out, int threads) {
+                          const void* x0, const cno_stop_t* stop, const cno_batch_out_t* out, int threads, int lbfgs_m) {
   if (!x0 || !out || d <= 0) return CNO_ERR_INVALID_ARGUMENT;
   Eigen::cno_policy_ref() = policy;
   int rc = 0;
@@ -731,10 +744,10 @@ int cno_ref_minimize_expr(int expr, double param, int solver, int linesearch, in
     uint32_t counter = 0;
     int r;
     if (dtype == CNO_F64) {
-      const ExprJob<double> j{solver, linesearch, d, b, static_cast<const double*>(x0) + b * d, stop, out, nullptr, nullptr, &counter};
+      const ExprJob<double> j{solver, lbfgs_m, linesearch, d, b, static_cast<const double*>(x0) + b * d, stop, out, nullptr, nullptr, &counter};
       r = expr_dispatch<double>(expr, param, j);
     } else {
-      const ExprJob<float> j{solver, linesearch, d, b, static_cast<const float*>(x0) + b * d, stop, out, nullptr, nullptr, &counter};
+      const ExprJob<float> j{solver, lbfgs_m, linesearch, d, b, static_cast<const float*>(x0) + b * d, stop, out, nullptr, nullptr, &counter};
       r = expr_dispatch<float>(expr, param, j);
     }
     if (r) rc = r;
@@ -750,11 +763,11 @@ int cno_ref_evaluate_expr(int expr, double param, int dtype, int d, int policy, 
     uint32_t counter = 0;
     int r;
     if (dtype == CNO_F64) {
-      const ExprJob<double> j{-1, 0, d, b, static_cast<const double*>(x) + b * d, nullptr, nullptr,
+      const ExprJob<double> j{-1, 0, 0, d, b, static_cast<const double*>(x) + b * d, nullptr, nullptr,
                               static_cast<double*>(value), static_cast<double*>(gradient), &counter};
       r = expr_dispatch<double>(expr, param, j);
     } else {
-      const ExprJob<float> j{-1, 0, d, b, static_cast<const float*>(x) + b * d, nullptr, nullptr,
+      const ExprJob<float> j{-1, 0, 0, d, b, static_cast<const float*>(x) + b * d, nullptr, nullptr,
                              static_cast<float*>(value), static_cast<float*>(gradient), &counter};
       r = expr_dispatch<float>(expr, param, j);
     }

@@ -95,6 +95,8 @@ using SecondSum37 = SecondSum<double, 37>;
 #define X(tag, F) CNO_DECLARE_FUNCTION(tag, F) CNO_INSTANTIATE_FUNCTION(tag, F)
 CNO_TEST_TAGS(X)
 #undef X
+// Lbfgs<F, 5> on a user functor (lbfgs.h:40-41)
+CNO_INSTANTIATE_FUNCTION_M(bowl16m5, Bowl16, 5)  // (a second tag of the same type: symbols only, no LauncherTraits)
 
 // ---- one uniform entry point for the Python tests: builds the functor for (expr, dtype, d) and forwards ----
 enum { EXPR_BOWL = 0, EXPR_ROSEN_PLUS_HALF, EXPR_PROD, EXPR_SUB, EXPR_PENALTY, EXPR_ZERO_MUL, EXPR_SECOND_SUM,
@@ -117,6 +119,7 @@ struct TestCall {
   void* value;      // OP_EVALUATE
   void* gradient;
   size_t* bytes;    // OP_STATE_BYTES
+  int lbfgs_m;      // Lbfgs<F, m>: 0 = the tag's compiled m
 };
 
 #define FORWARD(tag, functor)                                                                                         \
@@ -124,10 +127,10 @@ struct TestCall {
     const auto f__ = functor;                                                                                         \
     switch (c->op) {                                                                                                  \
       case OP_MINIMIZE:                                                                                               \
-        return cno_##tag##_minimize(c->solver, c->mode, &f__, c->batch, c->x0, c->stop, c->out, c->workspace,         \
+        return cno_##tag##_minimize(c->solver, c->mode, c->lbfgs_m, &f__, c->batch, c->x0, c->stop, c->out, c->workspace,         \
                                     c->workspace_bytes, c->stream, c->info);                                          \
       case OP_STEPS:                                                                                                  \
-        return cno_##tag##_minimize_steps(c->solver, c->mode, &f__, c->batch, c->x0, c->stop, c->out, c->state,       \
+        return cno_##tag##_minimize_steps(c->solver, c->mode, c->lbfgs_m, &f__, c->batch, c->x0, c->stop, c->out, c->state,       \
                                           c->state_bytes, c->max_iterations, c->first_call, c->workspace,             \
                                           c->workspace_bytes, c->stream, c->info);                                    \
       case OP_STATE_BYTES: return cno_##tag##_state_bytes(c->solver, c->batch, c->bytes);                             \
@@ -140,6 +143,7 @@ extern "C" int cno_test_expr(int expr, double param, int dtype, int d, const Tes
   const bool f64 = dtype == CNO_F64;
   switch (expr) {
     case EXPR_BOWL:
+      if (f64 && d == 16 && c->lbfgs_m == 5) { Bowl16 b; b.c = param; FORWARD(bowl16m5, b); }
       if (f64 && d == 16) { Bowl16 b; b.c = param; FORWARD(bowl16, b); }
       if (f64 && d == 64) { Bowl64 b; b.c = param; FORWARD(bowl64, b); }
       if (!f64 && d == 37) { Bowl37f b; b.c = (float)param; FORWARD(bowl37f, b); }

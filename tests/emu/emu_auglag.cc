@@ -153,7 +153,7 @@ int run_solver(int solver, long long B, const void* x0, const cno_stop_t* stop, 
       cno::lbfgs_minimize_kernel<Fn, CNO_LBFGS_M, false, LS>(fn, (const T*)x0, B, sp, bo, &queue, cno::ResumeArgs{nullptr, 0, 0, 0});
     } else if (solver == CNO_BFGS) {
       if constexpr (Fn::Dim <= 32) cno::bfgs_minimize_kernel<Fn, LS>(fn, (const T*)x0, B, sp, bo, &queue);
-      else rc = CNO_ERR_UNSUPPORTED;
+      else cno::bfgs_smem_minimize_kernel<Fn, LS>(fn, (const T*)x0, B, sp, bo, &queue);  // H in shared memory
     } else if (solver == CNO_GRADIENT_DESCENT) {
       cno::descent_minimize_kernel<Fn, false, LS>(fn, (const T*)x0, B, sp, bo, &queue);
     } else if (solver == CNO_CONJUGATED_GRADIENT_DESCENT) {

@@ -29,7 +29,7 @@ def test_version_and_error_strings():
     L = _lib.lib()
     a, b = C.c_int(), C.c_int()
     L.cno_version(C.byref(a), C.byref(b))
-    assert (a.value, b.value) == (0, 1)
+    assert (a.value, b.value) == (0, 2)
     assert b"no CPU fallback" in L.cno_error_string(_lib.ERR_NO_DEVICE)
 
 

@@ -20,7 +20,7 @@ def test_cpp_programs_compile():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("exe", ["verify_host", "user_functor"])
+@pytest.mark.parametrize("exe", ["verify_host", "user_functor", "sharded_nccl"])
 def test_cpp_programs_pass_on_gpu(exe):
     path = os.path.join(BUILD, exe)
     if not os.path.exists(path):

@@ -471,3 +471,21 @@ def test_emulated_al_reference_kkt_known_answers_on_the_device_path(emu):
     assert abs(x[0] - 0.5) <= 1e-3 and abs(x[1] - 1.5) <= 1e-3 and 2.0 - (x[0] + x[1]) >= -1e-5
     assert r["inequality_multipliers"][0, 0] >= -1e-2
     _assert_same(r, ob.al_minimize(*args, data=data, **kw))
+
+
+@pytest.mark.parametrize("d,B,hz", [(37, 4, 0), (128, 2, 0), (37, 3, 1)])
+def test_emulated_bfgs_shared_memory_inverse_hessian_equals_oracle(emu, d, B, hz):
+    """bfgs_smem_minimize_kernel (csrc/cno_bfgs.cuh: Bfgs above d = 32, H in the warp's shared-memory slice)."""
+    x0 = ob.fill_uniform((B, d), 0, 5 + d, -2.0, 2.0)
+    stop = ob.default_stop()
+    stop.num_iterations = 40
+    prob = _problem(ob.FN_ROSENBROCK, x0)
+    r = dict(x=np.zeros_like(x0), value=np.zeros(B), gradient=np.zeros_like(x0), num_iterations=np.zeros(B, np.uint32),
+             status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32), x_delta=np.zeros(B), f_delta=np.zeros(B),
+             gradient_norm=np.zeros(B))
+    out = ob.BatchOut(*[r[n].ctypes.data for n, _ in ob.BatchOut._fields_])
+    assert emu.emu_minimize(ob.BFGS, hz, C.byref(prob), C.c_longlong(B), C.c_void_p(x0.ctypes.data), C.byref(stop),
+                            C.byref(out)) == 0
+    o = ob.minimize(ob.BFGS, ob.FN_ROSENBROCK, x0, stop=stop, linesearch=hz)
+    for key in SOLVER_KEYS:
+        assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key

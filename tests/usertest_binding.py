@@ -19,7 +19,7 @@ class TestCall(C.Structure):
                 ("state_bytes", C.c_size_t), ("max_iterations", C.c_int32), ("first_call", C.c_int32),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("stream", C.c_void_p),
                 ("info", C.POINTER(_lib.LaunchInfo)), ("value", C.c_void_p), ("gradient", C.c_void_p),
-                ("bytes", C.POINTER(C.c_size_t))]
+                ("bytes", C.POINTER(C.c_size_t)), ("lbfgs_m", C.c_int)]
 
 
 _handle = None
@@ -40,6 +40,14 @@ def lib():
 KEYS = ("x", "value", "gradient", "num_iterations", "status", "nfev", "x_delta", "f_delta", "gradient_norm")
 
 
+def _stop_ptr(stop):
+    """cno_stop_t* from any ctypes mirror of the struct (oracle_binding.Stop and _lib.Stop have one layout)."""
+    if stop is None:
+        return None
+    assert C.sizeof(stop) == C.sizeof(_lib.Stop)
+    return C.cast(C.pointer(stop), C.POINTER(_lib.Stop))
+
+
 def _outputs(B, d, dt, dev):
     t = dict(x=torch.empty(B, d, dtype=dt, device=dev), value=torch.empty(B, dtype=dt, device=dev),
              gradient=torch.empty(B, d, dtype=dt, device=dev),
@@ -57,15 +65,15 @@ def _numpy(t):
     return r
 
 
-def minimize(expr, solver, x0_np, *, param=0.0, mode=1, stop=None, dev="cuda:0"):
+def minimize(expr, solver, x0_np, *, param=0.0, mode=1, stop=None, dev="cuda:0", lbfgs_m=0):
     """cno_<tag>_minimize of the composite `expr` (ids = oracle_binding.EXPR_*)."""
     x0 = torch.from_numpy(np.ascontiguousarray(x0_np)).to(dev)
     B, d = x0.shape
     t, out = _outputs(B, d, x0.dtype, dev)
     ws = torch.zeros(256, dtype=torch.uint8, device=dev)
     info = _lib.LaunchInfo()
-    call = TestCall(OP_MINIMIZE, solver, mode, B, x0.data_ptr(), C.pointer(stop) if stop is not None else None,
-                    C.pointer(out), None, 0, 0, 0, ws.data_ptr(), 256, None, C.pointer(info), None, None, None)
+    call = TestCall(OP_MINIMIZE, solver, mode, B, x0.data_ptr(), _stop_ptr(stop),
+                    C.pointer(out), None, 0, 0, 0, ws.data_ptr(), 256, None, C.pointer(info), None, None, None, lbfgs_m)
     rc = lib().cno_test_expr(expr, param, 0 if x0.dtype == torch.float64 else 1, d, C.byref(call))
     torch.cuda.synchronize()
     if rc != 0:
@@ -91,7 +99,7 @@ def minimize_steps(expr, solver, x0_np, every, *, param=0.0, mode=1, stop=None, 
     state = torch.zeros(max(nbytes.value, 16), dtype=torch.uint8, device=dev)
     rounds, first = 0, 1
     while True:
-        call = TestCall(OP_STEPS, solver, mode, B, x0.data_ptr(), C.pointer(stop) if stop is not None else None,
+        call = TestCall(OP_STEPS, solver, mode, B, x0.data_ptr(), _stop_ptr(stop),
                         C.pointer(out), state.data_ptr(), state.numel(), every, first, ws.data_ptr(), 256, None, None,
                         None, None, None)
         rc = lib().cno_test_expr(expr, param, dt, d, C.byref(call))
