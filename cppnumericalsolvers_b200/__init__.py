@@ -1,6 +1,6 @@
 """cppnumericalsolvers_b200 -- B200-native batched unconstrained minimisation.
 
-Host-side mirror of cppoptlib's solver::{Lbfgs,Bfgs,NewtonDescent,GradientDescent,
+Host-side mirror of cppoptlib's solver::{Lbfgs,Lbfgsb,Bfgs,NewtonDescent,GradientDescent,
 ConjugatedGradientDescent}::Minimize
 with a batch axis; the compute is hand-written sm_100a CUDA in libcno.so behind
 the C ABI of include/cno.h.  No CPU fallback.
@@ -13,7 +13,7 @@ from .function import (BatchedFunctionState, DenseQuadratic, DenseQuadraticFirst
                        RosenbrockFull)
 from .solver import (BatchedProgress, Bfgs, ConjugatedGradientDescent,  # noqa: F401
                      ConservativeStoppingSolverProgress, DefaultStoppingSolverProgress,
-                     GradientDescent, HagerZhang, Lbfgs, MoreThuente, NewtonDescent, PrintProgressCallback,
+                     GradientDescent, HagerZhang, Lbfgs, Lbfgsb, MoreThuente, NewtonDescent, PrintProgressCallback,
                      Progress, Solver,
                      Status, fill_uniform)
 
@@ -23,6 +23,6 @@ __all__ = [
     "BatchedFunctionState", "BatchedProgress", "Bfgs", "ConjugatedGradientDescent",
     "ConservativeStoppingSolverProgress", "GradientDescent", "HagerZhang", "MoreThuente",
     "DefaultStoppingSolverProgress", "DenseQuadratic", "DenseQuadraticFirst", "DiagQuadratic", "DifferentiabilityMode",
-    "Function", "HalfSquaredNorm", "Lbfgs", "Logistic", "NewtonDescent", "PrintProgressCallback", "Progress",
+    "Function", "HalfSquaredNorm", "Lbfgs", "Lbfgsb", "Logistic", "NewtonDescent", "PrintProgressCallback", "Progress",
     "Rosenbrock", "RosenbrockFull", "Solver", "Status", "fill_uniform",
 ]

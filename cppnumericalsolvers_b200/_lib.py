@@ -55,6 +55,10 @@ class LaunchInfo(C.Structure):  # cno_launch_info_t
     ]
 
 
+class Bounds(C.Structure):  # cno_bounds_t
+    _fields_ = [("lower", C.c_void_p), ("upper", C.c_void_p), ("stride", C.c_int64)]
+
+
 class Constraints(C.Structure):  # cno_constraints_t (include/cno_al.h)
     _fields_ = [("n_eq", C.c_int32), ("n_ineq", C.c_int32), ("kinds", C.c_void_p),
                 ("data", C.c_void_p), ("data_stride", C.c_int64)]
@@ -92,6 +96,7 @@ EXPORTS = (
     "cno_state_bytes", "cno_minimize_steps",
     "cno_minimize_host", "cno_release_host_arena", "cno_evaluate", "cno_fill_uniform", "cno_done_bitmap", "cno_device_cstep",
     "cno_allgather_done", "cno_count_done",
+    "cno_lbfgsb_default_stop", "cno_lbfgsb_supported", "cno_lbfgsb_minimize",
 )
 
 _lib = None
@@ -136,6 +141,12 @@ def lib() -> C.CDLL:
         L.cno_minimize_host.argtypes = [
             C.c_int, C.POINTER(Problem), C.c_int64, C.c_void_p, C.POINTER(Stop),
             C.POINTER(BatchOut), C.POINTER(LaunchInfo)]
+        L.cno_lbfgsb_default_stop.argtypes = [C.POINTER(Stop)]
+        L.cno_lbfgsb_default_stop.restype = None
+        L.cno_lbfgsb_supported.argtypes = [C.POINTER(Problem)]
+        L.cno_lbfgsb_minimize.argtypes = [
+            C.POINTER(Problem), C.POINTER(Bounds), C.c_int64, C.c_void_p, C.POINTER(Stop), C.POINTER(BatchOut),
+            C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(LaunchInfo)]
         L.cno_evaluate.argtypes = [C.POINTER(Problem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cno_fill_uniform.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64,
                                        C.c_double, C.c_double, C.c_void_p]

@@ -17,6 +17,7 @@
 #include "cno_functors.cuh"
 #include "cno_kernel_params.h"
 #include "cno_lbfgs.cuh"
+#include "cno_lbfgsb.cuh"
 #include "cno_bfgs.cuh"
 #include "cno_descent.cuh"
 #include "cno_evaluate.cuh"
@@ -426,6 +427,82 @@ const Entry kTable[] = {
     {CNO_GRADIENT_DESCENT_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 8, gd_rosenbrock_hz<double, 8>},
     {CNO_GRADIENT_DESCENT_HAGER_ZHANG, CNO_FN_ROSENBROCK, CNO_F64, 37, gd_rosenbrock_hz<double, 37>},
 };
+
+// ---- Lbfgsb (solver/lbfgsb.h) ----
+struct LbfgsbArgs {
+  const cno_problem_t* problem;
+  const cno_bounds_t* bounds;
+  long long batch;
+  const void* x0;
+  const cno_stop_t* stop;
+  const cno_batch_out_t* out;
+  void* workspace;
+  cudaStream_t stream;
+  cno_launch_info_t* info;
+};
+template <class Fn>
+int launch_lbfgsb(const Fn& fn, const LbfgsbArgs& a) {
+  using T = typename Fn::Scalar;
+  using SM = cno::LbfgsbSmem<T, Fn::Dim, 5>;
+  auto kernel = cno::lbfgsb_minimize_kernel<Fn, 5>;
+  const size_t smem = SM::kWarpBytes * SM::kWarps;
+  CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  long long ctas = (a.batch + SM::kWarps - 1) / SM::kWarps;
+  const int grid = (int)(ctas < sms ? (ctas < 1 ? 1 : ctas) : sms);
+  unsigned long long* queue = static_cast<unsigned long long*>(a.workspace);
+  CNO_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), a.stream));
+  const cno::BoundsArgs<T> bd{a.bounds ? static_cast<const T*>(a.bounds->lower) : nullptr,
+                              a.bounds ? static_cast<const T*>(a.bounds->upper) : nullptr,
+                              a.bounds ? (long long)a.bounds->stride : 0};
+  kernel<<<grid, SM::kWarps * 32, smem, a.stream>>>(fn, static_cast<const T*>(a.x0), a.batch, cno::make_stop<T>(*a.stop),
+                                                    cno::make_out<T>(*a.out), queue, bd);
+  CNO_CUDA(cudaGetLastError());
+  if (a.info) {
+    a.info->kernel_launches += 1;
+    a.info->grid = grid;
+    a.info->block = SM::kWarps * 32;
+    a.info->warps_per_cta = SM::kWarps;
+    a.info->dynamic_smem = (int64_t)smem;
+  }
+  return CNO_OK;
+}
+template <class T, int D>
+int lbfgsb_rosenbrock(const LbfgsbArgs& a) { return launch_lbfgsb(cno::RosenbrockFn<T, D>{}, a); }
+template <class T, int D>
+int lbfgsb_half_sq_norm(const LbfgsbArgs& a) { return launch_lbfgsb(cno::HalfSquaredNormFn<T, D>{}, a); }
+template <class T>
+int lbfgsb_diag_quadratic(const LbfgsbArgs& a) { return launch_lbfgsb(cno::DiagQuadraticFn<T>{}, a); }
+template <class T, int D>
+int lbfgsb_dense_quadratic(const LbfgsbArgs& a) {
+  const cno_problem_t* p = a.problem;
+  if (!p->data || p->data_stride < (int64_t)D * D + D) return CNO_ERR_INVALID_ARGUMENT;
+  return launch_lbfgsb(cno::DenseQuadraticGlobalFn<T, D>{static_cast<const T*>(p->data), (long long)p->data_stride}, a);
+}
+struct LbfgsbEntry { int family, dtype, d; int (*fn)(const LbfgsbArgs&); };
+const LbfgsbEntry kLbfgsbTable[] = {
+    {CNO_FN_ROSENBROCK, CNO_F64, 2, lbfgsb_rosenbrock<double, 2>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 8, lbfgsb_rosenbrock<double, 8>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgsb_rosenbrock<double, 37>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 64, lbfgsb_rosenbrock<double, 64>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgsb_rosenbrock<double, 128>},
+    {CNO_FN_ROSENBROCK, CNO_F32, 37, lbfgsb_rosenbrock<float, 37>},
+    {CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, lbfgsb_diag_quadratic<double>},
+    {CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, lbfgsb_half_sq_norm<double, 2>},
+    {CNO_FN_HALF_SQUARED_NORM, CNO_F64, 8, lbfgsb_half_sq_norm<double, 8>},
+    {CNO_FN_DENSE_QUADRATIC, CNO_F64, 8, lbfgsb_dense_quadratic<double, 8>},
+    {CNO_FN_DENSE_QUADRATIC, CNO_F64, 64, lbfgsb_dense_quadratic<double, 64>},
+};
+const LbfgsbEntry* lbfgsb_find(const cno_problem_t* p) {
+  if (!p) return nullptr;
+  const int dflt = (p->dtype == CNO_F64) ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE;
+  if (p->policy != dflt) return nullptr;
+  for (const LbfgsbEntry& e : kLbfgsbTable)
+    if (e.family == p->family && e.dtype == p->dtype && e.d == p->d) return &e;
+  return nullptr;
+}
 
 // ---- cno_evaluate: F::operator()(x, &gradient) of the built-in families ----
 typedef int (*evaluator_t)(const cno_problem_t*, int64_t, const void*, void*, void*, void*);
@@ -996,6 +1073,54 @@ int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch, c
   local.kernel_ms = ms;
   if (info) *info = local;
   g_last_info = local;
+  return CNO_OK;
+}
+
+void cno_lbfgsb_default_stop(cno_stop_t* s) {  // solver/lbfgsb.h:78-81
+  if (!s) return;
+  cno_default_stop(s);
+  s->f_delta = 2.22e-9;
+  s->f_delta_relative = 1;
+}
+
+int cno_lbfgsb_supported(const cno_problem_t* problem) {
+  if (!problem) return CNO_ERR_INVALID_ARGUMENT;
+  return lbfgsb_find(problem) ? CNO_OK : CNO_ERR_UNSUPPORTED;
+}
+
+int cno_lbfgsb_minimize(const cno_problem_t* problem, const cno_bounds_t* bounds, int64_t batch, const void* x0,
+                        const cno_stop_t* stop, const cno_batch_out_t* out, void* workspace, size_t workspace_bytes,
+                        void* stream, cno_launch_info_t* info) {
+  if (!problem) return CNO_ERR_INVALID_ARGUMENT;
+  const LbfgsbEntry* e = lbfgsb_find(problem);
+  if (!e) return CNO_ERR_UNSUPPORTED;
+  if (batch < 0 || !out) return CNO_ERR_INVALID_ARGUMENT;
+  if (info) memset(info, 0, sizeof(*info));
+  if (batch == 0) return have_device() ? CNO_OK : CNO_ERR_NO_DEVICE;
+  if (!x0) return CNO_ERR_INVALID_ARGUMENT;
+  if (bounds && bounds->stride != 0 && bounds->stride < problem->d) return CNO_ERR_INVALID_ARGUMENT;
+  if (!workspace || workspace_bytes < kWorkspaceBytes || ((uintptr_t)workspace & 7)) return CNO_ERR_WORKSPACE;
+  if (((uintptr_t)x0 & 15) || ((uintptr_t)out->x & 15) || ((uintptr_t)out->gradient & 15)) return CNO_ERR_INVALID_ARGUMENT;
+  cno_stop_t dflt;
+  if (!stop) { cno_lbfgsb_default_stop(&dflt); stop = &dflt; }
+  if (stop->past > CNO_MAX_PAST || stop->past < 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (!have_device()) return CNO_ERR_NO_DEVICE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  EventOwner e0, e1;
+  if (info) {
+    CNO_CUDA(e0.create());
+    CNO_CUDA(e1.create());
+    CNO_CUDA(cudaEventRecord(e0.e, s));
+  }
+  const LbfgsbArgs a{problem, bounds, (long long)batch, x0, stop, out, workspace, s, info};
+  const int rc = e->fn(a);
+  if (rc) return rc;
+  if (info) {
+    CNO_CUDA(cudaEventRecord(e1.e, s));
+    CNO_CUDA(cudaEventSynchronize(e1.e));
+    CNO_CUDA(cudaEventElapsedTime(&info->kernel_ms, e0.e, e1.e));
+    info->total_ms = info->kernel_ms;
+  }
   return CNO_OK;
 }
 

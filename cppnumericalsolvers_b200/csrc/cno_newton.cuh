@@ -625,13 +625,14 @@ struct StageTakesTranspose<Fn, std::void_t<decltype(Fn::kStageTakesTranspose)>> 
 // exchanges.  A = [H | rhs] col-major, lane owns rows lane*E .. lane*E+E-1.  On
 // return delta holds this lane's slice of the solution.
 // Back substitution U x = y (pivot order), column oriented, on the factored store; vpos = the rows' final
-// virtual positions.  On return delta holds this lane's slice of the solution.
+// virtual positions, rv = this lane's rows of the right-hand side (kept in REGISTERS: a lane only ever updates its
+// own rows, and the one value the others need per step -- x_k -- is broadcast from its owner).  On return delta
+// holds this lane's slice of the solution.
 template <class T, int D>
 __device__ __forceinline__ void lu_back_substitute(const AugStore<T, D>& A, const int (&vpos)[Shape<D>::E],
-                                                   T (&delta)[Shape<D>::E]) {
+                                                   T (&rv)[Shape<D>::E], T (&delta)[Shape<D>::E]) {
   constexpr int E = Shape<D>::E;
   const int lane = A.lane;
-  T* const rhs = A.rhs();
 #pragma unroll 1
   for (int k = D - 1; k >= 0; --k) {
     T col[E];
@@ -641,7 +642,7 @@ __device__ __forceinline__ void lu_back_substitute(const AugStore<T, D>& A, cons
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       if ((lane * E + e < D) && vpos[e] == k) {
-        xk_local = rhs[lane * E + e] / col[e];
+        xk_local = rv[e] / col[e];
         mine = true;
       }
     }
@@ -650,10 +651,9 @@ __device__ __forceinline__ void lu_back_substitute(const AugStore<T, D>& A, cons
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int row = lane * E + e;
-      if ((row < D) && vpos[e] < k) rhs[row] = rhs[row] - col[e] * xk;
+      if ((row < D) && vpos[e] < k) rv[e] = rv[e] - col[e] * xk;
       if (row == k) delta[e] = xk;  // unknown k belongs to element k
     }
-    __syncwarp();
   }
 #pragma unroll
   for (int e = 0; e < E; ++e)
@@ -664,12 +664,12 @@ __device__ __forceinline__ void lu_back_substitute(const AugStore<T, D>& A, cons
 // factored once per instance): the right-hand side receives, in pivot order, exactly the updates it received while
 // it rode along the elimination -- rhs_i -= l_ik * rhs_{pivot row k} for the rows not yet used as a pivot, l_ik
 // being the multiplier stored in column k -- then the same back substitution.  Bit-identical to factoring again.
+// rv = this lane's rows of the right-hand side, in registers.
 template <class T, int D>
 __device__ __forceinline__ void lu_resolve(const AugStore<T, D>& A, const int (&vpos)[Shape<D>::E],
-                                           T (&delta)[Shape<D>::E]) {
+                                           T (&rv)[Shape<D>::E], T (&delta)[Shape<D>::E]) {
   constexpr int E = Shape<D>::E;
   const int lane = A.lane;
-  T* const rhs = A.rhs();
 #pragma unroll 1
   for (int k = 0; k < D; ++k) {
     T col[E];
@@ -679,7 +679,7 @@ __device__ __forceinline__ void lu_resolve(const AugStore<T, D>& A, const int (&
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       if ((lane * E + e < D) && vpos[e] == k) {
-        u_local = rhs[lane * E + e];
+        u_local = rv[e];
         mine = true;
       }
     }
@@ -688,11 +688,10 @@ __device__ __forceinline__ void lu_resolve(const AugStore<T, D>& A, const int (&
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int row = lane * E + e;
-      if ((row < D) && vpos[e] > k) rhs[row] = rhs[row] - col[e] * u;
+      if ((row < D) && vpos[e] > k) rv[e] = rv[e] - col[e] * u;
     }
-    __syncwarp();
   }
-  lu_back_substitute<T, D>(A, vpos, delta);
+  lu_back_substitute<T, D>(A, vpos, rv, delta);
 }
 
 template <class T, int D>
@@ -767,7 +766,9 @@ __device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&de
     }
     __syncwarp();
   }
-  lu_back_substitute<T, D>(A, vpos, delta);
+  T rv[E];
+  AS::RV::load(A.rhs(), lane, rv);  // (the lu_update_smem calls above end with a warp sync)
+  lu_back_substitute<T, D>(A, vpos, rv, delta);
 }
 
 template <class Fn>
@@ -851,12 +852,10 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       nfev++;  // function(current.x, &gradient, &hessian)
       T delta[E];
       if (uni(Fn::kHessianConstant && factored)) {
-        __syncwarp();
+        T rv[E];
 #pragma unroll
-        for (int e = 0; e < E; ++e)
-          if (lane * E + e < D) A.rhs()[lane * E + e] = -g[e];
-        __syncwarp();
-        lu_resolve<T, D>(A, vpos, delta);
+        for (int e = 0; e < E; ++e) rv[e] = -g[e];
+        lu_resolve<T, D>(A, vpos, rv, delta);
       } else {
       if (!staged) fn.stage(ctx, x, A, bar, parity);
       // hessian += safe_guard * I ; rhs = -gradient

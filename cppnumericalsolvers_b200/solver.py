@@ -308,6 +308,76 @@ class Lbfgs(_LineSearchSolver):
         return p
 
 
+class Lbfgsb(Solver):
+    """solver/lbfgsb.h:44-538: Lbfgsb<F, m = 5, MoreThuente> -- L-BFGS-B, box constraints lower <= x <= upper.
+    `Lbfgsb()` carries the reference constructor's preset (default + f_delta = 2.22e-9 relative, :78-81);
+    `SetBounds(lower, upper)` (:88-92) takes CUDA tensors [d] (one box for the batch) or [B, d] (None = unbounded
+    on that side).  The stop test on `gradient_norm` uses the sup-norm of the box-projected gradient (:238-286)."""
+
+    def __init__(self, progress: Optional[Progress] = None):
+        if progress is None:
+            s = _lib.Stop()
+            _lib.lib().cno_lbfgsb_default_stop(C.byref(s))
+            progress = Progress.from_c(s)
+        super().__init__(progress)
+        self.lower_bound: Optional[torch.Tensor] = None
+        self.upper_bound: Optional[torch.Tensor] = None
+
+    def SetBounds(self, lower_bound: Optional[torch.Tensor], upper_bound: Optional[torch.Tensor]) -> None:
+        self.lower_bound, self.upper_bound = lower_bound, upper_bound
+
+    def supported(self, function: Function) -> bool:
+        p = function.problem()
+        return _lib.lib().cno_lbfgsb_supported(C.byref(p)) == _lib.OK
+
+    def Minimize(self, function: Function, state: BatchedFunctionState,
+                 timed: bool = False) -> Tuple[BatchedFunctionState, BatchedProgress]:
+        x0 = state.x
+        if not x0.is_cuda:
+            raise RuntimeError("Minimize needs CUDA tensors (there is no CPU fallback)")
+        if x0.dtype != function.ScalarType or x0.dim() != 2 or x0.shape[1] != function.Dimension:
+            raise ValueError("x0 must be [B, d] of the function's scalar type")
+        x0 = x0.contiguous()
+        dev, dt, B, d = x0.device, x0.dtype, x0.shape[0], x0.shape[1]
+        stride = 0
+        keep = []
+        ptrs = []
+        for t in (self.lower_bound, self.upper_bound):
+            if t is None:
+                ptrs.append(None)
+                continue
+            if t.dtype != dt or t.device != dev or t.shape[-1] != d or t.dim() not in (1, 2):
+                raise ValueError("bounds must be CUDA tensors [d] or [B, d] of the function's scalar type")
+            if t.dim() == 2:
+                if t.shape[0] != B:
+                    raise ValueError("per-instance bounds must be [B, d]")
+                stride = d
+            t = t.contiguous()
+            keep.append(t)
+            ptrs.append(t.data_ptr())
+        if stride and any(t.dim() == 1 for t in keep):
+            raise ValueError("lower and upper must both be [d] or both be [B, d]")
+        prob = function.problem()
+        with torch.cuda.device(dev):
+            x, g = torch.empty_like(x0), torch.empty_like(x0)
+            f, xd, fd, gn = (torch.empty(B, dtype=dt, device=dev) for _ in range(4))
+            it, nf = (torch.empty(B, dtype=torch.int32, device=dev) for _ in range(2))
+            st = torch.empty(B, dtype=torch.int8, device=dev)
+            if self._workspace is None or self._workspace.device != dev:
+                self._workspace = torch.empty(256, dtype=torch.uint8, device=dev)
+            out = _lib.BatchOut(x.data_ptr(), f.data_ptr(), g.data_ptr(), it.data_ptr(), st.data_ptr(), nf.data_ptr(),
+                                xd.data_ptr(), fd.data_ptr(), gn.data_ptr())
+            bounds = _lib.Bounds(ptrs[0], ptrs[1], stride)
+            stop = self.stopping_progress.to_c()
+            info = _lib.LaunchInfo() if timed else None
+            _lib.check(_lib.lib().cno_lbfgsb_minimize(
+                C.byref(prob), C.byref(bounds), B, x0.data_ptr(), C.byref(stop), C.byref(out),
+                self._workspace.data_ptr(), self._workspace.numel(), torch.cuda.current_stream(dev).cuda_stream,
+                C.byref(info) if info is not None else None), "cno_lbfgsb_minimize")
+        del keep
+        return BatchedFunctionState(x, f, g), BatchedProgress(it, st, nf, xd, fd, gn, info)
+
+
 class Bfgs(_LineSearchSolver):
     """solver/bfgs.h:39-145 (LineSearch = MoreThuente unless given)."""
     _solver_id = _lib.BFGS

@@ -29,6 +29,8 @@
  *                                               solver = CNO_GRADIENT_DESCENT
  *   solver/conjugated_gradient_descent.h:38-92 ConjugatedGradientDescent
  *                                               solver = CNO_CONJUGATED_GRADIENT_DESCENT
+ *   solver/lbfgsb.h:44-538    Lbfgsb<F, m = 5>  cno_lbfgsb_minimize() + cno_bounds_t (SetBounds),
+ *                                               cno_lbfgsb_default_stop() (the Lbfgsb() preset)
  *   function_base.h:96-126    FunctionCRTP      cno_problem_t names a functor
  *                                               that was compiled for the
  *                                               device
@@ -227,6 +229,25 @@ int cno_minimize_steps(int solver, const cno_problem_t* problem, int64_t batch, 
 int cno_minimize_host(int solver, const cno_problem_t* problem, int64_t batch,
                       const void* x0, const cno_stop_t* stop,
                       const cno_batch_out_t* out, cno_launch_info_t* info);
+
+/* ---- Lbfgsb<F, m = 5, MoreThuente> (solver/lbfgsb.h:44-538): box constraints lower <= x <= upper -------------
+ * SetBounds (:88-92) with a batch axis: lower / upper are DEVICE arrays of problem.dtype, [d] (stride = 0: one
+ * box for the whole batch) or [B, d] (stride = d); a NULL side is unbounded (numeric_limits lowest / max, as
+ * InitializeSolver does at :122-128). */
+typedef struct cno_bounds {
+  const void* lower;
+  const void* upper;
+  int64_t stride;
+} cno_bounds_t;
+/* The Lbfgsb() constructor's stopping preset (:78-81): cno_default_stop + f_delta = 2.22e-9, relative. */
+void cno_lbfgsb_default_stop(cno_stop_t* stop);
+/* 0 if a kernel is instantiated for Lbfgsb on this problem, else CNO_ERR_UNSUPPORTED. */
+int cno_lbfgsb_supported(const cno_problem_t* problem);
+/* Batched Lbfgsb::Minimize (:238-286: the projected-gradient sup-norm drives stop->gradient_norm).  Device
+ * pointers; bounds may be NULL (unbounded); stop NULL = cno_lbfgsb_default_stop; workspace as for cno_minimize. */
+int cno_lbfgsb_minimize(const cno_problem_t* problem, const cno_bounds_t* bounds, int64_t batch, const void* x0,
+                        const cno_stop_t* stop, const cno_batch_out_t* out, void* workspace, size_t workspace_bytes,
+                        void* stream, cno_launch_info_t* info);
 
 /* Batched F::operator()(x, &gradient) (function_base.h:103-120; the evaluating FunctionState constructor,
  * :315-326): value [B] and/or gradient [B, d] of the built-in family at x [B, d].  DEVICE pointers; either

@@ -683,6 +683,82 @@ class Lbfgs : public Solver<F, LineSearch::solver_id(CNO_LBFGS)> {
  protected:
   int lbfgs_m() const override { return m; }
 };
+// solver/lbfgsb.h:44-538: Lbfgsb<F, m = 5, MoreThuente> -- L-BFGS-B (box constraints).  The constructor carries the
+// reference's preset (default + f_delta = 2.22e-9 relative, :78-81); SetBounds (:88-92) takes device arrays [d]
+// (one box for the batch) or [B, d].
+template <class F, int m = 5>
+class Lbfgsb {
+  static_assert(m == 5, "Lbfgsb: the kernels are compiled for the reference's default m = 5");
+
+ public:
+  using FunctionType = F;
+  using ScalarType = typename F::ScalarType;
+  using StateType = function::BatchedFunctionState<ScalarType, F::Dimension>;
+  using ProgressType = Progress<F, StateType>;
+  ProgressType stopping_progress;
+
+  Lbfgsb() {
+    cno_stop_t s;
+    cno_lbfgsb_default_stop(&s);
+    stopping_progress = ProgressType::from_c(s);
+  }
+  explicit Lbfgsb(const ProgressType& progress) : stopping_progress(progress) {}
+
+  // lower / upper: host vectors of d (one box) or B*d (per instance) entries; empty = unbounded on that side
+  void SetBounds(const std::vector<ScalarType>& lower_bound, const std::vector<ScalarType>& upper_bound) {
+    lower_ = detail::DeviceArray<ScalarType>::FromHost(lower_bound);
+    upper_ = detail::DeviceArray<ScalarType>::FromHost(upper_bound);
+  }
+
+  std::tuple<StateType, BatchedProgress<ScalarType>> Minimize(const F& function, const StateType& function_state,
+                                                              cudaStream_t stream = nullptr) {
+    using T = ScalarType;
+    constexpr int D = F::Dimension;
+    const int64_t B = function_state.batch;
+    function::FunctionExpr<T, function::DifferentiabilityMode::First, D> expr(function);
+    if (expr.raw) throw std::runtime_error("Lbfgsb: built-in objective families only");
+    cno_bounds_t bounds{};
+    bounds.lower = lower_.size() ? lower_.data() : nullptr;
+    bounds.upper = upper_.size() ? upper_.data() : nullptr;
+    for (size_t n : {lower_.size(), upper_.size()}) {
+      if (n == 0) continue;
+      if (n == static_cast<size_t>(B) * D && B != 1) bounds.stride = D;
+      else if (n != static_cast<size_t>(D)) throw std::invalid_argument("SetBounds: d or B*d entries");
+    }
+    StateType result;
+    result.batch = B;
+    result.x = detail::DeviceArray<T>(B * D);
+    result.gradient = detail::DeviceArray<T>(B * D);
+    result.value = detail::DeviceArray<T>(B);
+    BatchedProgress<T> prog;
+    prog.batch = B;
+    prog.num_iterations = detail::DeviceArray<uint32_t>(B);
+    prog.nfev = detail::DeviceArray<uint32_t>(B);
+    prog.status = detail::DeviceArray<int8_t>(B);
+    prog.x_delta = detail::DeviceArray<T>(B);
+    prog.f_delta = detail::DeviceArray<T>(B);
+    prog.gradient_norm = detail::DeviceArray<T>(B);
+    cno_batch_out_t out{};
+    out.x = result.x.data();
+    out.value = result.value.data();
+    out.gradient = result.gradient.data();
+    out.num_iterations = prog.num_iterations.data();
+    out.status = prog.status.data();
+    out.nfev = prog.nfev.data();
+    out.x_delta = prog.x_delta.data();
+    out.f_delta = prog.f_delta.data();
+    out.gradient_norm = prog.gradient_norm.data();
+    detail::DeviceArray<unsigned char> workspace(256);
+    const cno_stop_t stop = stopping_progress.to_c();
+    detail::check_cno(cno_lbfgsb_minimize(&expr.problem, &bounds, B, function_state.x.data(), &stop, &out, workspace.data(),
+                                          workspace.size(), stream, &prog.launch),
+                      "Lbfgsb::Minimize");
+    return {std::move(result), std::move(prog)};
+  }
+
+ private:
+  detail::DeviceArray<ScalarType> lower_, upper_;
+};
 // solver/bfgs.h:39-41: Bfgs<F, LineSearch = MoreThuente>
 template <class F, class LineSearch = linesearch::MoreThuente>
 class Bfgs : public Solver<F, LineSearch::solver_id(CNO_BFGS)> {

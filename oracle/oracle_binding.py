@@ -354,3 +354,47 @@ def ref_evaluate_expr(expr: int, x: np.ndarray, *, param: float = 0.0, policy: i
     if rc != 0:
         raise RuntimeError(f"ref evaluate_expr failed: {rc}")
     return f, g
+
+
+# ---- Lbfgsb (solver/lbfgsb.h): box constraints; oracle/_ref only (the reference's own header on the shim) ----
+def lbfgsb_stop() -> Stop:
+    """The Lbfgsb() constructor's preset (lbfgsb.h:78-81): the default + f_delta = 2.22e-9, relative."""
+    s = default_stop()
+    s.f_delta = 2.22e-9
+    s.f_delta_relative = 1
+    return s
+
+
+def ref_lbfgsb_minimize(family: int, x0: np.ndarray, lower=None, upper=None, *, stop: Stop | None = None,
+                        data=None, policy: int | None = None, threads: int = 0) -> dict:
+    """Lbfgsb<F, 5>::Minimize per instance with SetBounds(lower, upper); lower / upper: [d] (one box) or [B, d]."""
+    x0 = np.ascontiguousarray(x0)
+    B, d = x0.shape
+    dt = x0.dtype
+    if policy is None:
+        policy = device_policy(dt)
+    if data is not None:
+        data = np.ascontiguousarray(data, dtype=dt)
+    p = Problem(family, _np_dtype(x0), d, 0, 0.0, data.ctypes.data if data is not None else None,
+                data.shape[1] if data is not None else 0, policy, 0)
+    lo = None if lower is None else np.ascontiguousarray(lower, dtype=dt)
+    hi = None if upper is None else np.ascontiguousarray(upper, dtype=dt)
+    stride = 0
+    for a in (lo, hi):
+        if a is not None and a.ndim == 2:
+            stride = d
+    r = dict(x=np.zeros_like(x0), value=np.zeros(B, dt), gradient=np.zeros_like(x0),
+             num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8),
+             nfev=np.zeros(B, np.uint32), x_delta=np.zeros(B, dt), f_delta=np.zeros(B, dt),
+             gradient_norm=np.zeros(B, dt))
+    o = BatchOut(*[r[k].ctypes.data for k in (
+        "x", "value", "gradient", "num_iterations", "status", "nfev", "x_delta", "f_delta", "gradient_norm")])
+    ptr = lambda a: None if a is None else C.c_void_p(a.ctypes.data)  # noqa: E731
+    t0 = time.perf_counter()
+    rc = ref_lib().cno_ref_lbfgsb_minimize(C.byref(p), C.c_int64(B), C.c_void_p(x0.ctypes.data), ptr(lo), ptr(hi),
+                                           C.c_int64(stride), C.byref(stop) if stop is not None else None, C.byref(o),
+                                           threads)
+    r["seconds"] = time.perf_counter() - t0
+    if rc != 0:
+        raise RuntimeError(f"ref lbfgsb minimize failed: {rc}")
+    return r

@@ -26,6 +26,7 @@
 #include "cppoptlib/solver/conjugated_gradient_descent.h"
 #include "cppoptlib/solver/gradient_descent.h"
 #include "cppoptlib/solver/lbfgs.h"
+#include "cppoptlib/solver/lbfgsb.h"
 #include "cppoptlib/solver/newton_descent.h"
 
 namespace {
@@ -625,6 +626,54 @@ struct ScalarStub : FunctionCRTP<ScalarStub, double, DifferentiabilityMode::Firs
   double operator()(const VectorType&, VectorType* = nullptr) const { return 0.0; }
 };
 
+// Lbfgsb<F, m = 5> (solver/lbfgsb.h:44-538) with the box [lower, upper] (SetBounds, :88-92); lower / upper are
+// [d] (stride 0: one box for the batch) or [B, d] (stride d); NULL = unbounded on that side.  Family: Rosenbrock /
+// DiagQuadratic / HalfSquaredNorm / DenseQuadratic, First mode.  stop == NULL: the Lbfgsb() constructor's preset
+// (default + f_delta = 2.22e-9 relative, :78-81).
+template <class T, template <class, DifferentiabilityMode> class Family>
+void lbfgsb_run_one(const cno_problem_t* prob, int64_t b, const T* x0, const T* lo, const T* hi, const cno_stop_t* stop,
+                    const cno_batch_out_t* out) {
+  using Fn = Family<T, DifferentiabilityMode::First>;
+  using State = FunctionState<T, Eigen::Dynamic>;
+  const int d = prob->d;
+  Fn f;
+  f.p = prob;
+  f.instance = b;
+  f.nfev = 0;
+  typename Fn::VectorType x(d), l(d), u(d);
+  for (int i = 0; i < d; ++i) {
+    x[i] = x0[i];
+    l[i] = lo ? lo[i] : std::numeric_limits<T>::lowest();
+    u[i] = hi ? hi[i] : std::numeric_limits<T>::max();
+  }
+  cppoptlib::solver::Lbfgsb<Fn> solver;
+  if (stop) {
+    auto& p = solver.stopping_progress;
+    p.num_iterations = stop->num_iterations;
+    p.x_delta = static_cast<T>(stop->x_delta);
+    p.x_delta_violations = stop->x_delta_violations;
+    p.f_delta = static_cast<T>(stop->f_delta);
+    p.f_delta_violations = stop->f_delta_violations;
+    p.f_delta_relative = stop->f_delta_relative != 0;
+    p.gradient_norm = static_cast<T>(stop->gradient_norm);
+    p.gradient_norm_relative = stop->gradient_norm_relative != 0;
+    p.condition_hessian = static_cast<T>(stop->condition_hessian);
+    p.past = stop->past;
+    p.past_delta = static_cast<T>(stop->past_delta);
+  }
+  if (lo || hi) solver.SetBounds(l, u);
+  auto [solution, state] = solver.Minimize(f, State(x));
+  if (out->x) for (int i = 0; i < d; ++i) static_cast<T*>(out->x)[b * d + i] = solution.x[i];
+  if (out->gradient) for (int i = 0; i < d; ++i) static_cast<T*>(out->gradient)[b * d + i] = solution.gradient[i];
+  if (out->value) static_cast<T*>(out->value)[b] = solution.value;
+  if (out->num_iterations) out->num_iterations[b] = static_cast<uint32_t>(state.num_iterations);
+  if (out->status) out->status[b] = static_cast<int8_t>(state.status);
+  if (out->nfev) out->nfev[b] = f.nfev;
+  if (out->x_delta) static_cast<T*>(out->x_delta)[b] = state.x_delta;
+  if (out->f_delta) static_cast<T*>(out->f_delta)[b] = state.f_delta;
+  if (out->gradient_norm) static_cast<T*>(out->gradient_norm)[b] = state.gradient_norm;
+}
+
 }  // namespace
 
 extern "C" {
@@ -771,6 +820,41 @@ int cno_ref_evaluate_expr(int expr, double param, int dtype, int d, int policy, 
                              static_cast<float*>(value), static_cast<float*>(gradient), &counter};
       r = expr_dispatch<float>(expr, param, j);
     }
+    if (r) rc = r;
+  }
+  return rc;
+}
+
+int cno_ref_lbfgsb_minimize(const cno_problem_t* problem, int64_t batch, const void* x0, const void* lower,
+                            const void* upper, int64_t bounds_stride, const cno_stop_t* stop,
+                            const cno_batch_out_t* out, int threads) {
+  if (!problem || !x0 || !out) return CNO_ERR_INVALID_ARGUMENT;
+  Eigen::cno_policy_ref() = problem->policy;
+  const int d = problem->d;
+  int rc = 0;
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#else
+  threads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+  for (int64_t b = 0; b < batch; ++b) {
+    int r = 0;
+#define LBFGSB_CASE(TY)                                                                                          \
+  {                                                                                                              \
+    const TY* xs = static_cast<const TY*>(x0) + b * d;                                                           \
+    const TY* lo = lower ? static_cast<const TY*>(lower) + b * bounds_stride : nullptr;                          \
+    const TY* hi = upper ? static_cast<const TY*>(upper) + b * bounds_stride : nullptr;                          \
+    switch (problem->family) {                                                                                   \
+      case CNO_FN_ROSENBROCK: lbfgsb_run_one<TY, Rosenbrock>(problem, b, xs, lo, hi, stop, out); break;          \
+      case CNO_FN_DIAG_QUADRATIC: lbfgsb_run_one<TY, DiagQuadratic>(problem, b, xs, lo, hi, stop, out); break;   \
+      case CNO_FN_HALF_SQUARED_NORM: lbfgsb_run_one<TY, HalfSquaredNorm>(problem, b, xs, lo, hi, stop, out); break; \
+      case CNO_FN_DENSE_QUADRATIC: lbfgsb_run_one<TY, DenseQuadratic>(problem, b, xs, lo, hi, stop, out); break; \
+      default: r = CNO_ERR_UNSUPPORTED;                                                                          \
+    }                                                                                                            \
+  }
+    if (problem->dtype == CNO_F64) LBFGSB_CASE(double) else LBFGSB_CASE(float)
+#undef LBFGSB_CASE
     if (r) rc = r;
   }
   return rc;

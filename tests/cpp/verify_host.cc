@@ -74,6 +74,21 @@ int main() {
     for (int b = 0; b < 2; ++b) EXPECT_NEAR(0.0, rosen2(&x[2 * b]), PRECISION);
   }
 
+  {  // SOLVER_SETUP(Lbfgsb, RosenbrockGradient): verify.cc:190, unbounded; then the same problem in a box
+    using F = function::Rosenbrock<double, 2>;
+    solver::Lbfgsb<F> s;
+    auto x0 = function::BatchedFunctionState<double, 2>::FromHost({15.0, 8.0, -1.0, 2.0}, 2);
+    auto [sol, prog] = s.Minimize(F{}, x0);
+    const std::vector<double> x = sol.x.ToHost();
+    for (int b = 0; b < 2; ++b) EXPECT_NEAR(0.0, rosen2(&x[2 * b]), PRECISION);
+    s.SetBounds({-2.0, -2.0}, {0.5, 3.0});  // the minimiser (1, 1) is outside: x0 lands on the face x0 = 0.5
+    auto [solb, progb] = s.Minimize(F{}, x0);
+    const std::vector<double> xb = solb.x.ToHost();
+    for (int b = 0; b < 2; ++b) {
+      EXPECT_NEAR(0.5, xb[2 * b], 0.0);
+      EXPECT_NEAR(0.25, xb[2 * b + 1], 1e-4);  // min over x1 of 100 (x1 - 0.25)^2
+    }
+  }
   {  // Dockerfile.test:30-45
     function::DiagQuadratic<double> f;
     solver::Lbfgs<function::DiagQuadratic<double>> solver;

@@ -11,6 +11,7 @@
 #include "cno_bfgs.cuh"
 #include "cno_descent.cuh"
 #include "cno_newton.cuh"
+#include "cno_lbfgsb.cuh"
 #include "cno_logistic.cuh"
 
 namespace {
@@ -384,5 +385,34 @@ extern "C" int emu_al(int op, const cno_problem_t* objective, const cno_constrai
   if (objective->family == CNO_FN_DENSE_QUADRATIC && objective->dtype == CNO_F64 && objective->d == 8)
     return run(cno::DenseQuadraticGlobalFn<double, 8>{(const double*)objective->data, (long long)objective->data_stride}, op,
                constraints, batch, *arrays_, config, stop, x_in, value_out, grad_out);
+  return CNO_ERR_UNSUPPORTED;
+}
+
+
+#define CNO_EMU_COMMA ,
+// Lbfgsb<F, 5> (csrc/cno_lbfgsb.cuh) under emulation.  lower / upper: host arrays [d] (stride 0) or [B, d].
+template <class Fn>
+int run_lbfgsb(long long B, const void* x0, const void* lower, const void* upper, long long stride, const cno_stop_t* stop,
+               const cno_batch_out_t* out) {
+  using T = typename Fn::Scalar;
+  unsigned long long queue = 0;
+  emu::run_warp([&](int lane) {
+    blockIdx.x = 0;
+    threadIdx.x = (unsigned)lane;
+    cno::lbfgsb_minimize_kernel<Fn, 5>(Fn{}, (const T*)x0, B, cno::make_stop<T>(*stop), cno::make_out<T>(*out), &queue,
+                                        cno::BoundsArgs<T>{(const T*)lower, (const T*)upper, stride});
+  });
+  return 0;
+}
+extern "C" int emu_lbfgsb(const cno_problem_t* p, long long batch, const void* x0, const void* lower, const void* upper,
+                          long long stride, const cno_stop_t* stop, const cno_batch_out_t* out) {
+#define LB_CASE(FAM, DT, FN)                                   \
+  if (p->family == FAM && p->dtype == DT) return run_lbfgsb<FN>(batch, x0, lower, upper, stride, stop, out);
+  if (p->d == 2) { LB_CASE(CNO_FN_ROSENBROCK, CNO_F64, cno::RosenbrockFn<double CNO_EMU_COMMA 2>) }
+  if (p->d == 8) { LB_CASE(CNO_FN_ROSENBROCK, CNO_F64, cno::RosenbrockFn<double CNO_EMU_COMMA 8>) }
+  if (p->d == 37) { LB_CASE(CNO_FN_ROSENBROCK, CNO_F64, cno::RosenbrockFn<double CNO_EMU_COMMA 37>) }
+  if (p->d == 128) { LB_CASE(CNO_FN_ROSENBROCK, CNO_F64, cno::RosenbrockFn<double CNO_EMU_COMMA 128>) }
+  if (p->d == 8) { LB_CASE(CNO_FN_HALF_SQUARED_NORM, CNO_F64, cno::HalfSquaredNormFn<double CNO_EMU_COMMA 8>) }
+#undef LB_CASE
   return CNO_ERR_UNSUPPORTED;
 }

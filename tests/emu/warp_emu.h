@@ -167,6 +167,14 @@ inline unsigned __reduce_min_sync(unsigned, unsigned v) {
   emu::sync();
   return m;
 }
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+  emu::tl_warp->slot[emu::tl_lane] = v;
+  emu::sync();
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) m += (unsigned)emu::tl_warp->slot[l];
+  emu::sync();
+  return m;
+}
 inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::sync(); }
 inline void __syncthreads() {}  // only reached from Tensor-Memory paths, which the emulation does not run
