@@ -1,0 +1,124 @@
+"""BASELINE.json configs[1..4] at their FULL batch sizes on the device, each checked against the CPU oracle on a
+strided sample of the very batch that ran (iteration counts, status and x* bit for bit) plus size-independent
+properties over the whole batch.  (VERDICT r1 weak #1b: C3 was only checked at B = 96, C5 at B = 192.)
+The inputs are the ones bench.py / bench_configs.py time (same generators, same seeds)."""
+import numpy as np
+import pytest
+import torch
+
+import bench_configs
+import cppnumericalsolvers_b200 as cn
+from oracle import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SAMPLES = 64
+
+
+def _sample(B):
+    return np.arange(0, B, B // SAMPLES)[:SAMPLES]
+
+
+def _terminated(pr):
+    st = pr.status.cpu().numpy()
+    assert np.all((st >= 1) & (st <= 4)), np.bincount(st.astype(np.int64) + 1)
+    return st
+
+
+def test_c2_lbfgs_rosenbrock_d128_full_batch_2e20():
+    B, d = 1 << 20, 128
+    x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
+    cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
+    st, pr = cn.Lbfgs().Minimize(cn.Rosenbrock(d), cn.BatchedFunctionState(x0))
+    torch.cuda.synchronize()
+    _terminated(pr)
+    idx = _sample(B)
+    tidx = torch.from_numpy(idx).to(DEV)
+    o = ob.minimize(ob.LBFGS, ob.FN_ROSENBROCK, x0[tidx].cpu().numpy())
+    assert np.array_equal(pr.num_iterations[tidx].cpu().numpy().astype(np.uint32), o["num_iterations"])
+    assert np.array_equal(pr.status[tidx].cpu().numpy(), o["status"])
+    assert np.array_equal(st.x[tidx].cpu().numpy().view(np.uint64), o["x"].view(np.uint64))
+    assert np.array_equal(st.value[tidx].cpu().numpy().view(np.uint64), o["value"].view(np.uint64))
+    xi = st.x[:, :-1]
+    f_chk = ((1 - xi) ** 2 + 100 * (st.x[:, 1:] - xi ** 2) ** 2).sum(1)
+    assert torch.allclose(st.value, f_chk, rtol=1e-12, atol=1e-12)  # FunctionState invariant over the whole batch
+    bm = pr.done_bitmap()
+    assert bool((bm == -1).all().item())  # one bit per instance, all set
+
+
+def test_c3_lbfgs_logistic_full_batch_2e18():
+    """n = 256, d = 64, fp32, B = 2^18 (17 GB of per-instance data, generated on the device as bench_configs does)."""
+    B, n, d, lam = 1 << 18, 256, 64, 1e-2
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(0)
+    data = torch.empty(B, d * n + n, dtype=torch.float32, device=DEV)
+    chunk = 1 << 14
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        X = torch.rand(hi - lo, n, d, device=DEV, generator=gen) * 2 - 1
+        ws = torch.randn(hi - lo, d, device=DEV, generator=gen)
+        y = torch.sign(torch.einsum("bnd,bd->bn", X, ws) + 0.1 * torch.randn(hi - lo, n, device=DEV, generator=gen))
+        y[y == 0] = 1
+        data[lo:hi, : d * n] = X.transpose(1, 2).reshape(hi - lo, -1)
+        data[lo:hi, d * n:] = y
+        del X, ws, y
+    x0 = torch.zeros(B, d, dtype=torch.float32, device=DEV)
+    st, pr = cn.Lbfgs().Minimize(cn.Logistic(data, n, d, lam), cn.BatchedFunctionState(x0))
+    torch.cuda.synchronize()
+    _terminated(pr)
+    idx = _sample(B)
+    tidx = torch.from_numpy(idx).to(DEV)
+    o = ob.minimize(ob.LBFGS, ob.FN_LOGISTIC, np.zeros((SAMPLES, d), np.float32), data=data[tidx].cpu().numpy(), n=n, param=lam)
+    assert np.array_equal(pr.num_iterations[tidx].cpu().numpy().astype(np.uint32), o["num_iterations"])
+    assert np.array_equal(pr.status[tidx].cpu().numpy(), o["status"])
+    assert np.array_equal(st.x[tidx].cpu().numpy().view(np.uint32), o["x"].view(np.uint32))
+    assert bool((st.value < n * np.log(2.0)).all().item())  # below f(w0 = 0) everywhere
+
+
+def test_c4_bfgs_rosenbrock_d32_full_batch_2e19():
+    B, d = 1 << 19, 32
+    x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
+    cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
+    st, pr = cn.Bfgs().Minimize(cn.Rosenbrock(d), cn.BatchedFunctionState(x0))
+    torch.cuda.synchronize()
+    _terminated(pr)
+    idx = _sample(B)
+    tidx = torch.from_numpy(idx).to(DEV)
+    o = ob.minimize(ob.BFGS, ob.FN_ROSENBROCK, x0[tidx].cpu().numpy())
+    assert np.array_equal(pr.num_iterations[tidx].cpu().numpy().astype(np.uint32), o["num_iterations"])
+    assert np.array_equal(st.x[tidx].cpu().numpy().view(np.uint64), o["x"].view(np.uint64))
+    xi = st.x[:, :-1]
+    f_chk = ((1 - xi) ** 2 + 100 * (st.x[:, 1:] - xi ** 2) ** 2).sum(1)
+    assert torch.allclose(st.value, f_chk, rtol=1e-12, atol=1e-12)
+
+
+def test_c5_newton_dense_quadratic_d64_full_batch_2e17():
+    B, d = 1 << 17, 64
+    gen = torch.Generator(device=DEV)
+    gen.manual_seed(0)
+    data = torch.empty(B, d * d + d, dtype=torch.float64, device=DEV)
+    eye = torch.eye(d, dtype=torch.float64, device=DEV)
+    chunk = 1 << 13
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        M = torch.rand(hi - lo, d, d, dtype=torch.float64, device=DEV, generator=gen) * 2 - 1
+        A = torch.bmm(M.transpose(1, 2), M) / d + eye
+        A = (A + A.transpose(1, 2)) / 2
+        data[lo:hi, : d * d] = A.transpose(1, 2).reshape(hi - lo, -1)
+        data[lo:hi, d * d:] = torch.rand(hi - lo, d, dtype=torch.float64, device=DEV, generator=gen) * 2 - 1
+    x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
+    cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
+    st, pr = cn.NewtonDescent().Minimize(cn.DenseQuadratic(data, d), cn.BatchedFunctionState(x0))
+    torch.cuda.synchronize()
+    _terminated(pr)
+    idx = _sample(B)
+    tidx = torch.from_numpy(idx).to(DEV)
+    o = ob.minimize(ob.NEWTON, ob.FN_DENSE_QUADRATIC, x0[tidx].cpu().numpy(), data=data[tidx].cpu().numpy())
+    assert np.array_equal(pr.num_iterations[tidx].cpu().numpy().astype(np.uint32), o["num_iterations"])
+    assert np.array_equal(pr.status[tidx].cpu().numpy(), o["status"])
+    assert np.array_equal(st.x[tidx].cpu().numpy().view(np.uint64), o["x"].view(np.uint64))
+    # the answer solves A x = b: residual of the whole batch (north_star: x* within 1e-10 relative in fp64)
+    A = data[:, : d * d].view(B, d, d).transpose(1, 2)
+    res = torch.bmm(A, st.x.unsqueeze(2)).squeeze(2) - data[:, d * d:]
+    assert float(res.abs().max()) < 1e-4  # the default preset stops on |g| < 1e-5 (relative); g = A x - b
+    assert bench_configs is not None
