@@ -207,7 +207,7 @@ def test_oracle_equals_reference_dense_quadratic():
 
 
 @pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(GOLDEN, "*_rosenbrock_*.npz"))
-                                        if not os.path.basename(p).startswith(("al_", "hz_"))))  # incl. gd_*, cg_*
+                                        if not os.path.basename(p).startswith(("al_", "hz_", "lbfgsb_"))))  # incl. gd_*, cg_* (lbfgsb_*: tests/test_lbfgsb.py)
 def test_oracle_reproduces_committed_reference_fixtures(path):
     """Fixtures were produced by oracle/_ref (tests/golden/make_golden.py)."""
     z = np.load(path)
