@@ -101,7 +101,7 @@ def run_config(which: str, scale: int = 0, reps: int = 3) -> dict:
         cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
         return run("c4 bfgs rosenbrock d32 f64", cn.Bfgs(), cn.Rosenbrock(32), x0,
                    lambda it, nf: (8 * (2 * 32 * 32 + 4 * 32) * it).sum(), reps)
-    if which == "c5":  # NewtonDescent dense quadratic d=64 fp64, B = 2^17
+    if which in ("c5", "c5t"):  # NewtonDescent dense quadratic d=64 fp64, B = 2^17; c5t = CNO_POLICY_DMMA_LU (tensor core)
         B, d = (1 << 17) >> scale, 64
         data = torch.empty(B, d * d + d, dtype=torch.float64, device=DEV)
         chunk = 1 << 13
@@ -116,7 +116,9 @@ def run_config(which: str, scale: int = 0, reps: int = 3) -> dict:
         x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
         cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
         flops = lambda it: float(((2.0 / 3.0) * d ** 3 + 4.0 * d * d) * it.sum())  # noqa: E731  SURVEY.md 8(d)
-        rec = run("c5 newton dense quadratic d64 f64", cn.NewtonDescent(), cn.DenseQuadratic(data, d), x0,
+        tensor = which == "c5t"
+        rec = run("c5 newton dense quadratic d64 f64" + (" policy=dmma_lu (FP64 tensor-core factorisation)" if tensor else ""),
+                  cn.NewtonDescent(), cn.DenseQuadratic(data, d, policy=cn._lib.POLICY_DMMA_LU if tensor else None), x0,
                   lambda it, nf: (8 * (d * d + 3 * d) * it).sum(), reps)
         rec["algorithmic_TFLOPs"] = flops(np.full(B, rec["mean_iterations"])) / rec["kernel_ms"] / 1e9
         return rec

@@ -17,7 +17,7 @@ LBFGS, BFGS, NEWTON, GRADIENT_DESCENT, CONJUGATED_GRADIENT_DESCENT = 0, 1, 2, 3,
 LBFGS_HAGER_ZHANG, BFGS_HAGER_ZHANG, GRADIENT_DESCENT_HAGER_ZHANG = 5, 6, 7
 F64, F32 = 0, 1
 FN_ROSENBROCK, FN_DIAG_QUADRATIC, FN_HALF_SQUARED_NORM, FN_LOGISTIC, FN_DENSE_QUADRATIC = range(5)
-POLICY_WARP_TREE, POLICY_EIGEN_SSE2, POLICY_DMMA_TREE = 0, 1, 2
+POLICY_WARP_TREE, POLICY_EIGEN_SSE2, POLICY_DMMA_TREE, POLICY_DMMA_LU = 0, 1, 2, 3
 OK, ERR_INVALID_ARGUMENT, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
 
 

@@ -22,6 +22,7 @@
 #include "cno_descent.cuh"
 #include "cno_evaluate.cuh"
 #include "cno_newton.cuh"
+#include "cno_newton_dmma.cuh"
 #include "cno_logistic.cuh"
 #include "cno_auglag.cuh"
 #include "cno_auglag_host.h"
@@ -233,6 +234,41 @@ int newton_dense_quadratic(const LaunchArgs& a) {
   return launch_newton<cno::DenseQuadraticFn<T, D>>(
       cno::DenseQuadraticFn<T, D>{static_cast<const T*>(p->data), (long long)p->data_stride}, a);
 }
+// CNO_POLICY_DMMA_LU: d = 64 fp64 dense quadratic, blocked LU with the trailing update on the FP64 tensor core
+// (csrc/cno_newton_dmma.cuh).
+int newton_dense_quadratic_dmma(const LaunchArgs& a) {
+  using Fn = cno::DenseQuadraticDmmaFn;
+  using SM = cno::NewtonDmmaSmem;
+  const cno_problem_t* p = a.problem;
+  if (!p->data || p->data_stride < (int64_t)64 * 64 + 64) return CNO_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)p->data & 15) || ((size_t)p->data_stride * sizeof(double)) % 16) return CNO_ERR_INVALID_ARGUMENT;
+  if (a.stop->condition_hessian > 0) return CNO_ERR_UNSUPPORTED;  // see cno_newton.cuh
+  Fn fn;
+  fn.data = static_cast<const double*>(p->data);
+  fn.stride = (long long)p->data_stride;
+  auto kernel = cno::newton_dmma_minimize_kernel<Fn>;
+  const size_t smem = SM::kWarpBytes * SM::kWarps;
+  CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  long long ctas = (a.batch + SM::kWarps - 1) / SM::kWarps;
+  const int grid = (int)(ctas < sms ? (ctas < 1 ? 1 : ctas) : sms);
+  unsigned long long* queue = static_cast<unsigned long long*>(a.workspace);
+  CNO_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), a.stream));
+  const cno::StopParams<double> stop = cno::make_stop<double>(*a.stop);
+  const cno::BatchOut<double> out = cno::make_out<double>(*a.out);
+  kernel<<<grid, SM::kWarps * 32, smem, a.stream>>>(fn, static_cast<const double*>(a.x0), a.batch, stop, out, queue);
+  CNO_CUDA(cudaGetLastError());
+  if (a.info) {
+    a.info->kernel_launches += 1;
+    a.info->grid = grid;
+    a.info->block = SM::kWarps * 32;
+    a.info->warps_per_cta = SM::kWarps;
+    a.info->dynamic_smem = (int64_t)smem;
+  }
+  return CNO_OK;
+}
 template <class T, int D>
 int newton_rosenbrock(const LaunchArgs& a) {
   return launch_newton<cno::RosenbrockFullFn<T, D>>(cno::RosenbrockFullFn<T, D>{}, a);
@@ -402,6 +438,7 @@ const Entry kTable[] = {
     {CNO_BFGS, CNO_FN_DIAG_QUADRATIC, CNO_F64, 2, bfgs_diag_quadratic<double>},
     {CNO_BFGS, CNO_FN_HALF_SQUARED_NORM, CNO_F64, 2, bfgs_half_sq_norm<double, 2>},
     {CNO_NEWTON, CNO_FN_DENSE_QUADRATIC, CNO_F64, 64, newton_dense_quadratic<double, 64>},
+    {CNO_NEWTON, CNO_FN_DENSE_QUADRATIC, CNO_F64, 64, newton_dense_quadratic_dmma, CNO_POLICY_DMMA_LU},
     {CNO_NEWTON, CNO_FN_DENSE_QUADRATIC, CNO_F64, 12, newton_dense_quadratic<double, 12>},
     {CNO_NEWTON, CNO_FN_DENSE_QUADRATIC, CNO_F32, 64, newton_dense_quadratic<float, 64>},
     {CNO_NEWTON, CNO_FN_ROSENBROCK, CNO_F64, 2, newton_rosenbrock<double, 2>},

@@ -84,10 +84,12 @@ def Logistic(data: torch.Tensor, n: int, d: int, lam: float) -> Function:
                     param=lam, data=data)
 
 
-def DenseQuadratic(data: torch.Tensor, d: int) -> Function:
-    """0.5 x'Ax - b'x; data[b] = [A (d x d col-major) | b (d)]; Second mode."""
+def DenseQuadratic(data: torch.Tensor, d: int, policy: Optional[int] = None) -> Function:
+    """0.5 x'Ax - b'x; data[b] = [A (d x d col-major, bitwise symmetric) | b (d)]; Second mode.
+    policy = POLICY_DMMA_LU (d = 64 fp64): NewtonDescent factors the Hessian with fused multiply-subtracts, the
+    trailing update of the blocked elimination on the FP64 tensor core (include/cno.h, csrc/cno_newton_dmma.cuh)."""
     return Function(d, data.dtype, DifferentiabilityMode.Second, _lib.FN_DENSE_QUADRATIC,
-                    data=data)
+                    data=data, policy=policy)
 
 
 def DenseQuadraticFirst(data: torch.Tensor, d: int) -> Function:

@@ -113,7 +113,13 @@ typedef enum cno_family {
 typedef enum cno_policy {
   CNO_POLICY_WARP_TREE = 0,  /* lane-blocked partials + xor butterfly (fp32 kernels) */
   CNO_POLICY_EIGEN_SSE2 = 1, /* model of Eigen 3.4 SSE2 redux (oracle only) */
-  CNO_POLICY_DMMA_TREE = 2   /* lane-blocked partials + two FP64 tensor-core MMAs (fp64 kernels) */
+  CNO_POLICY_DMMA_TREE = 2,  /* lane-blocked partials + two FP64 tensor-core MMAs (fp64 kernels) */
+  /* CNO_POLICY_DMMA_TREE for every sum, and hessian.lu().solve (newton_descent.h:76) with every
+   * multiply-subtract of the elimination and of both substitutions FUSED (a - l*u rounded once, the
+   * contraction a -march=native build of the reference makes): the form the FP64 tensor core
+   * evaluates, so the blocked elimination's trailing update runs as DMMA.8x8x4 (NewtonDescent,
+   * d = 64 fp64; csrc/cno_newton_dmma.cuh).  Oracle twin: lu_solve(..., fused = 1). */
+  CNO_POLICY_DMMA_LU = 3
 } cno_policy_t;
 
 /* Stopping thresholds: the fields of solver::Progress that

@@ -277,6 +277,9 @@ template <class T, int D>
 struct DenseQuadratic : FunctionCRTP<DenseQuadratic<T, D>, T, DifferentiabilityMode::Second, D> {
   const T* data = nullptr;
   int64_t data_stride = 0;
+  // -1 = the default arithmetic of the dtype; CNO_POLICY_DMMA_LU (D = 64, double): NewtonDescent's factorisation with
+  // fused multiply-subtracts, the trailing update on the FP64 tensor core (include/cno.h)
+  int policy = -1;
 };
 
 namespace detail_builtin {
@@ -316,6 +319,7 @@ struct LauncherTraits<DenseQuadratic<T, D>> {
     e.problem = detail_builtin::make<T, D>(CNO_FN_DENSE_QUADRATIC);
     e.problem.data = f.data;
     e.problem.data_stride = f.data_stride;
+    if (f.policy >= 0) e.problem.policy = f.policy;
   }
 };
 

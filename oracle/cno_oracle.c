@@ -29,6 +29,7 @@ static inline int problem_lbfgs_m(const cno_problem_t* p) {
 #define R_EPS DBL_EPSILON
 #define R_SQRT sqrt
 #define R_FABS fabs
+#define R_FMA fma
 #define R_FMAX fmax
 #define R_ISFINITE isfinite
 #define R_IS_F32 0
@@ -38,6 +39,7 @@ static inline int problem_lbfgs_m(const cno_problem_t* p) {
 #undef R_EPS
 #undef R_SQRT
 #undef R_FABS
+#undef R_FMA
 #undef R_FMAX
 #undef R_ISFINITE
 #undef R_IS_F32
@@ -48,6 +50,7 @@ static inline int problem_lbfgs_m(const cno_problem_t* p) {
 #define R_EPS FLT_EPSILON
 #define R_SQRT sqrtf
 #define R_FABS fabsf
+#define R_FMA fmaf
 #define R_FMAX fmaxf
 #define R_ISFINITE isfinite
 #define R_IS_F32 1

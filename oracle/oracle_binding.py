@@ -18,7 +18,7 @@ REF_LIB = os.path.join(HERE, "_ref", "libcno_ref.so")
 
 LBFGS, BFGS, NEWTON, GRADIENT_DESCENT, CONJUGATED_GRADIENT_DESCENT = 0, 1, 2, 3, 4
 FN_ROSENBROCK, FN_DIAG_QUADRATIC, FN_HALF_SQUARED_NORM, FN_LOGISTIC, FN_DENSE_QUADRATIC = range(5)
-POLICY_WARP_TREE, POLICY_EIGEN_SSE2, POLICY_DMMA_TREE = 0, 1, 2
+POLICY_WARP_TREE, POLICY_EIGEN_SSE2, POLICY_DMMA_TREE, POLICY_DMMA_LU = 0, 1, 2, 3
 
 
 def device_policy(dtype) -> int:

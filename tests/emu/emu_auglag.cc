@@ -11,6 +11,7 @@
 #include "cno_bfgs.cuh"
 #include "cno_descent.cuh"
 #include "cno_newton.cuh"
+#include "cno_newton_dmma.cuh"
 #include "cno_lbfgsb.cuh"
 #include "cno_logistic.cuh"
 
@@ -215,6 +216,20 @@ int run_newton(const Fn& fn, long long B, const void* x0, const cno_stop_t* stop
 
 extern "C" int emu_newton(const cno_problem_t* p, long long batch, const void* x0, const cno_stop_t* stop,
                           const cno_batch_out_t* out) {
+  if (p->policy == CNO_POLICY_DMMA_LU) {  // csrc/cno_newton_dmma.cuh: blocked LU, trailing update as DMMA.8x8x4
+    if (!(p->family == CNO_FN_DENSE_QUADRATIC && p->dtype == CNO_F64 && p->d == 64)) return CNO_ERR_UNSUPPORTED;
+    cno::DenseQuadraticDmmaFn fn;
+    fn.data = static_cast<const double*>(p->data);
+    fn.stride = (long long)p->data_stride;
+    unsigned long long queue = 0;
+    emu::run_warp([&](int lane) {
+      blockIdx.x = 0;
+      threadIdx.x = (unsigned)lane;
+      cno::newton_dmma_minimize_kernel<cno::DenseQuadraticDmmaFn>(fn, (const double*)x0, batch, cno::make_stop<double>(*stop),
+                                                                 cno::make_out<double>(*out), &queue);
+    });
+    return 0;
+  }
   if (p->family == CNO_FN_DENSE_QUADRATIC) {
 #define NEWTON_CASE(DT, TY, DIM)                                                                   \
   if (p->dtype == DT && p->d == DIM)                                                               \

@@ -68,6 +68,7 @@ struct Warp {
   SpinBarrier bar;
   uint64_t slot[32];
   double dslot[32];
+  double dslot2[32];
   uint32_t tmem[32][512];  // Tensor Memory window of the emulated warp: [lane][column], 32-bit cells
 };
 inline thread_local int tl_lane = 0;
@@ -101,6 +102,24 @@ inline void dmma_ones(double& d0, double& d1, double b) {
   d0 = col(2 * j);
   d1 = col(2 * j + 1);
   sync();
+}
+
+// General D = A*B + C (mma.sync.m8n8k4.f64): lane supplies A[lane/4][lane%4], B[lane%4][lane/4] and C[lane/4][2*(lane%4)
+// + {0,1}]; every element is the FMA chain d = c; d = fma(A[m][k], B[k][n], d), k = 0..3 (tools/dmma_probe.cu).
+inline void dmma(double& d0, double& d1, double a, double b, double c0, double c1) {
+  tl_warp->dslot[tl_lane] = a;
+  tl_warp->dslot2[tl_lane] = b;
+  sync();
+  const int mrow = tl_lane >> 2, j = tl_lane & 3;
+  auto el = [&](int n, double c) {
+    double d = c;
+    for (int k = 0; k < 4; ++k) d = std::fma(tl_warp->dslot[4 * mrow + k], tl_warp->dslot2[4 * n + k], d);
+    return d;
+  };
+  const double r0 = el(2 * j, c0), r1 = el(2 * j + 1, c1);
+  sync();
+  d0 = r0;
+  d1 = r1;
 }
 
 // tcgen05.st / tcgen05.ld .32x32b.xN: lane l moves N consecutive 32-bit columns of its own TMEM lane

@@ -49,6 +49,24 @@ def main():
                             status=r["status"], nfev=r["nfev"], solver=solver, family=family,
                             policy=(policy if policy is not None else ob.device_policy(dtype)))
         print(name, "mean iters", r["num_iterations"].mean())
+    if not only or "newton_" in only:
+        # NewtonDescent on per-instance dense quadratics, d = 64, under CNO_POLICY_DMMA_LU (every multiply-subtract
+        # of lu().solve() fused): what the tensor-core kernel csrc/cno_newton_dmma.cuh must reproduce
+        rng = np.random.default_rng(SEED)
+        B, d = 12, 64
+        M = rng.uniform(-1, 1, (B, d, d))
+        A = np.einsum("bki,bkj->bij", M, M) / d + np.eye(d)
+        A = (A + A.transpose(0, 2, 1)) / 2
+        A[3] = (M[3] + M[3].T) / 2   # symmetric indefinite: the pivots move
+        bvec = rng.uniform(-1, 1, (B, d))
+        data = np.ascontiguousarray(np.concatenate([A.transpose(0, 2, 1).reshape(B, -1), bvec], axis=1))
+        x0 = ob.fill_uniform((B, d), 0, SEED, -2.0, 2.0, np.float64)
+        r = ob.minimize(ob.NEWTON, ob.FN_DENSE_QUADRATIC, x0, data=data, impl="ref", policy=ob.POLICY_DMMA_LU)
+        np.savez_compressed(os.path.join(HERE, "newton_dense_quadratic_d64_dmma_lu.npz"), x0=x0, data=data, x=r["x"],
+                            value=r["value"], gradient=r["gradient"], num_iterations=r["num_iterations"],
+                            status=r["status"], nfev=r["nfev"], solver=ob.NEWTON, family=ob.FN_DENSE_QUADRATIC,
+                            policy=ob.POLICY_DMMA_LU)
+        print("newton_dense_quadratic_d64_dmma_lu", "iters", r["num_iterations"])
     if only and "pins" not in only:
         return
     # the two verify.cc starts + Dockerfile.test + AL-test half norm (reference code, d = 2)

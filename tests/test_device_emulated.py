@@ -313,6 +313,63 @@ def test_emulation_reproduces_the_newton_kernel(emu, family, dtype, d):
         assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
 
 
+def _newton_pivot_cases(d=64, B=8):
+    """Symmetric indefinite matrices (pivots move in every panel), exact ties, a zero row / column, a NaN entry, an
+    anti-diagonal permutation matrix."""
+    rng = np.random.default_rng(17)
+    A = np.zeros((B, d, d))
+    for b in range(B):
+        M = rng.uniform(-1, 1, (d, d))
+        S = (M + M.T) / 2
+        if b == 1:
+            S = np.round(S * 4) / 4
+        if b == 2:
+            S[:, 5] = 0.0
+            S[5, :] = 0.0
+        if b == 3:
+            S[7, 9] = S[9, 7] = np.nan
+        if b == 4:
+            S = np.eye(d)[::-1].copy()
+        A[b] = S
+    bvec = rng.uniform(-1, 1, (B, d))
+    return np.ascontiguousarray(np.concatenate([A.transpose(0, 2, 1).reshape(B, -1), bvec], axis=1))
+
+
+@pytest.mark.parametrize("case", ["spd", "pivoting", "huge", "tiny"])
+def test_emulation_tensor_core_newton_equals_the_fused_oracle(emu, case):
+    """csrc/cno_newton_dmma.cuh (CNO_POLICY_DMMA_LU) under emulation, DMMA.8x8x4 as the FMA chain measured on B200:
+    the BLOCKED elimination (register panels, U12 in the B-fragment layout, tensor-core trailing update, blocked
+    substitutions) equals the oracle's UNBLOCKED lu_solve with fused multiply-subtracts bit for bit."""
+    d = 64
+    if case == "spd":
+        B, data = 3, _spd_data(3, d, 9)
+    else:
+        data = _newton_pivot_cases(d) * {"pivoting": 1.0, "huge": 1e150, "tiny": 1e-150}[case]
+        B = data.shape[0]
+    x0 = ob.fill_uniform((B, d), 0, 5, -2.0, 2.0, np.float64)
+    prob = ob.Problem(ob.FN_DENSE_QUADRATIC, ob._np_dtype(x0), d, 0, 0.0, data.ctypes.data, data.shape[1],
+                      ob.POLICY_DMMA_LU, 0)
+    stop = ob.default_stop()
+    stop.num_iterations = 4
+    r = dict(x=np.zeros_like(x0), value=np.zeros(B), gradient=np.zeros_like(x0),
+             num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32),
+             x_delta=np.zeros(B), f_delta=np.zeros(B), gradient_norm=np.zeros(B))
+    out = ob.BatchOut(*[r[n].ctypes.data for n, _ in ob.BatchOut._fields_])
+    assert emu.emu_newton(C.byref(prob), C.c_longlong(B), C.c_void_p(x0.ctypes.data), C.byref(stop), C.byref(out)) == 0
+    o = ob.minimize(ob.NEWTON, ob.FN_DENSE_QUADRATIC, x0, data=data, stop=stop, policy=ob.POLICY_DMMA_LU)
+    for key in SOLVER_KEYS:
+        u, v = r[key], o[key]
+        if u.dtype.kind == "f":  # (a NaN's sign / payload is not part of the contract)
+            nan = np.isnan(u)
+            assert np.array_equal(nan, np.isnan(v)), key
+            u, v = np.where(nan, 0, u), np.where(nan, 0, v)
+        assert np.array_equal(u.view(np.uint8), v.view(np.uint8)), key
+    if case == "spd":  # the policy changes the rounding, not the answer
+        o0 = ob.minimize(ob.NEWTON, ob.FN_DENSE_QUADRATIC, x0, data=data, stop=stop)
+        assert not np.array_equal(o0["x"].view(np.uint64), o["x"].view(np.uint64))
+        assert np.allclose(o0["x"], o["x"], rtol=1e-9, atol=1e-12)
+
+
 def test_emulation_reproduces_the_logistic_kernel(emu):
     """L-BFGS on the logistic-regression functor (csrc/cno_logistic.cuh): per-instance data staged by TMA bulk
     copies into shared memory and by tcgen05.st into Tensor Memory -- under emulation a memcpy and a host array."""

@@ -170,6 +170,42 @@ def test_oracle_equals_reference_headers(dtype, policy, solver, d):
     assert _same(a, b)
 
 
+def test_fused_lu_oracle_equals_reference_headers():
+    """CNO_POLICY_DMMA_LU: the oracle's lu_solve(fused = 1) == the reference's newton_descent.h / armijo.h /
+    progress.h on the shim whose lu().solve() fuses every multiply-subtract under this policy; d = 64 (the shape
+    the tensor-core kernel is built for), 12 and Rosenbrock d = 8; and the committed fixture."""
+    if not ob.ref_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(11)
+    for d, B in ((64, 6), (12, 5)):
+        M = rng.uniform(-1, 1, (B, d, d))
+        A = np.einsum("bki,bkj->bij", M, M) / d + np.eye(d)
+        A = (A + A.transpose(0, 2, 1)) / 2
+        if d == 64:
+            A[1] = (M[1] + M[1].T) / 2  # indefinite: pivots move
+        bvec = rng.uniform(-1, 1, (B, d))
+        data = np.concatenate([A.transpose(0, 2, 1).reshape(B, -1), bvec], axis=1)
+        x0 = rng.uniform(-2, 2, (B, d))
+        stop = ob.default_stop()
+        stop.num_iterations = 6
+        a = ob.minimize(ob.NEWTON, ob.FN_DENSE_QUADRATIC, x0, data=data, impl="oracle", policy=ob.POLICY_DMMA_LU, stop=stop)
+        b = ob.minimize(ob.NEWTON, ob.FN_DENSE_QUADRATIC, x0, data=data, impl="ref", policy=ob.POLICY_DMMA_LU, stop=stop)
+        assert _same(a, b)
+        c = ob.minimize(ob.NEWTON, ob.FN_DENSE_QUADRATIC, x0, data=data, impl="oracle", stop=stop)
+        assert not np.array_equal(a["x"].view(np.uint64), c["x"].view(np.uint64))
+    x0 = ob.fill_uniform((16, 8), 8000, 99, -2.0, 2.0)
+    assert _same(ob.minimize(ob.NEWTON, ob.FN_ROSENBROCK, x0, policy=ob.POLICY_DMMA_LU, impl="oracle"),
+                 ob.minimize(ob.NEWTON, ob.FN_ROSENBROCK, x0, policy=ob.POLICY_DMMA_LU, impl="ref"))
+
+
+def test_fused_lu_oracle_reproduces_committed_reference_fixture():
+    """tests/golden/newton_dense_quadratic_d64_dmma_lu.npz was produced by oracle/_ref (make_golden.py)."""
+    z = np.load(os.path.join(GOLDEN, "newton_dense_quadratic_d64_dmma_lu.npz"))
+    r = ob.minimize(ob.NEWTON, ob.FN_DENSE_QUADRATIC, z["x0"], data=z["data"], policy=ob.POLICY_DMMA_LU)
+    for k in ("x", "value", "gradient", "num_iterations", "status", "nfev"):
+        assert np.array_equal(r[k].view(np.uint8), z[k].view(np.uint8)), k
+
+
 @pytest.mark.parametrize("policy", [ob.POLICY_WARP_TREE, ob.POLICY_EIGEN_SSE2, ob.POLICY_DMMA_TREE])
 @pytest.mark.parametrize("solver,dtype,d", [
     (ob.GRADIENT_DESCENT, np.float64, 2), (ob.GRADIENT_DESCENT, np.float64, 8),
