@@ -415,7 +415,8 @@ def main():
         del x0, state, prog
         torch.cuda.empty_cache()
         import bench_configs
-        other = [bench_configs.run_config(c) for c in ("c3", "c4", "c5")]
+        # c5t = config 5 under CNO_POLICY_DMMA_LU (NewtonDescent's factorisation on the FP64 tensor core)
+        other = [bench_configs.run_config(c) for c in ("c3", "c4", "c5", "c5t")]
 
     if rank == 0:
         cpu = None

@@ -117,7 +117,8 @@ def run_config(which: str, scale: int = 0, reps: int = 3) -> dict:
         cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
         flops = lambda it: float(((2.0 / 3.0) * d ** 3 + 4.0 * d * d) * it.sum())  # noqa: E731  SURVEY.md 8(d)
         tensor = which == "c5t"
-        rec = run("c5 newton dense quadratic d64 f64" + (" policy=dmma_lu (FP64 tensor-core factorisation)" if tensor else ""),
+        rec = run(("c5t newton dense quadratic d64 f64 policy=dmma_lu (FP64 tensor-core factorisation)" if tensor
+                   else "c5 newton dense quadratic d64 f64"),
                   cn.NewtonDescent(), cn.DenseQuadratic(data, d, policy=cn._lib.POLICY_DMMA_LU if tensor else None), x0,
                   lambda it, nf: (8 * (d * d + 3 * d) * it).sum(), reps)
         rec["algorithmic_TFLOPs"] = flops(np.full(B, rec["mean_iterations"])) / rec["kernel_ms"] / 1e9

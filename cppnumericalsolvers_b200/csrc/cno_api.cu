@@ -653,6 +653,18 @@ __global__ void count_bits_kernel(const uint32_t* words, long long bits, unsigne
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, (unsigned long long)c);
 }
 
+__global__ void div_check_kernel(const double* a, const double* b, long long n, double* helper, double* plain,
+                                 int* accepted) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool ok;
+  const double q = cno::div_with(a[i], b[i], cno::div_rcp(b[i]), ok);
+  const double p = a[i] / b[i];
+  helper[i] = ok ? q : p;
+  plain[i] = p;
+  accepted[i] = ok ? 1 : 0;
+}
+
 __global__ void cstep_kernel(double* io, int* flags) {
   bool brackt = flags[0] != 0;
   int info = flags[1];
@@ -1288,6 +1300,30 @@ int cno_device_cstep(double io[11], int* brackt, int* info, int* ret) {
   *brackt = fl[0];
   *info = fl[1];
   *ret = fl[2];
+  return CNO_OK;
+}
+
+int cno_device_div_check(const double* a, const double* b, int64_t n, double* helper, double* plain,
+                         int32_t* accepted) {
+  if (!a || !b || !helper || !plain || !accepted || n < 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (!have_device()) return CNO_ERR_NO_DEVICE;
+  if (n == 0) return CNO_OK;
+  DeviceBuffer da, db, dh, dp, dk;
+  const size_t bytes = (size_t)n * sizeof(double);
+  CNO_CUDA(da.alloc(bytes));
+  CNO_CUDA(db.alloc(bytes));
+  CNO_CUDA(dh.alloc(bytes));
+  CNO_CUDA(dp.alloc(bytes));
+  CNO_CUDA(dk.alloc((size_t)n * sizeof(int)));
+  CNO_CUDA(cudaMemcpy(da.p, a, bytes, cudaMemcpyHostToDevice));
+  CNO_CUDA(cudaMemcpy(db.p, b, bytes, cudaMemcpyHostToDevice));
+  div_check_kernel<<<(unsigned)((n + 255) / 256), 256>>>(static_cast<const double*>(da.p), static_cast<const double*>(db.p),
+                                                         (long long)n, static_cast<double*>(dh.p),
+                                                         static_cast<double*>(dp.p), static_cast<int*>(dk.p));
+  CNO_CUDA(cudaGetLastError());
+  CNO_CUDA(cudaMemcpy(helper, dh.p, bytes, cudaMemcpyDeviceToHost));
+  CNO_CUDA(cudaMemcpy(plain, dp.p, bytes, cudaMemcpyDeviceToHost));
+  CNO_CUDA(cudaMemcpy(accepted, dk.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
   return CNO_OK;
 }
 

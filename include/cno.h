@@ -294,6 +294,13 @@ int cno_count_done(const uint32_t* all_words, int32_t ranks, size_t words_per_ra
  * brackt/info in-out, ret = cstep's return value. */
 int cno_device_cstep(double io[11], int* brackt, int* info, int* ret);
 
+/* Device-side check hook for the division helper of csrc/cno_newton_dmma.cuh (the reciprocal refinement of a
+ * divisor computed once, the quotient finished in three operations): for i < n it writes
+ * helper[i] = div_with(a[i], b[i], div_rcp(b[i])) where the helper's range test accepts the operands (else the plain
+ * quotient, as the kernels do), plain[i] = a[i] / b[i], accepted[i] = the range test.  Host pointers, f64. */
+int cno_device_div_check(const double* a, const double* b, int64_t n, double* helper, double* plain,
+                         int32_t* accepted);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif
