@@ -235,19 +235,13 @@ int newton_dense_quadratic(const LaunchArgs& a) {
       cno::DenseQuadraticFn<T, D>{static_cast<const T*>(p->data), (long long)p->data_stride}, a);
 }
 // CNO_POLICY_DMMA_LU: d = 64 fp64 dense quadratic, blocked LU with the trailing update on the FP64 tensor core
-// (csrc/cno_newton_dmma.cuh).
-int newton_dense_quadratic_dmma(const LaunchArgs& a) {
+// (csrc/cno_newton_dmma.cuh).  kLayout = the CTA's warp population (matrices in shared memory / Tensor Memory / both).
+template <int kLayout>
+int launch_newton_dmma(const cno::DenseQuadraticDmmaFn& fn, const LaunchArgs& a) {
   using Fn = cno::DenseQuadraticDmmaFn;
-  using SM = cno::NewtonDmmaSmem;
-  const cno_problem_t* p = a.problem;
-  if (!p->data || p->data_stride < (int64_t)64 * 64 + 64) return CNO_ERR_INVALID_ARGUMENT;
-  if (((uintptr_t)p->data & 15) || ((size_t)p->data_stride * sizeof(double)) % 16) return CNO_ERR_INVALID_ARGUMENT;
-  if (a.stop->condition_hessian > 0) return CNO_ERR_UNSUPPORTED;  // see cno_newton.cuh
-  Fn fn;
-  fn.data = static_cast<const double*>(p->data);
-  fn.stride = (long long)p->data_stride;
-  auto kernel = cno::newton_dmma_minimize_kernel<Fn>;
-  const size_t smem = SM::kWarpBytes * SM::kWarps;
+  using SM = cno::NewtonDmmaSmem<kLayout>;
+  auto kernel = cno::newton_dmma_minimize_kernel<Fn, kLayout>;
+  const size_t smem = SM::kBytes;
   CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = 0;
   int rc = device_sm_count(&sms);
@@ -268,6 +262,22 @@ int newton_dense_quadratic_dmma(const LaunchArgs& a) {
     a.info->dynamic_smem = (int64_t)smem;
   }
   return CNO_OK;
+}
+int newton_dense_quadratic_dmma(const LaunchArgs& a) {
+  const cno_problem_t* p = a.problem;
+  if (!p->data || p->data_stride < (int64_t)64 * 64 + 64) return CNO_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)p->data & 15) || ((size_t)p->data_stride * sizeof(double)) % 16) return CNO_ERR_INVALID_ARGUMENT;
+  if (a.stop->condition_hessian > 0) return CNO_ERR_UNSUPPORTED;  // see cno_newton.cuh
+  cno::DenseQuadraticDmmaFn fn;
+  fn.data = static_cast<const double*>(p->data);
+  fn.stride = (long long)p->data_stride;
+  // CNO_NEWTON_DMMA_LAYOUT = 0 / 1 / 2 picks the warp population (measurement knob; results are identical)
+  const char* env = getenv("CNO_NEWTON_DMMA_LAYOUT");
+  const int layout = env ? atoi(env) : 2;
+  if (layout == 0) return launch_newton_dmma<0>(fn, a);
+  if (layout == 1) return launch_newton_dmma<1>(fn, a);
+  if (layout == 3) return launch_newton_dmma<3>(fn, a);
+  return launch_newton_dmma<2>(fn, a);
 }
 template <class T, int D>
 int newton_rosenbrock(const LaunchArgs& a) {

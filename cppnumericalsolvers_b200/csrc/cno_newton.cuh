@@ -331,6 +331,34 @@ __device__ __forceinline__ void gemv_global(const T* __restrict__ H, const T* ve
   }
 }
 
+// Two products with the SAME matrix in ONE pass over it: outa = H va, outb = H vb (each exactly as gemv_global
+// computes it: j ascending from the first product).  The matrix is the instance's 32 KB block in L2: a constant
+// Hessian is read once per iteration (Armijo's slope and the first trial evaluation together) instead of twice.
+template <class T, int D>
+__device__ __forceinline__ void gemv2_global(const T* __restrict__ H, const T* veca, const T* vecb, int lane,
+                                             T (&outa)[Shape<D>::E], T (&outb)[Shape<D>::E]) {
+  constexpr int E = Shape<D>::E;
+  constexpr int kU = (E <= 2) ? 16 : 8;
+#pragma unroll 1
+  for (int j0 = 0; j0 < D; j0 += kU) {
+    T c[kU][E];
+#pragma unroll
+    for (int t = 0; t < kU; ++t)
+      if (j0 + t < D) load_row<T, D>(H + (size_t)(j0 + t) * D, lane, c[t]);
+#pragma unroll
+    for (int t = 0; t < kU; ++t) {
+      if (j0 + t < D) {
+        const T va = veca[j0 + t], vb = vecb[j0 + t];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          outa[e] = (j0 + t == 0) ? (c[t][e] * va) : (outa[e] + c[t][e] * va);
+          outb[e] = (j0 + t == 0) ? (c[t][e] * vb) : (outb[e] + c[t][e] * vb);
+        }
+      }
+    }
+  }
+}
+
 // 0.5 x'Ax - b'x with per-instance [A (d x d col-major, bitwise symmetric) | b].
 // Reference analogue: src/examples/debug.cc:43-65.  (Ax)_i = sum_j A_ij x_j,
 // j ascending from the first product.  The Hessian is CONSTANT, so the solver factors H + 1e-5 I once per
@@ -382,6 +410,26 @@ struct DenseQuadraticFn {
     SV::store(vec, c.lane, v);
     __syncwarp();
     gemv_global<T, D>(data + c.instance * stride, vec, c.lane, out);
+  }
+
+  // hess_times(v) and operator()(x, grad) together, A read once (gemv2_global); vec and vec2: D scalars of
+  // warp-private scratch each.  Same bits as the two separate calls.
+  __device__ __forceinline__ T hess_times_and_eval(const EvalCtx& c, const T (&v)[E], T (&hv)[E], const T (&x)[E],
+                                                   T (&grad)[E], T* vec, T* vec2) const {
+    using SV = SmemRowVec<T, D>;
+    const T* src = data + c.instance * stride;
+    __syncwarp();
+    SV::store(vec, c.lane, v);
+    SV::store(vec2, c.lane, x);
+    __syncwarp();
+    T Ax[E], bb[E];
+    gemv2_global<T, D>(src, vec, vec2, c.lane, hv, Ax);
+    load_row<T, D>(src + D * D, c.lane, bb);
+#pragma unroll
+    for (int e = 0; e < E; ++e) grad[e] = (c.lane * E + e < D) ? (Ax[e] - bb[e]) : T(0);
+    T p1 = lane_dot<T, E>(x, Ax), p2 = lane_dot<T, E>(bb, x);
+    warp_sum2(p1, p2);
+    return T(0.5) * p1 - p2;
   }
 
   // value/gradient with A and b read from global memory (the store holds the LU factors).
@@ -896,8 +944,15 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       const T half_cc = T(0.5) * cc * cc;
 #pragma unroll
       for (int e = 0; e < E; ++e) sd[e] = half_cc * delta[e];
+      T alpha = T(1.0);
+      T xt[E], gt[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) xt[e] = x[e] + alpha * delta[e];
+      T ft;
       if constexpr (Fn::kHessianConstant) {
-        fn.hess_times(ctx, sd, r, vec);  // ((0.5 c^2) d') H from global memory; the store keeps the factors
+        // ((0.5 c^2) d') H and the first trial evaluation in one pass over A (global memory / L2; the store keeps the
+        // factors; the right-hand-side column of the store is free after the solve and serves as the second vector)
+        ft = fn.hess_times_and_eval(ctx, sd, r, xt, gt, vec, A.rhs());
       } else {
         // unshifted H(x) again (its transpose where the functor tells them apart: the slope below is d'H)
         if constexpr (StageTakesTranspose<Fn>::value) fn.stage(ctx, x, A, bar, parity, true);
@@ -910,11 +965,7 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       T p1 = lane_dot<T, E>(g, delta), p2 = lane_dot<T, E>(r, delta);
       warp_sum2(p1, p2);
       const T cache = cc * p1 + p2;
-      T alpha = T(1.0);
-      T xt[E], gt[E];
-#pragma unroll
-      for (int e = 0; e < E; ++e) xt[e] = x[e] + alpha * delta[e];
-      T ft = fn(ctx, xt, &gt, A, vec);
+      if constexpr (!Fn::kHessianConstant) ft = fn(ctx, xt, &gt, A, vec);
       nfev++;
       while (uni(ft > f + alpha * cache)) {
         alpha *= rho;

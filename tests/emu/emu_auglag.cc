@@ -221,12 +221,18 @@ extern "C" int emu_newton(const cno_problem_t* p, long long batch, const void* x
     cno::DenseQuadraticDmmaFn fn;
     fn.data = static_cast<const double*>(p->data);
     fn.stride = (long long)p->data_stride;
+    // p->n selects the store the emulated warp uses: 0 = shared memory, 1 = Tensor Memory (a host array here)
     unsigned long long queue = 0;
+    const int layout = p->n;
     emu::run_warp([&](int lane) {
       blockIdx.x = 0;
       threadIdx.x = (unsigned)lane;
-      cno::newton_dmma_minimize_kernel<cno::DenseQuadraticDmmaFn>(fn, (const double*)x0, batch, cno::make_stop<double>(*stop),
-                                                                 cno::make_out<double>(*out), &queue);
+      if (layout == 1)
+        cno::newton_dmma_minimize_kernel<cno::DenseQuadraticDmmaFn, 1>(fn, (const double*)x0, batch, cno::make_stop<double>(*stop),
+                                                                      cno::make_out<double>(*out), &queue);
+      else
+        cno::newton_dmma_minimize_kernel<cno::DenseQuadraticDmmaFn, 0>(fn, (const double*)x0, batch, cno::make_stop<double>(*stop),
+                                                                      cno::make_out<double>(*out), &queue);
     });
     return 0;
   }

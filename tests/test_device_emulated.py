@@ -335,8 +335,9 @@ def _newton_pivot_cases(d=64, B=8):
     return np.ascontiguousarray(np.concatenate([A.transpose(0, 2, 1).reshape(B, -1), bvec], axis=1))
 
 
+@pytest.mark.parametrize("store", ["shared_memory", "tensor_memory"])
 @pytest.mark.parametrize("case", ["spd", "pivoting", "huge", "tiny"])
-def test_emulation_tensor_core_newton_equals_the_fused_oracle(emu, case):
+def test_emulation_tensor_core_newton_equals_the_fused_oracle(emu, case, store):
     """csrc/cno_newton_dmma.cuh (CNO_POLICY_DMMA_LU) under emulation, DMMA.8x8x4 as the FMA chain measured on B200:
     the BLOCKED elimination (register panels, U12 in the B-fragment layout, tensor-core trailing update, blocked
     substitutions) equals the oracle's UNBLOCKED lu_solve with fused multiply-subtracts bit for bit."""
@@ -347,8 +348,10 @@ def test_emulation_tensor_core_newton_equals_the_fused_oracle(emu, case):
         data = _newton_pivot_cases(d) * {"pivoting": 1.0, "huge": 1e150, "tiny": 1e-150}[case]
         B = data.shape[0]
     x0 = ob.fill_uniform((B, d), 0, 5, -2.0, 2.0, np.float64)
-    prob = ob.Problem(ob.FN_DENSE_QUADRATIC, ob._np_dtype(x0), d, 0, 0.0, data.ctypes.data, data.shape[1],
-                      ob.POLICY_DMMA_LU, 0)
+    # (the harness reads the store of the emulated warp from the problem's n field: the matrix in shared memory in
+    # fragment order, or in Tensor Memory -- a host array under emulation -- with the small shared-memory panels)
+    prob = ob.Problem(ob.FN_DENSE_QUADRATIC, ob._np_dtype(x0), d, 1 if store == "tensor_memory" else 0, 0.0,
+                      data.ctypes.data, data.shape[1], ob.POLICY_DMMA_LU, 0)
     stop = ob.default_stop()
     stop.num_iterations = 4
     r = dict(x=np.zeros_like(x0), value=np.zeros(B), gradient=np.zeros_like(x0),
