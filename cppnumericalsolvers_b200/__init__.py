@@ -11,7 +11,7 @@ from .constrained import (AugmentedLagrangeState, AugmentedLagrangian,  # noqa: 
 from .function import (BatchedFunctionState, DenseQuadratic, DenseQuadraticFirst, DiagQuadratic,  # noqa: F401
                        DifferentiabilityMode, Function, HalfSquaredNorm, Logistic, Rosenbrock,
                        RosenbrockFull)
-from .solver import (BatchedProgress, Bfgs, ConjugatedGradientDescent,  # noqa: F401
+from .solver import (BatchedProgress, Bfgs, ConditionHessian, ConjugatedGradientDescent,  # noqa: F401
                      ConservativeStoppingSolverProgress, DefaultStoppingSolverProgress,
                      GradientDescent, HagerZhang, Lbfgs, Lbfgsb, MoreThuente, NewtonDescent, PrintProgressCallback,
                      Progress, Solver,
@@ -20,7 +20,7 @@ from .solver import (BatchedProgress, Bfgs, ConjugatedGradientDescent,  # noqa: 
 __all__ = [
     "AugmentedLagrangeState", "AugmentedLagrangian", "AugmentedLagrangianConfig",
     "ConstrainedOptimizationProblem", "ConstrainedStop",
-    "BatchedFunctionState", "BatchedProgress", "Bfgs", "ConjugatedGradientDescent",
+    "BatchedFunctionState", "BatchedProgress", "Bfgs", "ConditionHessian", "ConjugatedGradientDescent",
     "ConservativeStoppingSolverProgress", "GradientDescent", "HagerZhang", "MoreThuente",
     "DefaultStoppingSolverProgress", "DenseQuadratic", "DenseQuadraticFirst", "DiagQuadratic", "DifferentiabilityMode",
     "Function", "HalfSquaredNorm", "Lbfgs", "Lbfgsb", "Logistic", "NewtonDescent", "PrintProgressCallback", "Progress",

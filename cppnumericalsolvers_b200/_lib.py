@@ -95,7 +95,7 @@ EXPORTS = (
     "cno_conservative_stop", "cno_supported", "cno_workspace_bytes", "cno_minimize",
     "cno_state_bytes", "cno_minimize_steps",
     "cno_minimize_host", "cno_release_host_arena", "cno_evaluate", "cno_fill_uniform", "cno_done_bitmap", "cno_device_cstep",
-    "cno_device_div_check",
+    "cno_device_div_check", "cno_condition_hessian",
     "cno_allgather_done", "cno_count_done",
     "cno_lbfgsb_default_stop", "cno_lbfgsb_supported", "cno_lbfgsb_minimize",
 )
@@ -154,6 +154,8 @@ def lib() -> C.CDLL:
         L.cno_done_bitmap.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.cno_device_cstep.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.cno_condition_hessian.argtypes = [C.POINTER(Problem), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_size_t, C.c_void_p]
         L.cno_device_div_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.cno_al_default_config.argtypes = [C.POINTER(AlConfig)]
         L.cno_al_default_config.restype = None

@@ -273,11 +273,12 @@ int newton_dense_quadratic_dmma(const LaunchArgs& a) {
   fn.stride = (long long)p->data_stride;
   // CNO_NEWTON_DMMA_LAYOUT = 0 / 1 / 2 picks the warp population (measurement knob; results are identical)
   const char* env = getenv("CNO_NEWTON_DMMA_LAYOUT");
-  const int layout = env ? atoi(env) : 2;
+  const int layout = env ? atoi(env) : 3;
   if (layout == 0) return launch_newton_dmma<0>(fn, a);
   if (layout == 1) return launch_newton_dmma<1>(fn, a);
-  if (layout == 3) return launch_newton_dmma<3>(fn, a);
-  return launch_newton_dmma<2>(fn, a);
+  if (layout == 2) return launch_newton_dmma<2>(fn, a);
+  if (layout == 4) return launch_newton_dmma<4>(fn, a);
+  return launch_newton_dmma<3>(fn, a);
 }
 template <class T, int D>
 int newton_rosenbrock(const LaunchArgs& a) {
@@ -381,6 +382,53 @@ int lbfgs_logistic(const LaunchArgs& a) {
     return CNO_ERR_INVALID_ARGUMENT;  // TMA bulk copies need 16-byte aligned blocks
   return launch_lbfgs<Fn, CNO_LBFGS_M>(Fn{static_cast<const T*>(p->data), (long long)p->data_stride, (T)p->param}, a);
 }
+
+// ---- Progress::condition_hessian on request (csrc/cno_newton.cuh: condition_hessian_kernel) ----
+struct CondArgs {
+  const cno_problem_t* problem;
+  long long batch;
+  const void* x;
+  void* out;
+  void* workspace;
+  cudaStream_t stream;
+};
+template <class Fn>
+int launch_condition(const Fn& fn, const CondArgs& a) {
+  using T = typename Fn::Scalar;
+  using CS = cno::ConditionSmem<T, Fn::Dim>;
+  auto kernel = cno::condition_hessian_kernel<Fn>;
+  const size_t smem = CS::kWarpBytes * CS::kWarps;
+  CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int sms = 0;
+  int rc = device_sm_count(&sms);
+  if (rc) return rc;
+  long long ctas = (a.batch + CS::kWarps - 1) / CS::kWarps;
+  const int grid = (int)(ctas < sms ? (ctas < 1 ? 1 : ctas) : sms);
+  unsigned long long* queue = static_cast<unsigned long long*>(a.workspace);
+  CNO_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), a.stream));
+  kernel<<<grid, CS::kWarps * 32, smem, a.stream>>>(fn, static_cast<const T*>(a.x), a.batch, static_cast<T*>(a.out), queue);
+  CNO_CUDA(cudaGetLastError());
+  return CNO_OK;
+}
+template <class T, int D>
+int condition_dense_quadratic(const CondArgs& a) {
+  const cno_problem_t* p = a.problem;
+  if (!p->data || p->data_stride < (int64_t)D * D + D) return CNO_ERR_INVALID_ARGUMENT;
+  if (((uintptr_t)p->data & 15) || ((size_t)p->data_stride * sizeof(T)) % 16) return CNO_ERR_INVALID_ARGUMENT;
+  return launch_condition(cno::DenseQuadraticFn<T, D>{static_cast<const T*>(p->data), (long long)p->data_stride}, a);
+}
+template <class T, int D>
+int condition_rosenbrock(const CondArgs& a) {
+  return launch_condition(cno::RosenbrockFullFn<T, D>{}, a);
+}
+struct CondEntry { int family, dtype, d; int (*fn)(const CondArgs&); };
+const CondEntry kCondTable[] = {  // the Second-mode built-ins of NewtonDescent
+    {CNO_FN_DENSE_QUADRATIC, CNO_F64, 64, condition_dense_quadratic<double, 64>},
+    {CNO_FN_DENSE_QUADRATIC, CNO_F64, 12, condition_dense_quadratic<double, 12>},
+    {CNO_FN_DENSE_QUADRATIC, CNO_F32, 64, condition_dense_quadratic<float, 64>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 2, condition_rosenbrock<double, 2>},
+    {CNO_FN_ROSENBROCK, CNO_F64, 8, condition_rosenbrock<double, 8>},
+};
 
 typedef int (*launcher_t)(const LaunchArgs&);
 
@@ -1193,6 +1241,25 @@ int cno_evaluate(const cno_problem_t* problem, int64_t batch, const void* x, voi
     if (e.family == problem->family && e.dtype == problem->dtype && e.d == problem->d) {
       if (!have_device()) return CNO_ERR_NO_DEVICE;
       return e.fn(problem, batch, x, value, gradient, stream);
+    }
+  return CNO_ERR_UNSUPPORTED;
+}
+
+int cno_condition_hessian(const cno_problem_t* problem, int64_t batch, const void* x, void* condition,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (!problem || batch < 0) return CNO_ERR_INVALID_ARGUMENT;
+  if (problem->dtype != CNO_F64 && problem->dtype != CNO_F32) return CNO_ERR_INVALID_ARGUMENT;
+  const int dflt = (problem->dtype == CNO_F64) ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE;
+  if (problem->policy != dflt) return CNO_ERR_UNSUPPORTED;  // (the fused-LU policy has no condition-number kernel)
+  for (const CondEntry& e : kCondTable)
+    if (e.family == problem->family && e.dtype == problem->dtype && e.d == problem->d) {
+      if (batch == 0) return CNO_OK;
+      if (!x || !condition || !workspace || workspace_bytes < sizeof(unsigned long long) ||
+          ((uintptr_t)workspace & 7) || ((uintptr_t)x & 15))
+        return CNO_ERR_INVALID_ARGUMENT;
+      if (!have_device()) return CNO_ERR_NO_DEVICE;
+      const CondArgs a{problem, (long long)batch, x, condition, workspace, static_cast<cudaStream_t>(stream)};
+      return e.fn(a);
     }
   return CNO_ERR_UNSUPPORTED;
 }

@@ -1013,6 +1013,171 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 #endif
 }
 
+// ---- Progress::condition_hessian on request (solver/progress.h:203-210) ------------------------------------------
+// condition_hessian = hessian.norm() * hessian.inverse().norm() at the state's x, which the reference evaluates in
+// every Progress::Update of a Second-mode function (one Hessian evaluation plus a full inverse: d solves) although no
+// preset tests it.  The fused solve kernels do not carry it; this kernel computes it for a batch of points -- the
+// final states of a solve, or the snapshots a callback sees -- one warp per point, with the store and the LU of
+// NewtonDescent: H(x) staged, factored ONCE, column j of the inverse = the re-solve with e_j (the same bits as the
+// d separate lu().solve(e_j) of the specification, oracle condition_hessian()).  Frobenius norms follow the policy's
+// sum over the d*d squared coefficients in column-major order: lane l owns the d*d/32 consecutive coefficients
+// l*E2 .. l*E2+E2-1 (in-lane binary tree), then the cross-lane policy sum.
+//   D = 64: a lane's coefficients are two whole columns; a column's tree is the owner lanes' in-lane pairs followed by
+//           an ASCENDING xor butterfly (1, 2, 4, 8, 16 = the binary tree over the column's 64 rows), so columns are
+//           reduced where they live (shared memory, Tensor Memory or the registers of a solve) -- no d*d scratch;
+//   else:   the inverse is written to a d*d shared-memory scratch and both matrices are read linearly.
+template <class T, int D>
+struct ConditionSmem {
+  using NS = NewtonSmem<T, D>;
+  static constexpr bool kColumnwise = (D == 64);
+  static constexpr int kInv = kColumnwise ? 0 : ((D * D + 3) / 4) * 4;
+  static constexpr int kWarpElems = NS::kWarpElems + kInv;
+  static constexpr size_t kWarpBytes = (size_t)kWarpElems * sizeof(T);
+  static constexpr int kWarpsFit = (int)(NS::kMaxSmem / kWarpBytes);
+  static constexpr int kWarps = kWarpsFit > NS::kCap ? NS::kCap : (kWarpsFit < 1 ? 1 : kWarpsFit);
+};
+
+// binary tree over a column's D = 64 squared entries (lane l holds rows 2l, 2l+1), the result in every lane
+template <class T>
+__device__ __forceinline__ T column_tree64(const T (&c)[2]) {
+  T p = c[0] * c[0] + c[1] * c[1];
+#pragma unroll
+  for (int off = 1; off <= 16; off <<= 1) p = p + __shfl_xor_sync(kFullMask, p, off);
+  return p;
+}
+
+template <class Fn>
+__global__ void __launch_bounds__(ConditionSmem<typename Fn::Scalar, Fn::Dim>::kWarps * 32, 1)
+condition_hessian_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ xs, const long long batch,
+                         typename Fn::Scalar* __restrict__ out, unsigned long long* __restrict__ queue) {
+  using T = typename Fn::Scalar;
+  constexpr int D = Fn::Dim;
+  constexpr int E = Shape<D>::E;
+  using SMN = NewtonSmem<T, D>;
+  using CS = ConditionSmem<T, D>;
+  using AS = AugStore<T, D>;
+
+  CNO_DYNAMIC_SMEM(smem_raw);
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  T* const aug = reinterpret_cast<T*>(smem_raw) + (size_t)warp * CS::kWarpElems;
+  T* const vec = aug + SMN::kAug;
+  T* const ring = vec + SMN::kVecPad;
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(ring + CNO_MAX_PAST);
+  T* const inv = aug + SMN::kWarpElems;  // (kInv scalars; not used when kColumnwise)
+  uint32_t parity = 0;
+  uint32_t tmem_base = 0;
+#ifndef CNO_WARP_EMULATION
+  if constexpr (AS::kSplit) {
+    __shared__ uint32_t tmem_base_s;
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       (uint32_t)__cvta_generic_to_shared(&tmem_base_s)),
+                   "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    tmem_base = tmem_base_s;
+  }
+#endif
+  const AS A{aug, tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * AS::kTmemCols), lane};
+  if (lane == 0) {
+    mbar_init(bar, 1);
+#ifndef CNO_WARP_EMULATION
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+  }
+  __syncwarp();
+
+  for (;;) {
+    unsigned long long b = 0;
+    if (lane == 0) b = atomicAdd(queue, 1ULL);
+    b = __shfl_sync(kFullMask, b, 0);
+    if (uni(b >= (unsigned long long)batch)) break;
+    const EvalCtx ctx{lane, (long long)b, nullptr};
+    T x[E];
+    load_row<T, D>(xs + b * D, lane, x);
+    fn.stage(ctx, x, A, bar, parity);  // the store holds H(x)
+    __syncwarp();
+
+    // ---- sum of the squared coefficients of H, policy order ----
+    T part_h = T(0), part_i = T(0);  // this lane's partials of the two sums
+    if constexpr (CS::kColumnwise) {
+#pragma unroll 1
+      for (int j = 0; j < D; ++j) {
+        T col[E];
+        aug_load_col<T, D>(A, j, col);
+        const T c = column_tree64<T>(col);
+        if (lane == (j >> 1)) part_h = (j & 1) ? (part_h + c) : c;
+      }
+    } else {
+      constexpr int E2 = (D * D + 31) / 32;
+      T v[E2];
+#pragma unroll
+      for (int t = 0; t < E2; ++t) {
+        const int i = lane * E2 + t;
+        const T h = (i < D * D) ? aug[i] : T(0);
+        v[t] = h * h;
+      }
+      part_h = lane_tree<T, E2>(v);
+    }
+
+    // ---- the inverse, column by column: factor once with e_0 riding along, then re-solve ----
+    int vpos[E];
+#pragma unroll 1
+    for (int j = 0; j < D; ++j) {
+      T delta[E];
+      if (j == 0) {  // uniform
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int row = lane * E + e;
+          if (row < D) A.rhs()[row] = (row == 0) ? T(1) : T(0);
+        }
+        __syncwarp();
+        lu_solve_inplace<T, D>(A, delta, vpos);
+      } else {
+        T rv[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) rv[e] = (lane * E + e == j) ? T(1) : T(0);
+        lu_resolve<T, D>(A, vpos, rv, delta);
+      }
+      if constexpr (CS::kColumnwise) {
+        const T c = column_tree64<T>(delta);
+        if (lane == (j >> 1)) part_i = (j & 1) ? (part_i + c) : c;
+      } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+          if (lane * E + e < D) inv[j * D + lane * E + e] = delta[e];
+      }
+    }
+    if constexpr (!CS::kColumnwise) {
+      constexpr int E2 = (D * D + 31) / 32;
+      __syncwarp();
+      T v[E2];
+#pragma unroll
+      for (int t = 0; t < E2; ++t) {
+        const int i = lane * E2 + t;
+        const T h = (i < D * D) ? inv[i] : T(0);
+        v[t] = h * h;
+      }
+      part_i = lane_tree<T, E2>(v);
+      __syncwarp();
+    }
+    warp_sum2(part_h, part_i);
+    if (lane == 0) out[b] = csqrt(part_h) * csqrt(part_i);
+    __syncwarp();
+  }
+#ifndef CNO_WARP_EMULATION
+  if constexpr (AS::kSplit) {
+    __syncthreads();
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+#endif
+}
+
 }  // namespace cno
 
 #endif  // CNO_NEWTON_CUH_

@@ -109,6 +109,23 @@ class BatchedProgress:
         return words
 
 
+def ConditionHessian(function: Function, x: torch.Tensor) -> torch.Tensor:
+    """Progress::condition_hessian (solver/progress.h:203-210) on request: H(x).norm() * H(x).inverse().norm() for every
+    row of x [B, d] -- what the reference's Progress::Update computes at each iteration of a Second-mode function
+    (and no preset tests).  Called on the x a solve returned it is the reference's final progress.condition_hessian."""
+    if not x.is_cuda or x.dim() != 2 or x.dtype != function.ScalarType or x.shape[1] != function.Dimension:
+        raise ValueError("x must be a CUDA tensor [B, d] of the function's scalar type")
+    x = x.contiguous()
+    out = torch.empty(x.shape[0], dtype=x.dtype, device=x.device)
+    ws = torch.zeros(256, dtype=torch.uint8, device=x.device)
+    prob = function.problem()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().cno_condition_hessian(C.byref(prob), x.shape[0], x.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                                    ws.numel(), torch.cuda.current_stream(x.device).cuda_stream),
+                   "cno_condition_hessian")
+    return out
+
+
 class Solver:
     """solver/solver.h:156-231 with a batch axis."""
     _solver_id = -1

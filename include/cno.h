@@ -288,6 +288,17 @@ int cno_allgather_done(void* comm, const uint32_t* local_words, uint32_t* all_wo
 int cno_count_done(const uint32_t* all_words, int32_t ranks, size_t words_per_rank, const int64_t* bits_per_rank,
                    int64_t* total_done, void* stream);
 
+/* Progress::condition_hessian on request (solver/progress.h:203-210): condition[b] = H(x_b).norm() *
+ * H(x_b).inverse().norm(), the value the reference's Progress::Update computes for a Second-mode function at
+ * every iteration (one Hessian evaluation and a full inverse) and no preset tests.  The fused solve kernels do
+ * not carry it (a non-zero cno_stop_t::condition_hessian is rejected); call this on the states whose condition
+ * number is wanted -- the returned x of a solve gives the reference's final progress.condition_hessian.
+ * x [B, d] and condition [B]: DEVICE pointers; workspace: >= 8 bytes of device scratch, 8-byte aligned.
+ * Second-mode built-ins under the dtype's default policy (CNO_FN_DENSE_QUADRATIC f64 d = 64 / 12, f32 d = 64;
+ * CNO_FN_ROSENBROCK f64 d = 2 / 8); otherwise CNO_ERR_UNSUPPORTED. */
+int cno_condition_hessian(const cno_problem_t* problem, int64_t batch, const void* x, void* condition,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Device-side known-answer hook for MoreThuente::cstep
  * (linesearch/more_thuente.h:261-407): runs the device cstep on one thread.
  * io = {stx, fx, dx, sty, fy, dy, stp, fp, dp, stpmin, stpmax} (host, f64),

@@ -185,6 +185,19 @@ struct FunctionExpr {
                                 : cno_evaluate(&problem, batch, x, value, gradient, stream);
     detail::check_cno(rc, "FunctionExpr::operator()");
   }
+
+  // Progress::condition_hessian (solver/progress.h:203-210) on request: condition[b] = H(x_b).norm() *
+  // H(x_b).inverse().norm() for x [B, d] -- the value the reference's Progress::Update computes at every
+  // iteration of a Second-mode function.  On the x a solve returned it is the reference's final
+  // progress.condition_hessian.  Device arrays; built-in Second-mode families (cno_condition_hessian).
+  void ConditionHessian(int64_t batch, const TScalar* x, TScalar* condition, cudaStream_t stream = nullptr) const {
+    static_assert(TMode == DifferentiabilityMode::Second, "condition_hessian is defined for Second-mode functions");
+    if (raw) detail::check_cno(CNO_ERR_UNSUPPORTED, "FunctionExpr::ConditionHessian (user functors)");
+    detail::DeviceArray<unsigned long long> ws(32);
+    detail::check_cno(cno_condition_hessian(&problem, batch, x, condition, ws.data(), ws.size() * sizeof(unsigned long long), stream),
+                      "FunctionExpr::ConditionHessian");
+    detail::check_cuda(cudaStreamSynchronize(stream), "FunctionExpr::ConditionHessian");
+  }
 };
 
 // function_base.h:298-332 as in the reference: one instance, host vectors (the B = 1 signature of

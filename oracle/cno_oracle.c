@@ -186,6 +186,21 @@ int cno_oracle_evaluate(const cno_problem_t* problem, int64_t batch,
   return CNO_OK;
 }
 
+/* progress.condition_hessian (solver/progress.h:203-210) at x[b], Second-mode families only. */
+int cno_oracle_condition_hessian(const cno_problem_t* problem, int64_t batch, const void* x, void* out) {
+  int rc = check_problem(CNO_NEWTON, problem);
+  if (rc) return rc;
+  const int d = problem->d;
+#pragma omp parallel for schedule(dynamic)
+  for (int64_t b = 0; b < batch; ++b) {
+    if (problem->dtype == CNO_F64)
+      ((double*)out)[b] = condition_hessian_at_f64(problem, b, (const double*)x + b * d);
+    else
+      ((float*)out)[b] = condition_hessian_at_f32(problem, b, (const float*)x + b * d);
+  }
+  return CNO_OK;
+}
+
 /* splitmix64 finaliser; counter-based. */
 static inline uint64_t mix64(uint64_t z) {
   z ^= z >> 30;

@@ -50,6 +50,10 @@ int cno_oracle_hz_search_poly(const double coef[5], double x0, double alpha_init
 int cno_oracle_evaluate(const cno_problem_t* problem, int64_t batch,
                         const void* x, void* f, void* g, void* H);
 
+/* Progress::condition_hessian (solver/progress.h:203-210) = H(x).norm() * H(x).inverse().norm() at
+ * x[b] (Second-mode families): out[B].  Oracle twin of cno_condition_hessian. */
+int cno_oracle_condition_hessian(const cno_problem_t* problem, int64_t batch, const void* x, void* out);
+
 /* Host twin of cno_fill_uniform (dst is a host pointer). */
 int cno_oracle_fill_uniform(int dtype, void* dst, int64_t first, int64_t count,
                             uint64_t seed, double lo, double hi);

@@ -319,6 +319,26 @@ def hz_search_poly(coef, x0: float, alpha_init: float, impl: str = "oracle"):
  EXPR_SECOND_PROD, EXPR_DOWNGRADE) = range(9)
 
 
+def condition_hessian(family: int, x: np.ndarray, *, policy: int | None = None, data=None, impl: str = "oracle"):
+    """progress.condition_hessian (solver/progress.h:203-210) = H(x).norm() * H(x).inverse().norm() per instance:
+    impl="oracle" the C restatement, impl="ref" the reference's own Progress::Update (oracle/_ref)."""
+    x = np.ascontiguousarray(x)
+    B, d = x.shape
+    dt = x.dtype
+    if policy is None:
+        policy = device_policy(dt)
+    if data is not None:
+        data = np.ascontiguousarray(data, dtype=dt)
+    prob = Problem(family, _np_dtype(x), d, 0, 0.0, data.ctypes.data if data is not None else None,
+                   data.shape[1] if data is not None else 0, policy, 2)
+    out = np.zeros(B, dt)
+    fn = oracle_lib().cno_oracle_condition_hessian if impl == "oracle" else ref_lib().cno_ref_condition_hessian
+    rc = fn(C.byref(prob), C.c_int64(B), C.c_void_p(x.ctypes.data), C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise RuntimeError(f"condition_hessian failed: {rc}")
+    return out
+
+
 def ref_minimize_expr(expr: int, solver: int, x0: np.ndarray, *, param: float = 0.0, stop: Stop | None = None,
                       linesearch: int = LS_MORE_THUENTE, policy: int | None = None, threads: int = 0,
                       lbfgs_m: int = 0) -> dict:

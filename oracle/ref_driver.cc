@@ -266,6 +266,35 @@ int dispatch_family(int solver, const cno_problem_t* prob, int64_t b,
   }
 }
 
+// progress.condition_hessian exactly as the reference's own Progress::Update (solver/progress.h:153-327; the
+// Second-mode block :203-210) leaves it for a state at x.
+template <class T, template <class, DifferentiabilityMode> class Family>
+T condition_one(const cno_problem_t* prob, int64_t b, const T* x0) {
+  using Fn = Family<T, DifferentiabilityMode::Second>;
+  using State = FunctionState<T, Eigen::Dynamic>;
+  Fn f;
+  f.p = prob;
+  f.instance = b;
+  f.nfev = 0;
+  typename Fn::VectorType x(prob->d);
+  for (int i = 0; i < prob->d; ++i) x[i] = x0[i];
+  const State state(f, x);
+  auto stop = cppoptlib::solver::DefaultStoppingSolverProgress<Fn, State>();
+  cppoptlib::solver::Progress<Fn, State> progress;
+  progress.Update(f, state, state, stop);
+  return progress.condition_hessian;
+}
+template <class T>
+int condition_family(const cno_problem_t* prob, int64_t b, const T* x, T* out) {
+  switch (prob->family) {
+    case CNO_FN_ROSENBROCK: *out = condition_one<T, Rosenbrock>(prob, b, x); return 0;
+    case CNO_FN_DIAG_QUADRATIC: *out = condition_one<T, DiagQuadratic>(prob, b, x); return 0;
+    case CNO_FN_HALF_SQUARED_NORM: *out = condition_one<T, HalfSquaredNorm>(prob, b, x); return 0;
+    case CNO_FN_DENSE_QUADRATIC: *out = condition_one<T, DenseQuadratic>(prob, b, x); return 0;
+    default: return CNO_ERR_UNSUPPORTED;
+  }
+}
+
 // ---- AugmentedLagrangian: the reference's own
 // augmented_lagrangian.h / function_penalty.h / function_expressions.h ----------
 // One constraint functor; row = [a (d) | t] (cno_al_oracle.h).
@@ -730,6 +759,22 @@ int cno_ref_minimize_ls(int solver, const cno_problem_t* problem, int64_t batch,
     int r = problem->dtype == CNO_F64
                 ? dispatch_family<double>(solver, problem, b, static_cast<const double*>(x0) + b * d, stop, out, linesearch)
                 : dispatch_family<float>(solver, problem, b, static_cast<const float*>(x0) + b * d, stop, out, linesearch);
+    if (r) rc = r;
+  }
+  return rc;
+}
+
+// Same contract as cno_oracle_condition_hessian, computed by the reference's own Progress::Update.
+int cno_ref_condition_hessian(const cno_problem_t* problem, int64_t batch, const void* x, void* out) {
+  if (!problem || !x || !out) return CNO_ERR_INVALID_ARGUMENT;
+  Eigen::cno_policy_ref() = problem->policy;
+  const int d = problem->d;
+  int rc = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t b = 0; b < batch; ++b) {
+    const int r = problem->dtype == CNO_F64
+                      ? condition_family<double>(problem, b, static_cast<const double*>(x) + b * d, static_cast<double*>(out) + b)
+                      : condition_family<float>(problem, b, static_cast<const float*>(x) + b * d, static_cast<float*>(out) + b);
     if (r) rc = r;
   }
   return rc;

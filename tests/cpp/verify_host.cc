@@ -74,6 +74,18 @@ int main() {
     for (int b = 0; b < 2; ++b) EXPECT_NEAR(0.0, rosen2(&x[2 * b]), PRECISION);
   }
 
+  {  // Progress::condition_hessian (progress.h:203-210) on request, at the minimiser (1, 1) of verify.cc:81-99's
+     // Hessian H = [[1200 x0^2 - 400 x1 + 1, -400 x0], [-400 x0, 200]] = [[801, -400], [-400, 200]], det H = 200:
+     // ||H||_F ||H^-1||_F = ||H||_F^2 / |det H| = 1001601 / 200
+    using F = function::RosenbrockFull<double, 2>;
+    function::FunctionExpr<double, function::DifferentiabilityMode::Second, 2> expr(F{});
+    auto x = detail::DeviceArray<double>::FromHost({1.0, 1.0, 1.0, 1.0});
+    detail::DeviceArray<double> cond(2);
+    expr.ConditionHessian(2, x.data(), cond.data());
+    const std::vector<double> c = cond.ToHost();
+    for (int b = 0; b < 2; ++b) EXPECT_NEAR(1001601.0 / 200.0, c[b], 1e-6);
+  }
+
   {  // SOLVER_SETUP(Lbfgsb, RosenbrockGradient): verify.cc:190, unbounded; then the same problem in a box
     using F = function::Rosenbrock<double, 2>;
     solver::Lbfgsb<F> s;

@@ -253,6 +253,36 @@ extern "C" int emu_newton(const cno_problem_t* p, long long batch, const void* x
   return CNO_ERR_UNSUPPORTED;
 }
 
+// Progress::condition_hessian on request (csrc/cno_newton.cuh: condition_hessian_kernel) under emulation.
+template <class Fn>
+int run_condition(const Fn& fn, long long B, const void* x, void* out) {
+  using T = typename Fn::Scalar;
+  unsigned long long queue = 0;
+  emu::run_warp([&](int lane) {
+    blockIdx.x = 0;
+    threadIdx.x = (unsigned)lane;
+    cno::condition_hessian_kernel<Fn>(fn, (const T*)x, B, (T*)out, &queue);
+  });
+  return 0;
+}
+extern "C" int emu_condition_hessian(const cno_problem_t* p, long long batch, const void* x, void* out) {
+  if (p->family == CNO_FN_DENSE_QUADRATIC) {
+#define COND_CASE(DT, TY, DIM)                                                                                       \
+  if (p->dtype == DT && p->d == DIM)                                                                                 \
+    return run_condition(cno::DenseQuadraticFn<TY, DIM>{static_cast<const TY*>(p->data), (long long)p->data_stride}, \
+                         batch, x, out);
+    COND_CASE(CNO_F64, double, 64)
+    COND_CASE(CNO_F64, double, 12)
+    COND_CASE(CNO_F32, float, 64)
+#undef COND_CASE
+  }
+  if (p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64 && p->d == 2)
+    return run_condition(cno::RosenbrockFullFn<double, 2>{}, batch, x, out);
+  if (p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64 && p->d == 8)
+    return run_condition(cno::RosenbrockFullFn<double, 8>{}, batch, x, out);
+  return CNO_ERR_UNSUPPORTED;
+}
+
 // L-BFGS on the logistic-regression functor (csrc/cno_logistic.cuh: per-instance data staged by TMA into shared
 // memory and by tcgen05.st into Tensor Memory) under emulation.
 extern "C" int emu_logistic(const cno_problem_t* p, long long batch, const void* x0, const cno_stop_t* stop,

@@ -313,6 +313,25 @@ def test_emulation_reproduces_the_newton_kernel(emu, family, dtype, d):
         assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
 
 
+@pytest.mark.parametrize("family,dtype,d", [(ob.FN_DENSE_QUADRATIC, np.float64, 64), (ob.FN_DENSE_QUADRATIC, np.float32, 64),
+                                            (ob.FN_DENSE_QUADRATIC, np.float64, 12), (ob.FN_ROSENBROCK, np.float64, 8),
+                                            (ob.FN_ROSENBROCK, np.float64, 2)])
+def test_emulation_condition_hessian_kernel_equals_the_oracle(emu, family, dtype, d):
+    """condition_hessian_kernel (Progress::condition_hessian on request, progress.h:203-210) under emulation == the
+    oracle == the reference's own Progress::Update (tests/test_oracle_pins.py) bit for bit: the Frobenius sums in the
+    policy's order, the inverse as d re-solves with one factorisation."""
+    B = 3
+    x = ob.fill_uniform((B, d), 0, 6, -2.0, 2.0, dtype)
+    data = _spd_data(B, d, 10, dtype) if family == ob.FN_DENSE_QUADRATIC else None
+    prob = ob.Problem(family, ob._np_dtype(x), d, 0, 0.0, data.ctypes.data if data is not None else None,
+                      data.shape[1] if data is not None else 0, ob.device_policy(x.dtype), 2)
+    out = np.zeros(B, dtype)
+    assert emu.emu_condition_hessian(C.byref(prob), C.c_longlong(B), C.c_void_p(x.ctypes.data), C.c_void_p(out.ctypes.data)) == 0
+    o = ob.condition_hessian(family, x, data=data)
+    assert np.array_equal(out.view(np.uint8), o.view(np.uint8))
+    assert np.all(out >= d * 0.99)  # ||H|| ||H^-1|| >= ||I||_F^2 / ... : at least d for the Frobenius norm
+
+
 def _newton_pivot_cases(d=64, B=8):
     """Symmetric indefinite matrices (pivots move in every panel), exact ties, a zero row / column, a NaN entry, an
     anti-diagonal permutation matrix."""

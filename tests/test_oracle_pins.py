@@ -198,6 +198,32 @@ def test_fused_lu_oracle_equals_reference_headers():
                  ob.minimize(ob.NEWTON, ob.FN_ROSENBROCK, x0, policy=ob.POLICY_DMMA_LU, impl="ref"))
 
 
+def test_condition_hessian_oracle_equals_reference_progress_update():
+    """progress.condition_hessian (progress.h:203-210): the oracle's restatement == the value the reference's own
+    Progress::Update leaves (oracle/_ref: H.norm() * H.inverse().norm() on the shim), fp64 (both LU policies), fp32,
+    dense quadratics and the Rosenbrock Hessian; and the known answer for H = I."""
+    if not ob.ref_available():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(1)
+    for d, B, dt in ((64, 4, np.float64), (12, 5, np.float64), (64, 3, np.float32)):
+        M = rng.uniform(-1, 1, (B, d, d))
+        A = np.einsum("bki,bkj->bij", M, M) / d + np.eye(d)
+        A = (A + A.transpose(0, 2, 1)) / 2
+        bvec = rng.uniform(-1, 1, (B, d))
+        data = np.concatenate([A.transpose(0, 2, 1).reshape(B, -1), bvec], 1).astype(dt)
+        x = rng.uniform(-2, 2, (B, d)).astype(dt)
+        for pol in ((None, ob.POLICY_DMMA_LU) if dt == np.float64 else (None,)):
+            a = ob.condition_hessian(ob.FN_DENSE_QUADRATIC, x, data=data, policy=pol)
+            r = ob.condition_hessian(ob.FN_DENSE_QUADRATIC, x, data=data, policy=pol, impl="ref")
+            assert np.array_equal(a.view(np.uint8), r.view(np.uint8))
+            truth = np.array([np.linalg.norm(A[i]) * np.linalg.norm(np.linalg.inv(A[i])) for i in range(B)])
+            assert np.allclose(a, truth, rtol=1e-4 if dt == np.float32 else 1e-10)
+    x = ob.fill_uniform((6, 8), 0, 3, -2.0, 2.0)
+    assert np.array_equal(ob.condition_hessian(ob.FN_ROSENBROCK, x).view(np.uint8),
+                          ob.condition_hessian(ob.FN_ROSENBROCK, x, impl="ref").view(np.uint8))
+    assert np.allclose(ob.condition_hessian(ob.FN_HALF_SQUARED_NORM, x), 8.0, rtol=1e-15)  # ||I||_F ||I^-1||_F = d
+
+
 def test_fused_lu_oracle_reproduces_committed_reference_fixture():
     """tests/golden/newton_dense_quadratic_d64_dmma_lu.npz was produced by oracle/_ref (make_golden.py)."""
     z = np.load(os.path.join(GOLDEN, "newton_dense_quadratic_d64_dmma_lu.npz"))
