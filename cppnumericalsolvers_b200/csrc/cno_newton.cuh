@@ -403,6 +403,22 @@ struct DenseQuadraticFn {
     parity ^= 1u;
   }
 
+  // The block of the instance this warp will solve NEXT, pulled into L2 while the current one is solved (the kernel
+  // reads its work queue one instance ahead): staging and the evaluations then read L2 instead of waiting on DRAM.
+  __device__ __forceinline__ void prefetch(long long instance, int lane) const {
+#ifndef CNO_WARP_EMULATION
+    const char* p = reinterpret_cast<const char*>(data + instance * stride);
+    constexpr int kLines = (int)(((size_t)(D * D + D) * sizeof(T) + 127) / 128);
+#pragma unroll
+    for (int i = 0; i < (kLines + 31) / 32; ++i) {
+      const int line = i * 32 + lane;
+      if (line < kLines) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (size_t)line * 128));
+    }
+#else
+    (void)instance; (void)lane;
+#endif
+  }
+
   // H v (= v'H: A is bitwise symmetric) for the Armijo slope, A streamed from global memory
   __device__ __forceinline__ void hess_times(const EvalCtx& c, const T (&v)[E], T (&out)[E], T* vec) const {
     using SV = SmemRowVec<T, D>;
@@ -665,6 +681,10 @@ struct SecondOrderAdapter {
   }
 };
 template <class Fn, class = void>
+struct FnPrefetches : std::false_type {};
+template <class Fn>
+struct FnPrefetches<Fn, std::void_t<decltype(&Fn::prefetch)>> : std::true_type {};
+template <class Fn, class = void>
 struct StageTakesTranspose : std::false_type {};
 template <class Fn>
 struct StageTakesTranspose<Fn, std::void_t<decltype(Fn::kStageTakesTranspose)>> : std::true_type {};
@@ -681,26 +701,67 @@ __device__ __forceinline__ void lu_back_substitute(const AugStore<T, D>& A, cons
                                                    T (&rv)[Shape<D>::E], T (&delta)[Shape<D>::E]) {
   constexpr int E = Shape<D>::E;
   const int lane = A.lane;
+  // The 64 quotients x_k = y_k / u_kk are the dependent chain of this loop.  Everything that does not depend on the
+  // running right-hand side leaves it: column k-1 is loaded while step k computes, the owner of row k and the
+  // reciprocal refinement of its divisor (div_rcp) are ready before y_k is, and the quotient is finished with
+  // div_with's three operations.  Its range test is collected over the whole loop; when an operand fell outside
+  // (rare: tiny / huge / non-finite), the loop is redone with the plain operator from the saved right-hand side.
+  T rv0[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) rv0[e] = rv[e];
+  bool all_ok = true;
+  T col[E], nxt[E];
+  aug_load_col<T, D>(A, D - 1, col);
 #pragma unroll 1
   for (int k = D - 1; k >= 0; --k) {
-    T col[E];
-    aug_load_col<T, D>(A, k, col);
-    T xk_local = T(0);
+    if (k > 0) aug_load_col<T, D>(A, k - 1, nxt);  // (uniform)
+    T dv = T(1), nv = T(1);
     bool mine = false;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       if ((lane * E + e < D) && vpos[e] == k) {
-        xk_local = rv[e] / col[e];
+        dv = col[e];
+        nv = rv[e];
         mine = true;
       }
     }
     const unsigned owner = __ballot_sync(kFullMask, mine);
-    const T xk = __shfl_sync(kFullMask, xk_local, __ffs(owner) - 1);
+    bool ok;
+    const T q = div_with(nv, dv, div_rcp(dv), ok);
+    all_ok = all_ok && ok;
+    const T xk = __shfl_sync(kFullMask, q, __ffs(owner) - 1);
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int row = lane * E + e;
       if ((row < D) && vpos[e] < k) rv[e] = rv[e] - col[e] * xk;
       if (row == k) delta[e] = xk;  // unknown k belongs to element k
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) col[e] = nxt[e];
+  }
+  if (uni(!all_ok)) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) rv[e] = rv0[e];
+#pragma unroll 1
+    for (int k = D - 1; k >= 0; --k) {
+      aug_load_col<T, D>(A, k, col);
+      T xk_local = T(0);
+      bool mine = false;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        if ((lane * E + e < D) && vpos[e] == k) {
+          xk_local = rv[e] / col[e];
+          mine = true;
+        }
+      }
+      const unsigned owner = __ballot_sync(kFullMask, mine);
+      const T xk = __shfl_sync(kFullMask, xk_local, __ffs(owner) - 1);
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int row = lane * E + e;
+        if ((row < D) && vpos[e] < k) rv[e] = rv[e] - col[e] * xk;
+        if (row == k) delta[e] = xk;
+      }
     }
   }
 #pragma unroll
@@ -718,10 +779,11 @@ __device__ __forceinline__ void lu_resolve(const AugStore<T, D>& A, const int (&
                                            T (&rv)[Shape<D>::E], T (&delta)[Shape<D>::E]) {
   constexpr int E = Shape<D>::E;
   const int lane = A.lane;
+  T col[E], nxt[E];
+  aug_load_col<T, D>(A, 0, col);
 #pragma unroll 1
   for (int k = 0; k < D; ++k) {
-    T col[E];
-    aug_load_col<T, D>(A, k, col);
+    if (k + 1 < D) aug_load_col<T, D>(A, k + 1, nxt);  // (uniform) the next column is on its way during this step
     T u_local = T(0);
     bool mine = false;
 #pragma unroll
@@ -738,6 +800,8 @@ __device__ __forceinline__ void lu_resolve(const AugStore<T, D>& A, const int (&
       const int row = lane * E + e;
       if ((row < D) && vpos[e] > k) rv[e] = rv[e] - col[e] * u;
     }
+#pragma unroll
+    for (int e = 0; e < E; ++e) col[e] = nxt[e];
   }
   lu_back_substitute<T, D>(A, vpos, rv, delta);
 }
@@ -771,10 +835,24 @@ __device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&de
     // warp arg-max: larger |v|, ties -> smaller virtual position.  A NaN at virtual position k stays the
     // pivot: the sequential scan of the specification starts from it and no comparison with a NaN is
     // true (oracle lu_solve); that also keeps the pivot position valid when every candidate is NaN.
-    const T bmax = warp_max_nonneg(best < T(0) ? T(0) : best);
-    const unsigned mypos = (best == bmax) ? (unsigned)bpos : 0xffffffffu;
-    const int pmax = (int)__reduce_min_sync(kFullMask, mypos);
-    const int ppos = uni(k_is_nan) ? k : pmax;
+    // Fast path (one REDUX + one vote): the high words (fp32: the whole pattern) of the lanes' best |v| decide when
+    // exactly one lane holds the largest one; a NaN at position k makes its lane win outright.  Otherwise (ties, a
+    // zero column, equal high words) the full comparison: low words, then the smallest position.
+    unsigned hkey;
+    if constexpr (sizeof(T) == 8) hkey = best < T(0) ? 0u : (unsigned)__double2hiint((double)best);
+    else hkey = best < T(0) ? 0u : __float_as_uint((float)best);
+    if (k_is_nan) hkey = 0xffffffffu;
+    const unsigned hmax = __reduce_max_sync(kFullMask, hkey);
+    const unsigned hset = __ballot_sync(kFullMask, hkey == hmax);
+    int ppos;
+    if (uni((hset & (hset - 1u)) == 0u)) {
+      ppos = __shfl_sync(kFullMask, k_is_nan ? k : bpos, __ffs(hset) - 1);
+    } else {
+      const T bmax = warp_max_nonneg(best < T(0) ? T(0) : best);
+      const unsigned mypos = (best == bmax) ? (unsigned)bpos : 0xffffffffu;
+      const int pmax = (int)__reduce_min_sync(kFullMask, mypos);
+      ppos = uni(k_is_nan) ? k : pmax;
+    }
     // the row at virtual position k and the pivot row exchange virtual positions
     T pivot_local = T(0);
     int prow_local = -1;
@@ -790,14 +868,29 @@ __device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&de
     const T pivot = __shfl_sync(kFullMask, pivot_local, src);
     const int prow = __shfl_sync(kFullMask, prow_local, src);
 
-    // ---- multipliers l_i = a_ik / pivot for rows not yet used as a pivot ----
+    // ---- multipliers l_i = a_ik / pivot for rows not yet used as a pivot: the quotients of a lane share the pivot's
+    //      reciprocal refinement and run side by side (div_rcp / div_with; the plain operator when the range test fails) ----
     T l[E];
     bool live[E];
+    {
+      const T rp = div_rcp(pivot);
+      bool okall = true;
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-      live[e] = (lane * E + e < D) && (vpos[e] > k);
-      l[e] = live[e] ? (col[e] / pivot) : T(0);
-      col[e] = live[e] ? l[e] : col[e];
+      for (int e = 0; e < E; ++e) {
+        live[e] = (lane * E + e < D) && (vpos[e] > k);
+        bool ok;
+        l[e] = div_with(live[e] ? col[e] : T(1), pivot, rp, ok);
+        okall = okall && ok;
+      }
+      if (uni(!okall)) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) l[e] = col[e] / pivot;
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        l[e] = live[e] ? l[e] : T(0);
+        col[e] = live[e] ? l[e] : col[e];
+      }
     }
     aug_store_col<T, D>(A, k, col);
     // ---- trailing update, columns k+1 .. D-1 and the right-hand side ----
@@ -865,11 +958,18 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   }
   __syncwarp();
 
+  // (the work queue is read one instance ahead, for the functors that prefetch their next block into L2)
+  unsigned long long bnext = 0;
+  if (lane == 0) bnext = atomicAdd(queue, 1ULL);
+  bnext = __shfl_sync(kFullMask, bnext, 0);
   for (;;) {
-    unsigned long long b = 0;
-    if (lane == 0) b = atomicAdd(queue, 1ULL);
-    b = __shfl_sync(kFullMask, b, 0);
+    const unsigned long long b = bnext;
     if (uni(b >= (unsigned long long)batch)) break;
+    if (lane == 0) bnext = atomicAdd(queue, 1ULL);
+    bnext = __shfl_sync(kFullMask, bnext, 0);
+    if constexpr (FnPrefetches<Fn>::value) {
+      if (uni(bnext < (unsigned long long)batch)) fn.prefetch((long long)bnext, lane);
+    }
     const EvalCtx ctx{lane, (long long)b, nullptr};
 
     T x[E], g[E];
