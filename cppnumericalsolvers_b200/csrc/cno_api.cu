@@ -535,11 +535,11 @@ struct LbfgsbArgs {
   cudaStream_t stream;
   cno_launch_info_t* info;
 };
-template <class Fn>
+template <class Fn, int M = 5>
 int launch_lbfgsb(const Fn& fn, const LbfgsbArgs& a) {
   using T = typename Fn::Scalar;
-  using SM = cno::LbfgsbSmem<T, Fn::Dim, 5>;
-  auto kernel = cno::lbfgsb_minimize_kernel<Fn, 5>;
+  using SM = cno::LbfgsbSmem<T, Fn::Dim, M>;
+  auto kernel = cno::lbfgsb_minimize_kernel<Fn, M>;
   const size_t smem = SM::kWarpBytes * SM::kWarps;
   CNO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int sms = 0;
@@ -576,8 +576,14 @@ int lbfgsb_dense_quadratic(const LbfgsbArgs& a) {
   if (!p->data || p->data_stride < (int64_t)D * D + D) return CNO_ERR_INVALID_ARGUMENT;
   return launch_lbfgsb(cno::DenseQuadraticGlobalFn<T, D>{static_cast<const T*>(p->data), (long long)p->data_stride}, a);
 }
-struct LbfgsbEntry { int family, dtype, d; int (*fn)(const LbfgsbArgs&); };
+// Lbfgsb<F, m> for m other than the default 5 (lbfgsb.h:44-45)
+template <class T, int D, int M>
+int lbfgsb_rosenbrock_m(const LbfgsbArgs& a) { return launch_lbfgsb<cno::RosenbrockFn<T, D>, M>(cno::RosenbrockFn<T, D>{}, a); }
+struct LbfgsbEntry { int family, dtype, d; int (*fn)(const LbfgsbArgs&); int m = 5; };
 const LbfgsbEntry kLbfgsbTable[] = {
+    {CNO_FN_ROSENBROCK, CNO_F64, 8, lbfgsb_rosenbrock_m<double, 8, 10>, 10},
+    {CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgsb_rosenbrock_m<double, 37, 10>, 10},
+    {CNO_FN_ROSENBROCK, CNO_F64, 128, lbfgsb_rosenbrock_m<double, 128, 10>, 10},
     {CNO_FN_ROSENBROCK, CNO_F64, 2, lbfgsb_rosenbrock<double, 2>},
     {CNO_FN_ROSENBROCK, CNO_F64, 8, lbfgsb_rosenbrock<double, 8>},
     {CNO_FN_ROSENBROCK, CNO_F64, 37, lbfgsb_rosenbrock<double, 37>},
@@ -594,8 +600,9 @@ const LbfgsbEntry* lbfgsb_find(const cno_problem_t* p) {
   if (!p) return nullptr;
   const int dflt = (p->dtype == CNO_F64) ? CNO_POLICY_DMMA_TREE : CNO_POLICY_WARP_TREE;
   if (p->policy != dflt) return nullptr;
+  const int m = p->lbfgs_m > 0 ? p->lbfgs_m : 5;  // cno_problem_t::lbfgs_m: pairs kept (0 = the reference's default, 5)
   for (const LbfgsbEntry& e : kLbfgsbTable)
-    if (e.family == p->family && e.dtype == p->dtype && e.d == p->d) return &e;
+    if (e.family == p->family && e.dtype == p->dtype && e.d == p->d && e.m == m) return &e;
   return nullptr;
 }
 

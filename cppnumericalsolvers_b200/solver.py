@@ -331,12 +331,13 @@ class Lbfgsb(Solver):
     `SetBounds(lower, upper)` (:88-92) takes CUDA tensors [d] (one box for the batch) or [B, d] (None = unbounded
     on that side).  The stop test on `gradient_norm` uses the sup-norm of the box-projected gradient (:238-286)."""
 
-    def __init__(self, progress: Optional[Progress] = None):
+    def __init__(self, progress: Optional[Progress] = None, m: int = 5):
         if progress is None:
             s = _lib.Stop()
             _lib.lib().cno_lbfgsb_default_stop(C.byref(s))
             progress = Progress.from_c(s)
         super().__init__(progress)
+        self.m = int(m)  # Lbfgsb<F, m>: pairs kept (compiled: 5 for every built-in, 10 for Rosenbrock d = 8 / 37 / 128)
         self.lower_bound: Optional[torch.Tensor] = None
         self.upper_bound: Optional[torch.Tensor] = None
 
@@ -345,6 +346,7 @@ class Lbfgsb(Solver):
 
     def supported(self, function: Function) -> bool:
         p = function.problem()
+        p.lbfgs_m = self.m
         return _lib.lib().cno_lbfgsb_supported(C.byref(p)) == _lib.OK
 
     def Minimize(self, function: Function, state: BatchedFunctionState,
@@ -375,6 +377,7 @@ class Lbfgsb(Solver):
         if stride and any(t.dim() == 1 for t in keep):
             raise ValueError("lower and upper must both be [d] or both be [B, d]")
         prob = function.problem()
+        prob.lbfgs_m = self.m
         with torch.cuda.device(dev):
             x, g = torch.empty_like(x0), torch.empty_like(x0)
             f, xd, fd, gn = (torch.empty(B, dtype=dt, device=dev) for _ in range(4))

@@ -705,7 +705,7 @@ class Lbfgs : public Solver<F, LineSearch::solver_id(CNO_LBFGS)> {
 // (one box for the batch) or [B, d].
 template <class F, int m = 5>
 class Lbfgsb {
-  static_assert(m == 5, "Lbfgsb: the kernels are compiled for the reference's default m = 5");
+  static_assert(m == 5 || m == 10, "Lbfgsb<F, m>: kernels are compiled for m = 5 (every built-in) and m = 10 (Rosenbrock)");
 
  public:
   using FunctionType = F;
@@ -734,6 +734,7 @@ class Lbfgsb {
     const int64_t B = function_state.batch;
     function::FunctionExpr<T, function::DifferentiabilityMode::First, D> expr(function);
     if (expr.raw) throw std::runtime_error("Lbfgsb: built-in objective families only");
+    expr.problem.lbfgs_m = m;
     cno_bounds_t bounds{};
     bounds.lower = lower_.size() ? lower_.data() : nullptr;
     bounds.upper = upper_.size() ? upper_.data() : nullptr;

@@ -386,8 +386,9 @@ def lbfgsb_stop() -> Stop:
 
 
 def ref_lbfgsb_minimize(family: int, x0: np.ndarray, lower=None, upper=None, *, stop: Stop | None = None,
-                        data=None, policy: int | None = None, threads: int = 0) -> dict:
-    """Lbfgsb<F, 5>::Minimize per instance with SetBounds(lower, upper); lower / upper: [d] (one box) or [B, d]."""
+                        data=None, policy: int | None = None, threads: int = 0, m: int = 0) -> dict:
+    """Lbfgsb<F, m>::Minimize per instance with SetBounds(lower, upper); lower / upper: [d] (one box) or [B, d];
+    m = 0 / 5: the reference's default, 10: Lbfgsb<F, 10> (Rosenbrock)."""
     x0 = np.ascontiguousarray(x0)
     B, d = x0.shape
     dt = x0.dtype
@@ -396,7 +397,7 @@ def ref_lbfgsb_minimize(family: int, x0: np.ndarray, lower=None, upper=None, *, 
     if data is not None:
         data = np.ascontiguousarray(data, dtype=dt)
     p = Problem(family, _np_dtype(x0), d, 0, 0.0, data.ctypes.data if data is not None else None,
-                data.shape[1] if data is not None else 0, policy, 0)
+                data.shape[1] if data is not None else 0, policy, 0, m)
     lo = None if lower is None else np.ascontiguousarray(lower, dtype=dt)
     hi = None if upper is None else np.ascontiguousarray(upper, dtype=dt)
     stride = 0

@@ -659,7 +659,7 @@ struct ScalarStub : FunctionCRTP<ScalarStub, double, DifferentiabilityMode::Firs
 // [d] (stride 0: one box for the batch) or [B, d] (stride d); NULL = unbounded on that side.  Family: Rosenbrock /
 // DiagQuadratic / HalfSquaredNorm / DenseQuadratic, First mode.  stop == NULL: the Lbfgsb() constructor's preset
 // (default + f_delta = 2.22e-9 relative, :78-81).
-template <class T, template <class, DifferentiabilityMode> class Family>
+template <class T, template <class, DifferentiabilityMode> class Family, int M = 5>
 void lbfgsb_run_one(const cno_problem_t* prob, int64_t b, const T* x0, const T* lo, const T* hi, const cno_stop_t* stop,
                     const cno_batch_out_t* out) {
   using Fn = Family<T, DifferentiabilityMode::First>;
@@ -675,7 +675,7 @@ void lbfgsb_run_one(const cno_problem_t* prob, int64_t b, const T* x0, const T* 
     l[i] = lo ? lo[i] : std::numeric_limits<T>::lowest();
     u[i] = hi ? hi[i] : std::numeric_limits<T>::max();
   }
-  cppoptlib::solver::Lbfgsb<Fn> solver;
+  cppoptlib::solver::Lbfgsb<Fn, M> solver;
   if (stop) {
     auto& p = solver.stopping_progress;
     p.num_iterations = stop->num_iterations;
@@ -891,7 +891,11 @@ int cno_ref_lbfgsb_minimize(const cno_problem_t* problem, int64_t batch, const v
     const TY* lo = lower ? static_cast<const TY*>(lower) + b * bounds_stride : nullptr;                          \
     const TY* hi = upper ? static_cast<const TY*>(upper) + b * bounds_stride : nullptr;                          \
     switch (problem->family) {                                                                                   \
-      case CNO_FN_ROSENBROCK: lbfgsb_run_one<TY, Rosenbrock>(problem, b, xs, lo, hi, stop, out); break;          \
+      case CNO_FN_ROSENBROCK:                                                                                    \
+        if (problem->lbfgs_m == 10) lbfgsb_run_one<TY, Rosenbrock, 10>(problem, b, xs, lo, hi, stop, out);       \
+        else if (problem->lbfgs_m == 0 || problem->lbfgs_m == 5) lbfgsb_run_one<TY, Rosenbrock>(problem, b, xs, lo, hi, stop, out); \
+        else r = CNO_ERR_UNSUPPORTED;                                                                            \
+        break;                                                                                                   \
       case CNO_FN_DIAG_QUADRATIC: lbfgsb_run_one<TY, DiagQuadratic>(problem, b, xs, lo, hi, stop, out); break;   \
       case CNO_FN_HALF_SQUARED_NORM: lbfgsb_run_one<TY, HalfSquaredNorm>(problem, b, xs, lo, hi, stop, out); break; \
       case CNO_FN_DENSE_QUADRATIC: lbfgsb_run_one<TY, DenseQuadratic>(problem, b, xs, lo, hi, stop, out); break; \

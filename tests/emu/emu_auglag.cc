@@ -442,7 +442,7 @@ extern "C" int emu_al(int op, const cno_problem_t* objective, const cno_constrai
 
 #define CNO_EMU_COMMA ,
 // Lbfgsb<F, 5> (csrc/cno_lbfgsb.cuh) under emulation.  lower / upper: host arrays [d] (stride 0) or [B, d].
-template <class Fn>
+template <class Fn, int M = 5>
 int run_lbfgsb(long long B, const void* x0, const void* lower, const void* upper, long long stride, const cno_stop_t* stop,
                const cno_batch_out_t* out) {
   using T = typename Fn::Scalar;
@@ -450,13 +450,20 @@ int run_lbfgsb(long long B, const void* x0, const void* lower, const void* upper
   emu::run_warp([&](int lane) {
     blockIdx.x = 0;
     threadIdx.x = (unsigned)lane;
-    cno::lbfgsb_minimize_kernel<Fn, 5>(Fn{}, (const T*)x0, B, cno::make_stop<T>(*stop), cno::make_out<T>(*out), &queue,
+    cno::lbfgsb_minimize_kernel<Fn, M>(Fn{}, (const T*)x0, B, cno::make_stop<T>(*stop), cno::make_out<T>(*out), &queue,
                                         cno::BoundsArgs<T>{(const T*)lower, (const T*)upper, stride});
   });
   return 0;
 }
 extern "C" int emu_lbfgsb(const cno_problem_t* p, long long batch, const void* x0, const void* lower, const void* upper,
                           long long stride, const cno_stop_t* stop, const cno_batch_out_t* out) {
+  if (p->lbfgs_m == 10) {  // Lbfgsb<F, 10>
+    if (p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64 && p->d == 8)
+      return run_lbfgsb<cno::RosenbrockFn<double, 8>, 10>(batch, x0, lower, upper, stride, stop, out);
+    if (p->family == CNO_FN_ROSENBROCK && p->dtype == CNO_F64 && p->d == 37)
+      return run_lbfgsb<cno::RosenbrockFn<double, 37>, 10>(batch, x0, lower, upper, stride, stop, out);
+    return CNO_ERR_UNSUPPORTED;
+  }
 #define LB_CASE(FAM, DT, FN)                                   \
   if (p->family == FAM && p->dtype == DT) return run_lbfgsb<FN>(batch, x0, lower, upper, stride, stop, out);
   if (p->d == 2) { LB_CASE(CNO_FN_ROSENBROCK, CNO_F64, cno::RosenbrockFn<double CNO_EMU_COMMA 2>) }

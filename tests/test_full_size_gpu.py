@@ -92,7 +92,11 @@ def test_c4_bfgs_rosenbrock_d32_full_batch_2e19():
     assert torch.allclose(st.value, f_chk, rtol=1e-12, atol=1e-12)
 
 
-def test_c5_newton_dense_quadratic_d64_full_batch_2e17():
+@pytest.mark.parametrize("policy", [None, ob.POLICY_DMMA_LU], ids=["default_policy", "tensor_core_policy"])
+def test_c5_newton_dense_quadratic_d64_full_batch_2e17(policy):
+    """BASELINE config 5 at its full batch, under the default arithmetic (csrc/cno_newton.cuh) and with the factorisation
+    on the FP64 tensor core (CNO_POLICY_DMMA_LU, csrc/cno_newton_dmma.cuh): strided oracle samples of the same batch under
+    the same policy, bit for bit."""
     B, d = 1 << 17, 64
     gen = torch.Generator(device=DEV)
     gen.manual_seed(0)
@@ -108,12 +112,12 @@ def test_c5_newton_dense_quadratic_d64_full_batch_2e17():
         data[lo:hi, d * d:] = torch.rand(hi - lo, d, dtype=torch.float64, device=DEV, generator=gen) * 2 - 1
     x0 = torch.empty(B, d, dtype=torch.float64, device=DEV)
     cn.fill_uniform(x0, 0, 12345, -2.0, 2.0)
-    st, pr = cn.NewtonDescent().Minimize(cn.DenseQuadratic(data, d), cn.BatchedFunctionState(x0))
+    st, pr = cn.NewtonDescent().Minimize(cn.DenseQuadratic(data, d, policy=policy), cn.BatchedFunctionState(x0))
     torch.cuda.synchronize()
     _terminated(pr)
     idx = _sample(B)
     tidx = torch.from_numpy(idx).to(DEV)
-    o = ob.minimize(ob.NEWTON, ob.FN_DENSE_QUADRATIC, x0[tidx].cpu().numpy(), data=data[tidx].cpu().numpy())
+    o = ob.minimize(ob.NEWTON, ob.FN_DENSE_QUADRATIC, x0[tidx].cpu().numpy(), data=data[tidx].cpu().numpy(), policy=policy)
     assert np.array_equal(pr.num_iterations[tidx].cpu().numpy().astype(np.uint32), o["num_iterations"])
     assert np.array_equal(pr.status[tidx].cpu().numpy(), o["status"])
     assert np.array_equal(st.x[tidx].cpu().numpy().view(np.uint64), o["x"].view(np.uint64))

@@ -26,10 +26,10 @@ def emu():
     return C.CDLL(os.path.join(here, "libcno_emu.so"))
 
 
-def _emulated(emu, x0, lo, hi, stop=None):
+def _emulated(emu, x0, lo, hi, stop=None, m=0):
     B, d = x0.shape
     stop = stop if stop is not None else ob.lbfgsb_stop()
-    prob = ob.Problem(ob.FN_ROSENBROCK, 0, d, 0, 0.0, None, 0, ob.device_policy(x0.dtype), 0)
+    prob = ob.Problem(ob.FN_ROSENBROCK, 0, d, 0, 0.0, None, 0, ob.device_policy(x0.dtype), 0, m)
     r = dict(x=np.zeros_like(x0), value=np.zeros(B), gradient=np.zeros_like(x0), num_iterations=np.zeros(B, np.uint32),
              status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32), x_delta=np.zeros(B), f_delta=np.zeros(B),
              gradient_norm=np.zeros(B))
@@ -84,12 +84,29 @@ def test_emulated_lbfgsb_active_bounds_and_infeasible_start(emu):
     assert np.all(r["x"] <= 0.8) and np.all(r["x"] >= -0.5) and np.any(r["x"] == 0.8)
 
 
+@needs_ref
+def test_emulated_lbfgsb_m10_equals_reference_header(emu):
+    """Lbfgsb<F, 10> (lbfgsb.h:44-45: m is a template parameter): the kernel with ten pairs (2k up to 20 lanes of the
+    compact representation) == the reference's own Lbfgsb<F, 10>, bit for bit; it differs from m = 5."""
+    x0 = ob.fill_uniform((1, 8), 0, 9, -2.5, 2.5)
+    lo, hi = np.full(8, -1.0), np.full(8, 1.5)
+    stop = ob.lbfgsb_stop()
+    stop.num_iterations = 30  # (past ten iterations the history is full and wraps: both regimes are covered)
+    r = _emulated(emu, x0, lo, hi, stop=stop, m=10)
+    o = ob.ref_lbfgsb_minimize(ob.FN_ROSENBROCK, x0, lo, hi, stop=stop, m=10)
+    for k in KEYS:
+        assert np.array_equal(r[k].view(np.uint8), o[k].view(np.uint8)), k
+    o5 = ob.ref_lbfgsb_minimize(ob.FN_ROSENBROCK, x0, lo, hi, stop=stop)
+    assert not np.array_equal(o5["num_iterations"], o["num_iterations"]) or \
+        not np.array_equal(o5["x"].view(np.uint64), o["x"].view(np.uint64))
+
+
 # ---- GPU -----------------------------------------------------------------------------------------------------------
-def _gpu(x0, lo, hi, stop=None, fn=None):
+def _gpu(x0, lo, hi, stop=None, fn=None, m=5):
     import cppnumericalsolvers_b200 as cn
     dev = "cuda:0"
     d = x0.shape[1]
-    solver = cn.Lbfgsb() if stop is None else cn.Lbfgsb(cn.Progress.from_c(stop))
+    solver = cn.Lbfgsb(m=m) if stop is None else cn.Lbfgsb(cn.Progress.from_c(stop), m=m)
     t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
     solver.SetBounds(t(lo), t(hi))
     fn = fn if fn is not None else cn.Rosenbrock(d, torch.float64 if x0.dtype == np.float64 else torch.float32)
@@ -130,5 +147,24 @@ def test_gpu_lbfgsb_bitwise_equals_reference_header(d, B):
     stop = ob.lbfgsb_stop()
     stop.num_iterations = 80
     r, o = _gpu(x0[:32], None, None, stop), ob.ref_lbfgsb_minimize(ob.FN_ROSENBROCK, x0[:32], None, None, stop=stop)
+    for k in KEYS:
+        assert np.array_equal(r[k].view(np.uint8), o[k].view(np.uint8)), k
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("d,B", [(8, 128), (37, 96), (128, 48)])
+def test_gpu_lbfgsb_m10_bitwise_equals_reference_header(d, B):
+    """Lbfgsb<F, 10>: GPU == the reference's own Lbfgsb<F, 10> (oracle/_ref), per-instance boxes and unbounded."""
+    rng = np.random.default_rng(100 + d)
+    x0 = ob.fill_uniform((B, d), 0, 77 + d, -2.5, 2.5)
+    lo = rng.uniform(-1.5, -0.2, (B, d))
+    hi = lo + rng.uniform(0.3, 2.0, (B, d))
+    r, o = _gpu(x0, lo, hi, m=10), ob.ref_lbfgsb_minimize(ob.FN_ROSENBROCK, x0, lo, hi, m=10)
+    for k in KEYS:
+        assert np.array_equal(r[k].view(np.uint8), o[k].view(np.uint8)), k
+    stop = ob.lbfgsb_stop()
+    stop.num_iterations = 60
+    r, o = _gpu(x0[:24], None, None, stop, m=10), ob.ref_lbfgsb_minimize(ob.FN_ROSENBROCK, x0[:24], None, None, stop=stop, m=10)
     for k in KEYS:
         assert np.array_equal(r[k].view(np.uint8), o[k].view(np.uint8)), k
