@@ -199,71 +199,53 @@ struct LogisticFn {
     const T data_loss = warp_sum(lsum);
     const T reg = (T(0.5) * lambda) * warp_dot<T, E>(w, w);
     // ---- gradient g_i = reduce_samples(coef_j Xt[i][j]) + lambda w_i ----
-    // The 64 sample sums are reduced 32 at a time by a TRANSPOSING butterfly: at the level with offset `off` a lane
-    // keeps the half of its values whose feature index has the lane's `off` bit and adds the partner's partials of
-    // those features (own + received, exactly the term `p + shfl_xor(p, off)` of the plain butterfly, which the
-    // two partners compute identically); after the levels 16, 8, 4, 2, 1 lane l holds the total of feature l.  Same
-    // tree, same bits, 31 shuffles + 31 additions per 32 features instead of 160 + 160.
     if (grad) {
-      static_assert(D == 64 && DS == 32 && E == 2, "two batches of 32 features: shared memory, Tensor Memory");
-      T tot[2];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        T pf[32];
-        if (half == 0) {  // features 0 .. 31: shared memory
+      for (int e = 0; e < E; ++e) (*grad)[e] = T(0);
+#pragma unroll 2
+      for (int i0 = 0; i0 < D; i0 += 4) {  // 4 independent butterflies in flight
+        T p[4];
+        T xq[4][8];
+        if (i0 < DS) {  // (uniform) shared-memory half
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            T acc = T(0);
+          for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int cc = 0; cc < C; ++cc) {
-              T xv[4];
-              P4::get(*reinterpret_cast<const typename P4::type*>(Xt + i * N + cc * 128 + 4 * lane), xv);
-              const T part = (coef[cc * 4 + 0] * xv[0] + coef[cc * 4 + 1] * xv[1]) +
-                             (coef[cc * 4 + 2] * xv[2] + coef[cc * 4 + 3] * xv[3]);
-              acc = (cc == 0) ? part : (acc + part);
-            }
-            pf[i] = acc;
+            for (int cc = 0; cc < C; ++cc)
+              P4::get(*reinterpret_cast<const typename P4::type*>(Xt + (i0 + q) * N + cc * 128 + 4 * lane), &xq[q][cc * 4]);
+        } else {        // Tensor Memory half
+          uint32_t r[4][8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) tmem_ld4_issue(c.tmem + (i0 - DS + q) * 8, r[q]);
+          tmem_wait_ld_groups<4>(r);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int t = 0; t < 8; ++t) xq[q][t] = __uint_as_float(r[q][t]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          T acc = T(0);
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc) {
+            const T* xv = &xq[q][cc * 4];
+            const T part = (coef[cc * 4 + 0] * xv[0] + coef[cc * 4 + 1] * xv[1]) +
+                           (coef[cc * 4 + 2] * xv[2] + coef[cc * 4 + 3] * xv[3]);
+            acc = (cc == 0) ? part : (acc + part);
           }
-        } else {  // features 32 .. 63: Tensor Memory, 4 features per wait
-#pragma unroll
-          for (int i0 = 0; i0 < 32; i0 += 4) {
-            uint32_t r[4][8];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) tmem_ld4_issue(c.tmem + (i0 + q) * 8, r[q]);
-            tmem_wait_ld_groups<4>(r);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              T acc = T(0);
-#pragma unroll
-              for (int cc = 0; cc < C; ++cc) {
-                const T part = (coef[cc * 4 + 0] * __uint_as_float(r[q][cc * 4 + 0]) +
-                                coef[cc * 4 + 1] * __uint_as_float(r[q][cc * 4 + 1])) +
-                               (coef[cc * 4 + 2] * __uint_as_float(r[q][cc * 4 + 2]) +
-                                coef[cc * 4 + 3] * __uint_as_float(r[q][cc * 4 + 3]));
-                acc = (cc == 0) ? part : (acc + part);
-              }
-              pf[i0 + q] = acc;
-            }
-          }
+          p[q] = acc;
         }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
-          const bool hi = (lane & off) != 0;
 #pragma unroll
-          for (int i = 0; i < off; ++i) {
-            const T send = hi ? pf[i] : pf[i + off];
-            const T keep = hi ? pf[i + off] : pf[i];
-            pf[i] = keep + __shfl_xor_sync(kFullMask, send, off);
-          }
+          for (int q = 0; q < 4; ++q) p[q] = p[q] + __shfl_xor_sync(kFullMask, p[q], off);
         }
-        tot[half] = pf[0];  // the sample sum of feature 32 * half + lane
-      }
-      // lane l owns features 2l, 2l+1
 #pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int f = 2 * lane + e;
-        const T a = __shfl_sync(kFullMask, tot[0], f & 31), b = __shfl_sync(kFullMask, tot[1], f & 31);
-        (*grad)[e] = ((f < 32) ? a : b) + lambda * w[e];
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q;
+#pragma unroll
+          for (int e = 0; e < E; ++e)
+            if (lane * E + e == i) (*grad)[e] = p[q] + lambda * w[e];
+        }
       }
     }
     return data_loss + reg;
