@@ -140,6 +140,9 @@ typedef int (*RawMinimizeStepsFn)(int solver, int mode, int lbfgs_m, const void*
 typedef int (*RawEvaluateFn)(const void* functor_bytes, int64_t batch, const void* x, void* value, void* gradient,
                              void* stream);
 
+typedef int (*RawConditionFn)(const void* functor_bytes, int64_t batch, const void* x, void* condition, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 template <class F, class = void>
 struct LauncherTraits;  // specialised by CNO_DECLARE_FUNCTION / the built-ins below
 
@@ -157,6 +160,7 @@ struct FunctionExpr {
   RawStateBytesFn raw_state_bytes = nullptr;
   RawMinimizeStepsFn raw_steps = nullptr;
   RawEvaluateFn raw_evaluate = nullptr;
+  RawConditionFn raw_condition = nullptr;
   std::vector<unsigned char> pod;   // the user functor's bytes
   int dimension = TDimension;       // (TDimension == -1: taken from the bound function)
 
@@ -192,10 +196,11 @@ struct FunctionExpr {
   // progress.condition_hessian.  Device arrays; built-in Second-mode families (cno_condition_hessian).
   void ConditionHessian(int64_t batch, const TScalar* x, TScalar* condition, cudaStream_t stream = nullptr) const {
     static_assert(TMode == DifferentiabilityMode::Second, "condition_hessian is defined for Second-mode functions");
-    if (raw) detail::check_cno(CNO_ERR_UNSUPPORTED, "FunctionExpr::ConditionHessian (user functors)");
     detail::DeviceArray<unsigned long long> ws(32);
-    detail::check_cno(cno_condition_hessian(&problem, batch, x, condition, ws.data(), ws.size() * sizeof(unsigned long long), stream),
-                      "FunctionExpr::ConditionHessian");
+    const size_t wsb = ws.size() * sizeof(unsigned long long);
+    const int rc = raw ? (raw_condition ? raw_condition(pod.data(), batch, x, condition, ws.data(), wsb, stream) : CNO_ERR_UNSUPPORTED)
+                       : cno_condition_hessian(&problem, batch, x, condition, ws.data(), wsb, stream);
+    detail::check_cno(rc, "FunctionExpr::ConditionHessian");
     detail::check_cuda(cudaStreamSynchronize(stream), "FunctionExpr::ConditionHessian");
   }
 };
@@ -976,6 +981,9 @@ class AugmentedLagrangian {
                                             size_t workspace_bytes, void* stream, cno_launch_info_t* info);       \
   extern "C" int cno_##tag##_evaluate(const void* functor_bytes, int64_t batch, const void* x, void* value,       \
                                       void* gradient, void* stream);                                              \
+  extern "C" int cno_##tag##_condition_hessian(const void* functor_bytes, int64_t batch, const void* x,           \
+                                               void* condition, void* workspace, size_t workspace_bytes,         \
+                                               void* stream);                                                    \
   namespace cppoptlib::function {                                                                                 \
   template <>                                                                                                     \
   struct LauncherTraits<F> {                                                                                      \
@@ -986,6 +994,7 @@ class AugmentedLagrangian {
       e.raw_state_bytes = &cno_##tag##_state_bytes;                                                               \
       e.raw_steps = &cno_##tag##_minimize_steps;                                                                  \
       e.raw_evaluate = &cno_##tag##_evaluate;                                                                     \
+      e.raw_condition = &cno_##tag##_condition_hessian;                                                           \
       e.pod.assign(reinterpret_cast<const unsigned char*>(&f),                                                   \
                    reinterpret_cast<const unsigned char*>(&f) + sizeof(F));                                      \
     }                                                                                                             \

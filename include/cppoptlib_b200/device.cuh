@@ -24,6 +24,7 @@
 //   cno_<tag>_state_bytes /
 //   cno_<tag>_minimize_steps  OptimizationStep rounds + callback  (solver.h:163-176, 226-228; Lbfgs)
 //   cno_<tag>_evaluate        F::operator()(x, &grad) per instance (function_base.h:103-120)
+//   cno_<tag>_condition_hessian   Progress::condition_hessian at x per instance (progress.h:203-210; Second mode)
 #ifndef CPPOPTLIB_B200_DEVICE_CUH_
 #define CPPOPTLIB_B200_DEVICE_CUH_
 
@@ -145,6 +146,37 @@ inline int user_newton(const F& fn, int64_t batch, const void* x0, const cno_sto
   }
 }
 
+// Progress::condition_hessian on request (solver/progress.h:203-210; csrc/cno_newton.cuh: condition_hessian_kernel) for a
+// Second-mode user functor or composite: H(x) through hess_col, as NewtonDescent stages it.
+template <class F>
+inline int user_condition(const F& fn, int64_t batch, const void* x, void* condition, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if constexpr (F::Mode == 2 && HasHessCol<F>::value) {
+    using A = SecondOrderAdapter<F>;
+    using T = typename F::Scalar;
+    using CS = ConditionSmem<T, F::Dim>;
+    if (batch < 0) return CNO_ERR_INVALID_ARGUMENT;
+    if (batch == 0) return CNO_OK;
+    if (!x || !condition || !workspace || workspace_bytes < sizeof(unsigned long long) || ((uintptr_t)workspace & 7))
+      return CNO_ERR_INVALID_ARGUMENT;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return CNO_ERR_NO_DEVICE;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kernel = condition_hessian_kernel<A>;
+    const size_t smem = CS::kWarpBytes * CS::kWarps;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return CNO_ERR_CUDA;
+    long long ctas = (batch + CS::kWarps - 1) / CS::kWarps;
+    const int grid = (int)(ctas < sms ? (ctas < 1 ? 1 : ctas) : sms);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    unsigned long long* queue = static_cast<unsigned long long*>(workspace);
+    if (cudaMemsetAsync(queue, 0, sizeof(unsigned long long), s) != cudaSuccess) return CNO_ERR_CUDA;
+    kernel<<<grid, CS::kWarps * 32, smem, s>>>(A{fn}, static_cast<const T*>(x), (long long)batch, static_cast<T*>(condition), queue);
+    return cudaGetLastError() == cudaSuccess ? CNO_OK : CNO_ERR_CUDA;
+  } else {
+    return CNO_ERR_UNSUPPORTED;  // defined for second-order differentiable functions
+  }
+}
+
 template <class F, int M>
 inline int user_minimize(int solver, int mode, int lbfgs_m, const F& fn, int64_t batch, const void* x0, const cno_stop_t* stop,
                          const cno_batch_out_t* out, void* workspace, size_t workspace_bytes, void* stream,
@@ -237,6 +269,14 @@ inline int user_state_bytes(int solver, int64_t batch, size_t* bytes) {
     alignas(F) unsigned char raw__[sizeof(F)];                                                                 \
     memcpy(raw__, functor_bytes, sizeof(F));                                                                   \
     return cno::launch_evaluate<F>(*reinterpret_cast<const F*>(raw__), batch, x, value, gradient, stream);     \
+  }                                                                                                            \
+  extern "C" int cno_##tag##_condition_hessian(const void* functor_bytes, int64_t batch, const void* x,        \
+                                               void* condition, void* workspace, size_t workspace_bytes,      \
+                                               void* stream) {                                                \
+    alignas(F) unsigned char raw__[sizeof(F)];                                                                 \
+    memcpy(raw__, functor_bytes, sizeof(F));                                                                   \
+    return cno::user_condition<F>(*reinterpret_cast<const F*>(raw__), batch, x, condition, workspace,          \
+                                  workspace_bytes, stream);                                                    \
   }
 
 #endif  // CPPOPTLIB_B200_DEVICE_CUH_

@@ -560,6 +560,17 @@ int expr_first_mode(const Fn& f, const ExprJob<T>& j) {
 }
 template <class T, class Fn>
 int expr_second_mode(const Fn& f, const ExprJob<T>& j) {
+  if (j.solver == 100) {  // progress.condition_hessian as the reference's Progress::Update leaves it at x -> out->value
+    using State = FunctionState<T, Eigen::Dynamic>;
+    typename Fn::VectorType x(j.d);
+    for (int i = 0; i < j.d; ++i) x[i] = j.x[i];
+    const State state(f, x);
+    auto stop = cppoptlib::solver::DefaultStoppingSolverProgress<Fn, State>();
+    cppoptlib::solver::Progress<Fn, State> progress;
+    progress.Update(f, state, state, stop);
+    static_cast<T*>(j.out->value)[j.b] = progress.condition_hessian;
+    return 0;
+  }
   if (j.solver == CNO_NEWTON) { run_expr_solver<T, cppoptlib::solver::NewtonDescent<Fn>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out); return 0; }
   if (j.solver == CNO_LBFGS && j.linesearch == CNO_LS_MORE_THUENTE) {  // Lbfgs on a Second-mode function: preconditioner branch
     run_expr_solver<T, cppoptlib::solver::Lbfgs<Fn>>(f, j.counter, j.d, j.b, j.x, j.stop, j.out);

@@ -101,7 +101,7 @@ CNO_INSTANTIATE_FUNCTION_M(bowl16m5, Bowl16, 5)  // (a second tag of the same ty
 // ---- one uniform entry point for the Python tests: builds the functor for (expr, dtype, d) and forwards ----
 enum { EXPR_BOWL = 0, EXPR_ROSEN_PLUS_HALF, EXPR_PROD, EXPR_SUB, EXPR_PENALTY, EXPR_ZERO_MUL, EXPR_SECOND_SUM,
        EXPR_SECOND_PROD, EXPR_DOWNGRADE };
-enum { OP_MINIMIZE = 0, OP_STEPS = 1, OP_STATE_BYTES = 2, OP_EVALUATE = 3 };
+enum { OP_MINIMIZE = 0, OP_STEPS = 1, OP_STATE_BYTES = 2, OP_EVALUATE = 3, OP_CONDITION = 4 };
 
 struct TestCall {
   int op, solver, mode;
@@ -135,6 +135,8 @@ struct TestCall {
                                           c->workspace_bytes, c->stream, c->info);                                    \
       case OP_STATE_BYTES: return cno_##tag##_state_bytes(c->solver, c->batch, c->bytes);                             \
       case OP_EVALUATE: return cno_##tag##_evaluate(&f__, c->batch, c->x0, c->value, c->gradient, c->stream);         \
+      case OP_CONDITION: /* condition numbers -> c->value */                                                          \
+        return cno_##tag##_condition_hessian(&f__, c->batch, c->x0, c->value, c->workspace, c->workspace_bytes, c->stream); \
     }                                                                                                                 \
     return CNO_ERR_INVALID_ARGUMENT;                                                                                  \
   } while (0)

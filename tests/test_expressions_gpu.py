@@ -89,6 +89,19 @@ def test_second_mode_composites_newton_and_preconditioned_lbfgs(expr, d):
 
 
 @needs_ref
+@pytest.mark.parametrize("expr,d", [(ob.EXPR_SECOND_SUM, 8), (ob.EXPR_SECOND_SUM, 37), (ob.EXPR_SECOND_PROD, 2)])
+def test_condition_hessian_of_second_mode_composites(expr, d):
+    """Progress::condition_hessian (progress.h:203-210) of a composite on request (cno_<tag>_condition_hessian): the
+    Hessian composed node by node on the device -- for the product not bitwise symmetric -- against the reference's own
+    Progress::Update on the reference's own composite (oracle/_ref), bit for bit."""
+    x = _x0(24, d, 11 + d, lo=-1.5, hi=1.5)
+    got = ut.condition_hessian(expr, x)
+    ref = ob.ref_minimize_expr(expr, 100, x)["value"]  # solver id 100: the condition number of the composite at x
+    assert np.array_equal(got.view(np.uint64), ref.view(np.uint64))
+    assert np.all(got >= d * 0.99)
+
+
+@needs_ref
 def test_function_expr_downgrade_kat_and_first_mode_use():
     """src/test/augmented_lagrangian_test.cc:882-896: a Second-mode source bound through a First-mode FunctionExpr
     evaluates to 20.25 / (12, -3) at (3, -1.5); minimised as a First-mode function (no preconditioner branch)."""

@@ -10,7 +10,7 @@ from cppnumericalsolvers_b200 import _lib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "cpp", "build", "libcno_usertest.so")
-OP_MINIMIZE, OP_STEPS, OP_STATE_BYTES, OP_EVALUATE = range(4)
+OP_MINIMIZE, OP_STEPS, OP_STATE_BYTES, OP_EVALUATE, OP_CONDITION = range(5)
 
 
 class TestCall(C.Structure):
@@ -128,3 +128,18 @@ def evaluate(expr, x_np, *, param=0.0, dev="cuda:0"):
     if rc != 0:
         raise _lib.CnoError(rc, "cno_test_expr(evaluate)")
     return f.cpu().numpy(), g.cpu().numpy()
+
+
+def condition_hessian(expr, x_np, *, param=0.0, dev="cuda:0"):
+    """cno_<tag>_condition_hessian of the composite: Progress::condition_hessian (progress.h:203-210) per row of x."""
+    x = torch.from_numpy(np.ascontiguousarray(x_np)).to(dev)
+    B, d = x.shape
+    c = torch.empty(B, dtype=x.dtype, device=dev)
+    ws = torch.zeros(256, dtype=torch.uint8, device=dev)
+    call = TestCall(OP_CONDITION, 0, 2, B, x.data_ptr(), None, None, None, 0, 0, 0, ws.data_ptr(), ws.numel(), None, None,
+                    c.data_ptr(), None, None)
+    rc = lib().cno_test_expr(expr, param, 0 if x.dtype == torch.float64 else 1, d, C.byref(call))
+    torch.cuda.synchronize()
+    if rc != 0:
+        raise _lib.CnoError(rc, "cno_test_expr(condition_hessian)")
+    return c.cpu().numpy()
