@@ -967,9 +967,6 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     if (uni(b >= (unsigned long long)batch)) break;
     if (lane == 0) bnext = atomicAdd(queue, 1ULL);
     bnext = __shfl_sync(kFullMask, bnext, 0);
-    if constexpr (FnPrefetches<Fn>::value) {
-      if (uni(bnext < (unsigned long long)batch)) fn.prefetch((long long)bnext, lane);
-    }
     const EvalCtx ctx{lane, (long long)b, nullptr};
 
     T x[E], g[E];
@@ -1089,6 +1086,11 @@ newton_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       nfev++;  // Progress::Update's Hessian evaluation (progress.h:206-207)
       staged = false;  // (a non-constant Hessian is staged again at the new x; a constant one stays factored)
       progress_update<T>(prog, stop, ring, lane, prev_value, f, x_delta, gnorm_inf, x_inf);
+      if constexpr (FnPrefetches<Fn>::value) {
+        // the next instance's block into L2, one iteration ahead (not for the whole solve: two blocks per warp in
+        // flight all the time would fill the L2 and make the passes over the current block miss)
+        if (uni(prog.num_iterations == 1 && bnext < (unsigned long long)batch)) fn.prefetch((long long)bnext, lane);
+      }
     } while (uni(prog.status == CNO_STATUS_CONTINUE));
 
     if (out.x) store_row<T, D>(out.x + b * D, lane, x);
