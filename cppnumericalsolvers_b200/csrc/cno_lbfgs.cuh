@@ -135,8 +135,19 @@ __device__ __forceinline__ void progress_update(ProgressState<T>& p, const StopP
     bool fired = false;
     if (uni((int)p.num_iterations > pp)) {
       const T past_f = ring[p.ring_pos];
-      const T rate = cabs(past_f - cur_value) / smax(T(1), cabs(cur_value));
-      fired = rate < stop.past_delta;
+      // rate = |past_f - f| / max(1, |f|) < past_delta (:287-290)?  A difference above twice (below half) the product
+      // past_delta * max(1, |f|) decides it without the division: the quotient is then above 2 (below 0.5) past_delta
+      // up to two roundings.  In between, or with a non-finite operand: the specification's expression.
+      const T diff = cabs(past_f - cur_value), mag = smax(T(1), cabs(cur_value));
+      const T bound = stop.past_delta * mag;
+      if (cfinite(diff) && cfinite(bound) && bound > T(0) && diff > T(2) * bound) {
+        fired = false;
+      } else if (cfinite(diff) && cfinite(bound) && bound >= Num<T>::min_normal && diff < T(0.5) * bound) {
+        fired = true;
+      } else {
+        const T rate = diff / mag;
+        fired = rate < stop.past_delta;
+      }
     }
     if (uni(fired)) {
       status = CNO_STATUS_F_DELTA_VIOLATION;
@@ -327,7 +338,8 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
 
     do {  // solver.h:196-220
       // ================= Lbfgs::OptimizationStep (lbfgs.h:89-303) =========
-      const T relative_eps = eps * smax(T(1.0), csqrt(xx));  // :93-95
+      // relative_eps = eps * max(1, ||x||) (:93-95) enters ONE comparison, the descent test below; it is formed there,
+      // and only when a square-root-free bound does not already decide the comparison.
 
       // Second mode (:129-135): M^-1 = 1 / (|diag H| + eps); the gradient the reference
       // re-evaluates there is the state's gradient (same function, same x, same bits).
@@ -462,7 +474,18 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       T dginit = descent_direction;  // = g.(-q), bit for bit
       // The search runs along -q (the line search negates inside its products, cno_linesearch.cuh
       // kNeg), so no negated copy of q is ever made.
-      if (uni(!cfinite(descent_direction) || descent_direction > -eps * relative_eps)) {
+      // descent_direction > -eps * relative_eps?  |eps * relative_eps| <= eps^2 max(1, ||x||) (1 + 2^-50) and
+      // sqrt(t) <= max(1, t), so a finite direction below -2 eps^2 max(1, x.x) is below the exact threshold whatever
+      // its rounding: the comparison is false and neither the square root nor the products are needed.  Anything else
+      // (a non-finite operand, a direction that close to zero) takes the specification's expression.
+      bool fallback;
+      if (cfinite(descent_direction) && cfinite(xx) && descent_direction < -(T(2) * eps * eps) * smax(T(1), xx)) {
+        fallback = false;
+      } else {
+        const T relative_eps = eps * smax(T(1.0), csqrt(xx));  // :93-95
+        fallback = !cfinite(descent_direction) || descent_direction > -eps * relative_eps;
+      }
+      if (uni(fallback)) {
         // fallback: search_direction = -g, and the reference then searches
         // along -search_direction = +g: dginit = g.g >= 0.
 #pragma unroll
@@ -508,8 +531,21 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         T sy, ss, yy, xx_next;
         warp_sum4_p<P, T, E>(lane_dot_p<P, T, E>(sd, yd), lane_dot_p<P, T, E>(sd, sd),
                              lane_dot_p<P, T, E>(yd, yd), lane_dot_p<P, T, E>(xn, xn), rc, sy, ss, yy, xx_next);
-        const T sy_threshold = eps * csqrt(ss) * csqrt(yy);
-        if (uni(sy > sy_threshold)) {
+        // s.y > eps ||s|| ||y|| (:266)?  The threshold is eps sqrt(s.s) sqrt(y.y) up to 4 roundings, so with every
+        // quantity finite, s.y > 0 and (s.y)^2 in the normal range, (s.y)^2 > 2 eps^2 (s.s)(y.y) implies the exact
+        // comparison is true (the factor 2 dwarfs the rounding of both sides; a product (s.s)(y.y) that underflows
+        // only lowers the bound further below any representable (s.y)^2).  Otherwise: the specification's expression.
+        bool curvature_ok;
+        {
+          const T sy2 = sy * sy, ssyy = ss * yy;
+          if (sy > T(0) && cfinite(sy2) && cfinite(ssyy) && sy2 >= Num<T>::min_normal && sy2 > (T(2) * eps * eps) * ssyy) {
+            curvature_ok = true;
+          } else {
+            const T sy_threshold = eps * csqrt(ss) * csqrt(yy);
+            curvature_ok = sy > sy_threshold;
+          }
+        }
+        if (uni(curvature_ok)) {
           int slot;
           if (mem_count < M) {
             slot = mem_count;
