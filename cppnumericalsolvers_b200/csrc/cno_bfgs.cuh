@@ -127,7 +127,7 @@ bfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       y[0] = gn[0] - g[0];
       T ys = lane_dot<T, 1>(y, s), ss = lane_dot<T, 1>(s, s), yy = lane_dot<T, 1>(y, y);
       warp_sum3(ys, ss, yy);
-      if (uni(ys > eps * csqrt(ss) * csqrt(yy))) {
+      if (uni(curvature_above_eps<T>(ys, ss, yy))) {  // ys > eps ||s|| ||y|| (bfgs.h:125)
         const T rho = T(1) / ys;
         __syncwarp();
         va[lane] = y[0];
@@ -313,7 +313,7 @@ bfgs_smem_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x
       for (int e = 0; e < E; ++e) { s[e] = xn[e] - x[e]; y[e] = gn[e] - g[e]; }
       T ys = lane_dot<T, E>(y, s), ss = lane_dot<T, E>(s, s), yy = lane_dot<T, E>(y, y);
       warp_sum3(ys, ss, yy);
-      if (uni(ys > eps * csqrt(ss) * csqrt(yy))) {
+      if (uni(curvature_above_eps<T>(ys, ss, yy))) {  // ys > eps ||s|| ||y|| (bfgs.h:125)
         const T rho = T(1) / ys;
         __syncwarp();
         store_vec(va, y);

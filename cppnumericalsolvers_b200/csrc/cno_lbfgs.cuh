@@ -531,20 +531,8 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
         T sy, ss, yy, xx_next;
         warp_sum4_p<P, T, E>(lane_dot_p<P, T, E>(sd, yd), lane_dot_p<P, T, E>(sd, sd),
                              lane_dot_p<P, T, E>(yd, yd), lane_dot_p<P, T, E>(xn, xn), rc, sy, ss, yy, xx_next);
-        // s.y > eps ||s|| ||y|| (:266)?  The threshold is eps sqrt(s.s) sqrt(y.y) up to 4 roundings, so with every
-        // quantity finite, s.y > 0 and (s.y)^2 in the normal range, (s.y)^2 > 2 eps^2 (s.s)(y.y) implies the exact
-        // comparison is true (the factor 2 dwarfs the rounding of both sides; a product (s.s)(y.y) that underflows
-        // only lowers the bound further below any representable (s.y)^2).  Otherwise: the specification's expression.
-        bool curvature_ok;
-        {
-          const T sy2 = sy * sy, ssyy = ss * yy;
-          if (sy > T(0) && cfinite(sy2) && cfinite(ssyy) && sy2 >= Num<T>::min_normal && sy2 > (T(2) * eps * eps) * ssyy) {
-            curvature_ok = true;
-          } else {
-            const T sy_threshold = eps * csqrt(ss) * csqrt(yy);
-            curvature_ok = sy > sy_threshold;
-          }
-        }
+        // s.y > eps ||s|| ||y|| (:266), decided without the two square roots whenever a rigorous bound allows
+        const bool curvature_ok = curvature_above_eps<T>(sy, ss, yy);
         if (uni(curvature_ok)) {
           int slot;
           if (mem_count < M) {
