@@ -51,6 +51,21 @@ def test_newton_and_logistic_stage_with_tma(kernels):
         assert "UBLKCP" in k and "SYNCS" in k   # cp.async.bulk + mbarrier
 
 
+def test_newton_tensor_core_kernel_factors_on_the_fp64_tensor_core(kernels):
+    """newton_dmma_minimize_kernel (CNO_POLICY_DMMA_LU): the trailing update of the blocked elimination is DMMA.8x8x4
+    (many more than the 12 a kernel has for its reductions alone), the Tensor-Memory store moves tile rows with
+    tcgen05.ld / st (LDTM / STTM), the shared divisions start from MUFU.RCP64H, the next block is prefetched into L2."""
+    k = _find(kernels, "newton_dmma_minimize_kernel", "Li3E")   # the shipped warp population: 8 TMEM + 4 shared-memory warps
+    assert len(re.findall(r"\bDMMA\b", k)) >= 60
+    assert "LDTM" in k and "STTM" in k
+    assert "MUFU.RCP64H" in k
+    assert "CCTL" in k or "PREFETCH" in k.upper() or "LDG.E.LTC" in k or "CCTL.E.PF2" in k or "PF" in k
+    assert "BRA.DIV" not in k
+    # ... while the default-policy kernel stays free of tensor-core factorisation work (its DMMAs are the reductions)
+    k0 = _find(kernels, "newton_minimize_kernel", "DenseQuadraticFnIdLi64")
+    assert len(re.findall(r"\bDMMA\b", k0)) < 40
+
+
 def test_no_fma_contraction_in_fp32_kernels(kernels):
     """fp32 arithmetic must be FMUL/FADD (spec: products rounded before they are added);
     FFMA may only appear inside division / sqrt sequences, which are rare."""
