@@ -845,7 +845,7 @@ __device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&de
     const unsigned hmax = __reduce_max_sync(kFullMask, hkey);
     const unsigned hset = __ballot_sync(kFullMask, hkey == hmax);
     int ppos;
-    if (uni((hset & (hset - 1u)) == 0u)) {
+    if (uni_likely((hset & (hset - 1u)) == 0u)) {
       ppos = __shfl_sync(kFullMask, k_is_nan ? k : bpos, __ffs(hset) - 1);
     } else {
       const T bmax = warp_max_nonneg(best < T(0) ? T(0) : best);
@@ -882,7 +882,7 @@ __device__ __forceinline__ void lu_solve_inplace(const AugStore<T, D>& A, T (&de
         l[e] = div_with(live[e] ? col[e] : T(1), pivot, rp, ok);
         okall = okall && ok;
       }
-      if (uni(!okall)) {
+      if (uni_unlikely(!okall)) {
 #pragma unroll
         for (int e = 0; e < E; ++e) l[e] = col[e] / pivot;
       }
