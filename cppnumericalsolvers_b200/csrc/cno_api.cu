@@ -110,13 +110,13 @@ int launch_lbfgs(const Fn& fn, const LaunchArgs& a) {
   CNO_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned long long), a.stream));
   const cno::StopParams<T> stop = cno::make_stop<T>(*a.stop);
   const cno::BatchOut<T> out = cno::make_out<T>(*a.out);
-  kernel<<<grid, SM::kWarps * 32, smem, a.stream>>>(fn, static_cast<const T*>(a.x0), a.batch,
-                                                    stop, out, queue, a.resume);
+  kernel<<<grid, SM::kThreads, smem, a.stream>>>(fn, static_cast<const T*>(a.x0), a.batch,
+                                                 stop, out, queue, a.resume);
   CNO_CUDA(cudaGetLastError());
   if (a.info) {
     a.info->kernel_launches += 1;
     a.info->grid = grid;
-    a.info->block = SM::kWarps * 32;
+    a.info->block = SM::kThreads;
     a.info->warps_per_cta = SM::kWarps;
     a.info->dynamic_smem = (int64_t)smem;
   }

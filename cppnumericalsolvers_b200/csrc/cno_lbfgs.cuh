@@ -32,7 +32,7 @@
 
 namespace cno {
 
-template <class T, int D, int M, int kStage = 0, int kScratchPerLane = 0, int kFnTmem = 0, int kMaxW = 16>
+template <class T, int D, int M, int kStage = 0, int kScratchPerLane = 0, int kFnTmem = 0, int kMaxW = 16, int kHelpers = 0>
 struct LbfgsSmem {
   static constexpr int E = Shape<D>::E;
   static constexpr int kVec = 32 * E;                        // elements per stored vector
@@ -54,6 +54,11 @@ struct LbfgsSmem {
   static constexpr int kTmemWarpCap = kFnTmem > 0 ? 4 * (512 / kFnTmem) : kTmemYCap;
   static constexpr int kCap = kTmemWarpCap < kMaxWarps ? kTmemWarpCap : kMaxWarps;
   static constexpr int kWarps = kWarpsFit > kCap ? kCap : (kWarpsFit < 1 ? 1 : kWarpsFit);
+  // Functors with a helper warp per instance (FnHelperWarps): solver warps 0 .. kWarps-1, the helper of solver warp t is
+  // warp kHelperBase + t (with 5 solver warps: another sub-partition than its solver warp, 2-3 warps per sub-partition);
+  // the functor's Tensor Memory window belongs to the HELPER (its own lane quadrant).
+  static constexpr int kHelperBase = kWarps;
+  static constexpr int kThreads = 32 * (kHelpers > 0 ? 2 * kWarps : kWarps);
 };
 
 // y-history accessors: shared memory (chunk-interleaved) or Tensor Memory.
@@ -188,11 +193,11 @@ struct LbfgsPlan {
   static constexpr bool kPlain = std::is_same<LS, LsMoreThuente>::value && !IsSecondMode<Fn>::value && !kResume;
   using SM = LbfgsSmem<typename Fn::Scalar, Fn::Dim, M, StageElems<Fn>::value,
                        PolicyScratch<typename PolicyOf<Fn>::type>::kElemsPerLane, FnTmemCols<Fn>::value,
-                       kPlain ? FnPreferredWarps<Fn>::value : 16>;
+                       kPlain ? FnPreferredWarps<Fn>::value : 16, FnHelperWarps<Fn>::value>;
 };
 
 template <class Fn, int M, bool kResume = false, class LS = LsMoreThuente>
-__global__ void __launch_bounds__(LbfgsPlan<Fn, M, kResume, LS>::SM::kWarps * 32, 1)
+__global__ void __launch_bounds__(LbfgsPlan<Fn, M, kResume, LS>::SM::kThreads, 1)
 lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
                       const long long batch, const StopParams<typename Fn::Scalar> stop,
                       const BatchOut<typename Fn::Scalar> out,
@@ -211,7 +216,10 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   CNO_DYNAMIC_SMEM(smem_raw);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  T* const S = reinterpret_cast<T*>(smem_raw) + (size_t)warp * SM::kWarpElems;
+  constexpr int kHelpers = FnHelperWarps<Fn>::value;
+  // the instance slot this warp works for: its own, or (helper warps) the one of its solver warp
+  const int slot = (kHelpers > 0 && warp >= SM::kHelperBase) ? warp - SM::kHelperBase : warp;
+  T* const S = reinterpret_cast<T*>(smem_raw) + (size_t)slot * SM::kWarpElems;
   T* const Ysm = S + M * SM::kVec;     // (unused when the y-history lives in TMEM)
   T* const rho_s = S + (SM::kTmemY ? 1 : 2) * M * SM::kVec;  // 1 / (s_i . y_i) per slot
   uint32_t tmem_base = 0;
@@ -236,7 +244,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   }
   YHist<T, E, SM::kTmemY> Y;
   if constexpr (SM::kTmemY) {
-    Y.taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * SM::kTmemColsPerWarp);
+    Y.taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((slot >> 2) * SM::kTmemColsPerWarp);
   } else {
     Y.base = Ysm;
     Y.lane = lane;
@@ -250,12 +258,21 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
   const RedCtx<T> rc{red_scratch, lane};
   void* const stage_ptr = (kStage > 0) ? static_cast<void*>(S + SM::kHistElems) : static_cast<void*>(red_scratch);
   uint32_t stage_parity = 0;
+  // (with helper warps the window is the helper's: its own lane quadrant, one window per helper of that quadrant)
   const uint32_t fn_tmem = (kFnTmem > 0)
-                               ? tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * kFnTmem)
+                               ? tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) +
+                                     (uint32_t)(((kHelpers > 0 ? (warp >= SM::kHelperBase ? warp - SM::kHelperBase : 0) : warp) >> 2) * kFnTmem)
                                : 0u;
-  if constexpr (kStage > 0) fn.init_stage(EvalCtx{lane, 0, stage_ptr, fn_tmem});
+  bool solver_warp = true;
+  if constexpr (kHelpers > 0) {
+    solver_warp = uni(warp < SM::kWarps);
+    if (uni(warp >= SM::kHelperBase)) fn.helper(EvalCtx{lane, 0, stage_ptr, fn_tmem, slot});  // until its solver warp releases it
+  }
+  if constexpr (kStage > 0) {
+    if (solver_warp) fn.init_stage(EvalCtx{lane, 0, stage_ptr, fn_tmem, slot});
+  }
 
-  for (;;) {
+  for (; solver_warp;) {
     // ---- retire + refill: next instance from the global queue ----
     unsigned long long b = 0;
     if (lane == 0) b = atomicAdd(queue, 1ULL);
@@ -264,7 +281,7 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
     if constexpr (FnSkipsInstances<Fn>::value) {  // e.g. AugLagFn: the instance's outer loop has finished
       if (uni(!fn.active((long long)b))) continue;
     }
-    const EvalCtx ctx{lane, (long long)b, stage_ptr, fn_tmem};
+    const EvalCtx ctx{lane, (long long)b, stage_ptr, fn_tmem, slot};
     if constexpr (kStage > 0) fn.stage(ctx, stage_parity);  // per-instance data -> shared memory (TMA)
 
     T x[E], g[E];
@@ -618,6 +635,9 @@ lbfgs_minimize_kernel(const Fn fn, const typename Fn::Scalar* __restrict__ x0,
       if (out.gradient_norm) out.gradient_norm[b] = prog.gradient_norm;
     }
     __syncwarp();
+  }
+  if constexpr (kHelpers > 0) {
+    if (solver_warp) fn.release_helper(EvalCtx{lane, 0, stage_ptr, fn_tmem, slot});
   }
 #ifndef CNO_WARP_EMULATION
   if constexpr (kAllocTmem) {

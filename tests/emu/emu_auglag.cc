@@ -291,9 +291,11 @@ extern "C" int emu_logistic(const cno_problem_t* p, long long batch, const void*
   using Fn = cno::LogisticFn<float, 64, 256>;
   const Fn fn{static_cast<const float*>(p->data), (long long)p->data_stride, (float)p->param};
   unsigned long long queue = 0;
-  emu::run_warp([&](int lane) {
+  // one team of the kernel's CTA: solver warp 0 and its helper warp (the functor declares kHelperWarps)
+  using SM = cno::LbfgsPlan<Fn, CNO_LBFGS_M>::SM;
+  emu::run_team([&](int lane, int w) {
     blockIdx.x = 0;
-    threadIdx.x = (unsigned)lane;
+    threadIdx.x = (unsigned)(32 * (w ? SM::kHelperBase : 0) + lane);
     cno::lbfgs_minimize_kernel<Fn, CNO_LBFGS_M>(fn, (const float*)x0, batch, cno::make_stop<float>(*stop),
                                                 cno::make_out<float>(*out), &queue, cno::ResumeArgs{nullptr, 0, 0, 0});
   });

@@ -70,6 +70,8 @@ struct Warp {
   double dslot[32];
   double dslot2[32];
   uint32_t tmem[32][512];  // Tensor Memory window of the emulated warp: [lane][column], 32-bit cells
+  uint32_t (*tm)[512] = tmem;   // the window this warp addresses (a helper warp of a team shares its leader's: same lane quadrant)
+  SpinBarrier* team = nullptr;  // named barrier of a leader + helper team (bar.sync id, 64)
 };
 inline thread_local int tl_lane = 0;
 inline thread_local Warp* tl_warp = nullptr;
@@ -125,11 +127,11 @@ inline void dmma(double& d0, double& d1, double a, double b, double c0, double c
 // tcgen05.st / tcgen05.ld .32x32b.xN: lane l moves N consecutive 32-bit columns of its own TMEM lane
 inline void tmem_store(uint32_t taddr, const uint32_t* w, int n) {
   const uint32_t col = taddr & 0xffffu;
-  for (int i = 0; i < n; ++i) tl_warp->tmem[tl_lane][col + i] = w[i];
+  for (int i = 0; i < n; ++i) tl_warp->tm[tl_lane][col + i] = w[i];
 }
 inline void tmem_load(uint32_t taddr, uint32_t* w, int n) {
   const uint32_t col = taddr & 0xffffu;
-  for (int i = 0; i < n; ++i) w[i] = tl_warp->tmem[tl_lane][col + i];
+  for (int i = 0; i < n; ++i) w[i] = tl_warp->tm[tl_lane][col + i];
 }
 
 // Runs f(lane) on 32 lock-step threads = one warp.
@@ -144,6 +146,31 @@ inline void run_warp(const std::function<void(int)>& f) {
       tl_warp = &w;
       f(l);
     });
+  for (auto& t : ts) t.join();
+}
+// bar.sync id, 64: the two warps of a team meet (all 64 threads arrive)
+inline void team_sync() { tl_warp->team->arrive_and_wait(); }
+
+// Runs f(lane, w) on 64 lock-step threads = a leader warp (w = 0) and its helper warp (w = 1), which share the leader's
+// Tensor Memory window and a named barrier; shared memory is the kernel's function-static array, as for one warp.
+inline void run_team(const std::function<void(int, int)>& f) {
+  static Warp w_storage[2];
+  static SpinBarrier team_bar;
+  new (&team_bar) SpinBarrier();
+  team_bar.total = 64;
+  for (int w = 0; w < 2; ++w) {
+    new (&w_storage[w]) Warp();
+    w_storage[w].tm = w_storage[0].tmem;
+    w_storage[w].team = &team_bar;
+  }
+  std::vector<std::thread> ts;
+  for (int w = 0; w < 2; ++w)
+    for (int l = 0; l < 32; ++l)
+      ts.emplace_back([&, w, l] {
+        tl_lane = l;
+        tl_warp = &w_storage[w];
+        f(l, w);
+      });
   for (auto& t : ts) t.join();
 }
 }  // namespace emu
