@@ -191,11 +191,15 @@ struct LogisticFn {
         P4::get(*reinterpret_cast<const typename P4::type*>(X0 + (i0 + q) * 128 + 4 * c.lane), x[q]);
     }
   }
-  // margins z_j = sum_i Xt[i][j] w_i (i ascending) of the 4 samples this lane owns in its warp's chunk
+  // margins z_j = sum_i Xt[i][j] w_i (i ascending) of the 4 samples this lane owns in its warp's chunk.  The chain
+  // starts from -0: (-0) + p is p for every float p, the zeros with their signs included, so the first step leaves the
+  // first product exactly as the definition has it and every batch runs the same code.
   template <bool kHelper>
   __device__ __forceinline__ void margins(const EvalCtx& c, T (&z)[4]) const {
     const T* wv = static_cast<const T*>(c.stage) + kW;
     constexpr int NF = 8;  // features per batch of loads
+#pragma unroll
+    for (int t = 0; t < 4; ++t) z[t] = -T(0);
 #pragma unroll 1
     for (int i0 = 0; i0 < D; i0 += NF) {
       T x[NF][4];
@@ -207,28 +211,33 @@ struct LogisticFn {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const T prod = x[q4 + k][t] * w4[k];
-            if (q4 + k == 0) z[t] = (i0 == 0) ? prod : (z[t] + prod);  // (the chain starts with the first product)
-            else z[t] = z[t] + prod;
-          }
+          for (int t = 0; t < 4; ++t) z[t] = z[t] + x[q4 + k][t] * w4[k];
       }
     }
   }
-  // per-sample loss and coefficient of the chunk; returns the lane's loss partial of the chunk
+  // per-sample loss and coefficient of the chunk; returns the lane's loss partial of the chunk.  One sample per trip of a
+  // ROLLED loop (the four samples rotate through one set of registers): the compiler serialises the samples anyway
+  // (the exp early-out and the division slow paths are branches), so unrolled it is four times the code for nothing.
   template <bool kHelper>
   __device__ __forceinline__ T losses(const EvalCtx& c, const T (&z)[4], T (&coef)[4]) const {
     const T* y = static_cast<const T*>(c.stage) + kY;
-    T yv[4], ls[4];
+    T yv[4], ls[4], zz[4];
     P4::get(*reinterpret_cast<const typename P4::type*>(y + (kHelper ? 128 : 0) + 4 * c.lane), yv);
 #pragma unroll
+    for (int t = 0; t < 4; ++t) { zz[t] = z[t]; ls[t] = coef[t] = T(0); }
+#pragma unroll 1
     for (int t = 0; t < 4; ++t) {
-      const T m = yv[t] * z[t];
+      const T m = yv[0] * zz[0];
       const T e = cno_exp(-cabs(m));
       const T l1p = cno_log1p01<T>(e);
-      ls[t] = (m < T(0)) ? (l1p - m) : l1p;
+      const T l = (m < T(0)) ? (l1p - m) : l1p;
       const T sig = ((m < T(0)) ? T(1) : e) / (T(1) + e);  // 1 / (1 + e) or e / (1 + e): one division, the same operands
-      coef[t] = -(yv[t] * sig);
+      const T cf = -(yv[0] * sig);
+      // rotate: sample t+1 moves to the front, the results of sample t to the back
+      yv[0] = yv[1]; yv[1] = yv[2]; yv[2] = yv[3];
+      zz[0] = zz[1]; zz[1] = zz[2]; zz[2] = zz[3];
+      ls[0] = ls[1]; ls[1] = ls[2]; ls[2] = ls[3]; ls[3] = l;
+      coef[0] = coef[1]; coef[1] = coef[2]; coef[2] = coef[3]; coef[3] = cf;
     }
     return (ls[0] + ls[1]) + (ls[2] + ls[3]);
   }
