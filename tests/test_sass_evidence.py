@@ -51,6 +51,18 @@ def test_newton_and_logistic_stage_with_tma(kernels):
         assert "UBLKCP" in k and "SYNCS" in k   # cp.async.bulk + mbarrier
 
 
+def test_logistic_kernel_runs_two_warps_per_instance(kernels):
+    """LogisticFn declares a helper warp per instance (csrc/cno_logistic.cuh): the kernel meets it at named barriers
+    (BAR.SYNC with a register barrier id and 64 threads), the helper's chunk lives in Tensor Memory (LDTM / STTM), the
+    solver warp's chunk arrives by TMA bulk copies, and exp's scaling is a multiplication (no libdevice ldexpf call left:
+    the kernel's only subroutines are the division / square-root slow paths)."""
+    k = _find(kernels, "lbfgs_minimize_kernel", "LogisticFn")
+    assert len(re.findall(r"BAR\.SYNC\.DEFER_BLOCKING R\d+, 0x40", k)) >= 6
+    assert "LDTM" in k and "STTM" in k and "UBLKCP" in k
+    n_instr = len(re.findall(r"^\s+/\*[0-9a-f]{4,6}\*/", k, flags=re.M))
+    assert n_instr < 4500, n_instr   # code size is a performance property here (DESIGN.md 2.4: L0 instruction cache)
+
+
 def test_newton_tensor_core_kernel_factors_on_the_fp64_tensor_core(kernels):
     """newton_dmma_minimize_kernel (CNO_POLICY_DMMA_LU): the trailing update of the blocked elimination is DMMA.8x8x4
     (many more than the 12 a kernel has for its reductions alone), the Tensor-Memory store moves tile rows with
