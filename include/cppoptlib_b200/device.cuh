@@ -48,6 +48,9 @@ inline int launch_user(Kernel kernel, const Fn& fn, int64_t batch, const void* x
                        const cno_stop_t* stop, const cno_batch_out_t* out, void* workspace,
                        size_t workspace_bytes, void* stream, cno_launch_info_t* info, Extra... extra) {
   using T = typename Fn::Scalar;
+  // one warp per instance: the helper-warp extension of the functor concept (kHelperWarps, csrc/cno_logistic.cuh) is
+  // launched by the library's own launcher only (its CTA has two warps per instance)
+  static_assert(FnHelperWarps<Fn>::value == 0, "user functors run one warp per instance");
   if (batch < 0 || !out || !workspace || workspace_bytes < 8) return CNO_ERR_INVALID_ARGUMENT;
   if (info) *info = cno_launch_info_t{};
   if (batch == 0) return CNO_OK;
