@@ -394,8 +394,10 @@ def test_emulation_tensor_core_newton_equals_the_fused_oracle(emu, case, store):
 
 def test_emulation_reproduces_the_logistic_kernel(emu):
     """L-BFGS on the logistic-regression functor (csrc/cno_logistic.cuh): per-instance data staged by TMA bulk
-    copies into shared memory and by tcgen05.st into Tensor Memory -- under emulation a memcpy and a host array."""
-    B, n, d, lam = 1, 256, 64, 1e-2
+    copies into shared memory and by tcgen05.st into Tensor Memory -- under emulation a memcpy and a host array --
+    and evaluated by a TEAM of two warps (solver warp + helper warp, 64 lock-step threads meeting at the named
+    barrier; emu::run_team).  Three instances through one team: the data are re-staged and the helper re-armed."""
+    B, n, d, lam = 3, 256, 64, 1e-2
     rng = np.random.default_rng(3)
     X = rng.uniform(-1, 1, (B, n, d)).astype(np.float32)
     wstar = rng.normal(size=(B, d)).astype(np.float32)
