@@ -302,6 +302,33 @@ extern "C" int emu_logistic(const cno_problem_t* p, long long batch, const void*
   return 0;
 }
 
+// The logistic functor alone, evaluated by a team at given points: value only (g == nullptr: the helper gets the
+// value-only command) or value + gradient.  One team, the instances one after the other (staging included).
+extern "C" int emu_logistic_evaluate(const cno_problem_t* p, long long batch, const float* x, float* f, float* g) {
+  if (!(p->family == CNO_FN_LOGISTIC && p->dtype == CNO_F32 && p->d == 64 && p->n == 256)) return CNO_ERR_UNSUPPORTED;
+  using Fn = cno::LogisticFn<float, 64, 256>;
+  constexpr int E = Fn::E;
+  const Fn fn{static_cast<const float*>(p->data), (long long)p->data_stride, (float)p->param};
+  alignas(16) static float stage[Fn::kStageElems];
+  emu::run_team([&](int lane, int w) {
+    cno::EvalCtx ctx{lane, 0, stage, 0u, 0};
+    if (w == 1) { fn.helper(ctx); return; }
+    uint32_t parity = 0;
+    fn.init_stage(ctx);
+    for (long long b = 0; b < batch; ++b) {
+      ctx.instance = b;
+      fn.stage(ctx, parity);
+      float xv[E], gv[E];
+      for (int e = 0; e < E; ++e) xv[e] = x[b * 64 + lane * E + e];
+      const float v = g ? fn(ctx, xv, &gv) : fn(ctx, xv, nullptr);
+      if (lane == 0) f[b] = v;
+      if (g) for (int e = 0; e < E; ++e) g[b * 64 + lane * E + e] = gv[e];
+    }
+    fn.release_helper(ctx);
+  });
+  return 0;
+}
+
 // ---- cno::al_outer_loop (csrc/cno_auglag_host.h: the host side of cno_al_minimize) with an emulation backend ----
 template <class Obj>
 struct AlEmuBackend {

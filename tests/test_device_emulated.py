@@ -418,6 +418,34 @@ def test_emulation_reproduces_the_logistic_kernel(emu):
         assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
 
 
+def test_emulated_logistic_team_evaluates_like_the_oracle(emu):
+    """The functor alone, through both commands of its helper warp (value only / value + gradient), at points chosen
+    to reach every branch of the shared exp / log1p kernels: small weights, margins of a few tens, and margins beyond
+    the clamp (|m| > 87: exp returns 0) and just inside it (2^k with k near -126: the scaling is one multiplication on
+    the device side, ldexpf in the oracle)."""
+    B, n, d, lam = 6, 256, 64, 1e-2
+    rng = np.random.default_rng(11)
+    X = rng.uniform(-1, 1, (B, n, d)).astype(np.float32)
+    y = np.sign(rng.normal(size=(B, n))).astype(np.float32)
+    data = np.ascontiguousarray(np.concatenate([X.transpose(0, 2, 1).reshape(B, -1), y], axis=1))
+    scales = np.array([0.0, 0.1, 1.0, 5.0, 19.0, 40.0], np.float32)   # |m| up to ~ 4 scale sqrt(d / 3)
+    x = (rng.normal(size=(B, d)).astype(np.float32) * scales[:, None]).astype(np.float32)
+    prob = ob.Problem(ob.FN_LOGISTIC, ob._np_dtype(x), d, n, lam, data.ctypes.data, data.shape[1],
+                      ob.device_policy(x.dtype), 0)
+    fo, go = ob.evaluate(ob.FN_LOGISTIC, x, data=data, n=n, param=lam)
+    m = y * np.einsum("bnd,bd->bn", X.astype(np.float64), x.astype(np.float64))
+    assert np.abs(m).max() > 100 and ((np.abs(m) > 80) & (np.abs(m) < 87)).any()   # the clamp and the 2^-126 neighbourhood are hit
+    f = np.zeros(B, np.float32)
+    g = np.zeros((B, d), np.float32)
+    emu.emu_logistic_evaluate.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert emu.emu_logistic_evaluate(C.byref(prob), B, x.ctypes.data, f.ctypes.data, g.ctypes.data) == 0
+    assert np.array_equal(f.view(np.uint32), np.asarray(fo, np.float32).view(np.uint32))
+    assert np.array_equal(g.view(np.uint32), np.asarray(go, np.float32).view(np.uint32))
+    f2 = np.zeros(B, np.float32)
+    assert emu.emu_logistic_evaluate(C.byref(prob), B, x.ctypes.data, f2.ctypes.data, None) == 0   # value-only command
+    assert np.array_equal(f2.view(np.uint32), f.view(np.uint32))
+
+
 # ---- the host side of cno_al_minimize itself (csrc/cno_auglag_host.h) with an emulation backend ------------
 def emulated_cno_al_minimize(emu, family, x0, kinds, rows, n_eq, *, outer_stop=None, config=None, inner_stop=None,
                              eq0=None, ineq0=None, penalty0=None, data=None):
