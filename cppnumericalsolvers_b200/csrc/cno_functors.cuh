@@ -14,6 +14,14 @@
 //                                  Scalar (*grad)[E]) const;
 //   };
 //
+// Optional members the solver kernels look for (traits in cno_device.cuh):
+//   kStageElems + init_stage()/stage()  per-instance data staged into the warp's shared-memory slice (StageElems)
+//   kTmemCols                           a Tensor Memory window per instance (FnTmemCols)
+//   kPreferredWarps                     resident warps per CTA the functor's register budget allows (FnPreferredWarps)
+//   active(instance)                    instances the kernel skips (FnSkipsInstances; AugLagFn)
+//   kHelperWarps = 1 + helper()/release_helper()   a second warp per instance that the functor drives through a
+//                                       named barrier (FnHelperWarps; LogisticFn, built-in functors only)
+//
 // The operation order of each functor below is restated one-for-one by the
 // CPU oracle (oracle/cno_oracle_impl.inc: eval_*), so values and gradients
 // agree bit for bit.
