@@ -180,7 +180,7 @@ typedef struct cno_launch_info {
   int32_t kernel_launches; /* kernels of this library launched by the call */
   int32_t grid;            /* CTAs */
   int32_t block;           /* threads per CTA */
-  int32_t warps_per_cta;
+  int32_t warps_per_cta;   /* solver warps = resident instances per CTA (block / 32 is twice that for a functor with a helper warp per instance) */
   int64_t dynamic_smem;    /* bytes per CTA */
   float kernel_ms;         /* device time of the solve kernel(s), CUDA events */
   float total_ms;          /* cno_minimize_host: including H2D/D2H */
