@@ -256,6 +256,44 @@ def test_emulation_reproduces_gpu_validated_kernels(emu, solver, hz, dtype, d, l
         assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), key
 
 
+@pytest.mark.parametrize("solver,hz,dtype,d", [
+    (ob.LBFGS, 0, np.float64, 8), (ob.LBFGS, 1, np.float64, 8), (ob.LBFGS, 0, np.float32, 37), (ob.BFGS, 0, np.float64, 8),
+    (ob.GRADIENT_DESCENT, 0, np.float64, 8), (ob.CONJUGATED_GRADIENT_DESCENT, 0, np.float64, 8)])
+def test_emulated_kernels_follow_progress_update_under_random_settings(emu, solver, hz, dtype, d):
+    """The device progress_update (csrc/cno_lbfgs.cuh: the order of Progress::Update's tests, the allowed-violation
+    counters, relative thresholds, the past-f ring and its square-root-free plateau pre-test) against the oracle under
+    six random Progress settings per kernel family -- every output bit for bit."""
+    rng = np.random.default_rng(77 + 10 * solver + hz + d)
+    B = 3
+    seen = set()
+    for k in range(6):
+        stop = ob.default_stop()
+        stop.num_iterations = int(rng.choice([3, 7, 25, 40]))
+        stop.x_delta = float(rng.choice([0.0, 1e-9, 1e-4, 1e-2]))
+        stop.x_delta_violations = int(rng.integers(1, 4))
+        stop.f_delta = float(rng.choice([0.0, 0.0, 1e-8, 1e-3, 1e-1]))
+        stop.f_delta_violations = int(rng.integers(1, 4))
+        stop.f_delta_relative = int(rng.integers(0, 2))
+        stop.gradient_norm = float(rng.choice([0.0, 1e-5, 1e-2, 1.0]))
+        stop.gradient_norm_relative = int(rng.integers(0, 2))
+        stop.past = int(rng.integers(0, 9))
+        stop.past_delta = float(rng.choice([1e-10, 1e-6, 1e-2]))
+        x0 = ob.fill_uniform((B, d), 31 * k, 808 + d, -2.0, 2.0, dtype)
+        prob = _problem(ob.FN_ROSENBROCK, x0)
+        r = dict(x=np.zeros_like(x0), value=np.zeros(B, dtype), gradient=np.zeros_like(x0),
+                 num_iterations=np.zeros(B, np.uint32), status=np.zeros(B, np.int8), nfev=np.zeros(B, np.uint32),
+                 x_delta=np.zeros(B, dtype), f_delta=np.zeros(B, dtype), gradient_norm=np.zeros(B, dtype))
+        out = ob.BatchOut(*[r[n].ctypes.data for n, _ in ob.BatchOut._fields_])
+        assert emu.emu_minimize(solver, hz, C.byref(prob), C.c_longlong(B), C.c_void_p(x0.ctypes.data), C.byref(stop),
+                                C.byref(out)) == 0
+        o = ob.minimize(solver, ob.FN_ROSENBROCK, x0, stop=stop, linesearch=hz)
+        for key in SOLVER_KEYS:
+            assert np.array_equal(r[key].view(np.uint8), o[key].view(np.uint8)), (k, key, [getattr(stop, f[0]) for f in ob.Stop._fields_])
+        seen.update(int(v) for v in r["status"])
+    if solver == ob.LBFGS and d == 8:
+        assert len(seen) >= 2, seen   # (the sweep is not all iteration limits)
+
+
 def test_gradient_descent_hager_zhang_failed_search_rebuilds_point_from_step(emu):
     """Found by sweeping the emulated kernels against the oracle: when HagerZhang fails (non-finite
     evaluations) GradientDescent's next point is x - rate * g with rate = 0 (gradient_descent.h:72), i.e. NaN

@@ -170,6 +170,48 @@ def test_oracle_equals_reference_headers(dtype, policy, solver, d):
     assert _same(a, b)
 
 
+def _random_stop(rng):
+    """A random Progress setting that can fire every stopping rule of progress.h:212-300 within a few dozen iterations."""
+    s = ob.default_stop()
+    s.num_iterations = int(rng.choice([3, 7, 25, 60, 10000]))
+    s.x_delta = float(rng.choice([0.0, 1e-9, 1e-4, 1e-2]))
+    s.x_delta_violations = int(rng.integers(1, 4))
+    s.f_delta = float(rng.choice([0.0, 0.0, 1e-8, 1e-3, 1e-1]))
+    s.f_delta_violations = int(rng.integers(1, 4))
+    s.f_delta_relative = int(rng.integers(0, 2))
+    s.gradient_norm = float(rng.choice([0.0, 1e-5, 1e-2, 1.0]))
+    s.gradient_norm_relative = int(rng.integers(0, 2))
+    s.past = int(rng.integers(0, 9))
+    s.past_delta = float(rng.choice([1e-10, 1e-6, 1e-2]))
+    return s
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("solver", [ob.LBFGS, ob.BFGS, ob.NEWTON, ob.GRADIENT_DESCENT, ob.CONJUGATED_GRADIENT_DESCENT])
+def test_oracle_equals_reference_headers_under_random_progress_settings(solver, dtype):
+    """The ORDER of the tests in Progress::Update decides the reported status (SURVEY.md 3.4): 40 random settings per
+    solver -- iteration limits, x / f deltas with 1-3 allowed violations, absolute and relative thresholds, past windows
+    0-8 -- through the C oracle and through the reference's own progress.h (oracle/_ref); every output equal bit for
+    bit, and every solver's sweep ends in at least three different statuses."""
+    if not ob.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    if solver == ob.CONJUGATED_GRADIENT_DESCENT and dtype == np.float32:
+        pytest.skip("ConjugatedGradientDescent is fp64 only (the reference mixes double into ScalarType vectors)")
+    rng = np.random.default_rng(1234 + 10 * solver + (dtype == np.float32))
+    d, B = 8, 8
+    seen = set()
+    for k in range(40):
+        stop = _random_stop(rng)
+        if solver in (ob.GRADIENT_DESCENT, ob.CONJUGATED_GRADIENT_DESCENT):
+            stop.num_iterations = min(stop.num_iterations, 60)
+        x0 = ob.fill_uniform((B, d), 17 * k, 4321, -2.0, 2.0, dtype)
+        a = ob.minimize(solver, ob.FN_ROSENBROCK, x0, impl="oracle", stop=stop)
+        b = ob.minimize(solver, ob.FN_ROSENBROCK, x0, impl="ref", stop=stop)
+        assert _same(a, b), (k, [getattr(stop, f[0]) for f in ob.Stop._fields_])
+        seen.update(int(v) for v in a["status"])
+    assert len(seen) >= 3, seen
+
+
 def test_fused_lu_oracle_equals_reference_headers():
     """CNO_POLICY_DMMA_LU: the oracle's lu_solve(fused = 1) == the reference's newton_descent.h / armijo.h /
     progress.h on the shim whose lu().solve() fuses every multiply-subtract under this policy; d = 64 (the shape
